@@ -1,0 +1,44 @@
+"""Helpers to load tests/golden/*.npz and rebuild the seeded state dict / batch they were made with."""
+import os
+
+import numpy as np
+import torch
+
+from oracle.seeding import seeded_state_dict, synthetic_batch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+IMG_TINY = dict(block_type="MLPMixer", in_channels=3, hidden_dim=64, patch_size=16, image_size=[64, 48], token_dim=16,
+                channel_dim=96, num_mixers=1)
+TXT_TINY = dict(block_type="PNLPMixer", max_seq_len=24, hidden_dim=64, num_mixers=1, mlp_hidden_dim=48,
+                bottleneck_window_size=1, bottleneck_features_size=40)
+MM_TINY = dict(block_type="FusionMixer", fusion_function="ConcatFusion", hidden_dim=64, token_dim=16, channel_dim=96,
+               num_mixers=1)
+POS_WEIGHT = [4.57642832, 7.38544978, 10.79846869, 13.23391421, 15.59020924, 18.62735849, 22.48861048, 25.21711367,
+              74.50943396, 31.31641554, 31.79549114, 32.90833333, 39.64859438, 56.90201729, 40.46106557, 58.24483776,
+              67.3890785, 84.92473118, 58.33087149, 62.68253968, 114.13294798, 141.54121864, 116.83431953]
+
+KIND = {"avmnist_S_b8": "avmnist", "avmnist_S_sum_b8": "avmnist", "avmnist_M_b4": "avmnist",
+        "avmnist_B_b16": "avmnist", "mimic_H_b16": "mimic", "mmimdb_tiny_b6": ("mmimdb", IMG_TINY, TXT_TINY)}
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def rebuild(name, dtype=torch.float32, device="cpu", requires_grad=True):
+    z = load(name)
+    shapes = {k: tuple(int(t) for t in s.split(",")) for k, s in zip(z["meta.keys"].tolist(), z["meta.shapes"].tolist())}
+    seed, bsz = int(z["meta.seed"]), int(z["meta.batch"])
+    sd = {k: v.to(device).requires_grad_(requires_grad) for k, v in seeded_state_dict(shapes, seed, dtype).items()}
+    batch = synthetic_batch(KIND[name], bsz, seed, dtype)
+    mv = lambda t: t.to(device)
+    batch = {k: mv(v) for k, v in batch.items()} if isinstance(batch, dict) else tuple(mv(v) for v in batch)
+    return z, sd, batch
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
