@@ -1,0 +1,143 @@
+/* m2b200 - C ABI of the B200-native M2-Mixer training hot path (libm2b200.so).
+ *
+ * The reference (bezirganyan/m2-mixer) is pure Python with no FFI: its only seam for this path is the name registry
+ * modules.get_block_by_name / get_fusion_by_name / get_classifier_by_name (modules/__init__.py:12-26).  The drop-in
+ * nn.Modules in m2_mixer_b200/modules bind to these entry points through ctypes (m2_mixer_b200/_lib.py) and register
+ * them as torch.library ops (m2_mixer_b200/ops.py).  Each entry point below names the reference code it replaces.
+ *
+ * Conventions
+ *  - plain C: raw DEVICE pointers, explicit sizes, no torch types; fp32 unless a name ends in _bf16 / says bf16.
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it: no allocation, no host sync,
+ *    no global mutable state (only one-time cudaFuncSetAttribute).  The caller owns every buffer, including
+ *    `workspace` (size from the matching *_workspace_bytes query), and keeps them alive until the stream drains.
+ *  - return value: 0 = ok, otherwise an M2B200_ERR_* code (never throws, never aborts).
+ *  - precision: M2B200_FP32 = CUDA-core FP32 FMA + exact erf GELU (parity mode, <=1e-4 vs the fp32 reference);
+ *               M2B200_BF16 = tcgen05 tensor cores, bf16 operands / fp32 accumulate (<=2e-2 on logits).
+ *  - parameter-gradient outputs (dw*, db*, dln_*) are ACCUMULATED INTO (+=): zero them first or point them at a
+ *    running gradient buffer.  Activation-gradient outputs (dx, du) are overwritten unless stated otherwise.
+ *  - all fp32 pointers must be 16-byte aligned, hidden sizes D multiples of 8 in bf16 mode (4 in fp32 mode).
+ */
+#ifndef M2B200_H_
+#define M2B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M2B200_OK 0
+#define M2B200_ERR_ARG 1
+#define M2B200_ERR_ALIGN 2
+#define M2B200_ERR_WORKSPACE 3
+#define M2B200_ERR_LAUNCH 4
+#define M2B200_ERR_DRIVER 5
+
+#define M2B200_FP32 0
+#define M2B200_BF16 1
+
+#define M2B200_ACT_NONE 0
+#define M2B200_ACT_GELU 1
+#define M2B200_ACT_RELU 2
+
+int m2b200_abi_version(void);
+const char* m2b200_status_string(int status);
+
+/* bf16 operand cache of an fp32 [rows][cols] matrix, row stride ldd >= cols (pad columns zeroed).  The modules keep
+ * fp32 master weights in the reference's [out,in] state-dict layout and refresh this cache after every
+ * optimiser step. */
+int m2b200_cast_bf16(const float* src, int64_t lds, void* dst_bf16, int64_t ldd, int rows, int cols, void* stream);
+
+/* Generic GEMM  C[b] = act(A[b] (x) B[b] + bias) + residual  (see csrc/kernels.h GemmArgs for the full contract).
+ * precision FP32: A,B are fp32; BF16: A,B are bf16 (tcgen05 + TMA).  a_mn/b_mn = 1 means the operand is stored
+ * [K][M] / [K][N] (contraction axis outermost) - this is how the transposes of modules/mixer.py:32,34 and every
+ * weight-gradient contraction are expressed without materialising a permute. */
+int m2b200_gemm(int precision, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, int M, int N,
+                int K, int batch, int64_t a_batch_rows, int64_t b_batch_rows, const float* bias, int bias_mode, int act,
+                const float* residual, int64_t ldr, int64_t r_batch_stride, void* C, int c_bf16, int64_t ldc,
+                int64_t c_batch_stride, int accumulate, int splitk, void* stream);
+
+/* ---- MixerBlock.token_mix + residual: modules/mixer.py:30-35,43
+ *   u[b] = x[b] + Wt2 . GELU(Wt1 . LN(x[b]) + bt1) + bt2,   x,u [B][N][D], wt1 [T][N], wt2 [N][T]            */
+int m2b200_token_mix_fwd(const float* x, const float* ln_w, const float* ln_b, const float* wt1, const float* bt1,
+                         const float* wt2, const float* bt2, float* u, int B, int N, int D, int T, int precision,
+                         void* stream);
+size_t m2b200_token_mix_bwd_workspace_bytes(int B, int N, int D, int T);
+int m2b200_token_mix_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* wt1,
+                         const float* bt1, const float* wt2, float* dx, float* dln_w, float* dln_b, float* dwt1,
+                         float* dbt1, float* dwt2, float* dbt2, int B, int N, int D, int T, int precision, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---- MixerBlock.channel_mix + residual: modules/mixer.py:37-40,45
+ *   y = u + W2 . GELU(W1 . LN(u) + b1) + b2,   u,y [M][D] (M = B*N token rows), w1 [C][D], w2 [D][C]
+ * BF16 mode reads the bf16 caches w1_bf16 [C][D] and w2_bf16 [D][ldw2] (ldw2 = C rounded up to 8, pad zero).   */
+size_t m2b200_channel_mix_workspace_bytes(int M, int D, int C, int precision, int backward);
+int m2b200_channel_mix_fwd(const float* u, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
+                           const float* w2, const float* b2, const void* w1_bf16, const void* w2_bf16, int ldw2, float* y,
+                           int M, int D, int C, int precision, void* workspace, size_t workspace_bytes, void* stream);
+int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, const float* ln_b, const float* w1,
+                           const float* b1, const float* w2, const void* w1_bf16, const void* w2_bf16, int ldw2, float* du,
+                           float* dln_w, float* dln_b, float* dw1, float* db1, float* dw2, float* db2, int M, int D, int C,
+                           int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- nn.LayerNorm(hidden_dim) closing every stack: modules/mixer.py:131,161,185,263.
+ * Token row (b,n) is written to out + b*out_bstride + n*D so that an encoder can normalise straight into its slice
+ * of the fused-token buffer (zero-copy ConcatFusion, modules/fusion.py:117).  bwd: dx = LN'(dy) (+ dres).           */
+int m2b200_layernorm_fwd(const float* x, const float* w, const float* b, float* out, int B, int N, int D,
+                         int64_t out_bstride, void* stream);
+int m2b200_layernorm_bwd(const float* dy, int64_t dy_bstride, const float* x, const float* w, const float* dres, float* dx,
+                         float* dw, float* db, int B, int N, int D, void* stream);
+
+/* ---- Linear layers feeding the stacks: Conv2d patch embedding as a GEMM over gathered patches
+ * (modules/mixer.py:143-146), MLPMixerNoPatching.proj (:171), PNLPMixer.bottleneck (:244), MLP (modules/mlp.py).
+ *   y[M][N] = act(x[M][K] . w[N][K]^T + bias)                                                                     */
+size_t m2b200_linear_workspace_bytes(int M, int N, int K, int precision, int backward);
+int m2b200_linear_fwd(const float* x, const float* w, const void* w_bf16, int ldwb, const float* bias, int act, float* y,
+                      int M, int N, int K, int precision, void* workspace, size_t workspace_bytes, void* stream);
+/* dy is modified in place when act == RELU (masked by y > 0).  dx may be NULL (patch embedding: input needs no grad) */
+int m2b200_linear_bwd(float* dy, const float* x, const float* y, const float* w, const void* w_bf16, int ldwb, int act,
+                      float* dx, float* dw, float* db, int M, int N, int K, int precision, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* img [B][cin][H][W] -> cols [B*(H/P)*(W/P)][cin*P*P]  (row = patch in (h w) order, col = (c, py, px))              */
+int m2b200_patch_gather(const float* img, float* cols, int B, int cin, int H, int W, int P, void* stream);
+
+/* ---- ConcatFusion / SumFusion: modules/fusion.py:112-146, 207-221
+ * concat: dst[b][n_off + n][:] = src[b][n][:]  (accumulate=0)  |  split-add for the backward (swap src/dst strides) */
+int m2b200_copy_tokens(const float* src, int64_t src_bstride, float* dst, int64_t dst_bstride, int B, int64_t per_batch,
+                       int accumulate, void* stream);
+int m2b200_add(const float* a, const float* b, float* out, int64_t n, void* stream);
+
+/* ---- token mean-pool of a standalone StandardClassifier.forward (modules/classification.py:90):
+ *   out[b][d] = mean_n x[b][n][d]; the task modules use the fused heads kernel below instead.                      */
+int m2b200_mean_pool_fwd(const float* x, float* out, int B, int N, int D, void* stream);
+int m2b200_mean_pool_bwd(const float* dpooled, float* dx, int B, int N, int D, void* stream);
+
+/* ---- heads + multi-head loss: models/avmnist.py:267-312, models/mimic.py:106-142, models/mmimdb.py:106-147,
+ * modules/classification.py:84-90.  Up to 3 heads; head h mean-pools tok[h] ([B][ntok][dim], batch stride given)
+ * and applies Linear(dim -> K).  loss_kind 0: cross-entropy, int64 labels [B]; 1: BCE-with-logits with pos_weight,
+ * float labels [B][K].  loss = sum_h head_weight[h] * L_h  (weights are runtime scalars: the reference changes the
+ * fusion weight per epoch, avmnist.py:338-339).
+ *   logits [3][B][K], losses [4] = {loss, L_0, L_1, L_2}, preds int64 [3][B] (CE: argmax) or [3][B][K] (BCE: >0)   */
+int m2b200_heads_loss_fwd(const float* const* tok, const int64_t* tok_bstride, const int* ntok, const int* dim,
+                          const float* const* w, const float* const* b, int nheads, int B, int K, int loss_kind,
+                          const void* labels, const float* pos_weight, const float* head_weight, float* logits,
+                          float* losses, int64_t* preds, void* stream);
+/* dtok[h] may be NULL; accumulate_dtok[h] != 0 adds into dtok[h] (the fused-token gradient slices).  The upstream
+ * gradient of the total loss is grad_scale * (grad_scale_dev ? *grad_scale_dev : 1): the device scalar lets autograd
+ * hand over d(loss) without a host sync.                                                                            */
+int m2b200_heads_loss_bwd(const float* const* tok, const int64_t* tok_bstride, const int* ntok, const int* dim,
+                          const float* const* w, const float* const* b, int nheads, int B, int K, int loss_kind,
+                          const void* labels, const float* pos_weight, const float* head_weight, const float* logits,
+                          float grad_scale, const float* grad_scale_dev, float* const* dtok, const int64_t* dtok_bstride,
+                          const int* accumulate_dtok, float* const* dw, float* const* db, void* stream);
+
+/* ---- torch.optim.Adam as configured by the reference (models/avmnist.py:413-415) over one flat buffer.
+ * state_dev (optional, device float[2] = {lr, step}) makes lr/step device-resident (graph replay, LR scheduler).   */
+int m2b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, float grad_scale, float* state_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M2B200_H_ */

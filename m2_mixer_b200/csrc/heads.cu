@@ -1,0 +1,262 @@
+// Per-modality + fused classifier heads with their summed loss: one warp-shuffle reduction kernel.
+//
+// Reference arithmetic (not in modules/losses.py):
+//   logits_h = Linear_h(mean over tokens(x_h))                 models/avmnist.py:267-273, classification.py:90
+//   CE form : L_h = mean_b CE(logits_h, y);  loss = sum_h head_weight[h] * L_h      models/avmnist.py:276-291,
+//             (AV-MNIST: w = (w_f, ow, ow) * 3;  MIMIC: no *3, models/mimic.py:111-121)
+//   BCE form: L_h = mean_{b,k} BCEWithLogits(pos_weight)       models/mmimdb.py:47-50,115-125
+//   preds   : argmax (softmax is monotone) / logit > 0         models/avmnist.py:296-298, mmimdb.py:128-133
+// One warp per sample: lanes stride the hidden axis for the token mean-pool, K dot products are warp-reduced,
+// the per-sample loss terms are reduced per CTA and added to the 4 loss scalars with one atomic per CTA.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace m2 {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxK = 64;
+constexpr int kMaxPer = 32;   // hidden dim <= 1024
+
+struct HeadsDev {
+  const float* tok[3]; long long tok_bstride[3]; int ntok[3]; int dim[3];
+  const float* w[3]; const float* b[3];
+  int nheads, B, K, loss_kind;
+  const void* labels; const float* pos_weight;
+  float head_weight[3];
+};
+
+__device__ __forceinline__ void pool_tokens(const float* t, int ntok, int dim, int lane, float (&pooled)[kMaxPer]) {
+#pragma unroll
+  for (int i = 0; i < kMaxPer; ++i) pooled[i] = 0.f;
+  for (int n = 0; n < ntok; ++n) {
+    const float* r = t + static_cast<long long>(n) * dim;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+      const int d = lane + 32 * i;
+      if (d < dim) pooled[i] += r[d];
+    }
+  }
+  const float inv = 1.f / ntok;
+#pragma unroll
+  for (int i = 0; i < kMaxPer; ++i) pooled[i] *= inv;
+}
+
+__device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
+
+__global__ void __launch_bounds__(kThreads) heads_fwd_kernel(const HeadsDev a, float* __restrict__ logits,
+                                                             float* __restrict__ losses, long long* __restrict__ preds) {
+  __shared__ float s_logit[kWarps][kMaxK];
+  __shared__ float s_loss[kWarps][3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float lsum[3] = {0.f, 0.f, 0.f};
+  for (int b = blockIdx.x * kWarps + warp; b < a.B; b += gridDim.x * kWarps) {
+    for (int h = 0; h < a.nheads; ++h) {
+      float pooled[kMaxPer];
+      pool_tokens(a.tok[h] + b * a.tok_bstride[h], a.ntok[h], a.dim[h], lane, pooled);
+      for (int k = 0; k < a.K; ++k) {
+        const float* wr = a.w[h] + static_cast<long long>(k) * a.dim[h];
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) {
+          const int d = lane + 32 * i;
+          if (d < a.dim[h]) acc = fmaf(wr[d], pooled[i], acc);
+        }
+        acc = warp_sum(acc) + a.b[h][k];
+        if (lane == 0) {
+          s_logit[warp][k] = acc;
+          logits[(static_cast<long long>(h) * a.B + b) * a.K + k] = acc;
+        }
+      }
+      __syncwarp();
+      if (a.loss_kind == 0) {
+        // cross entropy: lanes stride k
+        float mx = -INFINITY;
+        int arg = 0;
+        for (int k = lane; k < a.K; k += 32) {
+          const float v = s_logit[warp][k];
+          if (v > mx) { mx = v; arg = k; }
+        }
+        // argmax with lowest-index tie-break (torch.argmax returns the first maximal index)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+          const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+          if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+        }
+        float se = 0.f;
+        for (int k = lane; k < a.K; k += 32) se += __expf(s_logit[warp][k] - mx);
+        se = warp_sum(se);
+        if (lane == 0) {
+          const long long y = static_cast<const long long*>(a.labels)[b];
+          lsum[h] += (mx + logf(se)) - s_logit[warp][y];
+          preds[static_cast<long long>(h) * a.B + b] = arg;
+        }
+      } else {
+        float l = 0.f;
+        for (int k = lane; k < a.K; k += 32) {
+          const float x = s_logit[warp][k];
+          const float y = static_cast<const float*>(a.labels)[static_cast<long long>(b) * a.K + k];
+          const float pw = a.pos_weight ? a.pos_weight[k] : 1.f;
+          l += pw * y * softplus(-x) + (1.f - y) * softplus(x);
+          preds[(static_cast<long long>(h) * a.B + b) * a.K + k] = x > 0.f ? 1 : 0;
+        }
+        l = warp_sum(l);
+        if (lane == 0) lsum[h] += l;
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) { s_loss[warp][0] = lsum[0]; s_loss[warp][1] = lsum[1]; s_loss[warp][2] = lsum[2]; }
+  __syncthreads();
+  if (threadIdx.x < a.nheads) {
+    const int h = threadIdx.x;
+    float t = 0.f;
+    for (int w = 0; w < kWarps; ++w) t += s_loss[w][h];
+    t *= (a.loss_kind == 0) ? 1.f / a.B : 1.f / (static_cast<float>(a.B) * a.K);
+    atomicAdd(&losses[1 + h], t);
+    atomicAdd(&losses[0], a.head_weight[h] * t);
+  }
+}
+
+struct HeadsBwdDev {
+  float* dtok[3]; long long dtok_bstride[3]; int accumulate[3];
+  float* dw[3]; float* db[3];
+  float grad_scale; const float* grad_scale_dev;
+};
+
+__global__ void __launch_bounds__(kThreads) heads_bwd_kernel(const HeadsDev a, const HeadsBwdDev g,
+                                                             const float* __restrict__ logits) {
+  extern __shared__ float sm[];   // per-head dW partial [K][dim] and db partial [K], laid out back to back
+  __shared__ float s_dl[kWarps][kMaxK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int off[4];
+  off[0] = 0;
+  for (int h = 0; h < a.nheads; ++h) off[h + 1] = off[h] + a.K * a.dim[h] + a.K;
+  for (int i = threadIdx.x; i < off[a.nheads]; i += kThreads) sm[i] = 0.f;
+  __syncthreads();
+  for (int b = blockIdx.x * kWarps + warp; b < a.B; b += gridDim.x * kWarps) {
+    for (int h = 0; h < a.nheads; ++h) {
+      const int dim = a.dim[h];
+      float pooled[kMaxPer];
+      pool_tokens(a.tok[h] + b * a.tok_bstride[h], a.ntok[h], dim, lane, pooled);
+      const float* lg = logits + (static_cast<long long>(h) * a.B + b) * a.K;
+      const float hw = a.head_weight[h] * g.grad_scale * (g.grad_scale_dev ? g.grad_scale_dev[0] : 1.f);
+      if (a.loss_kind == 0) {
+        float mx = -INFINITY;
+        for (int k = lane; k < a.K; k += 32) mx = fmaxf(mx, lg[k]);
+        mx = warp_max(mx);
+        float se = 0.f;
+        for (int k = lane; k < a.K; k += 32) se += __expf(lg[k] - mx);
+        se = warp_sum(se);
+        const long long y = static_cast<const long long*>(a.labels)[b];
+        for (int k = lane; k < a.K; k += 32)
+          s_dl[warp][k] = (__expf(lg[k] - mx) / se - (k == y ? 1.f : 0.f)) * hw / a.B;
+      } else {
+        for (int k = lane; k < a.K; k += 32) {
+          const float x = lg[k];
+          const float y = static_cast<const float*>(a.labels)[static_cast<long long>(b) * a.K + k];
+          const float pw = a.pos_weight ? a.pos_weight[k] : 1.f;
+          const float sg = 1.f / (1.f + __expf(-x));
+          s_dl[warp][k] = (-pw * y * (1.f - sg) + (1.f - y) * sg) * hw / (static_cast<float>(a.B) * a.K);
+        }
+      }
+      __syncwarp();
+      float* sdw = sm + off[h];
+      float* sdb = sdw + a.K * dim;
+      float dp[kMaxPer];
+#pragma unroll
+      for (int i = 0; i < kMaxPer; ++i) dp[i] = 0.f;
+      for (int k = 0; k < a.K; ++k) {
+        const float dl = s_dl[warp][k];
+        const float* wr = a.w[h] + static_cast<long long>(k) * dim;
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) {
+          const int d = lane + 32 * i;
+          if (d < dim) {
+            atomicAdd(&sdw[k * dim + d], dl * pooled[i]);
+            dp[i] = fmaf(wr[d], dl, dp[i]);
+          }
+        }
+        if (lane == 0) atomicAdd(&sdb[k], dl);
+      }
+      if (g.dtok[h]) {
+        const float inv = 1.f / a.ntok[h];
+        float* dt = g.dtok[h] + b * g.dtok_bstride[h];
+        for (int n = 0; n < a.ntok[h]; ++n) {
+#pragma unroll
+          for (int i = 0; i < kMaxPer; ++i) {
+            const int d = lane + 32 * i;
+            if (d < dim) {
+              float* p = dt + static_cast<long long>(n) * dim + d;
+              *p = g.accumulate[h] ? *p + dp[i] * inv : dp[i] * inv;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int h = 0; h < a.nheads; ++h) {
+    const int nw = a.K * a.dim[h];
+    for (int i = threadIdx.x; i < nw; i += kThreads) atomicAdd(&g.dw[h][i], sm[off[h] + i]);
+    for (int i = threadIdx.x; i < a.K; i += kThreads) atomicAdd(&g.db[h][i], sm[off[h] + nw + i]);
+  }
+}
+
+int fill_dev(const HeadsArgs& a, HeadsDev* d) {
+  if (a.nheads < 1 || a.nheads > 3 || a.B <= 0 || a.K <= 0 || a.K > kMaxK || !a.labels) return M2_ERR_ARG;
+  for (int h = 0; h < a.nheads; ++h) {
+    if (!a.tok[h] || !a.w[h] || !a.b[h] || a.ntok[h] <= 0 || a.dim[h] <= 0 || a.dim[h] > 32 * kMaxPer) return M2_ERR_ARG;
+    d->tok[h] = a.tok[h]; d->tok_bstride[h] = a.tok_bstride[h]; d->ntok[h] = a.ntok[h]; d->dim[h] = a.dim[h];
+    d->w[h] = a.w[h]; d->b[h] = a.b[h]; d->head_weight[h] = a.head_weight[h];
+  }
+  d->nheads = a.nheads; d->B = a.B; d->K = a.K; d->loss_kind = a.loss_kind;
+  d->labels = a.labels; d->pos_weight = a.pos_weight;
+  return M2_OK;
+}
+
+}  // namespace
+
+int heads_loss_fwd(const HeadsArgs& a, float* logits, float* losses, long long* preds, cudaStream_t s) {
+  HeadsDev d = {};
+  int rc = fill_dev(a, &d);
+  if (rc) return rc;
+  if (!logits || !losses || !preds) return M2_ERR_ARG;
+  if (cudaMemsetAsync(losses, 0, 4 * sizeof(float), s) != cudaSuccess) return M2_ERR_LAUNCH;
+  int grid = ceil_div(a.B, kWarps);
+  if (grid > 148 * 4) grid = 148 * 4;
+  heads_fwd_kernel<<<grid, kThreads, 0, s>>>(d, logits, losses, preds);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int heads_loss_bwd(const HeadsArgs& a, const float* logits, float grad_scale, const float* grad_scale_dev, float* dtok[3], long long dtok_bstride[3],
+                   int accumulate_dtok[3], float* dw[3], float* db[3], cudaStream_t s) {
+  HeadsDev d = {};
+  int rc = fill_dev(a, &d);
+  if (rc) return rc;
+  HeadsBwdDev g = {};
+  size_t smem = 0;
+  for (int h = 0; h < a.nheads; ++h) {
+    if (!dw[h] || !db[h]) return M2_ERR_ARG;
+    g.dtok[h] = dtok[h]; g.dtok_bstride[h] = dtok_bstride[h]; g.accumulate[h] = accumulate_dtok[h];
+    g.dw[h] = dw[h]; g.db[h] = db[h];
+    smem += static_cast<size_t>(a.K) * a.dim[h] + a.K;
+  }
+  smem *= sizeof(float);
+  g.grad_scale = grad_scale; g.grad_scale_dev = grad_scale_dev;
+  if (smem > 200 * 1024) return M2_ERR_ARG;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+    return M2_ERR_LAUNCH;
+  int grid = ceil_div(a.B, kWarps);
+  if (grid > 148) grid = 148;
+  heads_bwd_kernel<<<grid, kThreads, smem, s>>>(d, g, logits);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+}  // namespace m2

@@ -1,0 +1,329 @@
+// Bandwidth-bound row kernels around the GEMM chains: LayerNorm fwd/bwd, casts, column sums, GELU fwd/bwd for the
+// unfused path, patch gather (Conv2d with kernel == stride as a GEMM operand), token concat/split.
+// All fp32 math; one warp per row where a row reduction is needed, 128-bit accesses where alignment allows.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace m2 {
+namespace {
+
+constexpr int kNumSms = 148;
+
+// ------------------------------------------------------------------------------------------ cast
+__global__ void cast_pad_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+                                     long long ldd, int rows, int cols) {
+  const long long total = static_cast<long long>(rows) * ldd;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / ldd;
+    const int c = static_cast<int>(i - r * ldd);
+    dst[i] = __float2bfloat16(c < cols ? src[r * lds + c] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm forward
+// rows = B*N tokens; output row (b, n) goes to out + b*out_bstride + n*D  (lets an encoder's final LN write
+// straight into its slice of the fused-token buffer: zero-copy ConcatFusion, reference modules/fusion.py:117).
+template <bool kBf16Out>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                     const float* __restrict__ b, void* __restrict__ out, int rows, int D,
+                                                     int N, long long out_bstride, float* __restrict__ mean_out,
+                                                     float* __restrict__ rstd_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp; row < rows; row += nwarps) {
+    const float* xr = x + static_cast<long long>(row) * D;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / D;
+    float ss = 0.f;
+    for (int c = lane; c < D; c += 32) { const float d = xr[c] - mean; ss += d * d; }
+    const float rstd = rsqrtf(warp_sum(ss) / D + kLnEps);
+    const long long o = static_cast<long long>(row / N) * out_bstride + static_cast<long long>(row % N) * D;
+    for (int c = lane; c < D; c += 32) {
+      const float v = (xr[c] - mean) * rstd * w[c] + b[c];
+      if (kBf16Out) static_cast<__nv_bfloat16*>(out)[o + c] = __float2bfloat16(v);
+      else static_cast<float*>(out)[o + c] = v;
+    }
+    if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm backward
+// dy = grad wrt LN output (row (b,n) at dy + b*dy_bstride + n*D), x = LN input.
+// dx[row] = (dres ? dres[row] : 0) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * w
+// dw += sum_rows dy*xhat, db += sum_rows dy   (per-CTA partials in smem, then one atomicAdd per column per CTA)
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, long long dy_bstride, int N,
+                                                     const float* __restrict__ x, const float* __restrict__ w,
+                                                     const float* __restrict__ dres, float* __restrict__ dx,
+                                                     float* __restrict__ dw, float* __restrict__ db, int rows, int D) {
+  extern __shared__ float sm[];   // [2][D] per-CTA partial dw/db
+  float* sdw = sm;
+  float* sdb = sm + D;
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  // per-lane register partials for the columns this lane owns (c = lane + 32*i), flushed to smem at the end
+  constexpr int kMaxPer = 32;   // D <= 1024
+  float pdw[kMaxPer], pdb[kMaxPer];
+#pragma unroll
+  for (int i = 0; i < kMaxPer; ++i) { pdw[i] = 0.f; pdb[i] = 0.f; }
+  for (int row = warp; row < rows; row += nwarps) {
+    const float* xr = x + static_cast<long long>(row) * D;
+    const float* gr = dy + static_cast<long long>(row / N) * dy_bstride + static_cast<long long>(row % N) * D;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / D;
+    float ss = 0.f;
+    for (int c = lane; c < D; c += 32) { const float d = xr[c] - mean; ss += d * d; }
+    const float rstd = rsqrtf(warp_sum(ss) / D + kLnEps);
+    float sg = 0.f, sgx = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float xh = (xr[c] - mean) * rstd, g = gr[c] * w[c];
+      sg += g; sgx += g * xh;
+    }
+    sg = warp_sum(sg) / D; sgx = warp_sum(sgx) / D;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+      const int c = lane + 32 * i;
+      if (c < D) {
+        const float xh = (xr[c] - mean) * rstd, d = gr[c];
+        float v = rstd * (d * w[c] - sg - xh * sgx);
+        if (dres) v += dres[static_cast<long long>(row) * D + c];
+        dx[static_cast<long long>(row) * D + c] = v;
+        pdw[i] += d * xh;
+        pdb[i] += d;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxPer; ++i) {
+    const int c = lane + 32 * i;
+    if (c < D) { atomicAdd(&sdw[c], pdw[i]); atomicAdd(&sdb[c], pdb[i]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) { atomicAdd(&dw[c], sdw[c]); atomicAdd(&db[c], sdb[c]); }
+}
+
+// ------------------------------------------------------------------------------------------ column sums
+// out[c] += sum_r src[r][c].  CTA = 32 columns x 8 row-lanes; grid.y splits the rows.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, long long ld, int rows, int cols,
+                                                     float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) s += static_cast<float>(src[r * ld + c]);
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][tx];
+    atomicAdd(&out[c], t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ GELU fwd+bwd (unfused path)
+// h = pre-activation (bias already added). g_out = gelu(h) ; dh = dg * gelu'(h)  (dh may alias dg)
+template <typename TO>
+__global__ void gelu_fwd_bwd_kernel(const float* __restrict__ h, const float* dg, long long n, int cols,
+                                    long long ld_in, TO* __restrict__ g_out, TO* dh_out, long long ld_out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const float x = h[r * ld_in + c];
+    const float g = gelu_erf(x), d = dg[r * ld_in + c] * gelu_erf_grad(x);
+    g_out[r * ld_out + c] = static_cast<TO>(g);
+    dh_out[r * ld_out + c] = static_cast<TO>(d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ patch gather
+// img [B][cin][H][W] -> cols [(b, gy, gx)][(ci, py, px)], row stride ld (pad columns zeroed).
+// Reference: Conv2d(cin, D, p, p) + 'b c h w -> b (h w) c', modules/mixer.py:143-146.
+template <typename TO>
+__global__ void patch_gather_kernel(const float* __restrict__ img, TO* __restrict__ cols, int B, int cin, int H, int W,
+                                    int P, long long ld) {
+  const int gh = H / P, gw = W / P;
+  const int K = cin * P * P;
+  const long long total = static_cast<long long>(B) * gh * gw * ld;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / ld;
+    const int k = static_cast<int>(i - row * ld);
+    float v = 0.f;
+    if (k < K) {
+      const int px = k % P, py = (k / P) % P, ci = k / (P * P);
+      const int gx = static_cast<int>(row % gw), gy = static_cast<int>((row / gw) % gh);
+      const long long b = row / (static_cast<long long>(gw) * gh);
+      v = img[((b * cin + ci) * H + gy * P + py) * W + gx * P + px];
+    }
+    cols[i] = static_cast<TO>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ token concat / split
+// dst[b][n_off + n][d] = src[b][n][d]   (copy == 1)    or   dst[b][n][d] (+)= src[b][n_off + n][d]  (copy == 0)
+__global__ void concat_copy_kernel(const float* __restrict__ src, long long src_bstride, float* __restrict__ dst,
+                                   long long dst_bstride, int B, long long per_batch, int accumulate) {
+  const long long total = static_cast<long long>(B) * per_batch;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / per_batch, e = i - b * per_batch;
+    const float v = src[b * src_bstride + e];
+    float* d = dst + b * dst_bstride + e;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    o[i] = a[i] + b[i];
+}
+
+// pooled[b][d] = mean_n x[b][n][d]   |   dx[b][n][d] = dpooled[b][d] / N
+__global__ void mean_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int N, int D) {
+  const long long total = static_cast<long long>(B) * D;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / D;
+    const int d = static_cast<int>(i - b * D);
+    const float* p = x + b * N * D + d;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += p[static_cast<long long>(n) * D];
+    out[i] = s / N;
+  }
+}
+__global__ void mean_pool_bwd_kernel(const float* __restrict__ dp, float* __restrict__ dx, int B, int N, int D) {
+  const long long total = static_cast<long long>(B) * N * D;
+  const float inv = 1.f / N;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / (static_cast<long long>(N) * D);
+    const int d = static_cast<int>(i % D);
+    dx[i] = dp[b * D + d] * inv;
+  }
+}
+
+// dy *= (y > 0)   (ReLU backward, in place)
+__global__ void relu_bwd_kernel(float* dy, const float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    if (!(y[i] > 0.f)) dy[i] = 0.f;
+}
+
+inline int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  const long long cap = static_cast<long long>(kNumSms) * 16;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int cast_pad_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0 || ldd < cols) return M2_ERR_ARG;
+  cast_pad_bf16_kernel<<<grid_for(static_cast<long long>(rows) * ldd, 256), 256, 0, s>>>(src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int ln_fwd(const float* x, const float* w, const float* b, void* out, int out_bf16, int rows, int D, int N,
+           long long out_bstride, float* mean, float* rstd, cudaStream_t s) {
+  if (rows <= 0 || D <= 0 || N <= 0) return M2_ERR_ARG;
+  const int grid = grid_for(static_cast<long long>(rows) * 32, 256);
+  if (out_bf16) ln_fwd_kernel<true><<<grid, 256, 0, s>>>(x, w, b, out, rows, D, N, out_bstride, mean, rstd);
+  else ln_fwd_kernel<false><<<grid, 256, 0, s>>>(x, w, b, out, rows, D, N, out_bstride, mean, rstd);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int ln_bwd(const float* dy, long long dy_bstride, int N, const float* x, const float* w, const float* dres, float* dx,
+           float* dw, float* db, int rows, int D, cudaStream_t s) {
+  if (rows <= 0 || D <= 0 || D > 1024 || N <= 0) return M2_ERR_ARG;
+  int grid = grid_for(static_cast<long long>(rows) * 32, 256);
+  if (grid > kNumSms * 4) grid = kNumSms * 4;
+  ln_bwd_kernel<<<grid, 256, 2 * D * sizeof(float), s>>>(dy, dy_bstride, N, x, w, dres, dx, dw, db, rows, D);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int colsum_f32(const float* src, long long ld, int rows, int cols, float* out, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return M2_ERR_ARG;
+  dim3 grid(ceil_div(cols, 32), min(ceil_div(rows, 8), 64));
+  colsum_kernel<float><<<grid, 256, 0, s>>>(src, ld, rows, cols, out);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+int colsum_bf16(const void* src, long long ld, int rows, int cols, float* out, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return M2_ERR_ARG;
+  dim3 grid(ceil_div(cols, 32), min(ceil_div(rows, 8), 64));
+  colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src), ld, rows, cols, out);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int gelu_fwd_bwd(const float* h, const float* dg, int rows, int cols, long long ld_in, void* g_out, void* dh_out,
+                 long long ld_out, int out_bf16, cudaStream_t s) {
+  const long long n = static_cast<long long>(rows) * cols;
+  if (n <= 0) return M2_ERR_ARG;
+  if (out_bf16)
+    gelu_fwd_bwd_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>(h, dg, n, cols, ld_in, static_cast<__nv_bfloat16*>(g_out),
+                                                                       static_cast<__nv_bfloat16*>(dh_out), ld_out);
+  else
+    gelu_fwd_bwd_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(h, dg, n, cols, ld_in, static_cast<float*>(g_out),
+                                                               static_cast<float*>(dh_out), ld_out);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int patch_gather(const float* img, void* cols, int out_bf16, int B, int cin, int H, int W, int P, long long ld, cudaStream_t s) {
+  if (B <= 0 || cin <= 0 || P <= 0 || H % P || W % P || ld < static_cast<long long>(cin) * P * P) return M2_ERR_ARG;
+  const long long total = static_cast<long long>(B) * (H / P) * (W / P) * ld;
+  if (out_bf16) patch_gather_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(img, static_cast<__nv_bfloat16*>(cols), B, cin, H, W, P, ld);
+  else patch_gather_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(img, static_cast<float*>(cols), B, cin, H, W, P, ld);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int concat_copy(const float* src, long long src_bstride, float* dst, long long dst_bstride, int B, long long per_batch,
+                int accumulate, cudaStream_t s) {
+  if (B <= 0 || per_batch <= 0) return M2_ERR_ARG;
+  concat_copy_kernel<<<grid_for(B * per_batch, 256), 256, 0, s>>>(src, src_bstride, dst, dst_bstride, B, per_batch, accumulate);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int mean_pool_fwd(const float* x, float* out, int B, int N, int D, cudaStream_t s) {
+  if (B <= 0 || N <= 0 || D <= 0) return M2_ERR_ARG;
+  mean_pool_fwd_kernel<<<grid_for(static_cast<long long>(B) * D, 256), 256, 0, s>>>(x, out, B, N, D);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+int mean_pool_bwd(const float* dp, float* dx, int B, int N, int D, cudaStream_t s) {
+  if (B <= 0 || N <= 0 || D <= 0) return M2_ERR_ARG;
+  mean_pool_bwd_kernel<<<grid_for(static_cast<long long>(B) * N * D, 256), 256, 0, s>>>(dp, dx, B, N, D);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int relu_bwd(float* dy, const float* y, long long n, cudaStream_t s) {
+  if (n <= 0) return M2_ERR_ARG;
+  relu_bwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(dy, y, n);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int add_f32(const float* a, const float* b, float* o, long long n, cudaStream_t s) {
+  if (n <= 0) return M2_ERR_ARG;
+  add_kernel<<<grid_for(n, 256), 256, 0, s>>>(a, b, o, n);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+}  // namespace m2

@@ -1,0 +1,240 @@
+// Generic bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulator in TMEM), operands staged by TMA.
+//
+//   CTA tile 128 x 128 x 64, one CTA per (m-tile, n-tile, batch*split).  6 warps:
+//     warp 0   : TMA producer   (one lane)   - fills a kStages-deep smem ring, full/empty mbarriers
+//     warp 1   : MMA issuer     (one lane)   - 4 x tcgen05.mma (K=16 each) per stage, tcgen05.commit frees the slot
+//     warps 2-5: epilogue                    - tcgen05.ld the 128x128 fp32 accumulator (warp w owns TMEM lanes
+//                                              32*(w%4)..), bias / GELU / residual, store fp32 or bf16
+//   Both operands may be K-major (row-major [rows][K]) or MN-major (row-major [K][rows]); the latter is what the
+//   weight-gradient GEMMs (dW = dY^T . X, contraction over the token axis) and the transpose-free token-mixing
+//   GEMMs need, so no transposed copy is ever materialised ("operand layouts swapped").
+//   Ragged M/N/K edges rely on TMA out-of-bounds zero fill; stores are masked.
+#include "common.cuh"
+#include "kernels.h"
+#include "tmap.cuh"
+
+namespace m2 {
+
+namespace {
+
+constexpr int kBM = 128, kBN = 128, kBK = 64;
+constexpr int kStages = 5;
+constexpr int kTileBytes = kBM * kBK * 2;                  // 16 KB per operand per stage
+constexpr int kSmemBytes = kStages * 2 * kTileBytes + 256 + 1024;   // + barriers + alignment slack
+constexpr int kTmemCols = 128;
+
+struct GemmDev {
+  int M, N, K;
+  int splitk, k_tiles_per_split;
+  int a_batch_rows, b_batch_rows;
+  const float* bias; int bias_mode; int act;
+  const float* residual; long long ldr, r_batch_stride;
+  void* C; int c_bf16; long long ldc, c_batch_stride;
+  int accumulate;
+};
+
+template <bool kAMn, bool kBMn>
+__global__ void __launch_bounds__(192, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kTileBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * kStages * kTileBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* acc_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
+  const int batch = blockIdx.z / p.splitk, split = blockIdx.z % p.splitk;
+  const int k_tiles = ceil_div(p.K, kBK);
+  const int kt_begin = split * p.k_tiles_per_split;
+  const int kt_end = min(k_tiles, kt_begin + p.k_tiles_per_split);
+  const int nkt = kt_end - kt_begin;
+  if (nkt <= 0) return;   // uniform for the whole CTA (only possible for trailing splits)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int a_row0 = batch * p.a_batch_rows, b_row0 = batch * p.b_batch_rows;
+      for (int it = 0; it < nkt; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], 2 * kTileBytes);
+        const int k0 = (kt_begin + it) * kBK;
+        uint8_t* a = sA + s * kTileBytes;
+        uint8_t* b = sB + s * kTileBytes;
+        if (!kAMn) {
+          tma_load_2d(a, &tmA, &full[s], k0, a_row0 + m0);
+        } else {   // [64 k-rows][64 m] panels, two per 128-wide tile
+          tma_load_2d(a, &tmA, &full[s], m0, a_row0 + k0);
+          tma_load_2d(a + kTileBytes / 2, &tmA, &full[s], m0 + 64, a_row0 + k0);
+        }
+        if (!kBMn) {
+          tma_load_2d(b, &tmB, &full[s], k0, b_row0 + n0);
+        } else {
+          tma_load_2d(b, &tmB, &full[s], n0, b_row0 + k0);
+          tma_load_2d(b + kTileBytes / 2, &tmB, &full[s], n0 + 64, b_row0 + k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, kAMn ? 1 : 0, kBMn ? 1 : 0);
+      for (int it = 0; it < nkt; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a = smem_u32(sA + s * kTileBytes), b = smem_u32(sB + s * kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < kBK / 16; ++kk) {
+          // K-major: +16 elements = +32 B inside the 128-B swizzled row.  MN-major: +16 k-rows = +2048 B.
+          const uint64_t ad = kAMn ? umma_desc_sw128(a + kk * 2048, kTileBytes / 2, 1024) : umma_desc_sw128(a + kk * 32, 16, 1024);
+          const uint64_t bd = kBMn ? umma_desc_sw128(b + kk * 2048, kTileBytes / 2, 1024) : umma_desc_sw128(b + kk * 32, 16, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const bool lead = (split == 0);
+    const float rbias = (p.bias_mode == 2 && row_ok && lead) ? p.bias[row] : 0.f;
+    const long long coff = static_cast<long long>(batch) * p.c_batch_stride + static_cast<long long>(row) * p.ldc;
+    const float* res = (p.residual && lead) ? p.residual + static_cast<long long>(batch) * p.r_batch_stride +
+                                                  static_cast<long long>(row) * p.ldr : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kBN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+      tmem_ld_wait();
+      if (!row_ok || n0 + c0 >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = n0 + c0 + j;
+        float x = __uint_as_float(r[j]);
+        if (col < p.N) {
+          if (lead) {
+            if (p.bias_mode == 1) x += p.bias[col];
+            x += rbias;
+          }
+          if (p.act == 1) x = gelu_erf(x);
+          else if (p.act == 2) x = fmaxf(x, 0.f);
+          if (res) x += res[col];
+        }
+        v[j] = x;
+      }
+      const bool full_chunk = (n0 + c0 + 32 <= p.N);
+      if (p.c_bf16) {
+        __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + coff + n0 + c0;
+        if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 o = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
+                                 pack_bf16(v[j + 6], v[j + 7]));
+            *reinterpret_cast<uint4*>(c + j) = o;
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) c[j] = __float2bfloat16(v[j]);
+        }
+      } else {
+        float* c = reinterpret_cast<float*>(p.C) + coff + n0 + c0;
+        if (p.splitk > 1) {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) atomicAdd(c + j, v[j]);
+        } else if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(c + j);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(c + j) = o;
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) c[j] = p.accumulate ? c[j] + v[j] : v[j];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <bool kAMn, bool kBMn>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, dim3 grid, cudaStream_t s) {
+  auto kern = umma_gemm_kernel<kAMn, kBMn>;
+  static bool configured = false;   // immutable one-time attribute (idempotent; benign if raced)
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return M2_ERR_LAUNCH;
+    configured = true;
+  }
+  kern<<<grid, 192, kSmemBytes, s>>>(ta, tb, d);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+}  // namespace
+
+int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
+  if (!g.A || !g.B || !g.C || g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batch <= 0) return M2_ERR_ARG;
+  if (g.splitk < 1 || (g.splitk > 1 && (g.c_bf16 || g.act))) return M2_ERR_ARG;
+  if (g.bias_mode && !g.bias) return M2_ERR_ARG;
+  CUtensorMap ta, tb;
+  int rc;
+  {
+    const uint64_t ext = g.a_mn ? g.K : g.M, cols = g.a_mn ? g.M : g.K;
+    const uint64_t rows = static_cast<uint64_t>(g.batch - 1) * g.a_batch_rows + ext;
+    rc = make_tmap_bf16(&ta, g.A, rows, cols, g.lda, g.a_mn ? 64 : 128, 64);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t ext = g.b_mn ? g.K : g.N, cols = g.b_mn ? g.N : g.K;
+    const uint64_t rows = static_cast<uint64_t>(g.batch - 1) * g.b_batch_rows + ext;
+    rc = make_tmap_bf16(&tb, g.B, rows, cols, g.ldb, g.b_mn ? 64 : 128, 64);
+    if (rc) return rc;
+  }
+  GemmDev d;
+  d.M = g.M; d.N = g.N; d.K = g.K;
+  const int k_tiles = ceil_div(g.K, kBK);
+  d.splitk = g.splitk > k_tiles ? k_tiles : g.splitk;
+  d.k_tiles_per_split = ceil_div(k_tiles, d.splitk);
+  d.splitk = ceil_div(k_tiles, d.k_tiles_per_split);   // no empty trailing split
+  d.a_batch_rows = static_cast<int>(g.a_batch_rows); d.b_batch_rows = static_cast<int>(g.b_batch_rows);
+  d.bias = g.bias; d.bias_mode = g.bias_mode; d.act = g.act;
+  d.residual = g.residual; d.ldr = g.ldr; d.r_batch_stride = g.r_batch_stride;
+  d.C = g.C; d.c_bf16 = g.c_bf16; d.ldc = g.ldc; d.c_batch_stride = g.c_batch_stride;
+  d.accumulate = g.accumulate;
+  dim3 grid(ceil_div(g.M, kBM), ceil_div(g.N, kBN), g.batch * d.splitk);
+  if (grid.y > 65535 || grid.z > 65535) return M2_ERR_ARG;
+  if (g.a_mn) return g.b_mn ? launch<true, true>(ta, tb, d, grid, s) : launch<true, false>(ta, tb, d, grid, s);
+  return g.b_mn ? launch<false, true>(ta, tb, d, grid, s) : launch<false, false>(ta, tb, d, grid, s);
+}
+
+}  // namespace m2

@@ -1,0 +1,379 @@
+"""torch.library registration of the m2b200 C-ABI kernels (namespace ``m2b200``), CUDA-only.
+
+Thin by design: each op checks device / dtype / contiguity, allocates outputs and workspace with torch's caching
+allocator, passes ``torch.cuda.current_stream()`` and turns a non-zero status into an exception.  There is no CPU
+implementation and no composite fallback: calling an op with CPU tensors raises NotImplementedError from the
+dispatcher, a missing library raises at import of this module's first use.
+
+Autograd wiring lives in ``functional.py`` (``torch.autograd.Function`` wrappers that call the *_fwd / *_bwd ops).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF16, FP32, check
+
+_LIB = torch.library.Library("m2b200", "DEF")
+
+
+def _L():
+    return _lib.load()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"m2b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"m2b200: {name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ws(nbytes: int, like: torch.Tensor) -> Tuple[Optional[torch.Tensor], Optional[int]]:
+    if nbytes == 0:
+        return None, None
+    w = torch.empty(nbytes, dtype=torch.uint8, device=like.device)
+    return w, w.data_ptr()
+
+
+def _define(name: str, schema: str, fn):
+    _LIB.define(f"{name}{schema}")
+    _LIB.impl(name, fn, "CUDA")
+
+
+# ------------------------------------------------------------------------------------------------ bf16 cache
+def cast_bf16(w: torch.Tensor, ld: int) -> torch.Tensor:
+    w = _f32c(w, "w")
+    rows, cols = w.shape
+    out = torch.empty(rows, ld, dtype=torch.bfloat16, device=w.device)
+    check(_L().m2b200_cast_bf16(w.data_ptr(), cols, out.data_ptr(), ld, rows, cols, _stream()), "cast_bf16")
+    return out
+
+
+_define("cast_bf16", "(Tensor w, int ld) -> Tensor", cast_bf16)
+
+
+# ------------------------------------------------------------------------------------------------ token mixing
+def token_mix_fwd(x, ln_w, ln_b, w1, b1, w2, b2, precision: int):
+    x = _f32c(x, "x")
+    B, N, D = x.shape
+    T = w1.shape[0]
+    u = torch.empty_like(x)
+    check(_L().m2b200_token_mix_fwd(x.data_ptr(), _f32c(ln_w, "ln_w").data_ptr(), _f32c(ln_b, "ln_b").data_ptr(),
+                                    _f32c(w1, "w1").data_ptr(), _f32c(b1, "b1").data_ptr(), _f32c(w2, "w2").data_ptr(),
+                                    _f32c(b2, "b2").data_ptr(), u.data_ptr(), B, N, D, T, precision, _stream()),
+          "token_mix_fwd")
+    return u
+
+
+def token_mix_bwd(du, x, ln_w, ln_b, w1, b1, w2, precision: int):
+    du, x = _f32c(du, "du"), _f32c(x, "x")
+    B, N, D = x.shape
+    T = w1.shape[0]
+    dx = torch.empty_like(x)
+    z = lambda t: torch.zeros_like(t, memory_format=torch.contiguous_format)
+    dln_w, dln_b, dw1, db1, dw2 = z(ln_w), z(ln_b), z(w1), z(b1), z(w2)
+    db2 = torch.zeros(N, dtype=torch.float32, device=x.device)
+    nbytes = _L().m2b200_token_mix_bwd_workspace_bytes(B, N, D, T)
+    ws, wsp = _ws(nbytes, x)
+    check(_L().m2b200_token_mix_bwd(du.data_ptr(), x.data_ptr(), _f32c(ln_w, "ln_w").data_ptr(),
+                                    _f32c(ln_b, "ln_b").data_ptr(), _f32c(w1, "w1").data_ptr(), _f32c(b1, "b1").data_ptr(),
+                                    _f32c(w2, "w2").data_ptr(), dx.data_ptr(), dln_w.data_ptr(), dln_b.data_ptr(),
+                                    dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(), B, N, D, T, precision,
+                                    wsp, nbytes, _stream()), "token_mix_bwd")
+    return dx, dln_w, dln_b, dw1, db1, dw2, db2
+
+
+_define("token_mix_fwd", "(Tensor x, Tensor ln_w, Tensor ln_b, Tensor w1, Tensor b1, Tensor w2, Tensor b2, int precision) -> Tensor",
+        token_mix_fwd)
+_define("token_mix_bwd", "(Tensor du, Tensor x, Tensor ln_w, Tensor ln_b, Tensor w1, Tensor b1, Tensor w2, int precision) -> "
+        "(Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)", token_mix_bwd)
+
+
+# ------------------------------------------------------------------------------------------------ channel mixing
+def channel_mix_fwd(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, precision: int):
+    u = _f32c(u, "u")
+    D = u.shape[-1]
+    M = u.numel() // D
+    Cc = w1.shape[0]
+    y = torch.empty_like(u)
+    nbytes = _L().m2b200_channel_mix_workspace_bytes(M, D, Cc, precision, 0)
+    ws, wsp = _ws(nbytes, u)
+    ldw2 = 0 if w2b is None else w2b.shape[1]
+    check(_L().m2b200_channel_mix_fwd(u.data_ptr(), _f32c(ln_w, "ln_w").data_ptr(), _f32c(ln_b, "ln_b").data_ptr(),
+                                      _f32c(w1, "w1").data_ptr(), _f32c(b1, "b1").data_ptr(), _f32c(w2, "w2").data_ptr(),
+                                      _f32c(b2, "b2").data_ptr(), _ptr(w1b), _ptr(w2b), ldw2, y.data_ptr(), M, D, Cc,
+                                      precision, wsp, nbytes, _stream()), "channel_mix_fwd")
+    return y
+
+
+def channel_mix_bwd(dy, u, ln_w, ln_b, w1, b1, w2, w1b, w2b, precision: int):
+    dy, u = _f32c(dy, "dy"), _f32c(u, "u")
+    D = u.shape[-1]
+    M = u.numel() // D
+    Cc = w1.shape[0]
+    du = torch.empty_like(u)
+    z = lambda t: torch.zeros_like(t, memory_format=torch.contiguous_format)
+    dln_w, dln_b, dw1, db1, dw2 = z(ln_w), z(ln_b), z(w1), z(b1), z(w2)
+    db2 = torch.zeros(D, dtype=torch.float32, device=u.device)
+    nbytes = _L().m2b200_channel_mix_workspace_bytes(M, D, Cc, precision, 1)
+    ws, wsp = _ws(nbytes, u)
+    ldw2 = 0 if w2b is None else w2b.shape[1]
+    check(_L().m2b200_channel_mix_bwd(dy.data_ptr(), u.data_ptr(), _f32c(ln_w, "ln_w").data_ptr(),
+                                      _f32c(ln_b, "ln_b").data_ptr(), _f32c(w1, "w1").data_ptr(), _f32c(b1, "b1").data_ptr(),
+                                      _f32c(w2, "w2").data_ptr(), _ptr(w1b), _ptr(w2b), ldw2, du.data_ptr(),
+                                      dln_w.data_ptr(), dln_b.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(),
+                                      db2.data_ptr(), M, D, Cc, precision, wsp, nbytes, _stream()), "channel_mix_bwd")
+    return du, dln_w, dln_b, dw1, db1, dw2, db2
+
+
+_define("channel_mix_fwd", "(Tensor u, Tensor ln_w, Tensor ln_b, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor? w1b, "
+        "Tensor? w2b, int precision) -> Tensor", channel_mix_fwd)
+_define("channel_mix_bwd", "(Tensor dy, Tensor u, Tensor ln_w, Tensor ln_b, Tensor w1, Tensor b1, Tensor w2, Tensor? w1b, "
+        "Tensor? w2b, int precision) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)", channel_mix_bwd)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+def layernorm_fwd(x, w, b):
+    x = _f32c(x, "x")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    out = torch.empty_like(x)
+    check(_L().m2b200_layernorm_fwd(x.data_ptr(), _f32c(w, "w").data_ptr(), _f32c(b, "b").data_ptr(), out.data_ptr(), 1,
+                                    rows, D, 0, _stream()), "layernorm_fwd")
+    return out
+
+
+def layernorm_bwd(dy, x, w):
+    dy, x = _f32c(dy, "dy"), _f32c(x, "x")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    dx = torch.empty_like(x)
+    dw, db = torch.zeros_like(w), torch.zeros_like(w)
+    check(_L().m2b200_layernorm_bwd(dy.data_ptr(), 0, x.data_ptr(), _f32c(w, "w").data_ptr(), None, dx.data_ptr(),
+                                    dw.data_ptr(), db.data_ptr(), 1, rows, D, _stream()), "layernorm_bwd")
+    return dx, dw, db
+
+
+_define("layernorm_fwd", "(Tensor x, Tensor w, Tensor b) -> Tensor", layernorm_fwd)
+_define("layernorm_bwd", "(Tensor dy, Tensor x, Tensor w) -> (Tensor, Tensor, Tensor)", layernorm_bwd)
+
+
+# ------------------------------------------------------------------------------------------------ linear / patches
+def linear_fwd(x, w, wb, bias, act: int, precision: int):
+    x = _f32c(x, "x")
+    K = x.shape[-1]
+    M = x.numel() // K
+    N = w.shape[0]
+    y = torch.empty(*x.shape[:-1], N, dtype=torch.float32, device=x.device)
+    nbytes = _L().m2b200_linear_workspace_bytes(M, N, K, precision, 0)
+    ws, wsp = _ws(nbytes, x)
+    check(_L().m2b200_linear_fwd(x.data_ptr(), _f32c(w, "w").data_ptr(), _ptr(wb), 0 if wb is None else wb.shape[1],
+                                 None if bias is None else _f32c(bias, "bias").data_ptr(), act, y.data_ptr(), M, N, K,
+                                 precision, wsp, nbytes, _stream()), "linear_fwd")
+    return y
+
+
+def linear_bwd(dy, x, y, w, wb, act: int, need_dx: bool, precision: int):
+    x = _f32c(x, "x")
+    dy = _f32c(dy, "dy")
+    if act == _lib.ACT_RELU:
+        dy = dy.clone()   # masked in place by the kernel
+    K = x.shape[-1]
+    M = x.numel() // K
+    N = w.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.zeros_like(w, memory_format=torch.contiguous_format)
+    db = torch.zeros(N, dtype=torch.float32, device=x.device)
+    nbytes = _L().m2b200_linear_workspace_bytes(M, N, K, precision, 1)
+    ws, wsp = _ws(nbytes, x)
+    check(_L().m2b200_linear_bwd(dy.data_ptr(), x.data_ptr(), _ptr(y), _f32c(w, "w").data_ptr(), _ptr(wb),
+                                 0 if wb is None else wb.shape[1], act, _ptr(dx), dw.data_ptr(), db.data_ptr(), M, N, K,
+                                 precision, wsp, nbytes, _stream()), "linear_bwd")
+    if dx is None:
+        dx = torch.empty(0, dtype=torch.float32, device=x.device)
+    return dx, dw, db
+
+
+def patch_gather(img, patch: int):
+    img = _f32c(img, "img")
+    B, cin, H, W = img.shape
+    if H % patch or W % patch:
+        raise AssertionError("Image dimensions must be divisible by the patch size.")
+    cols = torch.empty(B, (H // patch) * (W // patch), cin * patch * patch, dtype=torch.float32, device=img.device)
+    check(_L().m2b200_patch_gather(img.data_ptr(), cols.data_ptr(), B, cin, H, W, patch, _stream()), "patch_gather")
+    return cols
+
+
+_define("linear_fwd", "(Tensor x, Tensor w, Tensor? wb, Tensor? bias, int act, int precision) -> Tensor", linear_fwd)
+_define("linear_bwd", "(Tensor dy, Tensor x, Tensor? y, Tensor w, Tensor? wb, int act, bool need_dx, int precision) -> "
+        "(Tensor, Tensor, Tensor)", linear_bwd)
+_define("patch_gather", "(Tensor img, int patch) -> Tensor", patch_gather)
+
+
+# ------------------------------------------------------------------------------------------------ fusion
+def concat_tokens(xs: Sequence[torch.Tensor]):
+    xs = [_f32c(x, "x") for x in xs]
+    B, D = xs[0].shape[0], xs[0].shape[-1]
+    ntot = sum(x.shape[1] for x in xs)
+    out = torch.empty(B, ntot, D, dtype=torch.float32, device=xs[0].device)
+    off = 0
+    for x in xs:
+        per = x.shape[1] * D
+        check(_L().m2b200_copy_tokens(x.data_ptr(), per, out.data_ptr() + off * 4, ntot * D, B, per, 0, _stream()),
+              "concat_tokens")
+        off += per
+    return out
+
+
+def split_tokens(g, sizes: Sequence[int]):
+    g = _f32c(g, "g")
+    B, ntot, D = g.shape
+    outs, off = [], 0
+    for n in sizes:
+        o = torch.empty(B, n, D, dtype=torch.float32, device=g.device)
+        check(_L().m2b200_copy_tokens(g.data_ptr() + off * 4, ntot * D, o.data_ptr(), n * D, B, n * D, 0, _stream()),
+              "split_tokens")
+        outs.append(o)
+        off += n * D
+    return outs
+
+
+def add(a, b):
+    a, b = _f32c(a, "a"), _f32c(b, "b")
+    if a.shape != b.shape:
+        raise RuntimeError("m2b200::add expects equal shapes")
+    out = torch.empty_like(a)
+    check(_L().m2b200_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()), "add")
+    return out
+
+
+def mean_pool_fwd(x):
+    x = _f32c(x, "x")
+    B, N, D = x.shape
+    out = torch.empty(B, D, dtype=torch.float32, device=x.device)
+    check(_L().m2b200_mean_pool_fwd(x.data_ptr(), out.data_ptr(), B, N, D, _stream()), "mean_pool_fwd")
+    return out
+
+
+def mean_pool_bwd(dp, n: int):
+    dp = _f32c(dp, "dp")
+    B, D = dp.shape
+    dx = torch.empty(B, n, D, dtype=torch.float32, device=dp.device)
+    check(_L().m2b200_mean_pool_bwd(dp.data_ptr(), dx.data_ptr(), B, n, D, _stream()), "mean_pool_bwd")
+    return dx
+
+
+_define("mean_pool_fwd", "(Tensor x) -> Tensor", mean_pool_fwd)
+_define("mean_pool_bwd", "(Tensor dp, int n) -> Tensor", mean_pool_bwd)
+_define("concat_tokens", "(Tensor[] xs) -> Tensor", concat_tokens)
+_define("split_tokens", "(Tensor g, int[] sizes) -> Tensor[]", split_tokens)
+_define("add", "(Tensor a, Tensor b) -> Tensor", add)
+
+
+# ------------------------------------------------------------------------------------------------ heads + loss
+def _heads_args(toks, ws, bs, head_weight):
+    n = len(toks)
+    arr_p = (C.c_void_p * 3)
+    tok = arr_p(*[t.data_ptr() for t in toks] + [None] * (3 - n))
+    w = arr_p(*[t.data_ptr() for t in ws] + [None] * (3 - n))
+    b = arr_p(*[t.data_ptr() for t in bs] + [None] * (3 - n))
+    bstride = (C.c_int64 * 3)(*[t.shape[1] * t.shape[2] for t in toks] + [0] * (3 - n))
+    ntok = (C.c_int * 3)(*[t.shape[1] for t in toks] + [0] * (3 - n))
+    dim = (C.c_int * 3)(*[t.shape[2] for t in toks] + [0] * (3 - n))
+    hw = (C.c_float * 3)(*list(head_weight) + [0.0] * (3 - n))
+    return tok, bstride, ntok, dim, w, b, hw
+
+
+def _as_tokens(t: torch.Tensor) -> torch.Tensor:
+    t = _f32c(t, "tokens")
+    return t.reshape(t.shape[0], -1, t.shape[-1])
+
+
+def heads_loss_fwd(toks: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], labels,
+                   pos_weight, head_weight: Sequence[float], loss_kind: int):
+    toks = [_as_tokens(t) for t in toks]
+    ws = [_f32c(w, "w") for w in ws]
+    bs = [_f32c(b, "b") for b in bs]
+    n, B, K = len(toks), toks[0].shape[0], ws[0].shape[0]
+    dev = toks[0].device
+    if loss_kind == 0:
+        labels = labels.to(torch.int64).contiguous()
+    else:
+        labels = labels.to(torch.float32).contiguous()
+    logits = torch.empty(3, B, K, dtype=torch.float32, device=dev)
+    losses = torch.empty(4, dtype=torch.float32, device=dev)
+    preds = torch.zeros((3, B) if loss_kind == 0 else (3, B, K), dtype=torch.int64, device=dev)
+    tok, bstride, ntok, dim, w, b, hw = _heads_args(toks, ws, bs, head_weight)
+    check(_L().m2b200_heads_loss_fwd(tok, bstride, ntok, dim, w, b, n, B, K, loss_kind, labels.data_ptr(),
+                                     _ptr(pos_weight), hw, logits.data_ptr(), losses.data_ptr(), preds.data_ptr(),
+                                     _stream()), "heads_loss_fwd")
+    return losses, logits, preds
+
+
+def heads_loss_bwd(toks, ws, bs, labels, pos_weight, head_weight, loss_kind: int, logits, grad_scale: float, grad_scale_dev=None):
+    toks = [_as_tokens(t) for t in toks]
+    ws = [_f32c(w, "w") for w in ws]
+    bs = [_f32c(b, "b") for b in bs]
+    n, B, K = len(toks), toks[0].shape[0], ws[0].shape[0]
+    labels = labels.to(torch.int64).contiguous() if loss_kind == 0 else labels.to(torch.float32).contiguous()
+    dtoks = [torch.empty_like(t) for t in toks]
+    dws = [torch.zeros_like(w) for w in ws]
+    dbs = [torch.zeros_like(b) for b in bs]
+    tok, bstride, ntok, dim, w, b, hw = _heads_args(toks, ws, bs, head_weight)
+    arr_p = (C.c_void_p * 3)
+    dtok = arr_p(*[t.data_ptr() for t in dtoks] + [None] * (3 - n))
+    dstride = (C.c_int64 * 3)(*[t.shape[1] * t.shape[2] for t in dtoks] + [0] * (3 - n))
+    acc = (C.c_int * 3)(0, 0, 0)
+    dw = arr_p(*[t.data_ptr() for t in dws] + [None] * (3 - n))
+    db = arr_p(*[t.data_ptr() for t in dbs] + [None] * (3 - n))
+    check(_L().m2b200_heads_loss_bwd(tok, bstride, ntok, dim, w, b, n, B, K, loss_kind, labels.data_ptr(),
+                                     _ptr(pos_weight), hw, _f32c(logits, "logits").data_ptr(), float(grad_scale),
+                                     None if grad_scale_dev is None else _f32c(grad_scale_dev, "grad_scale_dev").data_ptr(), dtok,
+                                     dstride, acc, dw, db, _stream()), "heads_loss_bwd")
+    return dtoks, dws, dbs
+
+
+_define("heads_loss_fwd", "(Tensor[] toks, Tensor[] ws, Tensor[] bs, Tensor labels, Tensor? pos_weight, float[] head_weight, "
+        "int loss_kind) -> (Tensor, Tensor, Tensor)", heads_loss_fwd)
+_define("heads_loss_bwd", "(Tensor[] toks, Tensor[] ws, Tensor[] bs, Tensor labels, Tensor? pos_weight, float[] head_weight, "
+        "int loss_kind, Tensor logits, float grad_scale, Tensor? grad_scale_dev) -> (Tensor[], Tensor[], Tensor[])", heads_loss_bwd)
+
+
+# ------------------------------------------------------------------------------------------------ optimiser / gemm
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float,
+              step: int, grad_scale: float, state: Optional[torch.Tensor] = None) -> None:
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError("m2b200::adam_step expects contiguous float32 CUDA buffers")
+    check(_L().m2b200_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+                                lr, beta1, beta2, eps, weight_decay, step, grad_scale, _ptr(state), _stream()), "adam_step")
+
+
+_define("adam_step", "(Tensor(a!) param, Tensor grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, float lr, float beta1, "
+        "float beta2, float eps, float weight_decay, int step, float grad_scale, Tensor? state) -> ()", adam_step)
+
+
+def gemm(precision: int, A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, *, batch: int = 1, a_batch_rows: int = 0,
+         b_batch_rows: int = 0, bias=None, bias_mode: int = 0, act: int = 0, residual=None, out_bf16: bool = False,
+         out: Optional[torch.Tensor] = None, accumulate: bool = False, splitk: int = 1) -> torch.Tensor:
+    """Direct access to the generic GEMM (tests / benchmarks).  A, B: 2-D row-major (fp32 for FP32, bf16 for BF16)."""
+    if out is None:
+        shape = (batch, M, N) if batch > 1 else (M, N)
+        mk = torch.zeros if (splitk > 1 or accumulate) else torch.empty
+        out = mk(shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=A.device)
+    check(_L().m2b200_gemm(precision, A.data_ptr(), int(a_mn), A.stride(0), B.data_ptr(), int(b_mn), B.stride(0), M, N, K,
+                           batch, a_batch_rows, b_batch_rows, _ptr(bias), bias_mode, act, _ptr(residual), N, M * N,
+                           out.data_ptr(), int(out_bf16), N, M * N, int(accumulate), splitk, _stream()), "gemm")
+    return out
