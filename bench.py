@@ -1,0 +1,301 @@
+"""Headline benchmark: train samples/s (fwd + bwd + optimizer step) of M2-Mixer on synthetic AV-MNIST-shaped data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config avmnist_B] [--batch 4096]
+
+Contract (see the task statement): one process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE), W untimed warm-up
+steps, EXACTLY K timed steps bracketed by barrier + synchronize, timed with CUDA events on the launching stream, MAX
+over ranks, rank 0 prints ONE JSON line.  `value` has inputs resident in HBM; `e2e` goes through the public API with
+pinned host buffers (H2D of the batch and D2H of the loss inside the timed region).  `--impl reference` times the
+reference's algorithm on the host CPU (the oracle port - the reference is pure Python/PyTorch and cannot travel to
+the GPU box as source; kind = "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train samples/s (fwd+bwd+step)"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="avmnist_B")
+    ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=128, help="bounded sample for the CPU legs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- model FLOPs
+def model_flops(cfg: dict) -> dict:
+    """Algorithmic GEMM FLOPs per sample (2*MACs), SURVEY 8(d): block fwd = 4NDT + 4NDC, patch embed fwd = 2 K D N,
+    heads = 3*2*D*K; fwd+bwd = 3 x fwd."""
+    m = cfg["modalities"]
+    tot, chan = 0.0, 0.0
+    npatch = []
+    for name in ("image", "audio"):
+        e = m[name]
+        n = (e["image_size"][0] // e["patch_size"]) * (e["image_size"][1] // e["patch_size"])
+        npatch.append(n)
+        d, t, c, L = e["hidden_dim"], e["token_dim"], e["channel_dim"], e["num_mixers"]
+        tot += 2.0 * e["in_channels"] * e["patch_size"] ** 2 * d * n
+        tot += L * (4.0 * n * d * t + 4.0 * n * d * c)
+        chan += L * 4.0 * n * d * c
+    f = m["multimodal"]
+    n = sum(npatch)
+    tot += f["num_mixers"] * (4.0 * n * f["hidden_dim"] * f["token_dim"] + 4.0 * n * f["hidden_dim"] * f["channel_dim"])
+    chan += f["num_mixers"] * 4.0 * n * f["hidden_dim"] * f["channel_dim"]
+    tot += 3 * 2.0 * f["hidden_dim"] * m["classification"]["num_classes"]
+    return {"fwd": tot, "fwd_bwd": 3 * tot, "channel_mix_fwd": chan}
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs
+def cpu_port_run(cfg: dict, bsz: int, steps: int, warmup: int, dropout: float):
+    """The reference's algorithm (oracle port) on the host cores: fwd + bwd + Adam step, fp32, all threads."""
+    import torch
+    from m2_mixer_b200 import models
+    from oracle import m2mixer_oracle as O
+    from oracle.seeding import seeded_state_dict, synthetic_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    shapes = {k: tuple(v.shape) for k, v in models.get_model(cfg["type"])(dict(cfg, dropout=0.0), {}).state_dict().items()}
+    sd = {k: v.requires_grad_(True) for k, v in seeded_state_dict(shapes, 42).items()}
+    names = list(sd)
+    m_ = [torch.zeros_like(sd[k]) for k in names]
+    v_ = [torch.zeros_like(sd[k]) for k in names]
+    batch = synthetic_batch("avmnist", bsz, 42)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.avmnist_shared_step(sd, batch, p=dropout, training=True)
+        grads = O.grads_of(out["loss"], sd)
+        with torch.no_grad():
+            O.adam_step([sd[k] for k in names], [grads[k] for k in names], m_, v_, it + 1, lr=1e-2)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": bsz * steps / total, "ms_per_step": 1e3 * total / steps, "cores": cores,
+            "sample": f"{steps} steps of batch {bsz} (fp32, dropout {dropout}, torch {torch.__version__} CPU, {cores} threads)"}
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    r = cpu_port_run(cfg, args.cpu_batch, args.steps, args.warmup, cfg.get("dropout", 0.0))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config} (reference algorithm on host CPU, bounded sample batch {args.cpu_batch})"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from m2_mixer_b200 import _lib, models, parallel, presets
+    from m2_mixer_b200.optim import FusedAdam
+
+    rank, local, world = parallel.init_from_env()
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU: the hot path has no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch
+    ref_dropout = cfg.get("dropout", 0.0)
+    cfg = dict(cfg, dropout=0.0)
+    torch.manual_seed(42)                                         # cfg seed (reference cfg train.seed)
+    model = models.get_model(cfg["type"])(cfg, dict(presets.AVMNIST_OPTIM)).to(dev).set_precision(args.precision)
+    model.train()
+    opt = FusedAdam(model.parameters(), lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    sync = parallel.attach(opt) if world > 1 else None
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    NB = 4   # rotate distinct batches: each is 218 MB of fp32 input, larger than the 126 MB L2
+    batches = [{"image": torch.randn(B, 1, 28, 28, device=dev, generator=g),
+                "audio": torch.randn(B, 1, 112, 112, device=dev, generator=g),
+                "label": torch.randint(0, 10, (B,), device=dev, generator=g)} for _ in range(NB)]
+
+    def step(batch):
+        opt.zero_grad()
+        loss = model.training_step(batch)
+        loss.backward()
+        if sync is not None:
+            sync.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms)
+
+    for i in range(args.warmup):
+        step(batches[i % NB])
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count()
+    ms = timed(lambda i: step(batches[i % NB]), args.steps)
+    launches = _lib.launch_count() - l0
+    clk = clocks.stop() if clocks else None
+
+    # ---- end to end through the public API from pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        host = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in batches[:2]]
+        devbuf = {k: torch.empty_like(v) for k, v in batches[0].items()}
+        sink = []
+
+        def e2e_step(i):
+            hb = host[i % 2]
+            for k in devbuf:
+                devbuf[k].copy_(hb[k], non_blocking=True)
+            sink.append(float(step(devbuf)))                      # D2H read of the loss every step
+
+        for i in range(2):
+            e2e_step(i)
+        ems = timed(e2e_step, args.steps)
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+        e2e = {"value": world * B * args.steps / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": ems / args.steps}
+
+    # ---- per-kernel device time (CUDA events on the launching stream) for the roofline of the dominant kernel
+    roof = None
+    if rank == 0:
+        with _lib.profile() as prof:
+            for i in range(3):
+                step(batches[i % NB])
+            torch.cuda.synchronize()
+        table = prof.table
+        mm = cfg["modalities"]
+        per_sample_chain = model_flops(cfg)["channel_mix_fwd"]          # 4*N*D*C summed over every block
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained")
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+        if peak is None:
+            peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+        cands = {k: v for k, v in table.items() if k in ("chain_fwd", "chain_bwd")}
+        if cands:
+            name = max(cands, key=lambda k: cands[k][1])
+            n, tot_ms = cands[name]
+            # both chains carry 4*M*D*C algorithmic FLOPs per launch (fwd: two GEMMs; bwd: dG and dXn; the recomputed
+            # H GEMM of the backward chain is NOT counted)
+            flops = per_sample_chain * B * 3                            # 3 profiled steps
+            ach = flops / (tot_ms / 1e3) / 1e12
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get(name)
+            roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": traffic, "launches": n, "avg_launch_ms": tot_ms / n, "peak_source": peak_src,
+                    "step_share": {k: round(v[1] / 3, 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_port_run(dict(cfg, dropout=ref_dropout), args.cpu_batch, 2, 1, ref_dropout)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        fl = model_flops(cfg)
+        value = world * B * args.steps / (ms / 1e3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": f"{args.config} ({cfg['type']}), per-GPU batch {B}, fwd+bwd+FusedAdam",
+                           "global_batch": world * B, "parallelism": f"dp{world}",
+                           "l2": f"{NB} rotating input batches of {B * (784 + 12544) * 4 >> 20} MiB each (> 126 MB L2)",
+                           "dropout": f"0.0 (reference cfg trains with {ref_dropout}; fused dropout not in this build)",
+                           "model_tflops_per_gpu": fl["fwd_bwd"] * value / world / 1e12,
+                           "frac_of_bf16_peak_burst": fl["fwd_bwd"] * value / world / 1e12 / 1644.4},
+                "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from m2_mixer_b200 import presets
+    cfg = presets.get(args.config)
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

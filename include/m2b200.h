@@ -58,16 +58,26 @@ int m2b200_gemm(int precision, const void* A, int a_mn, int64_t lda, const void*
                 const float* residual, int64_t ldr, int64_t r_batch_stride, void* C, int c_bf16, int64_t ldc,
                 int64_t c_batch_stride, int accumulate, int splitk, void* stream);
 
+/* ---- Dropout (nn.Dropout(p) twice per FeedForward, modules/mixer.py:16,18; once per MLP block, modules/mlp.py:17).
+ * Every op that contains a dropout site takes (dropout_p, seed): p = 0 disables it; otherwise the mask is a
+ * counter-based hash of (seed, site, element index) evaluated inside the fused epilogues and RE-evaluated by the
+ * backward kernels (nothing is stored).  The stream differs from torch's Philox by design (no bit parity);
+ * m2b200_dropout_mask exports the exact keep-mask (1/0) of a site for testing: index = r*ld + c with
+ *   site 0 token hidden   rows = B*T, ld = D        site 1 token out     rows = B*N, ld = D
+ *   site 2 channel hidden rows = M,   ld = up8(C)   site 3 channel out   rows = M,   ld = D      site 4 linear ld = N
+ * kept values are scaled by 65536 / (65536 - round(p*65536)).                                                        */
+int m2b200_dropout_mask(float* out, int rows, int cols, int64_t ld, float dropout_p, uint64_t seed, int site, void* stream);
+
 /* ---- MixerBlock.token_mix + residual: modules/mixer.py:30-35,43
  *   u[b] = x[b] + Wt2 . GELU(Wt1 . LN(x[b]) + bt1) + bt2,   x,u [B][N][D], wt1 [T][N], wt2 [N][T]            */
 int m2b200_token_mix_fwd(const float* x, const float* ln_w, const float* ln_b, const float* wt1, const float* bt1,
                          const float* wt2, const float* bt2, float* u, int B, int N, int D, int T, int precision,
-                         void* stream);
+                         float dropout_p, uint64_t seed, void* stream);
 size_t m2b200_token_mix_bwd_workspace_bytes(int B, int N, int D, int T);
 int m2b200_token_mix_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* wt1,
                          const float* bt1, const float* wt2, float* dx, float* dln_w, float* dln_b, float* dwt1,
-                         float* dbt1, float* dwt2, float* dbt2, int B, int N, int D, int T, int precision, void* workspace,
-                         size_t workspace_bytes, void* stream);
+                         float* dbt1, float* dwt2, float* dbt2, int B, int N, int D, int T, int precision, float dropout_p,
+                         uint64_t seed, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- MixerBlock.channel_mix + residual: modules/mixer.py:37-40,45
  *   y = u + W2 . GELU(W1 . LN(u) + b1) + b2,   u,y [M][D] (M = B*N token rows), w1 [C][D], w2 [D][C]
@@ -75,11 +85,13 @@ int m2b200_token_mix_bwd(const float* du, const float* x, const float* ln_w, con
 size_t m2b200_channel_mix_workspace_bytes(int M, int D, int C, int precision, int backward);
 int m2b200_channel_mix_fwd(const float* u, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
                            const float* w2, const float* b2, const void* w1_bf16, const void* w2_bf16, int ldw2, float* y,
-                           int M, int D, int C, int precision, void* workspace, size_t workspace_bytes, void* stream);
+                           int M, int D, int C, int precision, float dropout_p, uint64_t seed, void* workspace,
+                           size_t workspace_bytes, void* stream);
 int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, const float* ln_b, const float* w1,
                            const float* b1, const float* w2, const void* w1_bf16, const void* w2_bf16, int ldw2, float* du,
                            float* dln_w, float* dln_b, float* dw1, float* db1, float* dw2, float* db2, int M, int D, int C,
-                           int precision, void* workspace, size_t workspace_bytes, void* stream);
+                           int precision, float dropout_p, uint64_t seed, void* workspace, size_t workspace_bytes,
+                           void* stream);
 
 /* ---- nn.LayerNorm(hidden_dim) closing every stack: modules/mixer.py:131,161,185,263.
  * Token row (b,n) is written to out + b*out_bstride + n*D so that an encoder can normalise straight into its slice
@@ -94,11 +106,22 @@ int m2b200_layernorm_bwd(const float* dy, int64_t dy_bstride, const float* x, co
  *   y[M][N] = act(x[M][K] . w[N][K]^T + bias)                                                                     */
 size_t m2b200_linear_workspace_bytes(int M, int N, int K, int precision, int backward);
 int m2b200_linear_fwd(const float* x, const float* w, const void* w_bf16, int ldwb, const float* bias, int act, float* y,
-                      int M, int N, int K, int precision, void* workspace, size_t workspace_bytes, void* stream);
+                      int M, int N, int K, int precision, float dropout_p, uint64_t seed, void* workspace,
+                      size_t workspace_bytes, void* stream);
 /* dy is modified in place when act == RELU (masked by y > 0).  dx may be NULL (patch embedding: input needs no grad) */
 int m2b200_linear_bwd(float* dy, const float* x, const float* y, const float* w, const void* w_bf16, int ldwb, int act,
-                      float* dx, float* dw, float* db, int M, int N, int K, int precision, void* workspace,
-                      size_t workspace_bytes, void* stream);
+                      float* dx, float* dw, float* db, int M, int N, int K, int precision, float dropout_p, uint64_t seed,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* Patch embedding as gather + GEMM (modules/mixer.py:143-146).  `cols` (m2b200_patch_embed_cols_bytes) receives the
+ * gathered patch rows - bf16 [M][up8(K)] in BF16 mode, fp32 [M][K] in FP32 mode, M = B*(H/P)*(W/P), K = cin*P*P -
+ * and is what the backward's weight-gradient GEMM reads (there is no input gradient).  w is [D][K] (Conv2d weight
+ * [D][cin][P][P] viewed flat), y is [M][D] in 'b (h w) c' order.                                                    */
+size_t m2b200_patch_embed_cols_bytes(int B, int cin, int H, int W, int P, int precision);
+int m2b200_patch_embed_fwd(const float* img, const float* w, const void* w_bf16, int ldwb, const float* bias, void* cols,
+                           float* y, int B, int cin, int H, int W, int P, int D, int precision, void* stream);
+size_t m2b200_patch_embed_bwd_workspace_bytes(int M, int D, int precision);
+int m2b200_patch_embed_bwd(const float* dy, const void* cols, float* dw, float* db, int M, int D, int K, int precision,
+                           void* workspace, size_t workspace_bytes, void* stream);
 /* img [B][cin][H][W] -> cols [B*(H/P)*(W/P)][cin*P*P]  (row = patch in (h w) order, col = (c, py, px))              */
 int m2b200_patch_gather(const float* img, float* cols, int B, int cin, int H, int W, int P, void* stream);
 
@@ -136,6 +159,12 @@ int m2b200_heads_loss_bwd(const float* const* tok, const int64_t* tok_bstride, c
  * state_dev (optional, device float[2] = {lr, step}) makes lr/step device-resident (graph replay, LR scheduler).   */
 int m2b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, float grad_scale, float* state_dev, void* stream);
+
+/* ---- launch accounting (bench.py): total kernel launches since load; optional CUDA-event timing per kernel name.
+ * m2b200_profile_collect synchronises the recorded events and writes "name,launches,total_ms\n" lines.           */
+unsigned long long m2b200_launch_count(void);
+void m2b200_profile_enable(int on);
+size_t m2b200_profile_collect(char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

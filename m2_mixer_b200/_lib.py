@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libm2b200.so")
 FP32, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
-vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+vp, i32, i64, f32, sz, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
 PP = C.POINTER(C.c_void_p)
 PI64 = C.POINTER(C.c_int64)
 PI32 = C.POINTER(C.c_int)
@@ -27,17 +27,22 @@ PROTOTYPES = {
     "m2b200_cast_bf16": (i32, [vp, i64, vp, i64, i32, i32, vp]),
     "m2b200_gemm": (i32, [i32, vp, i32, i64, vp, i32, i64, i32, i32, i32, i32, i64, i64, vp, i32, i32, vp, i64, i64, vp,
                           i32, i64, i64, i32, i32, vp]),
-    "m2b200_token_mix_fwd": (i32, [vp] * 8 + [i32] * 5 + [vp]),
+    "m2b200_token_mix_fwd": (i32, [vp] * 8 + [i32] * 5 + [f32, u64, vp]),
     "m2b200_token_mix_bwd_workspace_bytes": (sz, [i32] * 4),
-    "m2b200_token_mix_bwd": (i32, [vp] * 14 + [i32] * 5 + [vp, sz, vp]),
+    "m2b200_token_mix_bwd": (i32, [vp] * 14 + [i32] * 5 + [f32, u64, vp, sz, vp]),
     "m2b200_channel_mix_workspace_bytes": (sz, [i32] * 5),
-    "m2b200_channel_mix_fwd": (i32, [vp] * 9 + [i32, vp] + [i32] * 4 + [vp, sz, vp]),
-    "m2b200_channel_mix_bwd": (i32, [vp] * 9 + [i32] + [vp] * 7 + [i32] * 4 + [vp, sz, vp]),
+    "m2b200_channel_mix_fwd": (i32, [vp] * 9 + [i32, vp] + [i32] * 4 + [f32, u64, vp, sz, vp]),
+    "m2b200_channel_mix_bwd": (i32, [vp] * 9 + [i32] + [vp] * 7 + [i32] * 4 + [f32, u64, vp, sz, vp]),
     "m2b200_layernorm_fwd": (i32, [vp] * 4 + [i32] * 3 + [i64, vp]),
     "m2b200_layernorm_bwd": (i32, [vp, i64] + [vp] * 6 + [i32] * 3 + [vp]),
     "m2b200_linear_workspace_bytes": (sz, [i32] * 5),
-    "m2b200_linear_fwd": (i32, [vp, vp, vp, i32, vp, i32, vp] + [i32] * 4 + [vp, sz, vp]),
-    "m2b200_linear_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp] + [i32] * 4 + [vp, sz, vp]),
+    "m2b200_linear_fwd": (i32, [vp, vp, vp, i32, vp, i32, vp] + [i32] * 4 + [f32, u64, vp, sz, vp]),
+    "m2b200_linear_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp] + [i32] * 4 + [f32, u64, vp, sz, vp]),
+    "m2b200_dropout_mask": (i32, [vp, i32, i32, i64, f32, u64, i32, vp]),
+    "m2b200_patch_embed_cols_bytes": (sz, [i32] * 6),
+    "m2b200_patch_embed_fwd": (i32, [vp, vp, vp, i32, vp, vp, vp] + [i32] * 8 + [vp]),
+    "m2b200_patch_embed_bwd_workspace_bytes": (sz, [i32] * 3),
+    "m2b200_patch_embed_bwd": (i32, [vp, vp, vp, vp] + [i32] * 4 + [vp, sz, vp]),
     "m2b200_patch_gather": (i32, [vp, vp] + [i32] * 5 + [vp]),
     "m2b200_copy_tokens": (i32, [vp, i64, vp, i64, i32, i64, i32, vp]),
     "m2b200_add": (i32, [vp, vp, vp, i64, vp]),
@@ -46,6 +51,9 @@ PROTOTYPES = {
     "m2b200_heads_loss_fwd": (i32, [PP, PI64, PI32, PI32, PP, PP, i32, i32, i32, i32, vp, vp, PF32, vp, vp, vp, vp]),
     "m2b200_heads_loss_bwd": (i32, [PP, PI64, PI32, PI32, PP, PP, i32, i32, i32, i32, vp, vp, PF32, vp, f32, vp, PP, PI64,
                                     PI32, PP, PP, vp]),
+    "m2b200_launch_count": (C.c_ulonglong, []),
+    "m2b200_profile_enable": (None, [i32]),
+    "m2b200_profile_collect": (sz, [C.c_char_p, sz]),
     "m2b200_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp, vp]),
 }
 
@@ -78,3 +86,27 @@ def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().m2b200_status_string(status).decode()
         raise M2B200Error(f"{what} failed: status {status} ({msg})")
+
+
+def launch_count() -> int:
+    return int(load().m2b200_launch_count())
+
+
+class profile:
+    """``with profile() as p: ...`` then ``p.table`` = {kernel name: (launches, total_ms)} measured with CUDA events
+    on the launching stream."""
+
+    def __enter__(self):
+        load().m2b200_profile_enable(1)
+        self.table = {}
+        return self
+
+    def __exit__(self, *exc):
+        lib = load()
+        lib.m2b200_profile_enable(0)
+        buf = C.create_string_buffer(1 << 16)
+        lib.m2b200_profile_collect(buf, len(buf))
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split(",")
+            self.table[name] = (int(n), float(ms))
+        return False

@@ -96,9 +96,10 @@ int m2b200_gemm(int precision, const void* A, int a_mn, int64_t lda, const void*
 // ------------------------------------------------------------------------------------------ token mixing
 int m2b200_token_mix_fwd(const float* x, const float* ln_w, const float* ln_b, const float* wt1, const float* bt1,
                          const float* wt2, const float* bt2, float* u, int B, int N, int D, int T, int precision,
-                         void* stream) {
+                         float dropout_p, uint64_t seed, void* stream) {
   if (!x || !ln_w || !ln_b || !wt1 || !bt1 || !wt2 || !bt2 || !u) return M2_ERR_ARG;
-  return token_mix_fwd(x, ln_w, ln_b, wt1, bt1, wt2, bt2, u, B, N, D, T, precision == M2B200_FP32, S(stream));
+  if (dropout_p < 0.f || dropout_p >= 1.f) return M2_ERR_ARG;
+  return token_mix_fwd(x, ln_w, ln_b, wt1, bt1, wt2, bt2, u, B, N, D, T, precision == M2B200_FP32, dropout_p, seed, S(stream));
 }
 
 size_t m2b200_token_mix_bwd_workspace_bytes(int B, int N, int D, int T) {
@@ -108,15 +109,15 @@ size_t m2b200_token_mix_bwd_workspace_bytes(int B, int N, int D, int T) {
 
 int m2b200_token_mix_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* wt1,
                          const float* bt1, const float* wt2, float* dx, float* dln_w, float* dln_b, float* dwt1,
-                         float* dbt1, float* dwt2, float* dbt2, int B, int N, int D, int T, int precision, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+                         float* dbt1, float* dwt2, float* dbt2, int B, int N, int D, int T, int precision, float dropout_p,
+                         uint64_t seed, void* workspace, size_t workspace_bytes, void* stream) {
   if (!du || !x || !ln_w || !ln_b || !wt1 || !bt1 || !wt2 || !dx || !dln_w || !dln_b || !dwt1 || !dbt1 || !dwt2 || !dbt2)
     return M2_ERR_ARG;
   Carver ws(workspace, workspace_bytes);
   float* dxn = ws.take<float>(static_cast<size_t>(B) * N * D);
   if (!ws.ok) return M2_ERR_WORKSPACE;
   M2_TRY(token_mix_bwd(du, x, ln_w, ln_b, wt1, bt1, wt2, dxn, dwt1, dbt1, dwt2, dbt2, B, N, D, T,
-                       precision == M2B200_FP32, S(stream)));
+                       precision == M2B200_FP32, dropout_p, seed, S(stream)));
   // dx = du (residual) + LayerNorm'(dxn);  dln_w/dln_b accumulate
   return ln_bwd(dxn, static_cast<long long>(N) * D, N, x, ln_w, du, dx, dln_w, dln_b, B * N, D, S(stream));
 }
@@ -130,7 +131,7 @@ size_t m2b200_channel_mix_workspace_bytes(int M, int D, int C, int precision, in
     if (path == kPathF32) b = up256(m * d * 4) + up256(m * c * 4);
     else if (path == kPathUnfusedBf16) b = up256(m * d * 2) + up256(m * c8 * 2);
   } else {
-    if (path == kPathF32) b = 2 * up256(m * d * 4) + 3 * up256(m * c * 4);
+    if (path == kPathF32) b = 3 * up256(m * d * 4) + 3 * up256(m * c * 4);
     else if (path == kPathFused) b = 2 * up256(m * d * 2) + 2 * up256(m * c8 * 2) + up256(m * d * 4);
     else b = 2 * up256(m * d * 2) + 2 * up256(m * c * 4) + 2 * up256(m * c8 * 2) + up256(m * d * 4);
   }
@@ -139,11 +140,14 @@ size_t m2b200_channel_mix_workspace_bytes(int M, int D, int C, int precision, in
 
 int m2b200_channel_mix_fwd(const float* u, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
                            const float* w2, const float* b2, const void* w1b, const void* w2b, int ldw2, float* y, int M,
-                           int D, int C, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+                           int D, int C, int precision, float dropout_p, uint64_t seed, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   if (!u || !ln_w || !ln_b || !b1 || !b2 || !y || M <= 0 || D <= 0 || C <= 0) return M2_ERR_ARG;
   if (!al16(u) || !al16(y) || !al16(ln_w) || !al16(ln_b) || !al16(b1) || !al16(b2) || D % 4) return M2_ERR_ALIGN;
+  if (dropout_p < 0.f || dropout_p >= 1.f) return M2_ERR_ARG;
   cudaStream_t s = S(stream);
   const ChainPath path = pick_path(D, precision, false);
+  const int c8 = up8(C);
   Carver ws(workspace, workspace_bytes);
   if (path == kPathF32) {
     if (!w1 || !w2) return M2_ERR_ARG;
@@ -153,35 +157,42 @@ int m2b200_channel_mix_fwd(const float* u, const float* ln_w, const float* ln_b,
     M2_TRY(ln_fwd(u, ln_w, ln_b, xn, 0, M, D, M, 0, nullptr, nullptr, s));
     GemmArgs g1 = gemm_args(xn, 0, D, w1, 0, D, M, C, D, h, 0, C);
     g1.bias = b1; g1.bias_mode = 1; g1.act = 1;
+    g1.drop_p = dropout_p; g1.drop_seed = seed; g1.drop_site = kSiteChannelHidden; g1.drop_ld = c8;
     M2_TRY(gemm_f32_simt(g1, s));
     GemmArgs g2 = gemm_args(h, 0, C, w2, 0, C, M, D, C, y, 0, D);
     g2.bias = b2; g2.bias_mode = 1; g2.residual = u; g2.ldr = D;
+    g2.drop_p = dropout_p; g2.drop_seed = seed; g2.drop_site = kSiteChannelOut; g2.drop_ld = D;
     return gemm_f32_simt(g2, s);
   }
   if (!w1b || !w2b || D % 8 || ldw2 % 8 || ldw2 < C) return M2_ERR_ARG;
-  if (path == kPathFused) return chain_fwd(u, ln_w, ln_b, w1b, b1, w2b, ldw2, b2, y, M, D, C, 0, s);
+  if (path == kPathFused) return chain_fwd(u, ln_w, ln_b, w1b, b1, w2b, ldw2, b2, y, M, D, C, 0, dropout_p, seed, s);
   // unfused bf16: LN -> GEMM(+b1, GELU) -> GEMM(+b2, +u)
-  const int c8 = up8(C);
   __nv_bfloat16* xn = ws.take<__nv_bfloat16>(static_cast<size_t>(M) * D);
   __nv_bfloat16* h = ws.take<__nv_bfloat16>(static_cast<size_t>(M) * c8);
   if (!ws.ok) return M2_ERR_WORKSPACE;
   M2_TRY(ln_fwd(u, ln_w, ln_b, xn, 1, M, D, M, 0, nullptr, nullptr, s));
   GemmArgs g1 = gemm_args(xn, 0, D, w1b, 0, D, M, C, D, h, 1, c8);
   g1.bias = b1; g1.bias_mode = 1; g1.act = 1;
+  g1.drop_p = dropout_p; g1.drop_seed = seed; g1.drop_site = kSiteChannelHidden; g1.drop_ld = c8;
   M2_TRY(gemm_bf16_umma(g1, s));
   GemmArgs g2 = gemm_args(h, 0, c8, w2b, 0, ldw2, M, D, C, y, 0, D);
   g2.bias = b2; g2.bias_mode = 1; g2.residual = u; g2.ldr = D;
+  g2.drop_p = dropout_p; g2.drop_seed = seed; g2.drop_site = kSiteChannelOut; g2.drop_ld = D;
   return gemm_bf16_umma(g2, s);
 }
 
 int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, const float* ln_b, const float* w1,
                            const float* b1, const float* w2, const void* w1b, const void* w2b, int ldw2, float* du,
                            float* dln_w, float* dln_b, float* dw1, float* db1, float* dw2, float* db2, int M, int D, int C,
-                           int precision, void* workspace, size_t workspace_bytes, void* stream) {
+                           int precision, float dropout_p, uint64_t seed, void* workspace, size_t workspace_bytes,
+                           void* stream) {
   if (!dy || !u || !ln_w || !ln_b || !b1 || !du || !dln_w || !dln_b || !dw1 || !db1 || !dw2 || !db2 || M <= 0 || D <= 0 ||
       C <= 0)
     return M2_ERR_ARG;
   if (!al16(dy) || !al16(u) || !al16(du) || !al16(ln_w) || !al16(ln_b) || !al16(b1) || D % 4) return M2_ERR_ALIGN;
+  if (dropout_p < 0.f || dropout_p >= 1.f) return M2_ERR_ARG;
+  const bool drop = dropout_p > 0.f;
+  const int c8 = up8(C);
   cudaStream_t s = S(stream);
   const ChainPath path = pick_path(D, precision, true);
   Carver ws(workspace, workspace_bytes);
@@ -190,31 +201,36 @@ int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, c
     if (!w1 || !w2) return M2_ERR_ARG;
     float* xn = ws.take<float>(md);
     float* dxn = ws.take<float>(md);
+    float* dym = ws.take<float>(md);
     float* h = ws.take<float>(mc);
     float* gbuf = ws.take<float>(mc);
     float* dh = ws.take<float>(mc);
     if (!ws.ok) return M2_ERR_WORKSPACE;
+    const float* dyb = dy;   // gradient of the (dropped) branch output
+    if (drop) {
+      M2_TRY(mask_scale(dy, D, dym, 0, D, M, D, dropout_p, seed, kSiteChannelOut, D, s));
+      dyb = dym;
+    }
     M2_TRY(ln_fwd(u, ln_w, ln_b, xn, 0, M, D, M, 0, nullptr, nullptr, s));
     GemmArgs gh = gemm_args(xn, 0, D, w1, 0, D, M, C, D, h, 0, C);          // H = Xn W1^T + b1
     gh.bias = b1; gh.bias_mode = 1;
     M2_TRY(gemm_f32_simt(gh, s));
-    GemmArgs gg = gemm_args(dy, 0, D, w2, 1, C, M, C, D, dh, 0, C);          // dG = dY W2   (W2 [D][C] as [K][N])
+    GemmArgs gg = gemm_args(dyb, 0, D, w2, 1, C, M, C, D, dh, 0, C);         // dG = dY W2   (W2 [D][C] as [K][N])
     M2_TRY(gemm_f32_simt(gg, s));
-    M2_TRY(gelu_fwd_bwd(h, dh, M, C, C, gbuf, dh, C, 0, s));                 // G, dH (in place over dG)
-    GemmArgs gw2 = gemm_args(dy, 1, D, gbuf, 1, C, D, C, M, dw2, 0, C);      // dW2 += dY^T G
+    M2_TRY(gelu_fwd_bwd(h, dh, M, C, C, gbuf, dh, C, 0, dropout_p, seed, kSiteChannelHidden, c8, s));   // G, dH in place
+    GemmArgs gw2 = gemm_args(dyb, 1, D, gbuf, 1, C, D, C, M, dw2, 0, C);     // dW2 += dY^T G
     gw2.accumulate = 1;
     M2_TRY(gemm_f32_simt(gw2, s));
     GemmArgs gw1 = gemm_args(dh, 1, C, xn, 1, D, C, D, M, dw1, 0, D);        // dW1 += dH^T Xn
     gw1.accumulate = 1;
     M2_TRY(gemm_f32_simt(gw1, s));
     M2_TRY(colsum_f32(dh, C, M, C, db1, s));
-    M2_TRY(colsum_f32(dy, D, M, D, db2, s));
+    M2_TRY(colsum_f32(dyb, D, M, D, db2, s));
     GemmArgs gx = gemm_args(dh, 0, C, w1, 1, D, M, D, C, dxn, 0, D);         // dXn = dH W1  (W1 [C][D] as [K][N])
     M2_TRY(gemm_f32_simt(gx, s));
     return ln_bwd(dxn, static_cast<long long>(M) * D, M, u, ln_w, dy, du, dln_w, dln_b, M, D, s);
   }
   if (!w1b || !w2b || D % 8 || ldw2 % 8 || ldw2 < C) return M2_ERR_ARG;
-  const int c8 = up8(C);
   const size_t mc8 = static_cast<size_t>(M) * c8;
   __nv_bfloat16* xn_b = ws.take<__nv_bfloat16>(md);
   __nv_bfloat16* dy_b = ws.take<__nv_bfloat16>(md);
@@ -223,13 +239,13 @@ int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, c
   float* dxn = ws.take<float>(md);
   if (path == kPathFused) {
     if (!ws.ok) return M2_ERR_WORKSPACE;
-    M2_TRY(chain_bwd(u, ln_w, ln_b, w1b, b1, w2b, ldw2, dy, xn_b, dy_b, g_b, dh_b, c8, dxn, M, D, C, 0, s));
+    M2_TRY(chain_bwd(u, ln_w, ln_b, w1b, b1, w2b, ldw2, dy, xn_b, dy_b, g_b, dh_b, c8, dxn, M, D, C, 0, dropout_p, seed, s));
   } else {
     float* h = ws.take<float>(mc);
     float* dg = ws.take<float>(mc);
     if (!ws.ok) return M2_ERR_WORKSPACE;
     M2_TRY(ln_fwd(u, ln_w, ln_b, xn_b, 1, M, D, M, 0, nullptr, nullptr, s));
-    M2_TRY(cast_pad_bf16(dy, D, dy_b, D, M, D, s));
+    M2_TRY(mask_scale(dy, D, dy_b, 1, D, M, D, dropout_p, seed, kSiteChannelOut, D, s));
     GemmArgs gh = gemm_args(xn_b, 0, D, w1b, 0, D, M, C, D, h, 0, C);
     gh.bias = b1; gh.bias_mode = 1;
     M2_TRY(gemm_bf16_umma(gh, s));
@@ -239,7 +255,7 @@ int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, c
       if (cudaMemsetAsync(g_b, 0, mc8 * 2, s) != cudaSuccess || cudaMemsetAsync(dh_b, 0, mc8 * 2, s) != cudaSuccess)
         return M2_ERR_LAUNCH;
     }
-    M2_TRY(gelu_fwd_bwd(h, dg, M, C, C, g_b, dh_b, c8, 1, s));
+    M2_TRY(gelu_fwd_bwd(h, dg, M, C, C, g_b, dh_b, c8, 1, dropout_p, seed, kSiteChannelHidden, c8, s));
     GemmArgs gx = gemm_args(dh_b, 0, c8, w1b, 1, D, M, D, C, dxn, 0, D);
     M2_TRY(gemm_bf16_umma(gx, s));
   }
@@ -253,7 +269,8 @@ int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, c
   if (gw1.splitk == 1) gw1.accumulate = 1;
   M2_TRY(gemm_bf16_umma(gw1, s));
   M2_TRY(colsum_bf16(dh_b, c8, M, C, db1, s));
-  M2_TRY(colsum_f32(dy, D, M, D, db2, s));
+  if (drop) M2_TRY(colsum_bf16(dy_b, D, M, D, db2, s));   // the masked gradient only exists as the bf16 operand copy
+  else M2_TRY(colsum_f32(dy, D, M, D, db2, s));
   return ln_bwd(dxn, static_cast<long long>(M) * D, M, u, ln_w, dy, du, dln_w, dln_b, M, D, s);
 }
 
@@ -278,13 +295,15 @@ size_t m2b200_linear_workspace_bytes(int M, int N, int K, int precision, int bac
 }
 
 int m2b200_linear_fwd(const float* x, const float* w, const void* w_bf16, int ldwb, const float* bias, int act, float* y,
-                      int M, int N, int K, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+                      int M, int N, int K, int precision, float dropout_p, uint64_t seed, void* workspace,
+                      size_t workspace_bytes, void* stream) {
   if (!x || !y || M <= 0 || N <= 0 || K <= 0) return M2_ERR_ARG;
   cudaStream_t s = S(stream);
   if (precision == M2B200_FP32) {
     if (!w) return M2_ERR_ARG;
     GemmArgs g = gemm_args(x, 0, K, w, 0, K, M, N, K, y, 0, N);
     g.bias = bias; g.bias_mode = bias ? 1 : 0; g.act = act;
+    g.drop_p = dropout_p; g.drop_seed = seed; g.drop_site = kSiteLinear; g.drop_ld = N;
     return gemm_f32_simt(g, s);
   }
   if (!w_bf16 || ldwb % 8 || ldwb < K) return M2_ERR_ARG;
@@ -295,15 +314,17 @@ int m2b200_linear_fwd(const float* x, const float* w, const void* w_bf16, int ld
   M2_TRY(cast_pad_bf16(x, K, xb, k8, M, K, s));
   GemmArgs g = gemm_args(xb, 0, k8, w_bf16, 0, ldwb, M, N, K, y, 0, N);
   g.bias = bias; g.bias_mode = bias ? 1 : 0; g.act = act;
+  g.drop_p = dropout_p; g.drop_seed = seed; g.drop_site = kSiteLinear; g.drop_ld = N;
   return gemm_bf16_umma(g, s);
 }
 
 int m2b200_linear_bwd(float* dy, const float* x, const float* y, const float* w, const void* w_bf16, int ldwb, int act,
-                      float* dx, float* dw, float* db, int M, int N, int K, int precision, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      float* dx, float* dw, float* db, int M, int N, int K, int precision, float dropout_p, uint64_t seed,
+                      void* workspace, size_t workspace_bytes, void* stream) {
   if (!dy || !x || !dw || M <= 0 || N <= 0 || K <= 0) return M2_ERR_ARG;
-  if (act == M2B200_ACT_GELU) return M2_ERR_ARG;
+  if (act == M2B200_ACT_GELU || dropout_p < 0.f || dropout_p >= 1.f) return M2_ERR_ARG;
   cudaStream_t s = S(stream);
+  if (dropout_p > 0.f) M2_TRY(mask_scale(dy, N, dy, 0, N, M, N, dropout_p, seed, kSiteLinear, N, s));
   if (act == M2B200_ACT_RELU) {
     if (!y) return M2_ERR_ARG;
     M2_TRY(relu_bwd(dy, y, static_cast<long long>(M) * N, s));
@@ -339,9 +360,66 @@ int m2b200_linear_bwd(float* dy, const float* x, const float* y, const float* w,
   return M2_OK;
 }
 
+// Patch embedding = gather (img -> one row per patch, bf16 in BF16 mode) + GEMM; the gathered rows are an explicit
+// output because the weight-gradient GEMM of the backward consumes them again (no dgrad: the image needs no gradient).
+size_t m2b200_patch_embed_cols_bytes(int B, int cin, int H, int W, int P, int precision) {
+  if (P <= 0 || H % P || W % P) return 0;
+  const size_t rows = static_cast<size_t>(B) * (H / P) * (W / P), k = static_cast<size_t>(cin) * P * P;
+  return precision == M2B200_FP32 ? rows * k * 4 : rows * static_cast<size_t>(up8(static_cast<int>(k))) * 2;
+}
+
+int m2b200_patch_embed_fwd(const float* img, const float* w, const void* w_bf16, int ldwb, const float* bias, void* cols,
+                           float* y, int B, int cin, int H, int W, int P, int D, int precision, void* stream) {
+  if (!img || !cols || !y || B <= 0 || cin <= 0 || P <= 0 || D <= 0 || H % P || W % P) return M2_ERR_ARG;
+  cudaStream_t s = S(stream);
+  const int M = B * (H / P) * (W / P), K = cin * P * P;
+  if (precision == M2B200_FP32) {
+    if (!w) return M2_ERR_ARG;
+    M2_TRY(patch_gather(img, cols, 0, B, cin, H, W, P, K, s));
+    GemmArgs g = gemm_args(cols, 0, K, w, 0, K, M, D, K, y, 0, D);
+    g.bias = bias; g.bias_mode = bias ? 1 : 0;
+    return gemm_f32_simt(g, s);
+  }
+  const int k8 = up8(K);
+  if (!w_bf16 || ldwb % 8 || ldwb < K) return M2_ERR_ARG;
+  M2_TRY(patch_gather(img, cols, 1, B, cin, H, W, P, k8, s));
+  GemmArgs g = gemm_args(cols, 0, k8, w_bf16, 0, ldwb, M, D, K, y, 0, D);
+  g.bias = bias; g.bias_mode = bias ? 1 : 0;
+  return gemm_bf16_umma(g, s);
+}
+
+size_t m2b200_patch_embed_bwd_workspace_bytes(int M, int D, int precision) {
+  return precision == M2B200_FP32 ? 0 : up256(static_cast<size_t>(M) * up8(D) * 2);
+}
+
+int m2b200_patch_embed_bwd(const float* dy, const void* cols, float* dw, float* db, int M, int D, int K, int precision,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dy || !cols || !dw || M <= 0 || D <= 0 || K <= 0) return M2_ERR_ARG;
+  cudaStream_t s = S(stream);
+  if (db) M2_TRY(colsum_f32(dy, D, M, D, db, s));
+  if (precision == M2B200_FP32) {
+    GemmArgs gw = gemm_args(dy, 1, D, cols, 1, K, D, K, M, dw, 0, K);     // dW[D][K] += dY^T cols
+    gw.accumulate = 1;
+    return gemm_f32_simt(gw, s);
+  }
+  const int k8 = up8(K), d8 = up8(D);
+  Carver ws(workspace, workspace_bytes);
+  __nv_bfloat16* dyb = ws.take<__nv_bfloat16>(static_cast<size_t>(M) * d8);
+  if (!ws.ok) return M2_ERR_WORKSPACE;
+  M2_TRY(cast_pad_bf16(dy, D, dyb, d8, M, D, s));
+  GemmArgs gw = gemm_args(dyb, 1, d8, cols, 1, k8, D, K, M, dw, 0, K);
+  gw.splitk = wgrad_splitk(D, K, M);
+  if (gw.splitk == 1) gw.accumulate = 1;
+  return gemm_bf16_umma(gw, s);
+}
+
 int m2b200_patch_gather(const float* img, float* cols, int B, int cin, int H, int W, int P, void* stream) {
   if (!img || !cols) return M2_ERR_ARG;
   return patch_gather(img, cols, 0, B, cin, H, W, P, static_cast<long long>(cin) * P * P, S(stream));
+}
+
+int m2b200_dropout_mask(float* out, int rows, int cols, int64_t ld, float dropout_p, uint64_t seed, int site, void* stream) {
+  return dropout_mask(out, rows, cols, ld, dropout_p, seed, site, S(stream));
 }
 
 // ------------------------------------------------------------------------------------------ fusion

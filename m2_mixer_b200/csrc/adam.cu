@@ -58,6 +58,7 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v)) & 15)
     return M2_ERR_ALIGN;
+  LaunchScope scope("adam", s, state_dev ? 2 : 1);
   if (state_dev) adam_tick_kernel<<<1, 1, 0, s>>>(state_dev);
   long long blocks = (n / 4 + 255) / 256;
   const int grid = static_cast<int>(blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks));

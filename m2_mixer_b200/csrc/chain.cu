@@ -32,7 +32,8 @@ namespace {
 
 constexpr int kRows = 128;      // token rows per CTA (UMMA M)
 constexpr int kCc = 64;         // channels per chunk
-constexpr int kThreads = 192;   // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue: two groups of 4 warps, group g owns chunks j = g (mod 2)
+constexpr int kMaxBiasSmemFwd = 32 * 1024, kMaxBiasSmemBwd = 24 * 1024;
 constexpr int kGBytes = kRows * kCc * 2;   // one [128 x 64] bf16 tile
 
 template <int DP>
@@ -44,8 +45,9 @@ struct Cfg {
   static constexpr int kStageBytes = kW1Bytes + kW2Bytes;
   static constexpr int kFwdStages = DP == 256 ? 2 : (DP == 128 ? 3 : 4);
   static constexpr int kBwdStages = DP == 128 ? 3 : 4;
-  static constexpr int kFwdSmem = kXBytes + kFwdStages * kStageBytes + 2 * kGBytes + 512 + 1024;
-  static constexpr int kBwdSmem = 2 * kXBytes + kBwdStages * kStageBytes + 2 * kGBytes + 512 + 1024;
+  // + barriers (256 B) + 1024 B alignment slack; the b1 vector is staged behind it when it fits (DP <= 128)
+  static constexpr int kFwdSmem = kXBytes + kFwdStages * kStageBytes + 2 * kGBytes + 256 + 1024;
+  static constexpr int kBwdSmem = 2 * kXBytes + kBwdStages * kStageBytes + 2 * kGBytes + 256 + 1024;
   static constexpr int kFwdTmem = (128 + DP) <= 256 ? 256 : 512;          // 2 x 64 (H) + DP (Y)
   static constexpr int kBwdTmem = 512;                                   // 2 x 64 (H) + 2 x 64 (dG) + DP (dXn)
 };
@@ -64,6 +66,8 @@ struct ChainParams {
   float* dxn;            // bwd out: dL/dLN(u) fp32 [M][D]
   int M, D, C, ldh;
   int exact_gelu;
+  int bias_smem;         // b1 (zero padded to a multiple of 64) is staged in shared memory
+  Drop dh, dout;         // dropout after GELU (index row*ldh + c) and after the second Linear (index row*D + d)
 };
 
 // LayerNorm `rows` of the tile into the swizzled bf16 A operand; optional bf16 copy to HBM.
@@ -113,14 +117,20 @@ __device__ __forceinline__ void ln_rows_to_smem(const ChainParams& p, int m0, ui
 
 // Plain fp32 rows -> swizzled bf16 A operand (+ bf16 copy to HBM).
 template <int DP>
-__device__ __forceinline__ void rows_to_smem(const float* src, int M, int D, int m0, uint8_t* sA, __nv_bfloat16* dst_b) {
+__device__ __forceinline__ void rows_to_smem(const float* src, int M, int D, int m0, uint8_t* sA, __nv_bfloat16* dst_b,
+                                             const Drop& drop) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < kRows; r += kThreads / 32) {
     const int row = m0 + r;
     for (int c = lane * 4; c < DP; c += 128) {
       uint2 o = make_uint2(0u, 0u);
       if (row < M && c < D) {
-        const float4 v = *reinterpret_cast<const float4*>(src + static_cast<long long>(row) * D + c);
+        float4 v = *reinterpret_cast<const float4*>(src + static_cast<long long>(row) * D + c);
+        if (drop.thresh) {   // gradient of the dropped branch output: dY * mask * scale
+          const unsigned long long i0 = static_cast<unsigned long long>(row) * D + c;
+          drop_apply2(drop, v.x, v.y, i0);
+          drop_apply2(drop, v.z, v.w, i0 + 2);
+        }
         o.x = pack_bf16(v.x, v.y);
         o.y = pack_bf16(v.z, v.w);
         if (dst_b) *reinterpret_cast<uint2*>(dst_b + static_cast<long long>(row) * D + c) = o;
@@ -160,6 +170,7 @@ chain_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   uint64_t* gempty = gfull + 2;     // [2]   GEMM2 done reading sG -> epilogue
   uint64_t* yfull = gempty + 2;     // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 1);
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kRows;
@@ -177,6 +188,8 @@ chain_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     tma_prefetch_desc(&tmW2);
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::kFwdTmem);
+  if (p.bias_smem)
+    for (int i = threadIdx.x; i < nchunks * kCc; i += kThreads) sBias[i] = i < p.C ? p.b1[i] : 0.f;
   __syncthreads();   // barriers initialised before the producer's early prefetch below
 
   // The weight ring does not depend on the activations: start filling it before the LayerNorm prologue.
@@ -236,11 +249,12 @@ chain_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       umma_commit(yfull);
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                // TMEM lane quadrant this warp may access (warp id % 4)
+    const int grp = (warp - 2) >> 2;       // epilogue group: chunks j = grp (mod 2), buffers Hacc[grp] / sG[grp]
     const int r = q * 32 + lane;           // row inside the tile == TMEM lane
     const int row = m0 + r;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    for (int j = 0; j < nchunks; ++j) {
+    for (int j = grp; j < nchunks; j += 2) {
       mbar_wait(&hfull[j & 1], (j >> 1) & 1);
       tc_fence_after();
       uint32_t h[64];
@@ -259,7 +273,11 @@ chain_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
         float b[8];
-        if (c0 + ch * 8 + 8 <= p.C) {
+        if (p.bias_smem) {
+          const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0 + ch * 8);
+          const float4 b1v = *reinterpret_cast<const float4*>(sBias + c0 + ch * 8 + 4);
+          b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1v.x; b[5] = b1v.y; b[6] = b1v.z; b[7] = b1v.w;
+        } else if (c0 + ch * 8 + 8 <= p.C) {
           const float4 b0 = *reinterpret_cast<const float4*>(p.b1 + c0 + ch * 8);
           const float4 b1v = *reinterpret_cast<const float4*>(p.b1 + c0 + ch * 8 + 4);
           b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1v.x; b[5] = b1v.y; b[6] = b1v.z; b[7] = b1v.w;
@@ -273,6 +291,11 @@ chain_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
           const float x = __uint_as_float(h[ch * 8 + e]) + b[e];
           v[e] = p.exact_gelu ? gelu_erf(x) : gelu_fast(x);
         }
+        if (p.dh.thresh) {
+          const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + c0 + ch * 8;
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) drop_apply2(p.dh, v[e], v[e + 1], i0 + e);
+        }
         *reinterpret_cast<uint4*>(g + sw128_offset(r, ch)) =
             make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
       }
@@ -283,7 +306,7 @@ chain_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     mbar_wait(yfull, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int d0 = 0; d0 < DP; d0 += 32) {
+    for (int d0 = grp * (DP / 2); d0 < (grp + 1) * (DP / 2); d0 += 32) {   // each group drains half of the columns
       uint32_t a[32];
       tmem_ld32(tY + lane_addr + d0, a);
       tmem_ld_wait();
@@ -296,10 +319,16 @@ chain_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             const float4 uu = *reinterpret_cast<const float4*>(urow + e);
             const float4 bb = *reinterpret_cast<const float4*>(p.b2 + d0 + e);
             float4 o;
-            o.x = uu.x + bb.x + __uint_as_float(a[e]);
-            o.y = uu.y + bb.y + __uint_as_float(a[e + 1]);
-            o.z = uu.z + bb.z + __uint_as_float(a[e + 2]);
-            o.w = uu.w + bb.w + __uint_as_float(a[e + 3]);
+            o.x = bb.x + __uint_as_float(a[e]);
+            o.y = bb.y + __uint_as_float(a[e + 1]);
+            o.z = bb.z + __uint_as_float(a[e + 2]);
+            o.w = bb.w + __uint_as_float(a[e + 3]);
+            if (p.dout.thresh) {
+              const unsigned long long i0 = static_cast<unsigned long long>(row) * p.D + d0 + e;
+              drop_apply2(p.dout, o.x, o.y, i0);
+              drop_apply2(p.dout, o.z, o.w, i0 + 2);
+            }
+            o.x += uu.x; o.y += uu.y; o.z += uu.z; o.w += uu.w;
             *reinterpret_cast<float4*>(yrow + e) = o;
           }
         }
@@ -332,6 +361,7 @@ chain_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   uint64_t* gempty = gfull + 2;     // [2]  dXn GEMM done with sdH
   uint64_t* yfull = gempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 1);
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kRows;
@@ -349,13 +379,15 @@ chain_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     tma_prefetch_desc(&tmW2);
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::kBwdTmem);
+  if (p.bias_smem)
+    for (int i = threadIdx.x; i < nchunks * kCc; i += kThreads) sBias[i] = i < p.C ? p.b1[i] : 0.f;
   __syncthreads();
   if (warp == 0 && lane == 0) {
     const int pre = nchunks < S ? nchunks : S;
     for (int j = 0; j < pre; ++j) load_weight_stage<DP>(sW + j * C::kStageBytes, &tmW1, &tmW2, &full[j], j * kCc);
   }
   ln_rows_to_smem<DP>(p, m0, sX, p.xn_b);
-  rows_to_smem<DP>(p.dy, p.M, p.D, m0, sdY, p.dy_b);
+  rows_to_smem<DP>(p.dy, p.M, p.D, m0, sdY, p.dy_b, p.dout);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -416,10 +448,11 @@ chain_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     }
   } else {
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int row = m0 + r;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    for (int j = 0; j < nchunks; ++j) {
+    for (int j = grp; j < nchunks; j += 2) {
       mbar_wait(&hfull[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const int c0 = j * kCc;
@@ -442,11 +475,19 @@ chain_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int cc = c0 + half * 32 + ch * 8;
-          float gv[8], dv[8];
+          float gv[8], dv[8], bias[8];
+          if (p.bias_smem) {
+            const float4 b0 = *reinterpret_cast<const float4*>(sBias + cc);
+            const float4 b1v = *reinterpret_cast<const float4*>(sBias + cc + 4);
+            bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+            bias[4] = b1v.x; bias[5] = b1v.y; bias[6] = b1v.z; bias[7] = b1v.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bias[e] = (cc + e < p.C) ? __ldg(p.b1 + cc + e) : 0.f;
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float bias = (cc + e < p.C) ? __ldg(p.b1 + cc + e) : 0.f;
-            const float x = __uint_as_float(h[ch * 8 + e]) + bias;
+            const float x = __uint_as_float(h[ch * 8 + e]) + bias[e];
             float dgelu;
             if (p.exact_gelu) {
               gv[e] = gelu_erf(x);
@@ -455,6 +496,14 @@ chain_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
               gv[e] = gelu_fast_grad(x, dgelu);
             }
             dv[e] = __uint_as_float(dg[ch * 8 + e]) * dgelu;
+          }
+          if (p.dh.thresh) {   // G' = m*s*G ; dH = dG' * m*s*gelu'(h)
+            const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + cc;
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              drop_apply2(p.dh, gv[e], gv[e + 1], i0 + e);
+              drop_apply2(p.dh, dv[e], dv[e + 1], i0 + e);
+            }
           }
           const uint4 go = make_uint4(pack_bf16(gv[0], gv[1]), pack_bf16(gv[2], gv[3]), pack_bf16(gv[4], gv[5]), pack_bf16(gv[6], gv[7]));
           const uint4 dh = make_uint4(pack_bf16(dv[0], dv[1]), pack_bf16(dv[2], dv[3]), pack_bf16(dv[4], dv[5]), pack_bf16(dv[6], dv[7]));
@@ -471,7 +520,7 @@ chain_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     mbar_wait(yfull, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int d0 = 0; d0 < DP; d0 += 32) {
+    for (int d0 = grp * (DP / 2); d0 < (grp + 1) * (DP / 2); d0 += 32) {
       uint32_t a[32];
       tmem_ld32(tDX + lane_addr + d0, a);
       tmem_ld_wait();
@@ -493,13 +542,19 @@ chain_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
 template <int DP, bool kBwd>
 int launch_chain(const CUtensorMap& t1, const CUtensorMap& t2, const ChainParams& p, cudaStream_t s) {
   auto kern = kBwd ? chain_bwd_kernel<DP> : chain_fwd_kernel<DP>;
-  constexpr int smem = kBwd ? Cfg<DP>::kBwdSmem : Cfg<DP>::kFwdSmem;
-  static bool configured = false;
-  if (!configured) {
+  constexpr int base = kBwd ? Cfg<DP>::kBwdSmem : Cfg<DP>::kFwdSmem;
+  constexpr int kMaxBias = DP > 128 ? 0 : (kBwd ? kMaxBiasSmemBwd : kMaxBiasSmemFwd);
+  const int bias_bytes = ceil_div(p.C, kCc) * kCc * 4;
+  ChainParams pp = p;
+  pp.bias_smem = bias_bytes <= kMaxBias ? 1 : 0;
+  const int smem = base + (pp.bias_smem ? bias_bytes : 0);
+  static int configured = 0;   // largest dynamic smem size opted into so far
+  if (smem > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return M2_ERR_LAUNCH;
-    configured = true;
+    configured = smem;
   }
-  kern<<<ceil_div(p.M, kRows), kThreads, smem, s>>>(t1, t2, p);
+  LaunchScope scope(kBwd ? "chain_bwd" : "chain_fwd", s);
+  kern<<<ceil_div(p.M, kRows), kThreads, smem, s>>>(t1, t2, pp);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }
@@ -518,7 +573,8 @@ bool chain_fwd_supported(int D) { return D >= 16 && D <= 256 && D % 8 == 0; }
 bool chain_bwd_supported(int D) { return D >= 16 && D <= 128 && D % 8 == 0; }
 
 int chain_fwd(const float* u, const float* ln_w, const float* ln_b, const void* w1b, const float* b1, const void* w2b,
-              int ldw2, const float* b2, float* y, int M, int D, int C, int exact_gelu, cudaStream_t s) {
+              int ldw2, const float* b2, float* y, int M, int D, int C, int exact_gelu, float drop_p, unsigned long long seed,
+              cudaStream_t s) {
   if (!chain_fwd_supported(D) || ldw2 % 8 || ldw2 < C) return M2_ERR_ARG;
   const int DP = D <= 64 ? 64 : (D <= 128 ? 128 : 256);
   CUtensorMap t1, t2;
@@ -526,7 +582,8 @@ int chain_fwd(const float* u, const float* ln_w, const float* ln_b, const void* 
   if (rc) return rc;
   ChainParams p = {};
   p.u = u; p.ln_w = ln_w; p.ln_b = ln_b; p.b1 = b1; p.b2 = b2; p.y = y;
-  p.M = M; p.D = D; p.C = C; p.exact_gelu = exact_gelu;
+  p.M = M; p.D = D; p.C = C; p.exact_gelu = exact_gelu; p.ldh = (C + 7) & ~7;
+  p.dh = make_drop(drop_p, seed, kSiteChannelHidden); p.dout = make_drop(drop_p, seed, kSiteChannelOut);
   if (DP == 64) return launch_chain<64, false>(t1, t2, p, s);
   if (DP == 128) return launch_chain<128, false>(t1, t2, p, s);
   return launch_chain<256, false>(t1, t2, p, s);
@@ -534,7 +591,7 @@ int chain_fwd(const float* u, const float* ln_w, const float* ln_b, const void* 
 
 int chain_bwd(const float* u, const float* ln_w, const float* ln_b, const void* w1b, const float* b1, const void* w2b,
               int ldw2, const float* dy, void* xn_b, void* dy_b, void* g_b, void* dh_b, int ldh, float* dxn, int M, int D,
-              int C, int exact_gelu, cudaStream_t s) {
+              int C, int exact_gelu, float drop_p, unsigned long long seed, cudaStream_t s) {
   if (!chain_bwd_supported(D) || ldw2 % 8 || ldw2 < C || ldh % 8 || ldh < C) return M2_ERR_ARG;
   const int DP = D <= 64 ? 64 : 128;
   CUtensorMap t1, t2;
@@ -545,6 +602,7 @@ int chain_bwd(const float* u, const float* ln_w, const float* ln_b, const void* 
   p.xn_b = static_cast<__nv_bfloat16*>(xn_b); p.dy_b = static_cast<__nv_bfloat16*>(dy_b);
   p.g_b = static_cast<__nv_bfloat16*>(g_b); p.dh_b = static_cast<__nv_bfloat16*>(dh_b);
   p.dxn = dxn; p.M = M; p.D = D; p.C = C; p.ldh = ldh; p.exact_gelu = exact_gelu;
+  p.dh = make_drop(drop_p, seed, kSiteChannelHidden); p.dout = make_drop(drop_p, seed, kSiteChannelOut);
   if (DP == 64) return launch_chain<64, true>(t1, t2, p, s);
   return launch_chain<128, true>(t1, t2, p, s);
 }

@@ -22,6 +22,13 @@
 
 namespace m2 {
 
+// RAII launch accounting (profile.cu): counts the launch, and brackets it with CUDA events when profiling is on.
+struct LaunchScope {
+  LaunchScope(const char* name, cudaStream_t s, int nkernels = 1);
+  ~LaunchScope();
+  const char* name_; cudaStream_t stream_; void* start_;
+};
+
 constexpr float kLnEps = 1e-5f;   // nn.LayerNorm default (reference modules/mixer.py:31)
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -63,6 +70,50 @@ __device__ __forceinline__ float gelu_fast_grad(float x, float& dgelu) {
   dgelu = fmaf(hx * (1.f - t * t), du, 0.5f + 0.5f * t);
   return fmaf(hx, t, hx);
 }
+
+// ------------------------------------------------------------------------------------------ dropout
+// Counter-based mask shared by every kernel (forward and the recomputing backward evaluate the same function):
+// one 32-bit hash per PAIR of consecutive elements, 16 random bits per element, keep iff bits >= thresh
+// (thresh = round(p * 65536), scale = 65536 / (65536 - thresh): unbiased for the realised keep probability).
+// Not bit-compatible with torch's Philox stream by design: tested statistically and through
+// m2b200_dropout_mask(), which exports exactly this function.
+struct Drop {
+  uint32_t key;      // per call-site key derived from (seed, site) on the host
+  uint32_t thresh;   // 0 = dropout off
+  float scale;
+};
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_pair_bits(uint32_t key, uint32_t pair_idx) { return mix32(pair_idx * 0x9E3779B9U + key); }
+__device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
+  const uint32_t h = drop_pair_bits(d.key, static_cast<uint32_t>(idx >> 1));
+  return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) >= d.thresh;
+}
+__device__ __forceinline__ float drop_apply(const Drop& d, float v, unsigned long long idx) {
+  return drop_keep(d, idx) ? v * d.scale : 0.f;
+}
+// two consecutive elements starting at an EVEN index: one hash
+__device__ __forceinline__ void drop_apply2(const Drop& d, float& v0, float& v1, unsigned long long even_idx) {
+  const uint32_t h = drop_pair_bits(d.key, static_cast<uint32_t>(even_idx >> 1));
+  v0 = (h & 0xFFFFu) >= d.thresh ? v0 * d.scale : 0.f;
+  v1 = (h >> 16) >= d.thresh ? v1 * d.scale : 0.f;
+}
+inline Drop make_drop(float p, unsigned long long seed, uint32_t site) {
+  Drop d;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (site + 1);   // splitmix64 of (seed, site)
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  d.key = static_cast<uint32_t>(z ^ (z >> 32));
+  long t = p > 0.f ? static_cast<long>(p * 65536.0f + 0.5f) : 0;
+  if (t > 65535) t = 65535;
+  d.thresh = static_cast<uint32_t>(t);
+  d.scale = 65536.0f / (65536.0f - static_cast<float>(t));
+  return d;
+}
+enum DropSite { kSiteTokenHidden = 0, kSiteTokenOut = 1, kSiteChannelHidden = 2, kSiteChannelOut = 3, kSiteLinear = 4 };
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -225,6 +225,7 @@ int heads_loss_fwd(const HeadsArgs& a, float* logits, float* losses, long long* 
   int rc = fill_dev(a, &d);
   if (rc) return rc;
   if (!logits || !losses || !preds) return M2_ERR_ARG;
+  LaunchScope scope("heads_loss_fwd", s);
   if (cudaMemsetAsync(losses, 0, 4 * sizeof(float), s) != cudaSuccess) return M2_ERR_LAUNCH;
   int grid = ceil_div(a.B, kWarps);
   if (grid > 148 * 4) grid = 148 * 4;
@@ -254,6 +255,7 @@ int heads_loss_bwd(const HeadsArgs& a, const float* logits, float grad_scale, co
     return M2_ERR_LAUNCH;
   int grid = ceil_div(a.B, kWarps);
   if (grid > 148) grid = 148;
+  LaunchScope scope("heads_loss_bwd", s);
   heads_bwd_kernel<<<grid, kThreads, smem, s>>>(d, g, logits);
   M2_LAUNCH_CHECK();
   return M2_OK;

@@ -9,7 +9,7 @@ namespace m2 {
 //   a_mn == 0: A is row-major [M][K] (K-major);   a_mn == 1: A is row-major [K][M] (MN-major)
 //   b_mn == 0: B is row-major [N][K] (K-major);   b_mn == 1: B is row-major [K][N] (MN-major)
 //   batch b adds a_batch_rows / b_batch_rows ROWS to the operand (0 = operand shared by all batches).
-//   epilogue: v = acc; v += bias (bias_mode 1: bias[n], 2: bias[m]); v = act(v) (1: erf GELU, 2: ReLU);
+//   epilogue: v = acc; v += bias (bias_mode 1: bias[n], 2: bias[m]); v = act(v) (1: erf GELU, 2: ReLU); v = drop(v);
 //             v += residual[b][m][n];  C = accumulate ? C + v : v.
 //   splitk > 1 (fp32 C only): K is cut into `splitk` ranges reduced with fp32 atomics INTO C (caller zeroes C
 //   or wants accumulation); bias/residual are applied by split 0; act must be 0.
@@ -22,6 +22,8 @@ struct GemmArgs {
   const float* residual; long long ldr; long long r_batch_stride;
   void* C; int c_bf16; long long ldc; long long c_batch_stride;
   int accumulate; int splitk;
+  // optional dropout applied after `act` and before `residual`; element index = m * drop_ld + n (batch ignored)
+  float drop_p; unsigned long long drop_seed; int drop_site; long long drop_ld;
 };
 
 int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s);   // A,B bf16; tcgen05 + TMA
@@ -32,10 +34,11 @@ int gemm_f32_simt(const GemmArgs& g, cudaStream_t s);    // A,B fp32; CUDA-core 
 bool chain_fwd_supported(int D);
 bool chain_bwd_supported(int D);
 int chain_fwd(const float* u, const float* ln_w, const float* ln_b, const void* w1b, const float* b1, const void* w2b,
-              int ldw2, const float* b2, float* y, int M, int D, int C, int exact_gelu, cudaStream_t s);
+              int ldw2, const float* b2, float* y, int M, int D, int C, int exact_gelu, float drop_p, unsigned long long seed,
+              cudaStream_t s);
 int chain_bwd(const float* u, const float* ln_w, const float* ln_b, const void* w1b, const float* b1, const void* w2b,
               int ldw2, const float* dy, void* xn_b, void* dy_b, void* g_b, void* dh_b, int ldh, float* dxn, int M, int D,
-              int C, int exact_gelu, cudaStream_t s);
+              int C, int exact_gelu, float drop_p, unsigned long long seed, cudaStream_t s);
 
 // ---- row kernels (rowops.cu)
 int cast_pad_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols, cudaStream_t s);
@@ -46,7 +49,13 @@ int ln_bwd(const float* dy, long long dy_bstride, int N, const float* x, const f
 int colsum_f32(const float* src, long long ld, int rows, int cols, float* out, cudaStream_t s);
 int colsum_bf16(const void* src, long long ld, int rows, int cols, float* out, cudaStream_t s);
 int gelu_fwd_bwd(const float* h, const float* dg, int rows, int cols, long long ld_in, void* g_out, void* dh_out,
-                 long long ld_out, int out_bf16, cudaStream_t s);
+                 long long ld_out, int out_bf16, float drop_p, unsigned long long seed, int site, long long drop_ld,
+                 cudaStream_t s);
+// dst = src * mask * scale (dst fp32 or bf16; dst may alias src when fp32); index = r * drop_ld + c
+int mask_scale(const float* src, long long lds, void* dst, int dst_bf16, long long ldd, int rows, int cols, float drop_p,
+               unsigned long long seed, int site, long long drop_ld, cudaStream_t s);
+// out[r][c] = 1/0 keep mask of (seed, site) at index r*ld + c  (test / debugging export of the kernels' mask function)
+int dropout_mask(float* out, int rows, int cols, long long ld, float drop_p, unsigned long long seed, int site, cudaStream_t s);
 int patch_gather(const float* img, void* cols, int out_bf16, int B, int cin, int H, int W, int P, long long ld, cudaStream_t s);
 int concat_copy(const float* src, long long src_bstride, float* dst, long long dst_bstride, int B, long long per_batch,
                 int accumulate, cudaStream_t s);
@@ -57,10 +66,11 @@ int mean_pool_bwd(const float* dp, float* dx, int B, int N, int D, cudaStream_t 
 
 // ---- token mixing (token_mix.cu)
 int token_mix_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1, const float* w2,
-                  const float* b2, float* u, int B, int N, int D, int T, int exact_gelu, cudaStream_t s);
+                  const float* b2, float* u, int B, int N, int D, int T, int exact_gelu, float drop_p,
+                  unsigned long long seed, cudaStream_t s);
 int token_mix_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
                   const float* w2, float* dxn, float* dw1, float* db1, float* dw2, float* db2,
-                  int B, int N, int D, int T, int exact_gelu, cudaStream_t s);
+                  int B, int N, int D, int T, int exact_gelu, float drop_p, unsigned long long seed, cudaStream_t s);
 
 // ---- heads + multi-head loss (heads.cu)
 struct HeadsArgs {

@@ -107,7 +107,44 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 }
 
 // ------------------------------------------------------------------------------------------ column sums
-// out[c] += sum_r src[r][c].  CTA = 32 columns x 8 row-lanes; grid.y splits the rows.
+// out[c] += sum_r src[r][c].  A thread owns kV consecutive columns (one 16-byte load per row), 8 row-lanes per CTA,
+// grid.y splits the rows; per-CTA partials are combined in shared memory and added with one atomic per column.
+template <typename T, int kV>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ src, long long ld, int rows, int cols,
+                                                         float* __restrict__ out) {
+  __shared__ float part[8][32 * kV + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + tx) * kV;
+  float acc[kV];
+#pragma unroll
+  for (int i = 0; i < kV; ++i) acc[i] = 0.f;
+  if (c0 < ld) {   // whole vectors lie inside the padded row (ld % kV == 0)
+    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src + static_cast<long long>(r) * ld + c0);
+      if constexpr (sizeof(T) == 2) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+      } else {
+        acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y); acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kV; ++i) part[ty][tx * kV + i] = acc[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * kV; i += 256) {
+    const int c = blockIdx.x * 32 * kV + i;
+    if (c < cols) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += part[j][i];
+      atomicAdd(&out[c], t);
+    }
+  }
+}
+
+// scalar fallback (unaligned base / leading dimension)
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, long long ld, int rows, int cols,
                                                      float* __restrict__ out) {
@@ -131,13 +168,19 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, 
 // h = pre-activation (bias already added). g_out = gelu(h) ; dh = dg * gelu'(h)  (dh may alias dg)
 template <typename TO>
 __global__ void gelu_fwd_bwd_kernel(const float* __restrict__ h, const float* dg, long long n, int cols,
-                                    long long ld_in, TO* __restrict__ g_out, TO* dh_out, long long ld_out) {
+                                    long long ld_in, TO* __restrict__ g_out, TO* dh_out, long long ld_out, const Drop drop,
+                                    long long drop_ld) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / cols;
     const int c = static_cast<int>(i - r * cols);
     const float x = h[r * ld_in + c];
-    const float g = gelu_erf(x), d = dg[r * ld_in + c] * gelu_erf_grad(x);
+    float g = gelu_erf(x), d = dg[r * ld_in + c] * gelu_erf_grad(x);
+    if (drop.thresh) {
+      const bool keep = drop_keep(drop, static_cast<unsigned long long>(r) * drop_ld + c);
+      g = keep ? g * drop.scale : 0.f;
+      d = keep ? d * drop.scale : 0.f;
+    }
     g_out[r * ld_out + c] = static_cast<TO>(g);
     dh_out[r * ld_out + c] = static_cast<TO>(d);
   }
@@ -146,6 +189,30 @@ __global__ void gelu_fwd_bwd_kernel(const float* __restrict__ h, const float* dg
 // ------------------------------------------------------------------------------------------ patch gather
 // img [B][cin][H][W] -> cols [(b, gy, gx)][(ci, py, px)], row stride ld (pad columns zeroed).
 // Reference: Conv2d(cin, D, p, p) + 'b c h w -> b (h w) c', modules/mixer.py:143-146.
+// 8 consecutive px per thread (needs P % 8 == 0, W % 4 == 0, 16-byte aligned image): two float4 loads, one 16 B store
+__global__ void patch_gather_bf16x8_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ cols, int B, int cin,
+                                           int H, int W, int P, long long ld) {
+  const int gh = H / P, gw = W / P;
+  const int K = cin * P * P, K8 = K / 8;
+  const long long total = static_cast<long long>(B) * gh * gw * (ld / 8);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / (ld / 8);
+    const int k8 = static_cast<int>(i - row * (ld / 8));
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (k8 < K8) {
+      const int k = k8 * 8;
+      const int px = k % P, py = (k / P) % P, ci = k / (P * P);
+      const int gx = static_cast<int>(row % gw), gy = static_cast<int>((row / gw) % gh);
+      const long long b = row / (static_cast<long long>(gw) * gh);
+      const float* p = img + ((b * cin + ci) * H + gy * P + py) * W + gx * P + px;
+      const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
+      o = make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+    }
+    *reinterpret_cast<uint4*>(cols + row * ld + k8 * 8) = o;
+  }
+}
+
 template <typename TO>
 __global__ void patch_gather_kernel(const float* __restrict__ img, TO* __restrict__ cols, int B, int cin, int H, int W,
                                     int P, long long ld) {
@@ -211,6 +278,29 @@ __global__ void mean_pool_bwd_kernel(const float* __restrict__ dp, float* __rest
   }
 }
 
+template <typename TO>
+__global__ void mask_scale_kernel(const float* src, long long lds, TO* dst, long long ldd, int rows, int cols, const Drop drop,
+                                  long long drop_ld) {
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    float v = src[r * lds + c];
+    if (drop.thresh) v = drop_apply(drop, v, static_cast<unsigned long long>(r) * drop_ld + c);
+    dst[r * ldd + c] = static_cast<TO>(v);
+  }
+}
+__global__ void dropout_mask_kernel(float* out, int rows, int cols, long long ld, const Drop drop) {
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    out[i] = (!drop.thresh || drop_keep(drop, static_cast<unsigned long long>(r) * ld + c)) ? 1.f : 0.f;
+  }
+}
+
 // dy *= (y > 0)   (ReLU backward, in place)
 __global__ void relu_bwd_kernel(float* dy, const float* __restrict__ y, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -227,6 +317,7 @@ inline int grid_for(long long n, int block) {
 }  // namespace
 
 int cast_pad_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols, cudaStream_t s) {
+  LaunchScope scope("cast_pad_bf16", s);
   if (rows <= 0 || cols <= 0 || ldd < cols) return M2_ERR_ARG;
   cast_pad_bf16_kernel<<<grid_for(static_cast<long long>(rows) * ldd, 256), 256, 0, s>>>(src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
   M2_LAUNCH_CHECK();
@@ -235,6 +326,7 @@ int cast_pad_bf16(const float* src, long long lds, void* dst, long long ldd, int
 
 int ln_fwd(const float* x, const float* w, const float* b, void* out, int out_bf16, int rows, int D, int N,
            long long out_bstride, float* mean, float* rstd, cudaStream_t s) {
+  LaunchScope scope("ln_fwd", s);
   if (rows <= 0 || D <= 0 || N <= 0) return M2_ERR_ARG;
   const int grid = grid_for(static_cast<long long>(rows) * 32, 256);
   if (out_bf16) ln_fwd_kernel<true><<<grid, 256, 0, s>>>(x, w, b, out, rows, D, N, out_bstride, mean, rstd);
@@ -245,47 +337,90 @@ int ln_fwd(const float* x, const float* w, const float* b, void* out, int out_bf
 
 int ln_bwd(const float* dy, long long dy_bstride, int N, const float* x, const float* w, const float* dres, float* dx,
            float* dw, float* db, int rows, int D, cudaStream_t s) {
+  LaunchScope scope("ln_bwd", s);
   if (rows <= 0 || D <= 0 || D > 1024 || N <= 0) return M2_ERR_ARG;
   int grid = grid_for(static_cast<long long>(rows) * 32, 256);
-  if (grid > kNumSms * 4) grid = kNumSms * 4;
+  if (grid > kNumSms) grid = kNumSms;   // one CTA per SM: 2*D global atomics per CTA, >= a dozen rows per warp
   ln_bwd_kernel<<<grid, 256, 2 * D * sizeof(float), s>>>(dy, dy_bstride, N, x, w, dres, dx, dw, db, rows, D);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }
 
 int colsum_f32(const float* src, long long ld, int rows, int cols, float* out, cudaStream_t s) {
+  LaunchScope scope("colsum_f32", s);
   if (rows <= 0 || cols <= 0) return M2_ERR_ARG;
-  dim3 grid(ceil_div(cols, 32), min(ceil_div(rows, 8), 64));
-  colsum_kernel<float><<<grid, 256, 0, s>>>(src, ld, rows, cols, out);
+  if (ld % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int gx = ceil_div(cols, 128);
+    dim3 grid(gx, max(1, min(ceil_div(rows, 32), ceil_div(148 * 4, gx))));
+    colsum_vec_kernel<float, 4><<<grid, 256, 0, s>>>(src, ld, rows, cols, out);
+  } else {
+    dim3 grid(ceil_div(cols, 32), min(ceil_div(rows, 8), 64));
+    colsum_kernel<float><<<grid, 256, 0, s>>>(src, ld, rows, cols, out);
+  }
   M2_LAUNCH_CHECK();
   return M2_OK;
 }
 int colsum_bf16(const void* src, long long ld, int rows, int cols, float* out, cudaStream_t s) {
+  LaunchScope scope("colsum_bf16", s);
   if (rows <= 0 || cols <= 0) return M2_ERR_ARG;
-  dim3 grid(ceil_div(cols, 32), min(ceil_div(rows, 8), 64));
-  colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src), ld, rows, cols, out);
+  if (ld % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int gx = ceil_div(cols, 256);
+    dim3 grid(gx, max(1, min(ceil_div(rows, 32), ceil_div(148 * 4, gx))));
+    colsum_vec_kernel<__nv_bfloat16, 8><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src), ld, rows, cols, out);
+  } else {
+    dim3 grid(ceil_div(cols, 32), min(ceil_div(rows, 8), 64));
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src), ld, rows, cols, out);
+  }
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int mask_scale(const float* src, long long lds, void* dst, int dst_bf16, long long ldd, int rows, int cols, float drop_p,
+               unsigned long long seed, int site, long long drop_ld, cudaStream_t s) {
+  LaunchScope scope("mask_scale", s);
+  const long long n = static_cast<long long>(rows) * cols;
+  if (n <= 0) return M2_ERR_ARG;
+  const Drop d = make_drop(drop_p, seed, site);
+  if (dst_bf16) mask_scale_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>(src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols, d, drop_ld);
+  else mask_scale_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(src, lds, static_cast<float*>(dst), ldd, rows, cols, d, drop_ld);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int dropout_mask(float* out, int rows, int cols, long long ld, float drop_p, unsigned long long seed, int site, cudaStream_t s) {
+  LaunchScope scope("dropout_mask", s);
+  const long long n = static_cast<long long>(rows) * cols;
+  if (n <= 0 || !out) return M2_ERR_ARG;
+  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, s>>>(out, rows, cols, ld, make_drop(drop_p, seed, site));
   M2_LAUNCH_CHECK();
   return M2_OK;
 }
 
 int gelu_fwd_bwd(const float* h, const float* dg, int rows, int cols, long long ld_in, void* g_out, void* dh_out,
-                 long long ld_out, int out_bf16, cudaStream_t s) {
+                 long long ld_out, int out_bf16, float drop_p, unsigned long long seed, int site, long long drop_ld,
+                 cudaStream_t s) {
+  const Drop drop = make_drop(drop_p, seed, site);
+  LaunchScope scope("gelu_fwd_bwd", s);
   const long long n = static_cast<long long>(rows) * cols;
   if (n <= 0) return M2_ERR_ARG;
   if (out_bf16)
     gelu_fwd_bwd_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>(h, dg, n, cols, ld_in, static_cast<__nv_bfloat16*>(g_out),
-                                                                       static_cast<__nv_bfloat16*>(dh_out), ld_out);
+                                                                       static_cast<__nv_bfloat16*>(dh_out), ld_out, drop, drop_ld);
   else
     gelu_fwd_bwd_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(h, dg, n, cols, ld_in, static_cast<float*>(g_out),
-                                                               static_cast<float*>(dh_out), ld_out);
+                                                               static_cast<float*>(dh_out), ld_out, drop, drop_ld);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }
 
 int patch_gather(const float* img, void* cols, int out_bf16, int B, int cin, int H, int W, int P, long long ld, cudaStream_t s) {
+  LaunchScope scope("patch_gather", s);
   if (B <= 0 || cin <= 0 || P <= 0 || H % P || W % P || ld < static_cast<long long>(cin) * P * P) return M2_ERR_ARG;
   const long long total = static_cast<long long>(B) * (H / P) * (W / P) * ld;
-  if (out_bf16) patch_gather_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(img, static_cast<__nv_bfloat16*>(cols), B, cin, H, W, P, ld);
+  if (out_bf16 && P % 8 == 0 && W % 4 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(cols) & 15) == 0)
+    patch_gather_bf16x8_kernel<<<grid_for(total / 8, 256), 256, 0, s>>>(img, static_cast<__nv_bfloat16*>(cols), B, cin, H, W, P, ld);
+  else if (out_bf16) patch_gather_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(img, static_cast<__nv_bfloat16*>(cols), B, cin, H, W, P, ld);
   else patch_gather_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(img, static_cast<float*>(cols), B, cin, H, W, P, ld);
   M2_LAUNCH_CHECK();
   return M2_OK;
@@ -293,6 +428,7 @@ int patch_gather(const float* img, void* cols, int out_bf16, int B, int cin, int
 
 int concat_copy(const float* src, long long src_bstride, float* dst, long long dst_bstride, int B, long long per_batch,
                 int accumulate, cudaStream_t s) {
+  LaunchScope scope("concat_copy", s);
   if (B <= 0 || per_batch <= 0) return M2_ERR_ARG;
   concat_copy_kernel<<<grid_for(B * per_batch, 256), 256, 0, s>>>(src, src_bstride, dst, dst_bstride, B, per_batch, accumulate);
   M2_LAUNCH_CHECK();
@@ -300,12 +436,14 @@ int concat_copy(const float* src, long long src_bstride, float* dst, long long d
 }
 
 int mean_pool_fwd(const float* x, float* out, int B, int N, int D, cudaStream_t s) {
+  LaunchScope scope("mean_pool_fwd", s);
   if (B <= 0 || N <= 0 || D <= 0) return M2_ERR_ARG;
   mean_pool_fwd_kernel<<<grid_for(static_cast<long long>(B) * D, 256), 256, 0, s>>>(x, out, B, N, D);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }
 int mean_pool_bwd(const float* dp, float* dx, int B, int N, int D, cudaStream_t s) {
+  LaunchScope scope("mean_pool_bwd", s);
   if (B <= 0 || N <= 0 || D <= 0) return M2_ERR_ARG;
   mean_pool_bwd_kernel<<<grid_for(static_cast<long long>(B) * N * D, 256), 256, 0, s>>>(dp, dx, B, N, D);
   M2_LAUNCH_CHECK();
@@ -313,6 +451,7 @@ int mean_pool_bwd(const float* dp, float* dx, int B, int N, int D, cudaStream_t 
 }
 
 int relu_bwd(float* dy, const float* y, long long n, cudaStream_t s) {
+  LaunchScope scope("relu_bwd", s);
   if (n <= 0) return M2_ERR_ARG;
   relu_bwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(dy, y, n);
   M2_LAUNCH_CHECK();
@@ -320,6 +459,7 @@ int relu_bwd(float* dy, const float* y, long long n, cudaStream_t s) {
 }
 
 int add_f32(const float* a, const float* b, float* o, long long n, cudaStream_t s) {
+  LaunchScope scope("add_f32", s);
   if (n <= 0) return M2_ERR_ARG;
   add_kernel<<<grid_for(n, 256), 256, 0, s>>>(a, b, o, n);
   M2_LAUNCH_CHECK();

@@ -19,6 +19,7 @@ struct SimtDev {
   const float* residual; long long ldr, r_batch_stride;
   float* C; long long ldc, c_batch_stride;
   int accumulate;
+  Drop drop; long long drop_ld;
 };
 
 __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtDev p) {
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtDev p) {
       else if (p.bias_mode == 2) v += p.bias[m];
       if (p.act == 1) v = gelu_erf(v);
       else if (p.act == 2) v = fmaxf(v, 0.f);
+      if (p.drop.thresh) v = drop_apply(p.drop, v, static_cast<unsigned long long>(m) * p.drop_ld + n);
       if (p.residual) v += p.residual[b * p.r_batch_stride + static_cast<long long>(m) * p.ldr + n];
       float* c = p.C + b * p.c_batch_stride + static_cast<long long>(m) * p.ldc + n;
       *c = p.accumulate ? *c + v : v;
@@ -100,8 +102,10 @@ int gemm_f32_simt(const GemmArgs& g, cudaStream_t s) {
   d.residual = g.residual; d.ldr = g.ldr; d.r_batch_stride = g.r_batch_stride;
   d.C = static_cast<float*>(g.C); d.ldc = g.ldc; d.c_batch_stride = g.c_batch_stride;
   d.accumulate = g.accumulate;
+  d.drop = make_drop(g.drop_p, g.drop_seed, g.drop_site); d.drop_ld = g.drop_ld;
   dim3 grid(ceil_div(g.M, TM), ceil_div(g.N, TN), g.batch);
   if (grid.y > 65535 || grid.z > 65535) return M2_ERR_ARG;
+  LaunchScope scope("simt_gemm", s);
   simt_gemm_kernel<<<grid, 256, 0, s>>>(d);
   M2_LAUNCH_CHECK();
   return M2_OK;

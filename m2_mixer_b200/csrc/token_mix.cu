@@ -34,7 +34,8 @@ template <int DT>
 __global__ void __launch_bounds__(kThreads) token_mix_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
     const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-    const float* __restrict__ b2, float* __restrict__ u, int B, int N, int D, int T, int exact_gelu) {
+    const float* __restrict__ b2, float* __restrict__ u, int B, int N, int D, int T, int exact_gelu, const Drop dh,
+    const Drop dout) {
   extern __shared__ float sm[];
   constexpr int LD = DT + 1;
   float* sXn = sm;                       // [N][LD]
@@ -59,15 +60,19 @@ __global__ void __launch_bounds__(kThreads) token_mix_fwd_kernel(
       float acc = b1[t];
       const float* wr = w1 + static_cast<long long>(t) * N;
       for (int n = 0; n < N; ++n) acc = fmaf(wr[n], sXn[n * LD + dd], acc);
-      sG[t * LD + dd] = exact_gelu ? gelu_erf(acc) : gelu_fast(acc);
+      float gv = exact_gelu ? gelu_erf(acc) : gelu_fast(acc);
+      if (dh.thresh) gv = drop_apply(dh, gv, (static_cast<unsigned long long>(b) * T + t) * D + d);
+      sG[t * LD + dd] = gv;
     }
     __syncthreads();
     if (dok) {
       for (int n = ty; n < N; n += TY) {
-        float acc = b2[n] + xb[static_cast<long long>(n) * D + d];
+        float acc = b2[n];
         const float* wr = w2 + static_cast<long long>(n) * T;
         for (int t = 0; t < T; ++t) acc = fmaf(wr[t], sG[t * LD + dd], acc);
-        u[(static_cast<long long>(b) * N + n) * D + d] = acc;
+        const long long o = (static_cast<long long>(b) * N + n) * D + d;
+        if (dout.thresh) acc = drop_apply(dout, acc, o);
+        u[o] = xb[static_cast<long long>(n) * D + d] + acc;
       }
     }
   }
@@ -81,7 +86,8 @@ __global__ void __launch_bounds__(kThreads) token_mix_bwd_kernel(
     const float* __restrict__ du, const float* __restrict__ x, const float* __restrict__ ln_w,
     const float* __restrict__ ln_b, const float* __restrict__ w1, const float* __restrict__ b1,
     const float* __restrict__ w2, float* __restrict__ dxn, float* __restrict__ dw1, float* __restrict__ db1,
-    float* __restrict__ dw2, float* __restrict__ db2, int B, int N, int D, int T, int exact_gelu, int reg_acc) {
+    float* __restrict__ dw2, float* __restrict__ db2, int B, int N, int D, int T, int exact_gelu, int reg_acc,
+    const Drop dh, const Drop dout) {
   extern __shared__ float sm[];
   constexpr int LD = DT + 1;
   float* sXn = sm;                    // [N][LD]
@@ -107,7 +113,9 @@ __global__ void __launch_bounds__(kThreads) token_mix_bwd_kernel(
     __syncthreads();
     for (int n = ty; n < N; n += TY) {
       sXn[n * LD + dd] = dok ? (xb[static_cast<long long>(n) * D + d] - stat[2 * n]) * stat[2 * n + 1] * gam + bet : 0.f;
-      sDU[n * LD + dd] = dok ? dub[static_cast<long long>(n) * D + d] : 0.f;
+      float dv = dok ? dub[static_cast<long long>(n) * D + d] : 0.f;
+      if (dok && dout.thresh) dv = drop_apply(dout, dv, (static_cast<unsigned long long>(b) * N + n) * D + d);
+      sDU[n * LD + dd] = dv;   // gradient of the (dropped) branch output; the residual path is added by ln_bwd
     }
     __syncthreads();
     for (int t = ty; t < T; t += TY) {
@@ -119,6 +127,11 @@ __global__ void __launch_bounds__(kThreads) token_mix_bwd_kernel(
       }
       float g, dgelu;
       if (exact_gelu) { g = gelu_erf(h); dgelu = gelu_erf_grad(h); } else { g = gelu_fast_grad(h, dgelu); }
+      if (dok && dh.thresh) {   // G' = m*s*G ; dH = dG' * m*s * gelu'(h)
+        const bool keep = drop_keep(dh, (static_cast<unsigned long long>(b) * T + t) * D + d);
+        g = keep ? g * dh.scale : 0.f;
+        dgelu = keep ? dgelu * dh.scale : 0.f;
+      }
       sG[t * LD + dd] = dok ? g : 0.f;
       sDH[t * LD + dd] = dok ? dg * dgelu : 0.f;
     }
@@ -185,6 +198,235 @@ __global__ void __launch_bounds__(kThreads) token_mix_bwd_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small-N specialisation (every shipped config: N <= 32, D in {32,64,128,256}): ONE THREAD PER (sample, hidden column).
+// The thread keeps its column of the [N x D] sample tile in registers, so LayerNorm -> Wt1 -> GELU -> Wt2 -> residual
+// needs no shared-memory tile and only two block reductions (the LN row statistics, reduced across the D threads of
+// a sample with warp shuffles).  x is read once and u written once, fully coalesced along d.
+template <int NMAX>
+__device__ __forceinline__ void small_ln(const float (&x)[NMAX], float (&xn)[NMAX], int N, int D, float gam, float bet,
+                                         float* red /*[8][NMAX]*/, int warp, int lane, int first_warp, int nwarps_sample) {
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n)
+    if (n < N) {
+      const float v = warp_sum(x[n]);
+      if (lane == 0) red[warp * NMAX + n] = v;
+    }
+  __syncthreads();
+  float mean[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n)
+    if (n < N) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps_sample; ++w) t += red[(first_warp + w) * NMAX + n];
+      mean[n] = t / D;
+    }
+  __syncthreads();
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n)
+    if (n < N) {
+      const float c = x[n] - mean[n];
+      const float v = warp_sum(c * c);
+      if (lane == 0) red[warp * NMAX + n] = v;
+    }
+  __syncthreads();
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n)
+    if (n < N) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps_sample; ++w) t += red[(first_warp + w) * NMAX + n];
+      xn[n] = (x[n] - mean[n]) * rsqrtf(t / D + kLnEps) * gam + bet;
+    }
+  __syncthreads();   // red is reused by the next slab
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(kThreads) token_mix_small_fwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+    const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+    const float* __restrict__ b2, float* __restrict__ u, int B, int N, int D, int T, int exact_gelu, const Drop dh,
+    const Drop dout) {
+  extern __shared__ float sm[];
+  float* sW1 = sm;                 // [T][N]
+  float* sW2t = sW1 + T * N;       // [T][N]  (transposed: both inner loops run over n with t fixed)
+  float* sB1 = sW2t + T * N;       // [T]
+  float* sB2 = sB1 + T;            // [N]
+  float* red = sB2 + N;            // [8][NMAX]
+  for (int i = threadIdx.x; i < T * N; i += kThreads) {
+    sW1[i] = w1[i];
+    const int t = i / N, n = i - t * N;
+    sW2t[i] = w2[n * T + t];
+  }
+  for (int i = threadIdx.x; i < T; i += kThreads) sB1[i] = b1[i];
+  for (int i = threadIdx.x; i < N; i += kThreads) sB2[i] = b2[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int spb = kThreads / D;                       // samples per CTA slab
+  const int s_in = threadIdx.x / D, d = threadIdx.x - s_in * D;
+  const int wps = D / 32, first_warp = s_in * wps;
+  const float gam = ln_w[d], bet = ln_b[d];
+  __syncthreads();
+  for (int b0 = blockIdx.x * spb; b0 < B; b0 += gridDim.x * spb) {
+    const int b = b0 + s_in;
+    const bool ok = b < B;
+    const float* xb = x + (static_cast<long long>(ok ? b : 0) * N) * D + d;
+    float xv[NMAX], xn[NMAX], acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+      xv[n] = (n < N && ok) ? xb[static_cast<long long>(n) * D] : 0.f;
+      acc[n] = 0.f;
+    }
+    small_ln<NMAX>(xv, xn, N, D, gam, bet, red, warp, lane, first_warp, wps);
+    for (int t = 0; t < T; ++t) {
+      float h = sB1[t];
+      const float* w1r = sW1 + t * N;
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) h = fmaf(w1r[n], xn[n], h);
+      float g = exact_gelu ? gelu_erf(h) : gelu_fast(h);
+      if (dh.thresh) g = drop_apply(dh, g, (static_cast<unsigned long long>(b) * T + t) * D + d);
+      const float* w2r = sW2t + t * N;
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) acc[n] = fmaf(w2r[n], g, acc[n]);
+    }
+    if (ok) {
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) {
+          const long long o = (static_cast<long long>(b) * N + n) * D + d;
+          float v = acc[n] + sB2[n];
+          if (dout.thresh) v = drop_apply(dout, v, o);
+          u[o] = xv[n] + v;
+        }
+    }
+  }
+}
+
+constexpr int kSmallLd = 260;   // row stride of the phase-2 tiles (float4-aligned, spreads rows over banks)
+
+template <int NMAX>
+__global__ void __launch_bounds__(kThreads) token_mix_small_bwd_kernel(
+    const float* __restrict__ du, const float* __restrict__ x, const float* __restrict__ ln_w,
+    const float* __restrict__ ln_b, const float* __restrict__ w1, const float* __restrict__ b1,
+    const float* __restrict__ w2, float* __restrict__ dxn, float* __restrict__ dw1, float* __restrict__ db1,
+    float* __restrict__ dw2, float* __restrict__ db2, int B, int N, int D, int T, int exact_gelu, const Drop dh,
+    const Drop dout) {
+  extern __shared__ float sm[];
+  float* sW1 = sm;                        // [T][N]
+  float* sW2t = sW1 + T * N;              // [T][N]
+  float* sB1 = sW2t + T * N;              // [T]
+  float* red = sB1 + T;                   // [8][NMAX]
+  float* tile = red + 8 * NMAX;
+  tile += (4 - ((tile - sm) & 3)) & 3;    // 16-byte align the float4 tiles
+  float* sDH = tile;                      // [T][kSmallLd]
+  float* sG = sDH + T * kSmallLd;         // [T][kSmallLd]
+  float* sXn = sG + T * kSmallLd;         // [N][kSmallLd]
+  float* sDU = sXn + N * kSmallLd;        // [N][kSmallLd]
+  for (int i = threadIdx.x; i < T * N; i += kThreads) {
+    sW1[i] = w1[i];
+    const int t = i / N, n = i - t * N;
+    sW2t[i] = w2[n * T + t];
+  }
+  for (int i = threadIdx.x; i < T; i += kThreads) sB1[i] = b1[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int spb = kThreads / D;
+  const int s_in = threadIdx.x / D, d = threadIdx.x - s_in * D;
+  const int wps = D / 32, first_warp = s_in * wps;
+  const float gam = ln_w[d], bet = ln_b[d];
+  const int NT = N * T, nred = NT + T + N;       // reduction outputs: dw1/dw2 pairs, db1, db2
+  float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
+  for (int b0 = blockIdx.x * spb; b0 < B; b0 += gridDim.x * spb) {
+    const int b = b0 + s_in;
+    const bool ok = b < B;
+    const long long base = (static_cast<long long>(ok ? b : 0) * N) * D + d;
+    float xv[NMAX], xn[NMAX], dub[NMAX], dx[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+      const bool in = n < N && ok;
+      xv[n] = in ? x[base + static_cast<long long>(n) * D] : 0.f;
+      float g = in ? du[base + static_cast<long long>(n) * D] : 0.f;
+      if (in && dout.thresh) g = drop_apply(dout, g, static_cast<unsigned long long>(base) + static_cast<unsigned long long>(n) * D);
+      dub[n] = g;
+      dx[n] = 0.f;
+    }
+    small_ln<NMAX>(xv, xn, N, D, gam, bet, red, warp, lane, first_warp, wps);
+    for (int t = 0; t < T; ++t) {
+      float h = sB1[t], dg = 0.f;
+      const float* w1r = sW1 + t * N;
+      const float* w2r = sW2t + t * N;
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) { h = fmaf(w1r[n], xn[n], h); dg = fmaf(w2r[n], dub[n], dg); }
+      float g, dgelu;
+      if (exact_gelu) { g = gelu_erf(h); dgelu = gelu_erf_grad(h); } else { g = gelu_fast_grad(h, dgelu); }
+      if (dh.thresh) {
+        const bool keep = drop_keep(dh, (static_cast<unsigned long long>(b) * T + t) * D + d);
+        g = keep ? g * dh.scale : 0.f;
+        dgelu = keep ? dgelu * dh.scale : 0.f;
+      }
+      const float dhv = ok ? dg * dgelu : 0.f;
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) dx[n] = fmaf(w1r[n], dhv, dx[n]);
+      sDH[t * kSmallLd + threadIdx.x] = dhv;
+      sG[t * kSmallLd + threadIdx.x] = ok ? g : 0.f;
+    }
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) {
+        sXn[n * kSmallLd + threadIdx.x] = ok ? xn[n] : 0.f;
+        sDU[n * kSmallLd + threadIdx.x] = dub[n];
+        if (ok) dxn[base + static_cast<long long>(n) * D] = dx[n];
+      }
+    __syncthreads();
+    // phase 2: reduce the slab's 256 columns into the weight-gradient accumulators (registers, across slabs)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = threadIdx.x + i * kThreads;
+      if (p < NT) {
+        const int t = p / N, n = p - t * N;
+        const float4* ph = reinterpret_cast<const float4*>(sDH + t * kSmallLd);
+        const float4* pg = reinterpret_cast<const float4*>(sG + t * kSmallLd);
+        const float4* px = reinterpret_cast<const float4*>(sXn + n * kSmallLd);
+        const float4* pu = reinterpret_cast<const float4*>(sDU + n * kSmallLd);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < kThreads / 4; ++c) {
+          const float4 hh = ph[c], gg = pg[c], xx = px[c], uu = pu[c];
+          s1 += hh.x * xx.x + hh.y * xx.y + hh.z * xx.z + hh.w * xx.w;
+          s2 += uu.x * gg.x + uu.y * gg.y + uu.z * gg.z + uu.w * gg.w;
+        }
+        a1[i] += s1; a2[i] += s2;
+      } else if (p < nred) {
+        const float4* pr = reinterpret_cast<const float4*>(p < NT + T ? sDH + (p - NT) * kSmallLd : sDU + (p - NT - T) * kSmallLd);
+        float s1 = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < kThreads / 4; ++c) { const float4 v = pr[c]; s1 += v.x + v.y + v.z + v.w; }
+        a1[i] += s1;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = threadIdx.x + i * kThreads;
+    if (p < NT) {
+      const int t = p / N, n = p - t * N;
+      atomicAdd(&dw1[static_cast<long long>(t) * N + n], a1[i]);
+      atomicAdd(&dw2[static_cast<long long>(n) * T + t], a2[i]);
+    } else if (p < NT + T) {
+      atomicAdd(&db1[p - NT], a1[i]);
+    } else if (p < nred) {
+      atomicAdd(&db2[p - NT - T], a1[i]);
+    }
+  }
+}
+
+inline bool small_ok(int N, int D, int T) {
+  return N <= 32 && (D == 32 || D == 64 || D == 128 || D == 256) && N * T + T + N <= 4 * kThreads && 2 * T + 2 * N <= 160;
+}
+
 template <typename K>
 int set_smem(K kern, size_t bytes) {
   if (bytes > 48 * 1024) {
@@ -199,8 +441,28 @@ constexpr size_t kMaxSmem = 220 * 1024;
 }  // namespace
 
 int token_mix_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1, const float* w2,
-                  const float* b2, float* u, int B, int N, int D, int T, int exact_gelu, cudaStream_t s) {
+                  const float* b2, float* u, int B, int N, int D, int T, int exact_gelu, float drop_p,
+                  unsigned long long seed, cudaStream_t s) {
   if (B <= 0 || N <= 0 || D <= 0 || T <= 0) return M2_ERR_ARG;
+  if (small_ok(N, D, T)) {
+    const Drop dh = make_drop(drop_p, seed, kSiteTokenHidden), dout = make_drop(drop_p, seed, kSiteTokenOut);
+    const int spb = kThreads / D;
+    int grid = ceil_div(B, spb);
+    if (grid > 148 * 8) grid = 148 * 8;
+    LaunchScope scope("token_mix_small_fwd", s);
+#define M2_TMS_FWD(NM_)                                                                                                  \
+  {                                                                                                                      \
+    const size_t smem = (static_cast<size_t>(2 * T * N + T + N) + 8 * NM_) * 4;                                          \
+    int rc = set_smem(token_mix_small_fwd_kernel<NM_>, smem);                                                            \
+    if (rc) return rc;                                                                                                   \
+    token_mix_small_fwd_kernel<NM_><<<grid, kThreads, smem, s>>>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, D, T, exact_gelu, \
+                                                                 dh, dout);                                              \
+  }
+    if (N <= 4) M2_TMS_FWD(4) else if (N <= 8) M2_TMS_FWD(8) else if (N <= 16) M2_TMS_FWD(16) else M2_TMS_FWD(32)
+#undef M2_TMS_FWD
+    M2_LAUNCH_CHECK();
+    return M2_OK;
+  }
   auto bytes = [&](int dt) { return static_cast<size_t>(N + T) * (dt + 1) * 4 + static_cast<size_t>(N) * 8; };
   int dt = 32;
   while (dt > 8 && bytes(dt) > kMaxSmem) dt >>= 1;
@@ -209,10 +471,13 @@ int token_mix_fwd(const float* x, const float* ln_w, const float* ln_b, const fl
   int gx = B < ceil_div(148 * 8, ds) ? B : ceil_div(148 * 8, ds);
   dim3 grid(gx, ds);
   int rc;
+  const Drop dh = make_drop(drop_p, seed, kSiteTokenHidden), dout = make_drop(drop_p, seed, kSiteTokenOut);
+  LaunchScope scope("token_mix_fwd", s);
 #define M2_TM_FWD(DT_)                                                                                         \
   rc = set_smem(token_mix_fwd_kernel<DT_>, bytes(DT_));                                                        \
   if (rc) return rc;                                                                                           \
-  token_mix_fwd_kernel<DT_><<<grid, kThreads, bytes(DT_), s>>>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, D, T, exact_gelu);
+  token_mix_fwd_kernel<DT_><<<grid, kThreads, bytes(DT_), s>>>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, D, T, exact_gelu, \
+                                                               dh, dout);
   if (dt == 32) { M2_TM_FWD(32) } else if (dt == 16) { M2_TM_FWD(16) } else { M2_TM_FWD(8) }
 #undef M2_TM_FWD
   M2_LAUNCH_CHECK();
@@ -221,8 +486,27 @@ int token_mix_fwd(const float* x, const float* ln_w, const float* ln_b, const fl
 
 int token_mix_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
                   const float* w2, float* dxn, float* dw1, float* db1, float* dw2, float* db2, int B, int N, int D, int T,
-                  int exact_gelu, cudaStream_t s) {
+                  int exact_gelu, float drop_p, unsigned long long seed, cudaStream_t s) {
   if (B <= 0 || N <= 0 || D <= 0 || T <= 0) return M2_ERR_ARG;
+  if (small_ok(N, D, T)) {
+    const Drop dh = make_drop(drop_p, seed, kSiteTokenHidden), dout = make_drop(drop_p, seed, kSiteTokenOut);
+    const int spb = kThreads / D;
+    int grid = ceil_div(B, spb);
+    if (grid > 148 * 2) grid = 148 * 2;
+    LaunchScope scope("token_mix_small_bwd", s);
+#define M2_TMS_BWD(NM_)                                                                                                  \
+  {                                                                                                                      \
+    const size_t smem = (static_cast<size_t>(2 * T * N + T) + 8 * NM_ + 4 + static_cast<size_t>(2 * T + 2 * N) * kSmallLd) * 4; \
+    int rc = set_smem(token_mix_small_bwd_kernel<NM_>, smem);                                                            \
+    if (rc) return rc;                                                                                                   \
+    token_mix_small_bwd_kernel<NM_><<<grid, kThreads, smem, s>>>(du, x, ln_w, ln_b, w1, b1, w2, dxn, dw1, db1, dw2, db2, B, \
+                                                                 N, D, T, exact_gelu, dh, dout);                         \
+  }
+    if (N <= 4) M2_TMS_BWD(4) else if (N <= 8) M2_TMS_BWD(8) else if (N <= 16) M2_TMS_BWD(16) else M2_TMS_BWD(32)
+#undef M2_TMS_BWD
+    M2_LAUNCH_CHECK();
+    return M2_OK;
+  }
   auto bytes = [&](int dt) { return static_cast<size_t>(2 * N + 2 * T) * (dt + 1) * 4 + static_cast<size_t>(N) * 8; };
   int dt = 32;
   while (dt > 8 && bytes(dt) > kMaxSmem) dt >>= 1;
@@ -233,11 +517,13 @@ int token_mix_bwd(const float* du, const float* x, const float* ln_w, const floa
   int gx = B < cap ? B : cap;
   dim3 grid(gx, ds);
   int rc;
+  const Drop dh = make_drop(drop_p, seed, kSiteTokenHidden), dout = make_drop(drop_p, seed, kSiteTokenOut);
+  LaunchScope scope("token_mix_bwd", s);
 #define M2_TM_BWD(DT_)                                                                                            \
   rc = set_smem(token_mix_bwd_kernel<DT_>, bytes(DT_));                                                           \
   if (rc) return rc;                                                                                              \
   token_mix_bwd_kernel<DT_><<<grid, kThreads, bytes(DT_), s>>>(du, x, ln_w, ln_b, w1, b1, w2, dxn, dw1, db1, dw2, db2, B, N, \
-                                                               D, T, exact_gelu, reg_acc);
+                                                               D, T, exact_gelu, reg_acc, dh, dout);
   if (dt == 32) { M2_TM_BWD(32) } else if (dt == 16) { M2_TM_BWD(16) } else { M2_TM_BWD(8) }
 #undef M2_TM_BWD
   M2_LAUNCH_CHECK();

@@ -31,6 +31,7 @@ struct GemmDev {
   const float* residual; long long ldr, r_batch_stride;
   void* C; int c_bf16; long long ldc, c_batch_stride;
   int accumulate;
+  Drop drop; long long drop_ld;
 };
 
 template <bool kAMn, bool kBMn>
@@ -141,6 +142,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (p.act == 1) x = gelu_erf(x);
           else if (p.act == 2) x = fmaxf(x, 0.f);
+          if (p.drop.thresh) x = drop_apply(p.drop, x, static_cast<unsigned long long>(row) * p.drop_ld + col);
           if (res) x += res[col];
         }
         v[j] = x;
@@ -162,8 +164,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         float* c = reinterpret_cast<float*>(p.C) + coff + n0 + c0;
         if (p.splitk > 1) {
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.N) atomicAdd(c + j, v[j]);
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)   // 128-bit reductions (red.global.add.v4.f32)
+              atomicAdd(reinterpret_cast<float4*>(c + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < p.N) atomicAdd(c + j, v[j]);
+          }
         } else if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -195,6 +203,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, dim3 
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return M2_ERR_LAUNCH;
     configured = true;
   }
+  LaunchScope scope(kAMn ? (kBMn ? "umma_gemm_tn" : "umma_gemm_tk") : (kBMn ? "umma_gemm_kn" : "umma_gemm_kk"), s);
   kern<<<grid, 192, kSmemBytes, s>>>(ta, tb, d);
   M2_LAUNCH_CHECK();
   return M2_OK;
@@ -231,6 +240,7 @@ int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
   d.residual = g.residual; d.ldr = g.ldr; d.r_batch_stride = g.r_batch_stride;
   d.C = g.C; d.c_bf16 = g.c_bf16; d.ldc = g.ldc; d.c_batch_stride = g.c_batch_stride;
   d.accumulate = g.accumulate;
+  d.drop = make_drop(g.drop_p, g.drop_seed, g.drop_site); d.drop_ld = g.drop_ld;
   dim3 grid(ceil_div(g.M, kBM), ceil_div(g.N, kBN), g.batch * d.splitk);
   if (grid.y > 65535 || grid.z > 65535) return M2_ERR_ARG;
   if (g.a_mn) return g.b_mn ? launch<true, true>(ta, tb, d, grid, s) : launch<true, false>(ta, tb, d, grid, s);

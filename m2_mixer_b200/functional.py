@@ -6,6 +6,7 @@ channel mixing) - no [tokens x channel_dim] hidden tensor is ever kept alive bet
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -30,62 +31,125 @@ def _up8(v: int) -> int:
     return (v + 7) // 8 * 8
 
 
+def _direct(params):
+    """Gradient destinations registered by FusedAdam (views into its flat gradient buffer).  When EVERY parameter of an
+    op has one, the backward kernels accumulate straight into them (no per-parameter zero-fill + AccumulateGrad add
+    launches) and autograd gets None for those inputs; data-parallel bucket hooks are notified through _m2_ready."""
+    dst = [getattr(p, "_m2_grad", None) if p is not None else None for p in params]
+    live = [d for p, d in zip(params, dst) if p is not None and p.requires_grad]
+    if live and all(d is not None for d in live) and len(live) == sum(1 for p in params if p is not None):
+        return dst
+    return None
+
+
+def _notify(params):
+    for p in params:
+        cb = getattr(p, "_m2_ready", None) if p is not None else None
+        if cb is not None:
+            cb()
+
+
+def _ret(direct, grads):
+    return tuple(None for _ in grads) if direct is not None else tuple(grads)
+
+
 class _TokenMix(Function):
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, precision):
-        u = _O.token_mix_fwd(x, ln_w, ln_b, w1, b1, w2, b2, precision)
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, precision, p, seed):
+        u = _O.token_mix_fwd(x, ln_w, ln_b, w1, b1, w2, b2, precision, p, seed)
         ctx.save_for_backward(x, ln_w, ln_b, w1, b1, w2)
-        ctx.precision = precision
+        ctx.precision, ctx.p, ctx.seed = precision, p, seed
+        ctx.params = (ln_w, ln_b, w1, b1, w2, b2)
         return u
 
     @staticmethod
     def backward(ctx, du):
         x, ln_w, ln_b, w1, b1, w2 = ctx.saved_tensors
-        dx, dln_w, dln_b, dw1, db1, dw2, db2 = _O.token_mix_bwd(du.contiguous(), x, ln_w, ln_b, w1, b1, w2, ctx.precision)
-        return dx, dln_w, dln_b, dw1, db1, dw2, db2, None
+        direct = _direct(ctx.params)
+        dx, *g = _O.token_mix_bwd(du.contiguous(), x, ln_w, ln_b, w1, b1, w2, ctx.precision, ctx.p, ctx.seed, direct)
+        if direct is not None:
+            _notify(ctx.params)
+        return (dx, *_ret(direct, g), None, None, None)
 
 
 class _ChannelMix(Function):
     @staticmethod
-    def forward(ctx, u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, precision):
-        y = _O.channel_mix_fwd(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, precision)
+    def forward(ctx, u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, precision, p, seed):
+        y = _O.channel_mix_fwd(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, precision, p, seed)
         ctx.save_for_backward(u, ln_w, ln_b, w1, b1, w2, w1b, w2b)
-        ctx.precision = precision
+        ctx.precision, ctx.p, ctx.seed = precision, p, seed
+        ctx.params = (ln_w, ln_b, w1, b1, w2, b2)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         u, ln_w, ln_b, w1, b1, w2, w1b, w2b = ctx.saved_tensors
-        du, dln_w, dln_b, dw1, db1, dw2, db2 = _O.channel_mix_bwd(dy.contiguous(), u, ln_w, ln_b, w1, b1, w2, w1b, w2b,
-                                                                 ctx.precision)
-        return du, dln_w, dln_b, dw1, db1, dw2, db2, None, None, None
+        direct = _direct(ctx.params)
+        du, *g = _O.channel_mix_bwd(dy.contiguous(), u, ln_w, ln_b, w1, b1, w2, w1b, w2b, ctx.precision, ctx.p, ctx.seed,
+                                    direct)
+        if direct is not None:
+            _notify(ctx.params)
+        return (du, *_ret(direct, g), None, None, None, None, None)
 
 
 class _LayerNorm(Function):
     @staticmethod
     def forward(ctx, x, w, b):
         ctx.save_for_backward(x, w)
+        ctx.params = (w, b)
         return _O.layernorm_fwd(x, w, b)
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        return _O.layernorm_bwd(dy.contiguous(), x, w)
+        direct = _direct(ctx.params)
+        dx, *g = _O.layernorm_bwd(dy.contiguous(), x, w, direct)
+        if direct is not None:
+            _notify(ctx.params)
+        return (dx, *_ret(direct, g))
 
 
 class _Linear(Function):
     @staticmethod
-    def forward(ctx, x, w, bias, wb, act, precision):
-        y = _O.linear_fwd(x, w, wb, bias, act, precision)
+    def forward(ctx, x, w, bias, wb, act, precision, p, seed):
+        y = _O.linear_fwd(x, w, wb, bias, act, precision, p, seed)
         ctx.save_for_backward(x, w, wb, y if act == ACT_RELU else None)
-        ctx.act, ctx.precision, ctx.has_bias = act, precision, bias is not None
+        ctx.act, ctx.precision, ctx.has_bias, ctx.p, ctx.seed = act, precision, bias is not None, p, seed
+        ctx.params = (w, bias)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, wb, y = ctx.saved_tensors
-        dx, dw, db = _O.linear_bwd(dy.contiguous(), x, y, w, wb, ctx.act, ctx.needs_input_grad[0], ctx.precision)
-        return (dx if ctx.needs_input_grad[0] else None), dw, (db if ctx.has_bias else None), None, None, None
+        direct = _direct(ctx.params) if ctx.has_bias else None
+        dx, dw, db = _O.linear_bwd(dy.contiguous(), x, y, w, wb, ctx.act, ctx.needs_input_grad[0], ctx.precision, ctx.p,
+                                   ctx.seed, direct)
+        if direct is not None:
+            _notify(ctx.params)
+            dw = db = None
+        return (dx if ctx.needs_input_grad[0] else None), dw, (db if ctx.has_bias else None), None, None, None, None, None
+
+
+class _PatchEmbed(Function):
+    """Conv2d(k = stride = patch) + 'b c h w -> b (h w) c' as gather + GEMM; the gathered (bf16) patch rows are
+    kept for the weight-gradient GEMM, there is no input gradient."""
+
+    @staticmethod
+    def forward(ctx, img, w, bias, wb, patch, precision):
+        y, cols = _O.patch_embed_fwd(img, w, wb, bias, patch, precision)
+        ctx.save_for_backward(cols, w)
+        ctx.precision, ctx.has_bias, ctx.params = precision, bias is not None, (w, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cols, w = ctx.saved_tensors
+        direct = _direct(ctx.params) if ctx.has_bias else None
+        dw, db = _O.patch_embed_bwd(dy.contiguous(), cols, w, ctx.has_bias, ctx.precision, direct)
+        if direct is not None:
+            _notify(ctx.params)
+            dw = db = None
+        return None, dw, (db if ctx.has_bias else None), None, None, None
 
 
 class _Concat(Function):
@@ -129,6 +193,7 @@ class _HeadsLoss(Function):
         losses, logits, preds = _O.heads_loss_fwd(toks, ws, bs, labels, pos_weight, list(head_weight), loss_kind)
         ctx.save_for_backward(labels, pos_weight, logits, *tensors)
         ctx.head_weight, ctx.loss_kind, ctx.n = list(head_weight), loss_kind, n
+        ctx.params = tuple(ws) + tuple(bs)
         ctx.mark_non_differentiable(logits, preds)
         ctx.tok_shapes = [t.shape for t in toks]
         return losses, logits, preds
@@ -140,43 +205,73 @@ class _HeadsLoss(Function):
         toks, ws, bs = list(tensors[:n]), list(tensors[n:2 * n]), list(tensors[2 * n:3 * n])
         # d(total)/d(.) scaled by the incoming gradient of losses[0]; per-head losses[1:] are reporting-only outputs
         # (passed as a device scalar: no host sync, CUDA-graph capturable)
+        direct = _direct(ctx.params)
         dt, dw, db = _O.heads_loss_bwd(toks, ws, bs, labels, pos_weight, ctx.head_weight, ctx.loss_kind, logits, 1.0,
-                                       dlosses.contiguous())
+                                       dlosses.contiguous(), direct)
         dt = [g.reshape(s) for g, s in zip(dt, ctx.tok_shapes)]
+        if direct is not None:
+            _notify(ctx.params)
+            dw, db = [None] * n, [None] * n
         return (None, None, None, None, None, *dt, *dw, *db)
 
 
 # ---------------------------------------------------------------------------------------------------- public API
-def token_mix(x, ln_w, ln_b, w1, b1, w2, b2, precision) -> torch.Tensor:
-    return _TokenMix.apply(x, ln_w, ln_b, w1, b1, w2, b2, precision_code(precision))
+_DROP_CALLS = 0
 
 
-def channel_mix(u, ln_w, ln_b, w1, b1, w2, b2, precision, w1b=None, w2b=None) -> torch.Tensor:
+def next_dropout_seed() -> int:
+    """A fresh 63-bit seed per dropout-carrying op call: deterministic after torch.manual_seed, different per rank."""
+    global _DROP_CALLS
+    _DROP_CALLS += 1
+    rank = int(os.environ.get("RANK", "0"))
+    z = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _DROP_CALLS * 0xD1B54A32D192ED03 + rank * 0x94D049BB133111EB)
+    return z & 0x7FFFFFFFFFFFFFFF
+
+
+def _drop_args(p: float, seed):
+    p = float(p)
+    if p <= 0.0:
+        return 0.0, 0
+    return p, int(next_dropout_seed() if seed is None else seed)
+
+
+def token_mix(x, ln_w, ln_b, w1, b1, w2, b2, precision, dropout_p: float = 0.0, seed=None) -> torch.Tensor:
+    p, seed = _drop_args(dropout_p, seed)
+    return _TokenMix.apply(x, ln_w, ln_b, w1, b1, w2, b2, precision_code(precision), p, seed)
+
+
+def channel_mix(u, ln_w, ln_b, w1, b1, w2, b2, precision, w1b=None, w2b=None, dropout_p: float = 0.0,
+                seed=None) -> torch.Tensor:
     prec = precision_code(precision)
+    p, seed = _drop_args(dropout_p, seed)
     if prec == BF16 and (w1b is None or w2b is None):
         with torch.no_grad():
             w1b = _O.cast_bf16(w1, w1.shape[1])
             w2b = _O.cast_bf16(w2, _up8(w2.shape[1]))
-    return _ChannelMix.apply(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, prec)
+    return _ChannelMix.apply(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, prec, p, seed)
 
 
 def layer_norm(x, w, b) -> torch.Tensor:
     return _LayerNorm.apply(x, w, b)
 
 
-def linear(x, w, bias=None, act: int = ACT_NONE, precision="bf16", wb=None) -> torch.Tensor:
+def linear(x, w, bias=None, act: int = ACT_NONE, precision="bf16", wb=None, dropout_p: float = 0.0, seed=None) -> torch.Tensor:
     prec = precision_code(precision)
+    p, seed = _drop_args(dropout_p, seed)
     if prec == BF16 and wb is None:
         with torch.no_grad():
             wb = _O.cast_bf16(w.reshape(w.shape[0], -1), _up8(w[0].numel()))
-    return _Linear.apply(x, w.reshape(w.shape[0], -1), bias, wb, act, prec)
+    return _Linear.apply(x, w.reshape(w.shape[0], -1), bias, wb, act, prec, p, seed)
 
 
 def patch_embed(img, conv_w, conv_b, patch: int, precision="bf16") -> torch.Tensor:
     """Conv2d(k = stride = patch) + 'b c h w -> b (h w) c' as gather + GEMM (reference modules/mixer.py:143-146)."""
-    with torch.no_grad():
-        cols = _O.patch_gather(img, patch)     # the input image needs no gradient
-    return linear(cols, conv_w, conv_b, ACT_NONE, precision)
+    prec = precision_code(precision)
+    wb = None
+    if prec == BF16:
+        with torch.no_grad():
+            wb = _O.cast_bf16(conv_w.reshape(conv_w.shape[0], -1), _up8(conv_w[0].numel()))
+    return _PatchEmbed.apply(img, conv_w, conv_b, wb, patch, prec)
 
 
 def mean_pool(x) -> torch.Tensor:

@@ -90,16 +90,15 @@ class MixerBlock(nn.Module):
         self.channel_mix = nn.Sequential(nn.LayerNorm(hidden_dim), FeedForward(hidden_dim, channel_dim, dropout))
 
     def forward(self, x):
-        if self.training and self.dropout_p > 0.0:
-            raise NotImplementedError("m2b200: fused dropout is not available in this build; construct with dropout=0.0 "
-                                      "(the kernels never silently skip it)")
+        p = self.dropout_p if self.training else 0.0     # nn.Dropout semantics: identity in eval mode
         if x.dim() != 3 or x.shape[1] != self.num_patch or x.shape[2] != self.hidden_dim:
             raise ValueError(f"MixerBlock expects [B, {self.num_patch}, {self.hidden_dim}], got {tuple(x.shape)}")
         ln1, tff = self.token_mix[0], self.token_mix[2]
         ln2, cff = self.channel_mix[0], self.channel_mix[1]
-        u = F.token_mix(x, ln1.weight, ln1.bias, tff.fc1.weight, tff.fc1.bias, tff.fc2.weight, tff.fc2.bias, self.precision)
+        u = F.token_mix(x, ln1.weight, ln1.bias, tff.fc1.weight, tff.fc1.bias, tff.fc2.weight, tff.fc2.bias, self.precision,
+                        dropout_p=p)
         return F.channel_mix(u, ln2.weight, ln2.bias, cff.fc1.weight, cff.fc1.bias, cff.fc2.weight, cff.fc2.bias,
-                             self.precision)
+                             self.precision, dropout_p=p)
 
 
 class _Stack(nn.Module):

@@ -25,11 +25,11 @@ class MLP(nn.Module):
             self.module_list.append(nn.Linear(hidden_dim, output_dim))
 
     def forward(self, x):
-        if self.training and self.dropout_p > 0.0:
-            raise NotImplementedError("m2b200: fused dropout is not available in this build; construct with dropout=0.0")
+        p = self.dropout_p if self.training else 0.0
         mods = list(self.module_list)
         for i, m in enumerate(mods):
             if isinstance(m, nn.Linear):
                 relu = i + 1 < len(mods) and isinstance(mods[i + 1], _Slot)
-                x = F.linear(x, m.weight, m.bias, ACT_RELU if relu else ACT_NONE, self.precision)
+                # hidden blocks are Linear -> ReLU -> Dropout; the optional output Linear has neither
+                x = F.linear(x, m.weight, m.bias, ACT_RELU if relu else ACT_NONE, self.precision, dropout_p=p if relu else 0.0)
         return x

@@ -47,6 +47,16 @@ def _ws(nbytes: int, like: torch.Tensor) -> Tuple[Optional[torch.Tensor], Option
     return w, w.data_ptr()
 
 
+def _grad_dst(grads, i: int, like: torch.Tensor) -> torch.Tensor:
+    """Destination of a parameter gradient: the caller's running buffer (accumulated into) or fresh zeros."""
+    if grads is not None and grads[i] is not None:
+        g = grads[i]
+        if not (g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.numel() == like.numel()):
+            raise RuntimeError("m2b200: gradient destination must be a contiguous float32 CUDA tensor of the parameter's size")
+        return g
+    return torch.zeros_like(like, memory_format=torch.contiguous_format)
+
+
 def _define(name: str, schema: str, fn):
     _LIB.define(f"{name}{schema}")
     _LIB.impl(name, fn, "CUDA")
@@ -65,44 +75,46 @@ _define("cast_bf16", "(Tensor w, int ld) -> Tensor", cast_bf16)
 
 
 # ------------------------------------------------------------------------------------------------ token mixing
-def token_mix_fwd(x, ln_w, ln_b, w1, b1, w2, b2, precision: int):
+def token_mix_fwd(x, ln_w, ln_b, w1, b1, w2, b2, precision: int, dropout_p: float = 0.0, seed: int = 0):
     x = _f32c(x, "x")
     B, N, D = x.shape
     T = w1.shape[0]
     u = torch.empty_like(x)
     check(_L().m2b200_token_mix_fwd(x.data_ptr(), _f32c(ln_w, "ln_w").data_ptr(), _f32c(ln_b, "ln_b").data_ptr(),
                                     _f32c(w1, "w1").data_ptr(), _f32c(b1, "b1").data_ptr(), _f32c(w2, "w2").data_ptr(),
-                                    _f32c(b2, "b2").data_ptr(), u.data_ptr(), B, N, D, T, precision, _stream()),
+                                    _f32c(b2, "b2").data_ptr(), u.data_ptr(), B, N, D, T, precision, dropout_p, seed,
+                                    _stream()),
           "token_mix_fwd")
     return u
 
 
-def token_mix_bwd(du, x, ln_w, ln_b, w1, b1, w2, precision: int):
+def token_mix_bwd(du, x, ln_w, ln_b, w1, b1, w2, precision: int, dropout_p: float = 0.0, seed: int = 0, grads=None):
     du, x = _f32c(du, "du"), _f32c(x, "x")
     B, N, D = x.shape
     T = w1.shape[0]
     dx = torch.empty_like(x)
-    z = lambda t: torch.zeros_like(t, memory_format=torch.contiguous_format)
-    dln_w, dln_b, dw1, db1, dw2 = z(ln_w), z(ln_b), z(w1), z(b1), z(w2)
-    db2 = torch.zeros(N, dtype=torch.float32, device=x.device)
+    dln_w, dln_b, dw1, db1, dw2 = (_grad_dst(grads, i, t) for i, t in enumerate((ln_w, ln_b, w1, b1, w2)))
+    db2 = _grad_dst(grads, 5, w2[:, 0])
     nbytes = _L().m2b200_token_mix_bwd_workspace_bytes(B, N, D, T)
     ws, wsp = _ws(nbytes, x)
     check(_L().m2b200_token_mix_bwd(du.data_ptr(), x.data_ptr(), _f32c(ln_w, "ln_w").data_ptr(),
                                     _f32c(ln_b, "ln_b").data_ptr(), _f32c(w1, "w1").data_ptr(), _f32c(b1, "b1").data_ptr(),
                                     _f32c(w2, "w2").data_ptr(), dx.data_ptr(), dln_w.data_ptr(), dln_b.data_ptr(),
                                     dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(), B, N, D, T, precision,
-                                    wsp, nbytes, _stream()), "token_mix_bwd")
+                                    dropout_p, seed, wsp, nbytes, _stream()), "token_mix_bwd")
     return dx, dln_w, dln_b, dw1, db1, dw2, db2
 
 
-_define("token_mix_fwd", "(Tensor x, Tensor ln_w, Tensor ln_b, Tensor w1, Tensor b1, Tensor w2, Tensor b2, int precision) -> Tensor",
+_define("token_mix_fwd", "(Tensor x, Tensor ln_w, Tensor ln_b, Tensor w1, Tensor b1, Tensor w2, Tensor b2, int precision, "
+        "float dropout_p=0.0, int seed=0) -> Tensor",
         token_mix_fwd)
-_define("token_mix_bwd", "(Tensor du, Tensor x, Tensor ln_w, Tensor ln_b, Tensor w1, Tensor b1, Tensor w2, int precision) -> "
+_define("token_mix_bwd", "(Tensor du, Tensor x, Tensor ln_w, Tensor ln_b, Tensor w1, Tensor b1, Tensor w2, int precision, "
+        "float dropout_p=0.0, int seed=0, Tensor?[]? grads=None) -> "
         "(Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)", token_mix_bwd)
 
 
 # ------------------------------------------------------------------------------------------------ channel mixing
-def channel_mix_fwd(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, precision: int):
+def channel_mix_fwd(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, precision: int, dropout_p: float = 0.0, seed: int = 0):
     u = _f32c(u, "u")
     D = u.shape[-1]
     M = u.numel() // D
@@ -114,19 +126,19 @@ def channel_mix_fwd(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, precision: int):
     check(_L().m2b200_channel_mix_fwd(u.data_ptr(), _f32c(ln_w, "ln_w").data_ptr(), _f32c(ln_b, "ln_b").data_ptr(),
                                       _f32c(w1, "w1").data_ptr(), _f32c(b1, "b1").data_ptr(), _f32c(w2, "w2").data_ptr(),
                                       _f32c(b2, "b2").data_ptr(), _ptr(w1b), _ptr(w2b), ldw2, y.data_ptr(), M, D, Cc,
-                                      precision, wsp, nbytes, _stream()), "channel_mix_fwd")
+                                      precision, dropout_p, seed, wsp, nbytes, _stream()), "channel_mix_fwd")
     return y
 
 
-def channel_mix_bwd(dy, u, ln_w, ln_b, w1, b1, w2, w1b, w2b, precision: int):
+def channel_mix_bwd(dy, u, ln_w, ln_b, w1, b1, w2, w1b, w2b, precision: int, dropout_p: float = 0.0, seed: int = 0,
+                    grads=None):
     dy, u = _f32c(dy, "dy"), _f32c(u, "u")
     D = u.shape[-1]
     M = u.numel() // D
     Cc = w1.shape[0]
     du = torch.empty_like(u)
-    z = lambda t: torch.zeros_like(t, memory_format=torch.contiguous_format)
-    dln_w, dln_b, dw1, db1, dw2 = z(ln_w), z(ln_b), z(w1), z(b1), z(w2)
-    db2 = torch.zeros(D, dtype=torch.float32, device=u.device)
+    dln_w, dln_b, dw1, db1, dw2 = (_grad_dst(grads, i, t) for i, t in enumerate((ln_w, ln_b, w1, b1, w2)))
+    db2 = _grad_dst(grads, 5, ln_w)
     nbytes = _L().m2b200_channel_mix_workspace_bytes(M, D, Cc, precision, 1)
     ws, wsp = _ws(nbytes, u)
     ldw2 = 0 if w2b is None else w2b.shape[1]
@@ -134,14 +146,16 @@ def channel_mix_bwd(dy, u, ln_w, ln_b, w1, b1, w2, w1b, w2b, precision: int):
                                       _f32c(ln_b, "ln_b").data_ptr(), _f32c(w1, "w1").data_ptr(), _f32c(b1, "b1").data_ptr(),
                                       _f32c(w2, "w2").data_ptr(), _ptr(w1b), _ptr(w2b), ldw2, du.data_ptr(),
                                       dln_w.data_ptr(), dln_b.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(),
-                                      db2.data_ptr(), M, D, Cc, precision, wsp, nbytes, _stream()), "channel_mix_bwd")
+                                      db2.data_ptr(), M, D, Cc, precision, dropout_p, seed, wsp, nbytes, _stream()),
+          "channel_mix_bwd")
     return du, dln_w, dln_b, dw1, db1, dw2, db2
 
 
 _define("channel_mix_fwd", "(Tensor u, Tensor ln_w, Tensor ln_b, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor? w1b, "
-        "Tensor? w2b, int precision) -> Tensor", channel_mix_fwd)
+        "Tensor? w2b, int precision, float dropout_p=0.0, int seed=0) -> Tensor", channel_mix_fwd)
 _define("channel_mix_bwd", "(Tensor dy, Tensor u, Tensor ln_w, Tensor ln_b, Tensor w1, Tensor b1, Tensor w2, Tensor? w1b, "
-        "Tensor? w2b, int precision) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)", channel_mix_bwd)
+        "Tensor? w2b, int precision, float dropout_p=0.0, int seed=0, Tensor?[]? grads=None) -> "
+        "(Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)", channel_mix_bwd)
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
@@ -155,23 +169,23 @@ def layernorm_fwd(x, w, b):
     return out
 
 
-def layernorm_bwd(dy, x, w):
+def layernorm_bwd(dy, x, w, grads=None):
     dy, x = _f32c(dy, "dy"), _f32c(x, "x")
     D = x.shape[-1]
     rows = x.numel() // D
     dx = torch.empty_like(x)
-    dw, db = torch.zeros_like(w), torch.zeros_like(w)
+    dw, db = _grad_dst(grads, 0, w), _grad_dst(grads, 1, w)
     check(_L().m2b200_layernorm_bwd(dy.data_ptr(), 0, x.data_ptr(), _f32c(w, "w").data_ptr(), None, dx.data_ptr(),
                                     dw.data_ptr(), db.data_ptr(), 1, rows, D, _stream()), "layernorm_bwd")
     return dx, dw, db
 
 
 _define("layernorm_fwd", "(Tensor x, Tensor w, Tensor b) -> Tensor", layernorm_fwd)
-_define("layernorm_bwd", "(Tensor dy, Tensor x, Tensor w) -> (Tensor, Tensor, Tensor)", layernorm_bwd)
+_define("layernorm_bwd", "(Tensor dy, Tensor x, Tensor w, Tensor?[]? grads=None) -> (Tensor, Tensor, Tensor)", layernorm_bwd)
 
 
 # ------------------------------------------------------------------------------------------------ linear / patches
-def linear_fwd(x, w, wb, bias, act: int, precision: int):
+def linear_fwd(x, w, wb, bias, act: int, precision: int, dropout_p: float = 0.0, seed: int = 0):
     x = _f32c(x, "x")
     K = x.shape[-1]
     M = x.numel() // K
@@ -181,26 +195,26 @@ def linear_fwd(x, w, wb, bias, act: int, precision: int):
     ws, wsp = _ws(nbytes, x)
     check(_L().m2b200_linear_fwd(x.data_ptr(), _f32c(w, "w").data_ptr(), _ptr(wb), 0 if wb is None else wb.shape[1],
                                  None if bias is None else _f32c(bias, "bias").data_ptr(), act, y.data_ptr(), M, N, K,
-                                 precision, wsp, nbytes, _stream()), "linear_fwd")
+                                 precision, dropout_p, seed, wsp, nbytes, _stream()), "linear_fwd")
     return y
 
 
-def linear_bwd(dy, x, y, w, wb, act: int, need_dx: bool, precision: int):
+def linear_bwd(dy, x, y, w, wb, act: int, need_dx: bool, precision: int, dropout_p: float = 0.0, seed: int = 0, grads=None):
     x = _f32c(x, "x")
     dy = _f32c(dy, "dy")
-    if act == _lib.ACT_RELU:
+    if act == _lib.ACT_RELU or dropout_p > 0.0:
         dy = dy.clone()   # masked in place by the kernel
     K = x.shape[-1]
     M = x.numel() // K
     N = w.shape[0]
     dx = torch.empty_like(x) if need_dx else None
-    dw = torch.zeros_like(w, memory_format=torch.contiguous_format)
-    db = torch.zeros(N, dtype=torch.float32, device=x.device)
+    dw = _grad_dst(grads, 0, w)
+    db = _grad_dst(grads, 1, w[:, 0])
     nbytes = _L().m2b200_linear_workspace_bytes(M, N, K, precision, 1)
     ws, wsp = _ws(nbytes, x)
     check(_L().m2b200_linear_bwd(dy.data_ptr(), x.data_ptr(), _ptr(y), _f32c(w, "w").data_ptr(), _ptr(wb),
                                  0 if wb is None else wb.shape[1], act, _ptr(dx), dw.data_ptr(), db.data_ptr(), M, N, K,
-                                 precision, wsp, nbytes, _stream()), "linear_bwd")
+                                 precision, dropout_p, seed, wsp, nbytes, _stream()), "linear_bwd")
     if dx is None:
         dx = torch.empty(0, dtype=torch.float32, device=x.device)
     return dx, dw, db
@@ -216,10 +230,59 @@ def patch_gather(img, patch: int):
     return cols
 
 
-_define("linear_fwd", "(Tensor x, Tensor w, Tensor? wb, Tensor? bias, int act, int precision) -> Tensor", linear_fwd)
-_define("linear_bwd", "(Tensor dy, Tensor x, Tensor? y, Tensor w, Tensor? wb, int act, bool need_dx, int precision) -> "
+_define("linear_fwd", "(Tensor x, Tensor w, Tensor? wb, Tensor? bias, int act, int precision, float dropout_p=0.0, int seed=0) "
+        "-> Tensor", linear_fwd)
+_define("linear_bwd", "(Tensor dy, Tensor x, Tensor? y, Tensor w, Tensor? wb, int act, bool need_dx, int precision, "
+        "float dropout_p=0.0, int seed=0, Tensor?[]? grads=None) -> "
         "(Tensor, Tensor, Tensor)", linear_bwd)
+def patch_embed_fwd(img, w, wb, bias, patch: int, precision: int):
+    img = _f32c(img, "img")
+    B, cin, H, W = img.shape
+    if H % patch or W % patch:
+        raise AssertionError("Image dimensions must be divisible by the patch size.")
+    D = w.shape[0]
+    n = (H // patch) * (W // patch)
+    nbytes = _L().m2b200_patch_embed_cols_bytes(B, cin, H, W, patch, precision)
+    cols = torch.empty(nbytes, dtype=torch.uint8, device=img.device)
+    y = torch.empty(B, n, D, dtype=torch.float32, device=img.device)
+    w2d = _f32c(w, "w").reshape(D, -1)
+    check(_L().m2b200_patch_embed_fwd(img.data_ptr(), w2d.data_ptr(), _ptr(wb), 0 if wb is None else wb.shape[1],
+                                      None if bias is None else _f32c(bias, "bias").data_ptr(), cols.data_ptr(), y.data_ptr(),
+                                      B, cin, H, W, patch, D, precision, _stream()), "patch_embed_fwd")
+    return y, cols
+
+
+def patch_embed_bwd(dy, cols, w, has_bias: bool, precision: int, grads=None):
+    dy = _f32c(dy, "dy")
+    D = dy.shape[-1]
+    M = dy.numel() // D
+    K = w[0].numel()
+    dw = _grad_dst(grads, 0, w)
+    db = _grad_dst(grads, 1, w.reshape(D, -1)[:, 0]) if has_bias else None
+    nbytes = _L().m2b200_patch_embed_bwd_workspace_bytes(M, D, precision)
+    ws, wsp = _ws(nbytes, dy)
+    check(_L().m2b200_patch_embed_bwd(dy.data_ptr(), cols.data_ptr(), dw.data_ptr(), _ptr(db), M, D, K, precision, wsp,
+                                      nbytes, _stream()), "patch_embed_bwd")
+    return dw, (db if db is not None else torch.empty(0, dtype=torch.float32, device=dy.device))
+
+
+_define("patch_embed_fwd", "(Tensor img, Tensor w, Tensor? wb, Tensor? bias, int patch, int precision) -> (Tensor, Tensor)",
+        patch_embed_fwd)
+_define("patch_embed_bwd", "(Tensor dy, Tensor cols, Tensor w, bool has_bias, int precision, Tensor?[]? grads=None) -> "
+        "(Tensor, Tensor)", patch_embed_bwd)
 _define("patch_gather", "(Tensor img, int patch) -> Tensor", patch_gather)
+
+
+def dropout_mask(rows: int, cols: int, ld: int, dropout_p: float, seed: int, site: int, device="cuda") -> torch.Tensor:
+    """Keep-mask (1/0) the kernels use for a dropout site (see include/m2b200.h); test helper."""
+    out = torch.empty(rows, cols, dtype=torch.float32, device=device)
+    check(_L().m2b200_dropout_mask(out.data_ptr(), rows, cols, ld, dropout_p, seed, site, _stream()), "dropout_mask")
+    return out
+
+
+def dropout_scale(p: float) -> float:
+    t = min(int(p * 65536.0 + 0.5), 65535) if p > 0 else 0
+    return 65536.0 / (65536.0 - t)
 
 
 # ------------------------------------------------------------------------------------------------ fusion
@@ -322,15 +385,16 @@ def heads_loss_fwd(toks: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs:
     return losses, logits, preds
 
 
-def heads_loss_bwd(toks, ws, bs, labels, pos_weight, head_weight, loss_kind: int, logits, grad_scale: float, grad_scale_dev=None):
+def heads_loss_bwd(toks, ws, bs, labels, pos_weight, head_weight, loss_kind: int, logits, grad_scale: float, grad_scale_dev=None,
+                   grads=None):
     toks = [_as_tokens(t) for t in toks]
     ws = [_f32c(w, "w") for w in ws]
     bs = [_f32c(b, "b") for b in bs]
     n, B, K = len(toks), toks[0].shape[0], ws[0].shape[0]
     labels = labels.to(torch.int64).contiguous() if loss_kind == 0 else labels.to(torch.float32).contiguous()
     dtoks = [torch.empty_like(t) for t in toks]
-    dws = [torch.zeros_like(w) for w in ws]
-    dbs = [torch.zeros_like(b) for b in bs]
+    dws = [_grad_dst(grads, i, w) for i, w in enumerate(ws)]
+    dbs = [_grad_dst(grads, n + i, b) for i, b in enumerate(bs)]
     tok, bstride, ntok, dim, w, b, hw = _heads_args(toks, ws, bs, head_weight)
     arr_p = (C.c_void_p * 3)
     dtok = arr_p(*[t.data_ptr() for t in dtoks] + [None] * (3 - n))
@@ -348,7 +412,8 @@ def heads_loss_bwd(toks, ws, bs, labels, pos_weight, head_weight, loss_kind: int
 _define("heads_loss_fwd", "(Tensor[] toks, Tensor[] ws, Tensor[] bs, Tensor labels, Tensor? pos_weight, float[] head_weight, "
         "int loss_kind) -> (Tensor, Tensor, Tensor)", heads_loss_fwd)
 _define("heads_loss_bwd", "(Tensor[] toks, Tensor[] ws, Tensor[] bs, Tensor labels, Tensor? pos_weight, float[] head_weight, "
-        "int loss_kind, Tensor logits, float grad_scale, Tensor? grad_scale_dev) -> (Tensor[], Tensor[], Tensor[])", heads_loss_bwd)
+        "int loss_kind, Tensor logits, float grad_scale, Tensor? grad_scale_dev, Tensor?[]? grads=None) -> "
+        "(Tensor[], Tensor[], Tensor[])", heads_loss_bwd)
 
 
 # ------------------------------------------------------------------------------------------------ optimiser / gemm

@@ -1,0 +1,121 @@
+"""CPU-side tests: C-ABI surface, drop-in module contracts, config plumbing.  No GPU, no compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from tests.golden_util import load
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "m2b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(m2b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from m2_mixer_b200 import _lib
+    lib = _lib.load()
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/m2b200.h but not exported by libm2b200.so"
+    assert set(_lib.PROTOTYPES) == set(names), "ctypes prototypes and the header disagree"
+    assert lib.m2b200_abi_version() == 1
+    assert lib.m2b200_status_string(0) == b"ok"
+    # workspace queries are pure host arithmetic
+    assert lib.m2b200_channel_mix_workspace_bytes(16384, 128, 3072, 1, 0) == 0          # fused forward: nothing
+    assert lib.m2b200_channel_mix_workspace_bytes(16384, 128, 3072, 1, 1) > 2 * 16384 * 3072 * 2
+    assert lib.m2b200_channel_mix_workspace_bytes(100, 128, 64, 0, 0) >= 100 * (128 + 64) * 4
+
+
+def test_ops_fail_loudly_without_cuda():
+    from m2_mixer_b200 import functional as F
+    x = torch.zeros(2, 4, 8)
+    w = torch.ones(8)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        F.layer_norm(x, w, w)
+
+
+@pytest.mark.parametrize("golden,preset", [("avmnist_S_b8", "avmnist_S"), ("avmnist_M_b4", "avmnist_M"),
+                                           ("avmnist_B_b16", "avmnist_B"), ("mimic_H_b16", "mimic_H"),
+                                           ("mmimdb_tiny_b6", "mmimdb_tiny")])
+def test_state_dict_layout_matches_reference(golden, preset):
+    """Key names AND shapes recorded from the reference's own modules (tests/golden/make_golden.py)."""
+    from m2_mixer_b200 import models, presets
+    cfg = presets.get(preset)
+    m = models.get_model(cfg["type"])(cfg, {})
+    z = load(golden)
+    ref = {k: tuple(int(t) for t in s.split(",")) for k, s in zip(z["meta.keys"].tolist(), z["meta.shapes"].tolist())}
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert ours == ref
+    assert all(v.dtype == torch.float32 for v in m.state_dict().values())
+
+
+def test_reference_ckpt_style_roundtrip(tmp_path):
+    from m2_mixer_b200 import models, presets
+    from oracle.seeding import seeded_state_dict
+    cfg = presets.get("avmnist_S")
+    m = models.AVMnistMixerMultiLoss(cfg, dict(presets.AVMNIST_OPTIM))
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 5)
+    path = tmp_path / "last.ckpt"
+    torch.save({"state_dict": sd, "epoch": 3}, path)          # Lightning checkpoints carry no hparams
+    m2 = models.AVMnistMixerMultiLoss.load_from_checkpoint(str(path), model_cfg=cfg, optimizer_cfg=dict(presets.AVMNIST_OPTIM))
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd[k])
+    assert m2.scheduler_patience == 2 and "scheduler_patience" not in m2.optimizer_cfg
+
+
+def test_constructor_contracts():
+    from m2_mixer_b200 import modules as M
+    blk = M.MLPMixer(in_channels=1, hidden_dim=32, patch_size=14, image_size=[28, 28], num_mixers=2, token_dim=16,
+                     channel_dim=256, dropout=0.1, block_type="MLPMixer", some_unknown_key=1)      # **kwargs swallowed
+    assert blk.num_patch == 4 and len(blk.mixer_blocks) == 2
+    with pytest.raises(AssertionError):
+        M.MLPMixer(in_channels=1, hidden_dim=32, patch_size=5, image_size=[28, 28], num_mixers=1, token_dim=4, channel_dim=8)
+    assert M.get_block_by_name(block_type="FusionMixer", hidden_dim=32, num_patches=8, num_mixers=1, token_dim=4,
+                               channel_dim=8, fusion_function="ConcatFusion").num_patch == 8
+    assert isinstance(M.get_fusion_by_name(fusion_function="SumFusion", useless_arg=3), M.SumFusion)
+    assert M.get_classifier_by_name(classifier="StandardClassifier", input_shape=[16, 49, 32],
+                                    num_classes=10).classifer.weight.shape == (10, 32)
+
+
+def test_fusion_shape_contracts():
+    """The pins of the reference's own tests (tests/modules/test_fusion.py:14-24, 38-47)."""
+    from m2_mixer_b200.modules import ConcatFusion, SumFusion
+    f = ConcatFusion(dim=1, useless_arg=None)
+    assert f.get_output_shape(20, 20, dim=1) == 40
+    assert f.get_output_shape(20, 20, dim=2) == 20
+    assert f.get_output_shape((10, 20, 30), (10, 20, 30)) == (10, 40, 30)
+    with pytest.raises(ValueError):
+        f.get_output_shape(torch.ones(10, 20, 30), torch.ones(10, 20, 30), dim=2)
+    s = SumFusion(useless_arg=None)
+    assert s.get_output_shape(20, 20, dim=1) == 20
+    assert s.get_output_shape((10, 20, 30), (10, 20, 30)) == (10, 20, 30)
+    with pytest.raises(ValueError):
+        s.get_output_shape(20, 30, dim=1)
+    with pytest.raises(ValueError):
+        s.get_output_shape(torch.ones(10, 20, 30), torch.ones(10, 20, 30), dim=2)
+
+
+def test_yaml_loader_coerces_and_overrides(tmp_path):
+    from m2_mixer_b200.config import deep_update, load_yaml
+    p = tmp_path / "c.yml"
+    p.write_text("train:\n  optimizer:\n    lr: 1e-2\n    betas: [0.9, 0.999]\n    eps: 1e-8\nmodel:\n  type: X\n  dropout: 0.5\n")
+    c = load_yaml(str(p))
+    assert isinstance(c.train.optimizer.lr, float) and c.train.optimizer.lr == 1e-2 and c.train.optimizer.eps == 1e-8
+    assert c.model.get("missing", 7) == 7 and c.model.type == "X"
+    deep_update(c, "model.modalities.image.hidden_dim", 64)
+    assert c.model.modalities.image.hidden_dim == 64
+
+
+def test_dropout_argument_validation():
+    from m2_mixer_b200 import modules as M
+    with pytest.raises(ValueError):
+        M.MixerBlock(32, 4, 8, 64, dropout=1.0)
+    blk = M.MixerBlock(32, 4, 8, 64, dropout=0.5)
+    assert blk.dropout_p == 0.5 and blk.token_mix[2].dropout_p == 0.5

@@ -1,0 +1,351 @@
+"""Parity of the CUDA path against (a) golden vectors recorded from the unmodified reference and (b) the CPU oracle
+restatement, through the public modules -> torch.library ops -> C ABI.  Needs a B200 (run with -m gpu).
+
+Tolerances (BASELINE.json north_star): fp32 mode <= 1e-4 relative on logits, losses and gradients;
+bf16 mode <= 2e-2 relative on logits.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from tests.golden_util import load, rebuild, rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+FP32_TOL = 1e-4
+BF16_LOGIT_TOL = 2e-2
+
+CASES = [("avmnist_S_b8", "avmnist_S"), ("avmnist_S_sum_b8", "avmnist_S"), ("avmnist_M_b4", "avmnist_M"),
+         ("avmnist_B_b16", "avmnist_B"), ("mimic_H_b16", "mimic_H"), ("mmimdb_tiny_b6", "mmimdb_tiny")]
+
+
+def build(preset, golden, precision):
+    from m2_mixer_b200 import models, presets
+    cfg = presets.get(preset)
+    cfg["dropout"] = 0.0                      # bit-parity with torch's Philox dropout stream is not defined
+    if "sum" in golden:
+        cfg["modalities"]["multimodal"]["fusion_function"] = "SumFusion"
+    m = models.get_model(cfg["type"])(cfg, {}).cuda().set_precision(precision)
+    z, sd, batch = rebuild(golden, torch.float32, "cuda", requires_grad=False)
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    return m, z, batch
+
+
+@pytest.mark.parametrize("golden,preset", CASES)
+def test_fp32_mode_matches_reference_golden(golden, preset):
+    m, z, batch = build(preset, golden, "fp32")
+    out = m.shared_step(batch, mode="train")
+    out["loss"].backward()
+    torch.cuda.synchronize()
+    for k in [k for k in z if k.startswith("out.")]:
+        assert rel_err(out[k[4:]], z[k]) < FP32_TOL, k
+    grads = dict(m.named_parameters())
+    for k in [k for k in z if k.startswith("gnorm.")]:
+        name, gn = k[6:], float(z[k])
+        g = grads[name].grad
+        if gn < 1e-9:     # exactly-zero gradient in exact arithmetic (see tests/test_oracle.py)
+            assert float(g.norm()) < 1e-5, k
+            continue
+        assert abs(float(g.norm()) - gn) < FP32_TOL * gn, k
+        assert rel_err(g.flatten()[:16], z["ghead." + name]) < 10 * FP32_TOL, k
+        if "grad." + name in z:
+            assert rel_err(g, z["grad." + name]) < FP32_TOL, k
+
+
+@pytest.mark.parametrize("golden,preset", CASES)
+def test_bf16_mode_logits_match_reference_golden(golden, preset):
+    m, z, batch = build(preset, golden, "bf16")
+    out = m.shared_step(batch, mode="train")
+    out["loss"].backward()
+    torch.cuda.synchronize()
+    for k in [k for k in z if k.startswith("out.") and "logits" in k]:
+        assert rel_err(out[k[4:]], z[k]) < BF16_LOGIT_TOL, k
+    for k in [k for k in z if k.startswith("out.loss")]:
+        assert rel_err(out[k[4:]], z[k]) < BF16_LOGIT_TOL, k
+    # gradients have no stated bf16 bar; they must still be close to the fp64 reference in aggregate
+    grads = dict(m.named_parameters())
+    num = den = 0.0
+    for k in [k for k in z if k.startswith("grad.")]:
+        g = grads[k[5:]].grad.double().cpu()
+        r = torch.as_tensor(z[k]).double()
+        num += float((g - r).pow(2).sum())
+        den += float(r.pow(2).sum())
+    if den > 0:
+        assert (num / den) ** 0.5 < 5e-2
+
+
+@pytest.mark.parametrize("name", ["block_odd", "block_b"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_mixer_block_golden(name, precision, tol):
+    from m2_mixer_b200 import modules as M
+    from oracle.seeding import seeded_state_dict
+    z = load(name)
+    B, N, D, T, C = (int(v) for v in z["meta.dims"])
+    if precision == "fp32" and D % 4:
+        pytest.skip("fp32 path needs D % 4 == 0")
+    if precision == "bf16" and D % 8:
+        pytest.skip("bf16 path needs D % 8 == 0")
+    blk = M.MixerBlock(D, N, T, C).cuda()
+    blk.precision = precision
+    sd = seeded_state_dict({k: tuple(v.shape) for k, v in blk.state_dict().items()}, 77)
+    blk.load_state_dict(sd)
+    x = torch.tensor(z["x"], dtype=torch.float32, device="cuda", requires_grad=True)
+    y = blk(x)
+    y.backward(torch.tensor(z["dy"], dtype=torch.float32, device="cuda"))
+    assert rel_err(y, z["y"]) < tol
+    assert rel_err(x.grad, z["dx"]) < tol * (1 if precision == "fp32" else 2)
+    for k, p in blk.named_parameters():
+        gn = float(z["gnorm." + k])
+        assert abs(float(p.grad.norm()) - gn) < (tol if precision == "fp32" else 5e-2) * gn + 1e-7, k
+
+
+def test_cuda_path_matches_cpu_oracle_on_fresh_seeds():
+    """Same seeded inputs through the oracle (CPU, fp64) and the CUDA path (fp32 mode), M2-Mixer-S at B=32."""
+    from m2_mixer_b200 import models, presets
+    from oracle import m2mixer_oracle as O
+    from oracle.seeding import seeded_state_dict, synthetic_batch
+    cfg = presets.get("avmnist_S")
+    cfg["dropout"] = 0.0
+    m = models.AVMnistMixerMultiLoss(cfg, {}).cuda().set_precision("fp32")
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd64 = {k: v.requires_grad_(True) for k, v in seeded_state_dict(shapes, 999, torch.float64).items()}
+    m.load_state_dict(seeded_state_dict(shapes, 999))
+    b64 = synthetic_batch("avmnist", 32, 999, torch.float64)
+    b32 = {k: v.cuda() for k, v in synthetic_batch("avmnist", 32, 999).items()}
+    ref = O.avmnist_shared_step(sd64, b64, fusion_loss_weight=0.5)
+    gref = O.grads_of(ref["loss"], sd64)
+    m.fusion_loss_weight = 0.5
+    out = m.shared_step(b32, mode="train")
+    out["loss"].backward()
+    for k in ("loss", "loss_image", "loss_audio", "loss_fusion", "logits", "image_logits", "audio_logits"):
+        assert rel_err(out[k], ref[k]) < FP32_TOL, k
+    assert torch.equal(out["preds"].cpu(), ref["preds"])
+    for k, p in m.named_parameters():
+        if float(gref[k].norm()) > 1e-9:
+            assert rel_err(p.grad, gref[k]) < FP32_TOL, k
+
+
+def test_eval_mode_and_frozen_branch():
+    from m2_mixer_b200 import models, presets
+    cfg = presets.get("avmnist_S")          # dropout 0.1: identity in eval mode, must run
+    m = models.AVMnistMixerMultiLoss(cfg, {}).cuda().eval()
+    from oracle.seeding import synthetic_batch
+    b = {k: v.cuda() for k, v in synthetic_batch("avmnist", 5, 3).items()}
+    out = m.validation_step(b)
+    assert out["logits"].shape == (5, 10) and out["preds"].dtype == torch.int64
+    m.modalities_freezed = True
+    assert rel_err(m.shared_step(b, mode="train")["loss"], out["loss_fusion"]) < 1e-6   # reference :292-293
+
+
+def test_ragged_and_empty_shapes():
+    from m2_mixer_b200 import functional as F
+    # one token row, rows not a multiple of the 128-row tile, C not a multiple of the 64-channel chunk
+    for M_, D, C in [(1, 64, 8), (129, 128, 72), (257, 32, 1)]:
+        u = torch.randn(M_, D, device="cuda")
+        w1, b1 = torch.randn(C, D, device="cuda") / D ** 0.5, torch.randn(C, device="cuda") * 0.1
+        w2, b2 = torch.randn(D, C, device="cuda") / C ** 0.5, torch.randn(D, device="cuda") * 0.1
+        g, be = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
+        ref = u + torch.nn.functional.gelu(torch.nn.functional.layer_norm(u, (D,), g, be) @ w1.t() + b1) @ w2.t() + b2
+        for prec, tol in (("fp32", 1e-5), ("bf16", 1e-2)):
+            y = F.channel_mix(u, g, be, w1, b1, w2, b2, prec)
+            assert rel_err(y, ref) < tol, (M_, D, C, prec)
+    with pytest.raises(Exception):
+        F.channel_mix(torch.zeros(0, 64, device="cuda"), g[:64], be[:64], w1[:, :64], b1, w2[:64], b2[:64], "bf16")
+
+
+def test_training_loss_curve_200_steps_tracks_oracle():
+    """200 Adam steps (lr 1e-2, the cfg value) on 4 cycling synthetic batches: CUDA fp32 / bf16 paths vs the oracle
+    restatement run on the same GPU in fp32 (the checker).  Curves must agree to well inside run-to-run noise."""
+    from m2_mixer_b200 import models, presets
+    from m2_mixer_b200.optim import FusedAdam
+    from oracle import m2mixer_oracle as O
+    from oracle.seeding import seeded_state_dict, synthetic_batch
+    cfg = presets.get("avmnist_S")
+    cfg["dropout"] = 0.0
+    batches = [{k: v.cuda() for k, v in synthetic_batch("avmnist", 64, 100 + i).items()} for i in range(4)]
+    curves = {}
+    for prec in ("fp32", "bf16"):
+        m = models.AVMnistMixerMultiLoss(cfg, {}).cuda().set_precision(prec)
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(seeded_state_dict(shapes, 7))
+        opt = FusedAdam(m.parameters(), lr=1e-2)
+        losses = []
+        for step in range(200):
+            opt.zero_grad()
+            loss = m.training_step(batches[step % 4])
+            loss.backward()
+            opt.step()
+            losses.append(loss.detach())
+        curves[prec] = torch.stack(losses).cpu()
+    sd = {k: v.cuda().requires_grad_(True) for k, v in seeded_state_dict(shapes, 7).items()}
+    ropt = torch.optim.Adam(list(sd.values()), lr=1e-2)
+    ref = []
+    for step in range(200):
+        ropt.zero_grad()
+        loss = O.avmnist_shared_step(sd, batches[step % 4])["loss"]
+        loss.backward()
+        ropt.step()
+        ref.append(loss.detach())
+    ref = torch.stack(ref).cpu()
+    assert float(ref[-1]) < 0.5 * float(ref[0])                       # it actually trains
+    assert float((curves["fp32"][:20] - ref[:20]).abs().max()) < 1e-3  # early steps: fp32 parity
+    for prec, tol in (("fp32", 0.05), ("bf16", 0.10)):                # whole curve: chaotic divergence is bounded
+        d = (curves[prec] - ref).abs() / ref.abs().clamp_min(0.05)
+        assert float(d.mean()) < tol, (prec, float(d.mean()))
+        assert float(curves[prec][-1]) < 0.5 * float(curves[prec][0])
+
+
+def test_kernel_selfcheck_suite():
+    """Every C-ABI op against fp64 torch references (tools/gpu_selfcheck.py), one subprocess per group."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_selfcheck.py")], capture_output=True, text=True,
+                       timeout=1500)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------------------------------------ dropout
+def _masks(ops, rows_h, cols_h, ld_h, rows_o, cols_o, p, seed, site_h, site_o):
+    s = ops.dropout_scale(p)
+    mh = ops.dropout_mask(rows_h, cols_h, ld_h, p, seed, site_h).double() * s
+    mo = ops.dropout_mask(rows_o, cols_o, cols_o, p, seed, site_o).double() * s
+    return mh, mo
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("M,D,C", [(300, 64, 200), (257, 128, 3078)])
+def test_channel_mix_dropout_matches_oracle_with_exported_mask(precision, tol, M, D, C):
+    """The fused kernels' dropout masks are exported (m2b200_dropout_mask) and fed to the fp64 restatement: forward and
+    every gradient must agree, which also proves the backward regenerates exactly the forward's mask."""
+    from m2_mixer_b200 import functional as F, ops
+    from oracle import m2mixer_oracle as O
+    torch.manual_seed(0)
+    p, seed = 0.3, 123456789
+    dev = "cuda"
+    u = torch.randn(M, D, device=dev)
+    prm = dict(ln_w=1 + 0.1 * torch.randn(D, device=dev), ln_b=0.1 * torch.randn(D, device=dev),
+               w1=torch.randn(C, D, device=dev) / D ** 0.5, b1=0.1 * torch.randn(C, device=dev),
+               w2=torch.randn(D, C, device=dev) / C ** 0.5, b2=0.1 * torch.randn(D, device=dev))
+    mh, mo = _masks(ops, M, C, (C + 7) // 8 * 8, M, D, p, seed, 2, 3)
+    keep = float((mh > 0).double().mean())
+    assert abs(keep - 0.7) < 4 * (0.21 / (M * C)) ** 0.5 + 1e-4
+    pd = {k: v.double().requires_grad_(True) for k, v in prm.items()}
+    ud = u.double().requires_grad_(True)
+    h = O.gelu_erf(O.layer_norm(ud, pd["ln_w"], pd["ln_b"]) @ pd["w1"].t() + pd["b1"]) * mh
+    yr = ud + (h @ pd["w2"].t() + pd["b2"]) * mo
+    pt = {k: v.clone().requires_grad_(True) for k, v in prm.items()}
+    ut = u.clone().requires_grad_(True)
+    y = F.channel_mix(ut, pt["ln_w"], pt["ln_b"], pt["w1"], pt["b1"], pt["w2"], pt["b2"], precision, dropout_p=p, seed=seed)
+    dy = torch.randn(M, D, device=dev)
+    yr.backward(dy.double())
+    y.backward(dy)
+    assert rel_err(y, yr) < tol
+    gtol = tol if precision == "fp32" else 3e-2
+    assert rel_err(ut.grad, ud.grad) < gtol
+    for k in prm:
+        assert rel_err(pt[k].grad, pd[k].grad) < gtol, k
+
+
+@pytest.mark.parametrize("B,N,D,T", [(9, 4, 128, 32), (3, 40, 48, 16)])
+def test_token_mix_dropout_matches_oracle_with_exported_mask(B, N, D, T):
+    from m2_mixer_b200 import functional as F, ops
+    from oracle import m2mixer_oracle as O
+    torch.manual_seed(1)
+    p, seed = 0.5, 42
+    dev = "cuda"
+    x = torch.randn(B, N, D, device=dev)
+    prm = dict(ln_w=1 + 0.1 * torch.randn(D, device=dev), ln_b=0.1 * torch.randn(D, device=dev),
+               w1=torch.randn(T, N, device=dev) / N ** 0.5, b1=0.1 * torch.randn(T, device=dev),
+               w2=torch.randn(N, T, device=dev) / T ** 0.5, b2=0.1 * torch.randn(N, device=dev))
+    mh, mo = _masks(ops, B * T, D, D, B * N, D, p, seed, 0, 1)
+    mh, mo = mh.view(B, T, D), mo.view(B, N, D)
+    pd = {k: v.double().requires_grad_(True) for k, v in prm.items()}
+    xd = x.double().requires_grad_(True)
+    h = O.gelu_erf(torch.einsum("tn,bnd->btd", pd["w1"], O.layer_norm(xd, pd["ln_w"], pd["ln_b"])) + pd["b1"][None, :, None]) * mh
+    ur = xd + (torch.einsum("nt,btd->bnd", pd["w2"], h) + pd["b2"][None, :, None]) * mo
+    pt = {k: v.clone().requires_grad_(True) for k, v in prm.items()}
+    xt = x.clone().requires_grad_(True)
+    u = F.token_mix(xt, pt["ln_w"], pt["ln_b"], pt["w1"], pt["b1"], pt["w2"], pt["b2"], "fp32", dropout_p=p, seed=seed)
+    du = torch.randn(B, N, D, device=dev)
+    ur.backward(du.double())
+    u.backward(du)
+    assert rel_err(u, ur) < 1e-5
+    assert rel_err(xt.grad, xd.grad) < 1e-4
+    for k in prm:
+        assert rel_err(pt[k].grad, pd[k].grad) < 1e-4, k
+
+
+def test_dropout_statistics_and_modes():
+    from m2_mixer_b200 import modules as M, ops
+    for p in (0.1, 0.3, 0.5):
+        m = ops.dropout_mask(2048, 512, 512, p, 7, 2)
+        n = m.numel()
+        assert abs(float(m.mean()) - (1 - p)) < 5 * (p * (1 - p) / n) ** 0.5 + 2e-5, p
+        assert abs(ops.dropout_scale(p) * (1 - round(p * 65536) / 65536) - 1) < 1e-6
+        # neighbouring elements and different seeds / sites are uncorrelated
+        a, b = m[:, 0::2].flatten(), m[:, 1::2].flatten()
+        assert abs(float(((a - a.mean()) * (b - b.mean())).mean())) < 5e-3
+        m2 = ops.dropout_mask(2048, 512, 512, p, 8, 2)
+        assert abs(float(((m - m.mean()) * (m2 - m2.mean())).mean())) < 5e-3
+    blk = M.MixerBlock(64, 8, 16, 96, dropout=0.5).cuda()
+    x = torch.randn(32, 8, 64, device="cuda")
+    blk.eval()
+    assert torch.equal(blk(x), blk(x))                       # identity in eval mode
+    blk.train()
+    y1, y2 = blk(x), blk(x)
+    assert not torch.equal(y1, y2)                           # fresh mask per call
+    torch.manual_seed(5); import m2_mixer_b200.functional as F; F._DROP_CALLS = 0; a = blk(x)
+    torch.manual_seed(5); F._DROP_CALLS = 0; b = blk(x)
+    assert torch.equal(a, b)                                 # reproducible under a seed
+    # unbiased: mean over many masks approaches the no-dropout output of the branch
+    blk.eval(); ref = blk(x); blk.train()
+    acc = torch.zeros_like(ref)
+    for _ in range(200):
+        acc += blk(x)
+    assert rel_err(acc / 200, ref) < 0.15
+
+
+def test_training_with_reference_dropout_learns():
+    """M2-Mixer-S with the cfg's dropout (0.1) and MIMIC-H (0.3, incl. the MLP encoder's dropout): loss goes down."""
+    from m2_mixer_b200 import models, presets
+    from m2_mixer_b200.optim import FusedAdam
+    from oracle.seeding import synthetic_batch
+    for name, kind, lr in (("avmnist_S", "avmnist", 1e-2), ("mimic_H", "mimic", 1e-2)):
+        cfg = presets.get(name)
+        torch.manual_seed(0)
+        m = models.get_model(cfg["type"])(cfg, {}).cuda().train()
+        opt = FusedAdam(m.parameters(), lr=lr)
+        bt = synthetic_batch(kind, 64, 3)
+        bt = {k: v.cuda() for k, v in bt.items()} if isinstance(bt, dict) else tuple(v.cuda() for v in bt)
+        losses = []
+        for _ in range(150):
+            opt.zero_grad()
+            loss = m.training_step(bt)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        assert sum(losses[-10:]) / 10 < 0.5 * sum(losses[:3]) / 3, (name, losses[:3], losses[-3:])
+
+
+def test_direct_gradient_accumulation_equals_autograd_path():
+    """FusedAdam registers flat-buffer destinations; the backward kernels then accumulate in place.  Same grads."""
+    from m2_mixer_b200 import models, presets
+    from m2_mixer_b200.optim import FusedAdam
+    from oracle.seeding import seeded_state_dict, synthetic_batch
+    cfg = presets.get("avmnist_S")
+    cfg["dropout"] = 0.0
+    bt = {k: v.cuda() for k, v in synthetic_batch("avmnist", 16, 1).items()}
+    grads = []
+    for use_opt in (False, True):
+        m = models.AVMnistMixerMultiLoss(cfg, {}).cuda().set_precision("fp32").train()
+        m.load_state_dict(seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 3))
+        if use_opt:
+            opt = FusedAdam(m.parameters(), lr=1e-2)
+            opt.zero_grad()
+        m.training_step(bt).backward()
+        grads.append({k: p.grad.clone() for k, p in m.named_parameters()})
+    for k in grads[0]:
+        assert rel_err(grads[1][k], grads[0][k]) < 1e-5 or float(grads[0][k].norm()) < 1e-6, k
