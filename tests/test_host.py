@@ -33,6 +33,35 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.m2b200_channel_mix_workspace_bytes(100, 128, 64, 0, 0) >= 100 * (128 + 64) * 4
 
 
+def test_ctypes_prototypes_match_header_signatures():
+    """Argument count and kind (pointer / int / int64 / float / size_t / uint64) of every ctypes prototype against the
+    parameter list parsed from include/m2b200.h - a mismatch here is a silent ABI break on the GPU box."""
+    import ctypes as C
+    from m2_mixer_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "m2b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    kinds = {C.c_void_p: "ptr", C.c_char_p: "ptr", C.c_int: "int", C.c_int64: "i64", C.c_float: "f32", C.c_size_t: "size",
+             C.c_uint64: "u64", C.c_ulonglong: "u64"}
+
+    def kind_of_decl(d):
+        d = d.strip()
+        if "*" in d:
+            return "ptr"
+        t = d.rsplit(" ", 1)[0].replace("const", "").strip()
+        return {"int": "int", "int64_t": "i64", "float": "f32", "size_t": "size", "uint64_t": "u64"}[t]
+
+    for name, (_res, args) in _lib.PROTOTYPES.items():
+        m = re.search(r"\b%s\s*\(([^)]*)\)" % name, src)
+        assert m, name
+        decl = m.group(1).strip()
+        params = [] if decl in ("", "void") else [x for x in decl.split(",")]
+        assert len(params) == len(args), f"{name}: header has {len(params)} parameters, ctypes prototype {len(args)}"
+        for i, (d, a) in enumerate(zip(params, args)):
+            k = kinds.get(a, "ptr")     # POINTER(...) types are pointers
+            same64 = {"size", "u64"}     # c_size_t and c_uint64 are one ctypes type on LP64
+            assert kind_of_decl(d) == k or {kind_of_decl(d), k} <= same64, f"{name} arg {i}: header `{d.strip()}` vs ctypes {a}"
+
+
 def test_ops_fail_loudly_without_cuda():
     from m2_mixer_b200 import functional as F
     x = torch.zeros(2, 4, 8)
