@@ -17,7 +17,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxK = 64;
-constexpr int kMaxPer = 32;   // hidden dim <= 1024
+constexpr int kMaxPerCap = 32;   // hidden dim <= 1024
 
 struct HeadsDev {
   const float* tok[3]; long long tok_bstride[3]; int ntok[3]; int dim[3];
@@ -27,6 +27,7 @@ struct HeadsDev {
   float head_weight[3];
 };
 
+template <int kMaxPer>
 __device__ __forceinline__ void pool_tokens(const float* t, int ntok, int dim, int lane, float (&pooled)[kMaxPer]) {
 #pragma unroll
   for (int i = 0; i < kMaxPer; ++i) pooled[i] = 0.f;
@@ -45,6 +46,7 @@ __device__ __forceinline__ void pool_tokens(const float* t, int ntok, int dim, i
 
 __device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
 
+template <int kMaxPer>
 __global__ void __launch_bounds__(kThreads) heads_fwd_kernel(const HeadsDev a, float* __restrict__ logits,
                                                              float* __restrict__ losses, long long* __restrict__ preds) {
   __shared__ float s_logit[kWarps][kMaxK];
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(kThreads) heads_fwd_kernel(const HeadsDev a, f
   for (int b = blockIdx.x * kWarps + warp; b < a.B; b += gridDim.x * kWarps) {
     for (int h = 0; h < a.nheads; ++h) {
       float pooled[kMaxPer];
-      pool_tokens(a.tok[h] + b * a.tok_bstride[h], a.ntok[h], a.dim[h], lane, pooled);
+      pool_tokens<kMaxPer>(a.tok[h] + b * a.tok_bstride[h], a.ntok[h], a.dim[h], lane, pooled);
       for (int k = 0; k < a.K; ++k) {
         const float* wr = a.w[h] + static_cast<long long>(k) * a.dim[h];
         float acc = 0.f;
@@ -126,6 +128,7 @@ struct HeadsBwdDev {
   float grad_scale; const float* grad_scale_dev;
 };
 
+template <int kMaxPer>
 __global__ void __launch_bounds__(kThreads) heads_bwd_kernel(const HeadsDev a, const HeadsBwdDev g,
                                                              const float* __restrict__ logits) {
   extern __shared__ float sm[];   // per-head dW partial [K][dim] and db partial [K], laid out back to back
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) heads_bwd_kernel(const HeadsDev a, c
     for (int h = 0; h < a.nheads; ++h) {
       const int dim = a.dim[h];
       float pooled[kMaxPer];
-      pool_tokens(a.tok[h] + b * a.tok_bstride[h], a.ntok[h], dim, lane, pooled);
+      pool_tokens<kMaxPer>(a.tok[h] + b * a.tok_bstride[h], a.ntok[h], dim, lane, pooled);
       const float* lg = logits + (static_cast<long long>(h) * a.B + b) * a.K;
       const float hw = a.head_weight[h] * g.grad_scale * (g.grad_scale_dev ? g.grad_scale_dev[0] : 1.f);
       if (a.loss_kind == 0) {
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(kThreads) heads_bwd_kernel(const HeadsDev a, c
 int fill_dev(const HeadsArgs& a, HeadsDev* d) {
   if (a.nheads < 1 || a.nheads > 3 || a.B <= 0 || a.K <= 0 || a.K > kMaxK || !a.labels) return M2_ERR_ARG;
   for (int h = 0; h < a.nheads; ++h) {
-    if (!a.tok[h] || !a.w[h] || !a.b[h] || a.ntok[h] <= 0 || a.dim[h] <= 0 || a.dim[h] > 32 * kMaxPer) return M2_ERR_ARG;
+    if (!a.tok[h] || !a.w[h] || !a.b[h] || a.ntok[h] <= 0 || a.dim[h] <= 0 || a.dim[h] > 32 * kMaxPerCap) return M2_ERR_ARG;
     d->tok[h] = a.tok[h]; d->tok_bstride[h] = a.tok_bstride[h]; d->ntok[h] = a.ntok[h]; d->dim[h] = a.dim[h];
     d->w[h] = a.w[h]; d->b[h] = a.b[h]; d->head_weight[h] = a.head_weight[h];
   }
@@ -229,7 +232,12 @@ int heads_loss_fwd(const HeadsArgs& a, float* logits, float* losses, long long* 
   if (cudaMemsetAsync(losses, 0, 4 * sizeof(float), s) != cudaSuccess) return M2_ERR_LAUNCH;
   int grid = ceil_div(a.B, kWarps);
   if (grid > 148 * 4) grid = 148 * 4;
-  heads_fwd_kernel<<<grid, kThreads, 0, s>>>(d, logits, losses, preds);
+  int per = 1;
+  for (int h = 0; h < a.nheads; ++h) per = per > ceil_div(a.dim[h], 32) ? per : ceil_div(a.dim[h], 32);
+  if (per <= 2) heads_fwd_kernel<2><<<grid, kThreads, 0, s>>>(d, logits, losses, preds);
+  else if (per <= 4) heads_fwd_kernel<4><<<grid, kThreads, 0, s>>>(d, logits, losses, preds);
+  else if (per <= 8) heads_fwd_kernel<8><<<grid, kThreads, 0, s>>>(d, logits, losses, preds);
+  else heads_fwd_kernel<32><<<grid, kThreads, 0, s>>>(d, logits, losses, preds);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }
@@ -250,13 +258,20 @@ int heads_loss_bwd(const HeadsArgs& a, const float* logits, float grad_scale, co
   smem *= sizeof(float);
   g.grad_scale = grad_scale; g.grad_scale_dev = grad_scale_dev;
   if (smem > 200 * 1024) return M2_ERR_ARG;
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
-    return M2_ERR_LAUNCH;
+  int per = 1;
+  for (int h = 0; h < a.nheads; ++h) per = per > ceil_div(a.dim[h], 32) ? per : ceil_div(a.dim[h], 32);
   int grid = ceil_div(a.B, kWarps);
   if (grid > 148) grid = 148;
   LaunchScope scope("heads_loss_bwd", s);
-  heads_bwd_kernel<<<grid, kThreads, smem, s>>>(d, g, logits);
+#define M2_HB(P_)                                                                                                      \
+  {                                                                                                                    \
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(heads_bwd_kernel<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                                 static_cast<int>(smem)) != cudaSuccess)                               \
+      return M2_ERR_LAUNCH;                                                                                            \
+    heads_bwd_kernel<P_><<<grid, kThreads, smem, s>>>(d, g, logits);                                                   \
+  }
+  if (per <= 2) M2_HB(2) else if (per <= 4) M2_HB(4) else if (per <= 8) M2_HB(8) else M2_HB(32)
+#undef M2_HB
   M2_LAUNCH_CHECK();
   return M2_OK;
 }

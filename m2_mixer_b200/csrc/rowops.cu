@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 // dy = grad wrt LN output (row (b,n) at dy + b*dy_bstride + n*D), x = LN input.
 // dx[row] = (dres ? dres[row] : 0) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * w
 // dw += sum_rows dy*xhat, db += sum_rows dy   (per-CTA partials in smem, then one atomicAdd per column per CTA)
+template <int kMaxPer>   // columns per lane: D <= 32 * kMaxPer
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, long long dy_bstride, int N,
                                                      const float* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ dres, float* __restrict__ dx,
@@ -65,35 +66,49 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   // per-lane register partials for the columns this lane owns (c = lane + 32*i), flushed to smem at the end
-  constexpr int kMaxPer = 32;   // D <= 1024
   float pdw[kMaxPer], pdb[kMaxPer];
 #pragma unroll
   for (int i = 0; i < kMaxPer; ++i) { pdw[i] = 0.f; pdb[i] = 0.f; }
   for (int row = warp; row < rows; row += nwarps) {
     const float* xr = x + static_cast<long long>(row) * D;
     const float* gr = dy + static_cast<long long>(row / N) * dy_bstride + static_cast<long long>(row % N) * D;
+    float xv[kMaxPer], gv[kMaxPer];   // the row stays in registers: x and dy are read exactly once
     float s = 0.f;
-    for (int c = lane; c < D; c += 32) s += xr[c];
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+      const int c = lane + 32 * i;
+      xv[i] = c < D ? xr[c] : 0.f;
+      gv[i] = c < D ? gr[c] : 0.f;
+      s += xv[i];
+    }
     const float mean = warp_sum(s) / D;
     float ss = 0.f;
-    for (int c = lane; c < D; c += 32) { const float d = xr[c] - mean; ss += d * d; }
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+      const float d = (lane + 32 * i < D) ? xv[i] - mean : 0.f;
+      ss += d * d;
+    }
     const float rstd = rsqrtf(warp_sum(ss) / D + kLnEps);
     float sg = 0.f, sgx = 0.f;
-    for (int c = lane; c < D; c += 32) {
-      const float xh = (xr[c] - mean) * rstd, g = gr[c] * w[c];
-      sg += g; sgx += g * xh;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+      const int c = lane + 32 * i;
+      if (c < D) {
+        xv[i] = (xv[i] - mean) * rstd;            // xhat
+        const float g = gv[i] * w[c];
+        sg += g; sgx += g * xv[i];
+      }
     }
     sg = warp_sum(sg) / D; sgx = warp_sum(sgx) / D;
 #pragma unroll
     for (int i = 0; i < kMaxPer; ++i) {
       const int c = lane + 32 * i;
       if (c < D) {
-        const float xh = (xr[c] - mean) * rstd, d = gr[c];
-        float v = rstd * (d * w[c] - sg - xh * sgx);
+        float v = rstd * (gv[i] * w[c] - sg - xv[i] * sgx);
         if (dres) v += dres[static_cast<long long>(row) * D + c];
         dx[static_cast<long long>(row) * D + c] = v;
-        pdw[i] += d * xh;
-        pdb[i] += d;
+        pdw[i] += gv[i] * xv[i];
+        pdb[i] += gv[i];
       }
     }
   }
@@ -340,8 +355,13 @@ int ln_bwd(const float* dy, long long dy_bstride, int N, const float* x, const f
   LaunchScope scope("ln_bwd", s);
   if (rows <= 0 || D <= 0 || D > 1024 || N <= 0) return M2_ERR_ARG;
   int grid = grid_for(static_cast<long long>(rows) * 32, 256);
-  if (grid > kNumSms) grid = kNumSms;   // one CTA per SM: 2*D global atomics per CTA, >= a dozen rows per warp
-  ln_bwd_kernel<<<grid, 256, 2 * D * sizeof(float), s>>>(dy, dy_bstride, N, x, w, dres, dx, dw, db, rows, D);
+  if (grid > kNumSms * 4) grid = kNumSms * 4;
+  const size_t sm = 2 * D * sizeof(float);
+  const int per = ceil_div(D, 32);
+#define M2_LNB(P_) ln_bwd_kernel<P_><<<grid, 256, sm, s>>>(dy, dy_bstride, N, x, w, dres, dx, dw, db, rows, D)
+  if (per <= 1) M2_LNB(1); else if (per <= 2) M2_LNB(2); else if (per <= 4) M2_LNB(4); else if (per <= 8) M2_LNB(8);
+  else if (per <= 16) M2_LNB(16); else M2_LNB(32);
+#undef M2_LNB
   M2_LAUNCH_CHECK();
   return M2_OK;
 }
