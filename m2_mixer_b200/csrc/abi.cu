@@ -44,7 +44,7 @@ GemmArgs gemm_args(const void* A, int a_mn, long long lda, const void* B, int b_
 // split-K factor for a token-axis (K = M rows) weight-gradient GEMM so that ~one wave of CTAs is launched
 int wgrad_splitk(int m_out, int n_out, int k) {
   const int tiles = ceil_div(m_out, 128) * ceil_div(n_out, 128);
-  int sk = ceil_div(148, tiles);
+  int sk = (148 * 2) / tiles;   // two resident CTAs per SM, never a partial extra wave
   const int k_tiles = ceil_div(k, 64);
   if (sk > k_tiles) sk = k_tiles;
   return sk < 1 ? 1 : sk;

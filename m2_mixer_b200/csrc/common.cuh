@@ -71,6 +71,44 @@ __device__ __forceinline__ float gelu_fast_grad(float x, float& dgelu) {
   return fmaf(hx, t, hx);
 }
 
+// ---- packed fp32x2 GELU (tanh form, see common.cuh) : half the issue slots of the scalar version
+__device__ __forceinline__ float tanh_ap(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  float2 x2 = __fmul2_rn(x, x);
+  x2.x = fminf(x2.x, 64.f); x2.y = fminf(x2.y, 64.f);       // |x| > 8: inner polynomial frozen, tanh saturates
+  float2 p = __ffma2_rn(x2, make_float2(kGc, kGc), make_float2(kGb, kGb));
+  p = __ffma2_rn(x2, p, make_float2(kGa, kGa));
+  const float2 u = __fmul2_rn(x, p);
+  const float2 t = make_float2(tanh_ap(u.x), tanh_ap(u.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
+}
+// returns GELU(x); dg = GELU'(x)
+__device__ __forceinline__ float2 gelu2_grad(float2 x, float2& dg) {
+  float2 x2 = __fmul2_rn(x, x);
+  const bool sx = x2.x > 64.f, sy = x2.y > 64.f;
+  x2.x = fminf(x2.x, 64.f); x2.y = fminf(x2.y, 64.f);
+  float2 p = __ffma2_rn(x2, make_float2(kGc, kGc), make_float2(kGb, kGb));
+  p = __ffma2_rn(x2, p, make_float2(kGa, kGa));
+  float2 du = __ffma2_rn(x2, make_float2(5.f * kGc, 5.f * kGc), make_float2(3.f * kGb, 3.f * kGb));
+  du = __ffma2_rn(x2, du, make_float2(kGa, kGa));
+  const float2 u = __fmul2_rn(x, p);
+  const float2 t = make_float2(tanh_ap(u.x), tanh_ap(u.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  // 0.5 (1 + t) + 0.5 x (1 - t^2) u'
+  const float2 omt2 = __ffma2_rn(make_float2(-t.x, -t.y), t, make_float2(1.f, 1.f));
+  const float2 a = __fmul2_rn(hx, omt2);
+  const float2 half1 = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  dg = __ffma2_rn(a, du, half1);
+  if (sx) dg.x = half1.x;    // saturated region: derivative of the frozen polynomial form
+  if (sy) dg.y = half1.y;
+  return __ffma2_rn(hx, t, hx);
+}
+
 // ------------------------------------------------------------------------------------------ dropout
 // Counter-based mask shared by every kernel (forward and the recomputing backward evaluate the same function):
 // one 32-bit hash per PAIR of consecutive elements, 16 random bits per element, keep iff bits >= thresh

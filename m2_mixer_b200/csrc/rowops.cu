@@ -134,14 +134,23 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ s
 #pragma unroll
   for (int i = 0; i < kV; ++i) acc[i] = 0.f;
   if (c0 < ld) {   // whole vectors lie inside the padded row (ld % kV == 0)
-    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + static_cast<long long>(r) * ld + c0);
-      if constexpr (sizeof(T) == 2) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    const int step = gridDim.y * 8;
+    for (int r = blockIdx.y * 8 + ty; r < rows; r += 4 * step) {
+      uint4 v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
-      } else {
-        acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y); acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
+      for (int k = 0; k < 4; ++k)   // four independent 16-byte loads in flight per thread
+        v[k] = (r + k * step < rows) ? *reinterpret_cast<const uint4*>(src + static_cast<long long>(r + k * step) * ld + c0)
+                                     : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (sizeof(T) == 2) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[k]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+        } else {
+          acc[0] += __uint_as_float(v[k].x); acc[1] += __uint_as_float(v[k].y);
+          acc[2] += __uint_as_float(v[k].z); acc[3] += __uint_as_float(v[k].w);
+        }
       }
     }
   }
@@ -355,7 +364,7 @@ int ln_bwd(const float* dy, long long dy_bstride, int N, const float* x, const f
   LaunchScope scope("ln_bwd", s);
   if (rows <= 0 || D <= 0 || D > 1024 || N <= 0) return M2_ERR_ARG;
   int grid = grid_for(static_cast<long long>(rows) * 32, 256);
-  if (grid > kNumSms * 4) grid = kNumSms * 4;
+  if (grid > kNumSms * 8) grid = kNumSms * 8;   // 64 resident warps per SM: the kernel is load-latency bound
   const size_t sm = 2 * D * sizeof(float);
   const int per = ceil_div(D, 32);
 #define M2_LNB(P_) ln_bwd_kernel<P_><<<grid, 256, sm, s>>>(dy, dy_bstride, N, x, w, dres, dx, dw, db, rows, D)

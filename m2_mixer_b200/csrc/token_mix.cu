@@ -240,6 +240,20 @@ __device__ __forceinline__ void small_ln(const float (&x)[NMAX], float (&xn)[NMA
   __syncthreads();   // red is reused by the next slab
 }
 
+// Weights are staged in shared memory padded to NMAX columns per row (zeros beyond N) so that the inner loops are
+// fully unrolled without predicates; two hidden units (t, t+1) are processed together with packed fp32x2 math.
+template <int NMAX>
+__device__ __forceinline__ void stage_weights(const float* w1, const float* b1, const float* w2, int N, int T, int Tp,
+                                              float* sW1, float* sW2t, float* sB1) {
+  for (int i = threadIdx.x; i < Tp * NMAX; i += kThreads) {
+    const int t = i / NMAX, n = i - t * NMAX;
+    const bool in = t < T && n < N;
+    sW1[i] = in ? w1[t * N + n] : 0.f;
+    sW2t[i] = in ? w2[n * T + t] : 0.f;
+  }
+  for (int i = threadIdx.x; i < Tp; i += kThreads) sB1[i] = i < T ? b1[i] : 0.f;
+}
+
 template <int NMAX>
 __global__ void __launch_bounds__(kThreads) token_mix_small_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
@@ -247,18 +261,14 @@ __global__ void __launch_bounds__(kThreads) token_mix_small_fwd_kernel(
     const float* __restrict__ b2, float* __restrict__ u, int B, int N, int D, int T, int exact_gelu, const Drop dh,
     const Drop dout) {
   extern __shared__ float sm[];
-  float* sW1 = sm;                 // [T][N]
-  float* sW2t = sW1 + T * N;       // [T][N]  (transposed: both inner loops run over n with t fixed)
-  float* sB1 = sW2t + T * N;       // [T]
-  float* sB2 = sB1 + T;            // [N]
-  float* red = sB2 + N;            // [8][NMAX]
-  for (int i = threadIdx.x; i < T * N; i += kThreads) {
-    sW1[i] = w1[i];
-    const int t = i / N, n = i - t * N;
-    sW2t[i] = w2[n * T + t];
-  }
-  for (int i = threadIdx.x; i < T; i += kThreads) sB1[i] = b1[i];
-  for (int i = threadIdx.x; i < N; i += kThreads) sB2[i] = b2[i];
+  const int Tp = (T + 1) & ~1;
+  float* sW1 = sm;                    // [Tp][NMAX]
+  float* sW2t = sW1 + Tp * NMAX;      // [Tp][NMAX]  (transposed: both inner loops run over n with t fixed)
+  float* sB1 = sW2t + Tp * NMAX;      // [Tp]
+  float* sB2 = sB1 + Tp;              // [NMAX]
+  float* red = sB2 + NMAX;            // [8][NMAX]
+  stage_weights<NMAX>(w1, b1, w2, N, T, Tp, sW1, sW2t, sB1);
+  for (int i = threadIdx.x; i < NMAX; i += kThreads) sB2[i] = i < N ? b2[i] : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int spb = kThreads / D;                       // samples per CTA slab
   const int s_in = threadIdx.x / D, d = threadIdx.x - s_in * D;
@@ -269,32 +279,38 @@ __global__ void __launch_bounds__(kThreads) token_mix_small_fwd_kernel(
     const int b = b0 + s_in;
     const bool ok = b < B;
     const float* xb = x + (static_cast<long long>(ok ? b : 0) * N) * D + d;
-    float xv[NMAX], xn[NMAX], acc[NMAX];
+    float xv[NMAX], xn[NMAX];
+    float2 acc[NMAX];                                 // (.x, .y) = partial sums of the even / odd hidden units
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) {
       xv[n] = (n < N && ok) ? xb[static_cast<long long>(n) * D] : 0.f;
-      acc[n] = 0.f;
+      xn[n] = 0.f;
+      acc[n] = make_float2(0.f, 0.f);
     }
     small_ln<NMAX>(xv, xn, N, D, gam, bet, red, warp, lane, first_warp, wps);
-    for (int t = 0; t < T; ++t) {
-      float h = sB1[t];
-      const float* w1r = sW1 + t * N;
+#pragma unroll 2
+    for (int t = 0; t < Tp; t += 2) {
+      const float* w1a = sW1 + t * NMAX;
+      float2 h = make_float2(sB1[t], sB1[t + 1]);
 #pragma unroll
-      for (int n = 0; n < NMAX; ++n)
-        if (n < N) h = fmaf(w1r[n], xn[n], h);
-      float g = exact_gelu ? gelu_erf(h) : gelu_fast(h);
-      if (dh.thresh) g = drop_apply(dh, g, (static_cast<unsigned long long>(b) * T + t) * D + d);
-      const float* w2r = sW2t + t * N;
+      for (int n = 0; n < NMAX; ++n) h = __ffma2_rn(make_float2(w1a[n], w1a[NMAX + n]), make_float2(xn[n], xn[n]), h);
+      float2 g;
+      if (exact_gelu) g = make_float2(gelu_erf(h.x), gelu_erf(h.y));
+      else g = gelu2(h);
+      if (dh.thresh) {
+        g.x = drop_apply(dh, g.x, (static_cast<unsigned long long>(b) * T + t) * D + d);
+        g.y = drop_apply(dh, g.y, (static_cast<unsigned long long>(b) * T + t + 1) * D + d);
+      }
+      const float* w2a = sW2t + t * NMAX;
 #pragma unroll
-      for (int n = 0; n < NMAX; ++n)
-        if (n < N) acc[n] = fmaf(w2r[n], g, acc[n]);
+      for (int n = 0; n < NMAX; ++n) acc[n] = __ffma2_rn(make_float2(w2a[n], w2a[NMAX + n]), g, acc[n]);
     }
     if (ok) {
 #pragma unroll
       for (int n = 0; n < NMAX; ++n)
         if (n < N) {
           const long long o = (static_cast<long long>(b) * N + n) * D + d;
-          float v = acc[n] + sB2[n];
+          float v = acc[n].x + acc[n].y + sB2[n];
           if (dout.thresh) v = drop_apply(dout, v, o);
           u[o] = xv[n] + v;
         }
@@ -312,22 +328,18 @@ __global__ void __launch_bounds__(kThreads) token_mix_small_bwd_kernel(
     float* __restrict__ dw2, float* __restrict__ db2, int B, int N, int D, int T, int exact_gelu, const Drop dh,
     const Drop dout) {
   extern __shared__ float sm[];
-  float* sW1 = sm;                        // [T][N]
-  float* sW2t = sW1 + T * N;              // [T][N]
-  float* sB1 = sW2t + T * N;              // [T]
-  float* red = sB1 + T;                   // [8][NMAX]
+  const int Tp = (T + 1) & ~1;
+  float* sW1 = sm;                        // [Tp][NMAX]
+  float* sW2t = sW1 + Tp * NMAX;          // [Tp][NMAX]
+  float* sB1 = sW2t + Tp * NMAX;          // [Tp]
+  float* red = sB1 + Tp;                  // [8][NMAX]
   float* tile = red + 8 * NMAX;
   tile += (4 - ((tile - sm) & 3)) & 3;    // 16-byte align the float4 tiles
-  float* sDH = tile;                      // [T][kSmallLd]
-  float* sG = sDH + T * kSmallLd;         // [T][kSmallLd]
-  float* sXn = sG + T * kSmallLd;         // [N][kSmallLd]
+  float* sDH = tile;                      // [Tp][kSmallLd]
+  float* sG = sDH + Tp * kSmallLd;        // [Tp][kSmallLd]
+  float* sXn = sG + Tp * kSmallLd;        // [N][kSmallLd]
   float* sDU = sXn + N * kSmallLd;        // [N][kSmallLd]
-  for (int i = threadIdx.x; i < T * N; i += kThreads) {
-    sW1[i] = w1[i];
-    const int t = i / N, n = i - t * N;
-    sW2t[i] = w2[n * T + t];
-  }
-  for (int i = threadIdx.x; i < T; i += kThreads) sB1[i] = b1[i];
+  stage_weights<NMAX>(w1, b1, w2, N, T, Tp, sW1, sW2t, sB1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int spb = kThreads / D;
   const int s_in = threadIdx.x / D, d = threadIdx.x - s_in * D;
@@ -340,7 +352,8 @@ __global__ void __launch_bounds__(kThreads) token_mix_small_bwd_kernel(
     const int b = b0 + s_in;
     const bool ok = b < B;
     const long long base = (static_cast<long long>(ok ? b : 0) * N) * D + d;
-    float xv[NMAX], xn[NMAX], dub[NMAX], dx[NMAX];
+    float xv[NMAX], xn[NMAX], dub[NMAX];
+    float2 dx[NMAX];
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) {
       const bool in = n < N && ok;
@@ -348,36 +361,48 @@ __global__ void __launch_bounds__(kThreads) token_mix_small_bwd_kernel(
       float g = in ? du[base + static_cast<long long>(n) * D] : 0.f;
       if (in && dout.thresh) g = drop_apply(dout, g, static_cast<unsigned long long>(base) + static_cast<unsigned long long>(n) * D);
       dub[n] = g;
-      dx[n] = 0.f;
+      xn[n] = 0.f;
+      dx[n] = make_float2(0.f, 0.f);
     }
     small_ln<NMAX>(xv, xn, N, D, gam, bet, red, warp, lane, first_warp, wps);
-    for (int t = 0; t < T; ++t) {
-      float h = sB1[t], dg = 0.f;
-      const float* w1r = sW1 + t * N;
-      const float* w2r = sW2t + t * N;
+#pragma unroll 2
+    for (int t = 0; t < Tp; t += 2) {
+      const float* w1a = sW1 + t * NMAX;
+      const float* w2a = sW2t + t * NMAX;
+      float2 h = make_float2(sB1[t], sB1[t + 1]), dg = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int n = 0; n < NMAX; ++n)
-        if (n < N) { h = fmaf(w1r[n], xn[n], h); dg = fmaf(w2r[n], dub[n], dg); }
-      float g, dgelu;
-      if (exact_gelu) { g = gelu_erf(h); dgelu = gelu_erf_grad(h); } else { g = gelu_fast_grad(h, dgelu); }
-      if (dh.thresh) {
-        const bool keep = drop_keep(dh, (static_cast<unsigned long long>(b) * T + t) * D + d);
-        g = keep ? g * dh.scale : 0.f;
-        dgelu = keep ? dgelu * dh.scale : 0.f;
+      for (int n = 0; n < NMAX; ++n) {
+        h = __ffma2_rn(make_float2(w1a[n], w1a[NMAX + n]), make_float2(xn[n], xn[n]), h);
+        dg = __ffma2_rn(make_float2(w2a[n], w2a[NMAX + n]), make_float2(dub[n], dub[n]), dg);
       }
-      const float dhv = ok ? dg * dgelu : 0.f;
+      float2 g, dgelu;
+      if (exact_gelu) {
+        g = make_float2(gelu_erf(h.x), gelu_erf(h.y));
+        dgelu = make_float2(gelu_erf_grad(h.x), gelu_erf_grad(h.y));
+      } else {
+        g = gelu2_grad(h, dgelu);
+      }
+      if (dh.thresh) {
+        const bool k0 = drop_keep(dh, (static_cast<unsigned long long>(b) * T + t) * D + d);
+        const bool k1 = drop_keep(dh, (static_cast<unsigned long long>(b) * T + t + 1) * D + d);
+        g.x = k0 ? g.x * dh.scale : 0.f; dgelu.x = k0 ? dgelu.x * dh.scale : 0.f;
+        g.y = k1 ? g.y * dh.scale : 0.f; dgelu.y = k1 ? dgelu.y * dh.scale : 0.f;
+      }
+      float2 dhv = __fmul2_rn(dg, dgelu);
+      if (!ok) { dhv = make_float2(0.f, 0.f); g = make_float2(0.f, 0.f); }
 #pragma unroll
-      for (int n = 0; n < NMAX; ++n)
-        if (n < N) dx[n] = fmaf(w1r[n], dhv, dx[n]);
-      sDH[t * kSmallLd + threadIdx.x] = dhv;
-      sG[t * kSmallLd + threadIdx.x] = ok ? g : 0.f;
+      for (int n = 0; n < NMAX; ++n) dx[n] = __ffma2_rn(make_float2(w1a[n], w1a[NMAX + n]), dhv, dx[n]);
+      sDH[t * kSmallLd + threadIdx.x] = dhv.x;
+      sDH[(t + 1) * kSmallLd + threadIdx.x] = dhv.y;
+      sG[t * kSmallLd + threadIdx.x] = g.x;
+      sG[(t + 1) * kSmallLd + threadIdx.x] = g.y;
     }
 #pragma unroll
     for (int n = 0; n < NMAX; ++n)
       if (n < N) {
         sXn[n * kSmallLd + threadIdx.x] = ok ? xn[n] : 0.f;
         sDU[n * kSmallLd + threadIdx.x] = dub[n];
-        if (ok) dxn[base + static_cast<long long>(n) * D] = dx[n];
+        if (ok) dxn[base + static_cast<long long>(n) * D] = dx[n].x + dx[n].y;
       }
     __syncthreads();
     // phase 2: reduce the slab's 256 columns into the weight-gradient accumulators (registers, across slabs)
@@ -424,7 +449,7 @@ __global__ void __launch_bounds__(kThreads) token_mix_small_bwd_kernel(
 }
 
 inline bool small_ok(int N, int D, int T) {
-  return N <= 32 && (D == 32 || D == 64 || D == 128 || D == 256) && N * T + T + N <= 4 * kThreads && 2 * T + 2 * N <= 160;
+  return N <= 32 && (D == 32 || D == 64 || D == 128 || D == 256) && N * T + T + N <= 4 * kThreads && 2 * T + 2 * N <= 160 && T <= 512;
 }
 
 template <typename K>
@@ -446,13 +471,13 @@ int token_mix_fwd(const float* x, const float* ln_w, const float* ln_b, const fl
   if (B <= 0 || N <= 0 || D <= 0 || T <= 0) return M2_ERR_ARG;
   if (small_ok(N, D, T)) {
     const Drop dh = make_drop(drop_p, seed, kSiteTokenHidden), dout = make_drop(drop_p, seed, kSiteTokenOut);
-    const int spb = kThreads / D;
+    const int spb = kThreads / D, Tp = (T + 1) & ~1;
     int grid = ceil_div(B, spb);
     if (grid > 148 * 8) grid = 148 * 8;
     LaunchScope scope("token_mix_small_fwd", s);
 #define M2_TMS_FWD(NM_)                                                                                                  \
   {                                                                                                                      \
-    const size_t smem = (static_cast<size_t>(2 * T * N + T + N) + 8 * NM_) * 4;                                          \
+    const size_t smem = (static_cast<size_t>(2 * Tp * NM_ + Tp + NM_) + 8 * NM_) * 4;                                    \
     int rc = set_smem(token_mix_small_fwd_kernel<NM_>, smem);                                                            \
     if (rc) return rc;                                                                                                   \
     token_mix_small_fwd_kernel<NM_><<<grid, kThreads, smem, s>>>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, D, T, exact_gelu, \
@@ -490,13 +515,13 @@ int token_mix_bwd(const float* du, const float* x, const float* ln_w, const floa
   if (B <= 0 || N <= 0 || D <= 0 || T <= 0) return M2_ERR_ARG;
   if (small_ok(N, D, T)) {
     const Drop dh = make_drop(drop_p, seed, kSiteTokenHidden), dout = make_drop(drop_p, seed, kSiteTokenOut);
-    const int spb = kThreads / D;
+    const int spb = kThreads / D, Tp = (T + 1) & ~1;
     int grid = ceil_div(B, spb);
-    if (grid > 148 * 2) grid = 148 * 2;
+    if (grid > 148 * 3) grid = 148 * 3;
     LaunchScope scope("token_mix_small_bwd", s);
 #define M2_TMS_BWD(NM_)                                                                                                  \
   {                                                                                                                      \
-    const size_t smem = (static_cast<size_t>(2 * T * N + T) + 8 * NM_ + 4 + static_cast<size_t>(2 * T + 2 * N) * kSmallLd) * 4; \
+    const size_t smem = (static_cast<size_t>(2 * Tp * NM_ + Tp) + 8 * NM_ + 4 + static_cast<size_t>(2 * Tp + 2 * N) * kSmallLd) * 4; \
     int rc = set_smem(token_mix_small_bwd_kernel<NM_>, smem);                                                            \
     if (rc) return rc;                                                                                                   \
     token_mix_small_bwd_kernel<NM_><<<grid, kThreads, smem, s>>>(du, x, ln_w, ln_b, w1, b1, w2, dxn, dw1, db1, dw2, db2, B, \

@@ -18,7 +18,7 @@ namespace m2 {
 namespace {
 
 constexpr int kBM = 128, kBN = 128, kBK = 64;
-constexpr int kStages = 5;
+constexpr int kStages = 3;   // 96 KB of operand ring: two CTAs per SM, one's epilogue overlaps the other's main loop
 constexpr int kTileBytes = kBM * kBK * 2;                  // 16 KB per operand per stage
 constexpr int kSmemBytes = kStages * 2 * kTileBytes + 256 + 1024;   // + barriers + alignment slack
 constexpr int kTmemCols = 128;
@@ -35,7 +35,7 @@ struct GemmDev {
 };
 
 template <bool kAMn, bool kBMn>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
