@@ -27,6 +27,8 @@
 //
 // D is padded in shared memory to DP in {64,128,256}; C is arbitrary (TMA zero-fills the ragged last chunk, the
 // bf16 weight copies are padded to a multiple of 8 columns so their row stride is 16-byte aligned).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap.cuh"
@@ -636,6 +638,14 @@ int make_weight_maps(CUtensorMap* t1, CUtensorMap* t2, const void* w1b, const vo
 
 }  // namespace
 
+int chain_generation() {
+  static const int gen = []() {
+    const char* e = getenv("M2B200_CHAIN_GEN");
+    return e ? atoi(e) : 2;
+  }();
+  return gen;
+}
+
 // Which hidden sizes the fused chains cover (others take the unfused GEMM path in abi.cu).
 bool chain_fwd_supported(int D) { return D >= 16 && D <= 256 && D % 8 == 0; }
 bool chain_bwd_supported(int D) { return D >= 16 && D <= 128 && D % 8 == 0; }
@@ -644,6 +654,8 @@ int chain_fwd(const float* u, const float* ln_w, const float* ln_b, const void* 
               int ldw2, const float* b2, float* y, int M, int D, int C, int exact_gelu, float drop_p, unsigned long long seed,
               cudaStream_t s) {
   if (!chain_fwd_supported(D) || ldw2 % 8 || ldw2 < C || exact_gelu) return M2_ERR_ARG;
+  if (chain_generation() != 1 && chain_fwd_ts_supported(D))
+    return chain_fwd_ts(u, ln_w, ln_b, w1b, b1, w2b, ldw2, b2, y, M, D, C, drop_p, seed, s);
   const int DP = D <= 64 ? 64 : (D <= 128 ? 128 : 256);
   CUtensorMap t1, t2;
   int rc = make_weight_maps(&t1, &t2, w1b, w2b, D, C, ldw2, DP);

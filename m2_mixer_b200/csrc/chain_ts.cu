@@ -1,0 +1,841 @@
+// Fused channel-mixing chains, generation 2: every row-tile operand lives in TENSOR MEMORY.
+//
+// Reference arithmetic: MixerBlock.channel_mix, modules/mixer.py:37-40,45
+//     y = u + Drop(W2 . Drop(GELU(W1 . LN(u) + b1)) + b2)     per token row (M = B*N rows, D hidden, C channel_dim)
+//
+// Why a second generation: in chain.cu the A operands (LN(u), G) are read from shared memory by every tcgen05.mma.
+// Per 64-channel chunk that is 32 KB (sX) + 16 KB (sG) of operand reads + 16 KB of epilogue stores on top of the
+// 32 KB of weight tiles, i.e. ~1000 cycles of the 128 B/clk shared-memory pipe for ~512 cycles of tensor work, and
+// the epilogue could not start a chunk before GEMM2 had drained its one staging tile.  Here
+//   * LN(u) is written ONCE per CTA into TMEM (bf16, DP/2 columns) and is the TMEM A operand of every GEMM1,
+//   * the epilogue writes G = GELU(H + b1) back to TMEM with tcgen05.st (4 rotating 32-column buffers) and GEMM2
+//     consumes it as a TMEM A operand (.kind::f16 "TS" form): shared memory only carries the weight tiles,
+//   * H has 3 accumulator buffers, GEMM1 runs 3 chunks ahead of the epilogue, the two epilogue groups never wait
+//     for a GEMM2 round trip,
+//   * the output tile is staged through the (then idle) weight ring so that u is read and y written coalesced.
+//
+// TMEM map (512 columns): [0,DP) Y accumulator | [DP, DP+DP/2) LN(u) bf16 | 3 x 64 H accumulators | 4 x 32 G bf16.
+#include "common.cuh"
+#include "kernels.h"
+#include "tmap.cuh"
+
+namespace m2 {
+namespace {
+
+constexpr int kRows = 128;      // token rows per CTA (UMMA M)
+constexpr int kCc = 64;         // channels per chunk
+constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue: two groups of 4 warps
+constexpr int kBarBytes = 512;
+
+template <int DP>
+struct CfgT {
+  static constexpr int kW1Bytes = kCc * DP * 2;      // [64 c-rows][DP d]
+  static constexpr int kW2Bytes = DP * kCc * 2;      // [DP d-rows][64 c]
+  static constexpr int S1 = 4, S2 = 4;               // weight ring depths
+  static constexpr int NB = 3;                       // H accumulator buffers (GEMM1 lookahead)
+  static constexpr int NG = 4;                       // G operand buffers
+  static constexpr int kRingBytes = S1 * kW1Bytes + S2 * kW2Bytes;
+  static constexpr int kXPitch = DP * 2 + 16;        // bf16 LN(u) staging row pitch (conflict-free row reads)
+  static constexpr int kXStage = kRows * kXPitch;
+  static constexpr int kOPitch = DP * 4 + 16;        // fp32 output staging row pitch (aliases the weight ring)
+  static_assert(kRows * kOPitch <= kRingBytes, "output staging must fit in the weight ring");
+  static constexpr int kSmem = kRingBytes + kXStage + kBarBytes + 1024;
+  static constexpr int kMaxBias = 32 * 1024;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kColY = 0;
+  static constexpr int kColX = DP;
+  static constexpr int kColH = DP + DP / 2;
+  static constexpr int kColG = kColH + NB * kCc;
+  static_assert(kColG + NG * (kCc / 2) <= 512, "TMEM budget");
+};
+
+struct TsParams {
+  const float* u;        // [M][D] block input (pre-LN residual stream)
+  const float* ln_w; const float* ln_b;
+  const float* b1;       // [C]
+  const float* b2;       // [D]
+  float* y;              // fwd: [M][D]
+  // backward (dgrad kernel)
+  const float* dy;       // [M][D]
+  float* du;             // [M][D]  = dy + LayerNorm'(dXn)
+  float* dln_w; float* dln_b; float* db2;   // [D] each, accumulated with atomics
+  __nv_bfloat16* xn_b;   // out: LN(u) bf16 [M][D]           (operand of the weight-gradient kernels)
+  __nv_bfloat16* dy_b;   // out: dY (masked) bf16 [M][D]
+  __nv_bfloat16* g_b;    // optional out: G  bf16 [M][ldh]   (nullptr: the weight-gradient kernel recomputes it)
+  __nv_bfloat16* dh_b;   // optional out: dH bf16 [M][ldh]
+  int M, D, C, ldh;
+  int bias_smem;
+  Drop dh, dout;
+};
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// registers -> TMEM: this thread's lane, 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// LayerNorm the tile's rows (warp per row, kB rows in flight) into a padded row-major bf16 staging tile.
+template <int DP>
+__device__ __forceinline__ void ln_rows_to_stage(const TsParams& p, int m0, uint8_t* stage, float* s_mean = nullptr,
+                                                 float* s_rstd = nullptr, __nv_bfloat16* xn_b = nullptr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kV = DP / 128 > 0 ? DP / 128 : 1;   // float4 per lane per row
+  constexpr int kB = 4;                             // rows in flight
+  constexpr int kW = kThreads / 32;
+  float4 gw[kV], gb[kV];
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    gw[i] = c < p.D ? *reinterpret_cast<const float4*>(p.ln_w + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gb[i] = c < p.D ? *reinterpret_cast<const float4*>(p.ln_b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_d = 1.f / static_cast<float>(p.D);
+  for (int r0 = warp * kB; r0 < kRows; r0 += kW * kB) {
+    float4 v[kB][kV];
+#pragma unroll
+    for (int b = 0; b < kB; ++b) {
+      const int row = m0 + r0 + b;
+#pragma unroll
+      for (int i = 0; i < kV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        v[b][i] = (r0 + b < kRows && row < p.M && c < p.D)
+                      ? *reinterpret_cast<const float4*>(p.u + static_cast<long long>(row) * p.D + c)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < kB; ++b) {
+      const int r = r0 + b, row = m0 + r;
+      if (r < kRows) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kV; ++i) s += v[b][i].x + v[b][i].y + v[b][i].z + v[b][i].w;
+        const float mean = warp_sum(s) * inv_d;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < kV; ++i) {
+          const int c = (i * 32 + lane) * 4;
+          if (c < p.D) {
+            const float a = v[b][i].x - mean, bb = v[b][i].y - mean, cc = v[b][i].z - mean, d = v[b][i].w - mean;
+            ss += a * a + bb * bb + cc * cc + d * d;
+          }
+        }
+        const float rstd = rsqrtf(warp_sum(ss) * inv_d + kLnEps);
+        if (s_mean && lane == 0) { s_mean[r] = mean; s_rstd[r] = rstd; }
+#pragma unroll
+        for (int i = 0; i < kV; ++i) {
+          const int c = (i * 32 + lane) * 4;
+          if (c < DP) {
+            uint2 o = make_uint2(0u, 0u);
+            if (row < p.M && c < p.D) {
+              o.x = pack_bf16((v[b][i].x - mean) * rstd * gw[i].x + gb[i].x, (v[b][i].y - mean) * rstd * gw[i].y + gb[i].y);
+              o.y = pack_bf16((v[b][i].z - mean) * rstd * gw[i].z + gb[i].z, (v[b][i].w - mean) * rstd * gw[i].w + gb[i].w);
+              if (xn_b) *reinterpret_cast<uint2*>(xn_b + static_cast<long long>(row) * p.D + c) = o;
+            }
+            *reinterpret_cast<uint2*>(stage + r * CfgT<DP>::kXPitch + c * 2) = o;
+          }
+        }
+      }
+    }
+  }
+}
+
+// One epilogue thread copies (its row) x (32 TMEM columns = 64 bf16) of a padded row-major bf16 staging tile into TMEM.
+__device__ __forceinline__ void stage_row_to_tmem(const uint8_t* stage_row, uint32_t taddr) {
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 q = *reinterpret_cast<const uint4*>(stage_row + i * 16);
+    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+  }
+  tmem_st32(taddr, v);
+}
+
+template <int DP>
+__device__ __forceinline__ void load_w1(uint8_t* slot, const CUtensorMap* tmW1, uint64_t* bar, int c0) {
+  mbar_arrive_expect_tx(bar, CfgT<DP>::kW1Bytes);
+#pragma unroll
+  for (int pnl = 0; pnl < DP / 64; ++pnl)          // [64 c-rows][64 d] panels
+    tma_load_2d(slot + pnl * (kCc * 128), tmW1, bar, pnl * 64, c0);
+}
+template <int DP>
+__device__ __forceinline__ void load_w2(uint8_t* slot, const CUtensorMap* tmW2, uint64_t* bar, int c0) {
+  mbar_arrive_expect_tx(bar, CfgT<DP>::kW2Bytes);
+  tma_load_2d(slot, tmW2, bar, c0, 0);              // [DP d-rows][64 c]
+}
+
+// ============================================================================================ forward
+template <int DP, bool kDrop>
+__global__ void __launch_bounds__(kThreads, 1)
+chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TsParams p) {
+  using C = CfgT<DP>;
+  constexpr int S1 = C::S1, S2 = C::S2, NB = C::NB, NG = C::NG;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW1 = smem;
+  uint8_t* sW2 = sW1 + S1 * C::kW1Bytes;
+  uint8_t* sStage = sW2 + S2 * C::kW2Bytes;          // LN(u) bf16 staging
+  uint8_t* sOut = smem;                              // fp32 output staging (aliases the ring once every MMA is done)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + C::kXStage);
+  uint64_t* w1full = bars;            // [S1]  TMA -> MMA
+  uint64_t* w1empty = w1full + S1;    // [S1]  GEMM1 done -> TMA
+  uint64_t* w2full = w1empty + S1;    // [S2]
+  uint64_t* w2empty = w2full + S2;    // [S2]  GEMM2 done -> TMA
+  uint64_t* hfull = w2empty + S2;     // [NB]  GEMM1 done -> epilogue
+  uint64_t* hempty = hfull + NB;      // [NB]  epilogue has read Hacc -> MMA
+  uint64_t* gfull = hempty + NB;      // [NG]  epilogue wrote G to TMEM -> MMA
+  uint64_t* gempty = gfull + NG;      // [NG]  GEMM2 done reading G -> epilogue
+  uint64_t* yfull = gempty + NG;      // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 1);
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kRows;
+  const int nch = ceil_div(p.C, kCc);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S1; ++i) { mbar_init(&w1full[i], 1); mbar_init(&w1empty[i], 1); }
+    for (int i = 0; i < S2; ++i) { mbar_init(&w2full[i], 1); mbar_init(&w2empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 128); }
+    for (int i = 0; i < NG; ++i) { mbar_init(&gfull[i], 128); mbar_init(&gempty[i], 1); }
+    mbar_init(yfull, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (p.bias_smem)
+    for (int i = threadIdx.x; i < nch * kCc; i += kThreads) sBias[i] = i < p.C ? p.b1[i] : 0.f;
+  __syncthreads();   // barriers initialised before the producer's early prefetch below
+
+  // The weight rings do not depend on the activations: start filling them before the LayerNorm prologue.
+  if (warp == 0 && lane == 0) {
+    for (int j = 0; j < (nch < S1 ? nch : S1); ++j) load_w1<DP>(sW1 + j * C::kW1Bytes, &tmW1, &w1full[j], j * kCc);
+    for (int j = 0; j < (nch < S2 ? nch : S2); ++j) load_w2<DP>(sW2 + j * C::kW2Bytes, &tmW2, &w2full[j], j * kCc);
+  }
+  ln_rows_to_stage<DP>(p, m0, sStage);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tY = tmem_base + C::kColY;
+  const uint32_t tX = tmem_base + C::kColX;
+
+  // staging -> TMEM (the A operand of every GEMM1): epilogue thread = TMEM lane = tile row; DP/2 columns
+  if (warp >= 2) {
+    const int q = warp & 3, grp = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    for (int cb = grp; cb < DP / 64; cb += 2)   // 32 TMEM columns (= 64 bf16 = 128 B of the staging row) per step
+      stage_row_to_tmem(sStage + r * C::kXPitch + cb * 128, tX + lane_addr + cb * 32);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // Refill both rings in the order the MMA issuer frees the slots: the prologue GEMM1s free W1 slots first, then
+      // iteration `it` of the issuer completes GEMM2(it) (frees a W2 slot) and GEMM1(it + NB) (frees a W1 slot).
+      auto refill_w1 = [&](int x) {
+        mbar_wait(&w1empty[x % S1], ((x / S1) & 1) ^ 1);
+        load_w1<DP>(sW1 + (x % S1) * C::kW1Bytes, &tmW1, &w1full[x % S1], x * kCc);
+      };
+      auto refill_w2 = [&](int y) {
+        mbar_wait(&w2empty[y % S2], ((y / S2) & 1) ^ 1);
+        load_w2<DP>(sW2 + (y % S2) * C::kW2Bytes, &tmW2, &w2full[y % S2], y * kCc);
+      };
+      int x = S1;   // next W1 chunk to load
+      for (; x < S1 + NB && x < nch; ++x) refill_w1(x);
+      for (int it = 0; it < nch; ++it) {
+        if (it + S2 < nch) refill_w2(it + S2);
+        if (x < nch) { refill_w1(x); ++x; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(kRows, kCc, 0, 0);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(kRows, DP, 0, 0);
+      auto gemm1 = [&](int j) {   // Hacc[j % NB] = LN(u) . W1_j^T      (A from TMEM)
+        const int s = j % S1, hb = j % NB;
+        mbar_wait(&w1full[s], (j / S1) & 1);
+        mbar_wait(&hempty[hb], ((j / NB) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t w1_addr = smem_u32(sW1 + s * C::kW1Bytes);
+        const uint32_t tH = tmem_base + C::kColH + hb * kCc;
+#pragma unroll
+        for (int kk = 0; kk < DP / 16; ++kk)
+          umma_bf16_ts(tH, tX + kk * 8, umma_desc_sw128(w1_addr + (kk >> 2) * (kCc * 128) + (kk & 3) * 32, 16, 1024), idesc1,
+                       kk > 0 ? 1u : 0u);
+        umma_commit(&w1empty[s]);
+        umma_commit(&hfull[hb]);
+      };
+      for (int j = 0; j < (nch < NB ? nch : NB); ++j) gemm1(j);
+      for (int j = 0; j < nch; ++j) {   // Yacc += G_j . W2_j^T (A from TMEM), then run GEMM1 NB chunks ahead
+        const int s = j % S2, gb = j % NG;
+        mbar_wait(&w2full[s], (j / S2) & 1);
+        mbar_wait(&gfull[gb], (j / NG) & 1);
+        tc_fence_after();
+        const uint32_t w2_addr = smem_u32(sW2 + s * C::kW2Bytes);
+        const uint32_t tG = tmem_base + C::kColG + gb * (kCc / 2);
+#pragma unroll
+        for (int kk = 0; kk < kCc / 16; ++kk)
+          umma_bf16_ts(tY, tG + kk * 8, umma_desc_sw128(w2_addr + kk * 32, 16, 1024), idesc2, (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&w2empty[s]);
+        umma_commit(&gempty[gb]);
+        if (j + NB < nch) gemm1(j + NB);
+      }
+      umma_commit(yfull);
+    }
+  } else {
+    const int q = warp & 3;                // TMEM lane quadrant this warp may access (warp id % 4)
+    const int grp = (warp - 2) >> 2;       // epilogue group: chunks j = grp (mod 2)
+    const int r = q * 32 + lane;           // row inside the tile == TMEM lane
+    const int row = m0 + r;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    for (int j = grp; j < nch; j += 2) {
+      const int hb = j % NB, gb = j % NG;
+      mbar_wait(&hfull[hb], (j / NB) & 1);
+      tc_fence_after();
+      uint32_t h[64];
+      {
+        uint32_t (&h0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&h[0]);
+        uint32_t (&h1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&h[32]);
+        tmem_ld32(tmem_base + C::kColH + lane_addr + hb * kCc, h0);
+        tmem_ld32(tmem_base + C::kColH + lane_addr + hb * kCc + 32, h1);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&hempty[hb]);
+      const int c0 = j * kCc;
+      uint32_t g[32];
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        float b[8];
+        if (p.bias_smem) {
+          const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0 + ch * 8);
+          const float4 b1v = *reinterpret_cast<const float4*>(sBias + c0 + ch * 8 + 4);
+          b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1v.x; b[5] = b1v.y; b[6] = b1v.z; b[7] = b1v.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) b[e] = (c0 + ch * 8 + e < p.C) ? __ldg(p.b1 + c0 + ch * 8 + e) : 0.f;
+        }
+        float2 v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          v[e] = gelu2(__fadd2_rn(make_float2(__uint_as_float(h[ch * 8 + 2 * e]), __uint_as_float(h[ch * 8 + 2 * e + 1])),
+                                  make_float2(b[2 * e], b[2 * e + 1])));
+        if (kDrop) {
+          const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + c0 + ch * 8;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) drop_apply2(p.dh, v[e].x, v[e].y, i0 + 2 * e);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) g[ch * 4 + e] = pack_bf16(v[e].x, v[e].y);
+      }
+      mbar_wait(&gempty[gb], ((j / NG) & 1) ^ 1);   // GEMM2(j - NG) has consumed this buffer
+      tc_fence_after();
+      tmem_st32(tmem_base + C::kColG + lane_addr + gb * (kCc / 2), g);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&gfull[gb]);
+    }
+    // final: y = u + Drop(Yacc + b2).  Pass 1: accumulator rows -> padded fp32 staging (each group half the columns).
+    mbar_wait(yfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int d0 = grp * (DP / 2); d0 < (grp + 1) * (DP / 2); d0 += 32) {
+      uint32_t a[32];
+      tmem_ld32(tY + lane_addr + d0, a);
+      tmem_ld_wait();
+      float* o = reinterpret_cast<float*>(sOut + r * C::kOPitch) + d0;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4)
+        *reinterpret_cast<float4*>(o + e) = make_float4(__uint_as_float(a[e]), __uint_as_float(a[e + 1]),
+                                                        __uint_as_float(a[e + 2]), __uint_as_float(a[e + 3]));
+    }
+    named_bar_sync(1, 256);
+    // Pass 2: warp per row, lanes along d: coalesced u read / y write, bias and dropout applied here.
+    const int ew = warp - 2;
+    constexpr int kRowsPerIter = DP == 128 ? 1 : 2;   // DP = 64: 16 lanes cover a row, two rows per warp step
+    const int d2 = DP == 128 ? lane * 4 : (lane & 15) * 4;
+    const int rsub = DP == 128 ? 0 : (lane >> 4);
+    if (d2 < p.D) {
+      const float4 bq = *reinterpret_cast<const float4*>(p.b2 + d2);
+#pragma unroll 4
+      for (int rr = ew * kRowsPerIter; rr < kRows; rr += 8 * kRowsPerIter) {
+        const int r2 = rr + rsub;
+        const int grow = m0 + r2;
+        if (grow < p.M) {
+          const float4 acc = *reinterpret_cast<const float4*>(sOut + r2 * C::kOPitch + d2 * 4);
+          float4 o = make_float4(acc.x + bq.x, acc.y + bq.y, acc.z + bq.z, acc.w + bq.w);
+          if (kDrop) {
+            const unsigned long long i0 = static_cast<unsigned long long>(grow) * p.D + d2;
+            drop_apply2(p.dout, o.x, o.y, i0);
+            drop_apply2(p.dout, o.z, o.w, i0 + 2);
+          }
+          const float4 uu = *reinterpret_cast<const float4*>(p.u + static_cast<long long>(grow) * p.D + d2);
+          o.x += uu.x; o.y += uu.y; o.z += uu.z; o.w += uu.w;
+          *reinterpret_cast<float4*>(p.y + static_cast<long long>(grow) * p.D + d2) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ============================================================================================ backward (dgrad)
+// Given dY: recompute H, form dG = dY.W2, dH = dG * GELU'(H + b1), accumulate dXn += dH.W1 in TMEM, then finish the
+// LayerNorm backward in the same kernel:  du = dy + LN'(dXn), dln_w / dln_b / db2 column sums (atomics).
+// TMEM map: [0,DP) dXn accumulator | LN(u) bf16 (DP/2) | dY bf16 (DP/2) | 2 x 64 H | 2 x 64 dG; the bf16 dH operand of
+// the dXn GEMM overwrites columns 0..31 of its own dG buffer (each thread only touches its own lane, and the
+// tensor pipe executes dXn(j) before the H/dG GEMMs of chunk j + 2 that reuse the buffer).
+template <int DP>
+struct CfgB {
+  static constexpr int kW1Bytes = kCc * DP * 2;
+  static constexpr int kW2Bytes = DP * kCc * 2;
+  static constexpr int S1 = 4, S2 = 3;
+  static constexpr int kRingBytes = S1 * kW1Bytes + S2 * kW2Bytes;
+  static constexpr int kXPitch = CfgT<DP>::kXPitch;
+  static constexpr int kXStage = kRows * kXPitch;
+  static constexpr int kOPitch = DP * 4 + 16;
+  static_assert(kRows * kOPitch <= kRingBytes, "output staging must fit in the weight ring");
+  static constexpr int kStatBytes = 2 * kRows * 4 + 3 * DP * 4;   // mean, rstd, column partials [3][DP]
+  static constexpr int kSmem = kRingBytes + 2 * kXStage + kStatBytes + kBarBytes + 1024;
+  static constexpr int kMaxBias = 16 * 1024;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kColDX = 0;
+  static constexpr int kColX = DP;
+  static constexpr int kColDY = DP + DP / 2;
+  static constexpr int kColH = 2 * DP;
+  static constexpr int kColG = 2 * DP + 2 * kCc;
+  static_assert(kColG + 2 * kCc <= 512, "TMEM budget");
+};
+
+// dY rows (masked by the output-site dropout) -> padded row-major bf16 staging (+ bf16 copy to HBM).
+template <int DP, bool kDrop>
+__device__ __forceinline__ void dy_rows_to_stage(const TsParams& p, int m0, uint8_t* stage) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kLanes = DP / 4;                 // lanes that cover one row
+  constexpr int kRowsPerIter = 32 / kLanes;      // 1 (DP = 128) or 2 (DP = 64)
+  const int c = (lane % kLanes) * 4;
+  for (int r0 = warp * kRowsPerIter; r0 < kRows; r0 += (kThreads / 32) * kRowsPerIter) {
+    const int r = r0 + lane / kLanes, row = m0 + r;
+    uint2 o = make_uint2(0u, 0u);
+    if (row < p.M && c < p.D) {
+      float4 v = *reinterpret_cast<const float4*>(p.dy + static_cast<long long>(row) * p.D + c);
+      if (kDrop) {   // gradient of the dropped branch output: dY * mask * scale
+        const unsigned long long i0 = static_cast<unsigned long long>(row) * p.D + c;
+        drop_apply2(p.dout, v.x, v.y, i0);
+        drop_apply2(p.dout, v.z, v.w, i0 + 2);
+      }
+      o.x = pack_bf16(v.x, v.y);
+      o.y = pack_bf16(v.z, v.w);
+      if (p.dy_b) *reinterpret_cast<uint2*>(p.dy_b + static_cast<long long>(row) * p.D + c) = o;
+    }
+    *reinterpret_cast<uint2*>(stage + r * CfgB<DP>::kXPitch + c * 2) = o;
+  }
+}
+
+template <int DP, bool kDrop, bool kStoreGH>
+__global__ void __launch_bounds__(kThreads, 1)
+chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TsParams p) {
+  using C = CfgB<DP>;
+  constexpr int S1 = C::S1, S2 = C::S2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW1 = smem;
+  uint8_t* sW2 = sW1 + S1 * C::kW1Bytes;
+  uint8_t* sStageX = sW2 + S2 * C::kW2Bytes;
+  uint8_t* sStageDY = sStageX + C::kXStage;
+  uint8_t* sOut = smem;                              // fp32 dXn staging (aliases the ring once every MMA is done)
+  float* sMean = reinterpret_cast<float*>(sStageDY + C::kXStage);
+  float* sRstd = sMean + kRows;
+  float* sCol = sRstd + kRows;                       // [3][DP]: dln_w, dln_b, db2 partial column sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 3 * DP);
+  uint64_t* w1full = bars;            // [S1]
+  uint64_t* w1empty = w1full + S1;    // [S1]  dXn GEMM done with the W1 chunk -> TMA
+  uint64_t* w2full = w1empty + S1;    // [S2]
+  uint64_t* w2empty = w2full + S2;    // [S2]  dG GEMM done -> TMA
+  uint64_t* hfull = w2empty + S2;     // [2]   H and dG accumulators of a chunk ready -> epilogue
+  uint64_t* dhfull = hfull + 2;       // [2]   epilogue wrote dH (bf16, TMEM) -> MMA
+  uint64_t* yfull = dhfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 1);
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kRows;
+  const int nch = ceil_div(p.C, kCc);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S1; ++i) { mbar_init(&w1full[i], 1); mbar_init(&w1empty[i], 1); }
+    for (int i = 0; i < S2; ++i) { mbar_init(&w2full[i], 1); mbar_init(&w2empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&hfull[i], 1); mbar_init(&dhfull[i], 128); }
+    mbar_init(yfull, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (p.bias_smem)
+    for (int i = threadIdx.x; i < nch * kCc; i += kThreads) sBias[i] = i < p.C ? p.b1[i] : 0.f;
+  for (int i = threadIdx.x; i < 3 * DP; i += kThreads) sCol[i] = 0.f;
+  __syncthreads();
+  if (warp == 0 && lane == 0) {
+    for (int j = 0; j < (nch < S1 ? nch : S1); ++j) load_w1<DP>(sW1 + j * C::kW1Bytes, &tmW1, &w1full[j], j * kCc);
+    for (int j = 0; j < (nch < S2 ? nch : S2); ++j) load_w2<DP>(sW2 + j * C::kW2Bytes, &tmW2, &w2full[j], j * kCc);
+  }
+  ln_rows_to_stage<DP>(p, m0, sStageX, sMean, sRstd, p.xn_b);
+  dy_rows_to_stage<DP, kDrop>(p, m0, sStageDY);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tDX = tmem_base + C::kColDX;
+  const uint32_t tX = tmem_base + C::kColX;
+  const uint32_t tDY = tmem_base + C::kColDY;
+
+  if (warp >= 2) {   // staging -> TMEM: group 0 copies LN(u), group 1 copies dY
+    const int q = warp & 3, grp = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint8_t* src = (grp == 0 ? sStageX : sStageDY) + r * C::kXPitch;
+    const uint32_t dst = (grp == 0 ? tX : tDY) + lane_addr;
+#pragma unroll
+    for (int cb = 0; cb < DP / 64; ++cb) stage_row_to_tmem(src + cb * 128, dst + cb * 32);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // Slot release order of the MMA issuer: hg(0), hg(1), then per iteration k: dx(k) frees W1 chunk k, hg(k + 2)
+      // frees W2 chunk k + 2.
+      auto refill_w1 = [&](int x) {
+        if (x >= nch) return;
+        mbar_wait(&w1empty[x % S1], ((x / S1) & 1) ^ 1);
+        load_w1<DP>(sW1 + (x % S1) * C::kW1Bytes, &tmW1, &w1full[x % S1], x * kCc);
+      };
+      auto refill_w2 = [&](int y) {
+        if (y >= nch) return;
+        mbar_wait(&w2empty[y % S2], ((y / S2) & 1) ^ 1);
+        load_w2<DP>(sW2 + (y % S2) * C::kW2Bytes, &tmW2, &w2full[y % S2], y * kCc);
+      };
+      refill_w2(S2);
+      refill_w2(S2 + 1);
+      for (int k = 0; S1 + k < nch || S2 + 2 + k < nch; ++k) {
+        refill_w1(S1 + k);
+        refill_w2(S2 + 2 + k);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idescH = umma_idesc_bf16(kRows, kCc, 0, 0);    // B (W1 chunk) K-major
+      constexpr uint32_t idescG = umma_idesc_bf16(kRows, kCc, 0, 1);    // B (W2 tile)  MN-major
+      constexpr uint32_t idescX = umma_idesc_bf16(kRows, DP, 0, 1);     // B (W1 chunk) MN-major
+      auto hg = [&](int j) {   // H[j&1] = LN(u) . W1_j^T ; dG[j&1] = dY . W2_j     (A operands from TMEM)
+        const int s1 = j % S1, s2 = j % S2, b = j & 1;
+        mbar_wait(&w1full[s1], (j / S1) & 1);
+        mbar_wait(&w2full[s2], (j / S2) & 1);
+        tc_fence_after();
+        const uint32_t w1_addr = smem_u32(sW1 + s1 * C::kW1Bytes);
+        const uint32_t w2_addr = smem_u32(sW2 + s2 * C::kW2Bytes);
+        const uint32_t tH = tmem_base + C::kColH + b * kCc;
+        const uint32_t tG = tmem_base + C::kColG + b * kCc;
+#pragma unroll
+        for (int kk = 0; kk < DP / 16; ++kk)
+          umma_bf16_ts(tH, tX + kk * 8, umma_desc_sw128(w1_addr + (kk >> 2) * (kCc * 128) + (kk & 3) * 32, 16, 1024), idescH,
+                       kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < DP / 16; ++kk)    // B = W2 tile [DP d-rows][64 c]: 16 d-rows per step = 2048 B
+          umma_bf16_ts(tG, tDY + kk * 8, umma_desc_sw128(w2_addr + kk * 2048, 8192, 1024), idescG, kk > 0 ? 1u : 0u);
+        umma_commit(&w2empty[s2]);
+        umma_commit(&hfull[b]);
+      };
+      hg(0);
+      if (nch > 1) hg(1);
+      for (int j = 0; j < nch; ++j) {   // dXn += dH_j . W1_j   (contraction over the 64 channels of the chunk)
+        const int s1 = j % S1, b = j & 1;
+        mbar_wait(&dhfull[b], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t w1_addr = smem_u32(sW1 + s1 * C::kW1Bytes);
+        const uint32_t tDH = tmem_base + C::kColG + b * kCc;
+#pragma unroll
+        for (int kk = 0; kk < kCc / 16; ++kk)   // B: 16 c-rows per step = 2048 B; d panels 8 KB apart (LBO)
+          umma_bf16_ts(tDX, tDH + kk * 8, umma_desc_sw128(w1_addr + kk * 2048, kCc * 128, 1024), idescX,
+                       (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&w1empty[s1]);
+        if (j + 2 < nch) hg(j + 2);
+      }
+      umma_commit(yfull);
+    }
+  } else {
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;       // group g owns chunks j = g (mod 2) and accumulator buffer g
+    const int r = q * 32 + lane;
+    const int row = m0 + r;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tH = tmem_base + C::kColH + lane_addr + grp * kCc;
+    const uint32_t tG = tmem_base + C::kColG + lane_addr + grp * kCc;
+    for (int j = grp; j < nch; j += 2) {
+      mbar_wait(&hfull[grp], (j >> 1) & 1);
+      tc_fence_after();
+      const int c0 = j * kCc;
+      uint32_t dhp[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t h[32], dg[32];
+        tmem_ld32(tH + half * 32, h);
+        tmem_ld32(tG + half * 32, dg);
+        tmem_ld_wait();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int cc = c0 + half * 32 + ch * 8;
+          float bias[8];
+          if (p.bias_smem) {
+            const float4 b0 = *reinterpret_cast<const float4*>(sBias + cc);
+            const float4 b1v = *reinterpret_cast<const float4*>(sBias + cc + 4);
+            bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+            bias[4] = b1v.x; bias[5] = b1v.y; bias[6] = b1v.z; bias[7] = b1v.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bias[e] = (cc + e < p.C) ? __ldg(p.b1 + cc + e) : 0.f;
+          }
+          float2 gv[4], dv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 dgelu;
+            gv[e] = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[ch * 8 + 2 * e]), __uint_as_float(h[ch * 8 + 2 * e + 1])),
+                                          make_float2(bias[2 * e], bias[2 * e + 1])), dgelu);
+            dv[e] = __fmul2_rn(make_float2(__uint_as_float(dg[ch * 8 + 2 * e]), __uint_as_float(dg[ch * 8 + 2 * e + 1])), dgelu);
+          }
+          if (kDrop) {   // G' = m*s*G ; dH = dG' * m*s*gelu'(h)
+            const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + cc;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (kStoreGH) drop_apply2(p.dh, gv[e].x, gv[e].y, i0 + 2 * e);
+              drop_apply2(p.dh, dv[e].x, dv[e].y, i0 + 2 * e);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dhp[half * 16 + ch * 4 + e] = pack_bf16(dv[e].x, dv[e].y);
+          if (kStoreGH) {
+            if (row < p.M && cc < p.ldh) {   // ldh is a multiple of 8 >= C: whole 16-byte chunks only
+              *reinterpret_cast<uint4*>(p.g_b + static_cast<long long>(row) * p.ldh + cc) =
+                  make_uint4(pack_bf16(gv[0].x, gv[0].y), pack_bf16(gv[1].x, gv[1].y), pack_bf16(gv[2].x, gv[2].y),
+                             pack_bf16(gv[3].x, gv[3].y));
+              *reinterpret_cast<uint4*>(p.dh_b + static_cast<long long>(row) * p.ldh + cc) =
+                  make_uint4(dhp[half * 16 + ch * 4], dhp[half * 16 + ch * 4 + 1], dhp[half * 16 + ch * 4 + 2],
+                             dhp[half * 16 + ch * 4 + 3]);
+            }
+          }
+        }
+      }
+      tmem_st32(tG, dhp);           // dH (bf16) over columns 0..31 of this chunk's dG buffer
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&dhfull[grp]);
+    }
+    // ---- final: LayerNorm backward fused on the accumulator.  Pass 1: dXn rows -> padded fp32 staging.
+    mbar_wait(yfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int d0 = grp * (DP / 2); d0 < (grp + 1) * (DP / 2); d0 += 32) {
+      uint32_t a[32];
+      tmem_ld32(tDX + lane_addr + d0, a);
+      tmem_ld_wait();
+      float* o = reinterpret_cast<float*>(sOut + r * C::kOPitch) + d0;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4)
+        *reinterpret_cast<float4*>(o + e) = make_float4(__uint_as_float(a[e]), __uint_as_float(a[e + 1]),
+                                                        __uint_as_float(a[e + 2]), __uint_as_float(a[e + 3]));
+    }
+    named_bar_sync(1, 256);
+    // Pass 2: kLanes lanes per row along d (coalesced u / dy reads, du writes):
+    //   g = dXn * gamma ; du = dy + rstd * (g - mean_d(g) - xhat * mean_d(g * xhat))
+    //   dln_w += sum_rows dXn * xhat ; dln_b += sum_rows dXn ; db2 += sum_rows dY(masked)
+    constexpr int kLanes = DP / 4;
+    constexpr int kRowsPerIter = 32 / kLanes;
+    const int ew = warp - 2;
+    const int d2 = (lane % kLanes) * 4;
+    const int rsub = lane / kLanes;
+    const float inv_d = 1.f / static_cast<float>(p.D);
+    const bool dok = d2 < p.D;
+    const float4 gam = dok ? *reinterpret_cast<const float4*>(p.ln_w + d2) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 aw = make_float4(0.f, 0.f, 0.f, 0.f), ab = aw, a2 = aw;
+#pragma unroll 2
+    for (int rr = ew * kRowsPerIter; rr < kRows; rr += 8 * kRowsPerIter) {
+      const int r2 = rr + rsub;
+      const int grow = m0 + r2;
+      const bool ok = dok && grow < p.M;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), uu = acc, dyv = acc;
+      if (ok) {
+        acc = *reinterpret_cast<const float4*>(sOut + r2 * C::kOPitch + d2 * 4);
+        uu = *reinterpret_cast<const float4*>(p.u + static_cast<long long>(grow) * p.D + d2);
+        dyv = *reinterpret_cast<const float4*>(p.dy + static_cast<long long>(grow) * p.D + d2);
+      }
+      const float mean = sMean[r2], rstd = sRstd[r2];
+      float4 xh = make_float4((uu.x - mean) * rstd, (uu.y - mean) * rstd, (uu.z - mean) * rstd, (uu.w - mean) * rstd);
+      if (!ok) xh = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 g = make_float4(acc.x * gam.x, acc.y * gam.y, acc.z * gam.z, acc.w * gam.w);
+      float s1 = g.x + g.y + g.z + g.w;
+      float s2 = g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
+#pragma unroll
+      for (int o = kLanes / 2; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      s1 *= inv_d; s2 *= inv_d;
+      if (ok) {
+        float4 o4;
+        o4.x = dyv.x + rstd * (g.x - s1 - xh.x * s2);
+        o4.y = dyv.y + rstd * (g.y - s1 - xh.y * s2);
+        o4.z = dyv.z + rstd * (g.z - s1 - xh.z * s2);
+        o4.w = dyv.w + rstd * (g.w - s1 - xh.w * s2);
+        *reinterpret_cast<float4*>(p.du + static_cast<long long>(grow) * p.D + d2) = o4;
+        if (kDrop) {
+          const unsigned long long i0 = static_cast<unsigned long long>(grow) * p.D + d2;
+          drop_apply2(p.dout, dyv.x, dyv.y, i0);
+          drop_apply2(p.dout, dyv.z, dyv.w, i0 + 2);
+        }
+        aw.x += acc.x * xh.x; aw.y += acc.y * xh.y; aw.z += acc.z * xh.z; aw.w += acc.w * xh.w;
+        ab.x += acc.x; ab.y += acc.y; ab.z += acc.z; ab.w += acc.w;
+        a2.x += dyv.x; a2.y += dyv.y; a2.z += dyv.z; a2.w += dyv.w;
+      }
+    }
+    if (dok) {
+      atomicAdd(&sCol[d2], aw.x); atomicAdd(&sCol[d2 + 1], aw.y); atomicAdd(&sCol[d2 + 2], aw.z); atomicAdd(&sCol[d2 + 3], aw.w);
+      atomicAdd(&sCol[DP + d2], ab.x); atomicAdd(&sCol[DP + d2 + 1], ab.y); atomicAdd(&sCol[DP + d2 + 2], ab.z); atomicAdd(&sCol[DP + d2 + 3], ab.w);
+      atomicAdd(&sCol[2 * DP + d2], a2.x); atomicAdd(&sCol[2 * DP + d2 + 1], a2.y); atomicAdd(&sCol[2 * DP + d2 + 2], a2.z); atomicAdd(&sCol[2 * DP + d2 + 3], a2.w);
+    }
+    named_bar_sync(1, 256);
+    for (int i = threadIdx.x - 64; i < 3 * DP; i += 256) {
+      const int which = i / DP, d = i % DP;
+      if (d < p.D) atomicAdd((which == 0 ? p.dln_w : which == 1 ? p.dln_b : p.db2) + d, sCol[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+template <int DP, bool kDrop>
+int launch_fwd(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p, cudaStream_t s) {
+  const int bias_bytes = ceil_div(p.C, kCc) * kCc * 4;
+  TsParams pp = p;
+  pp.bias_smem = bias_bytes <= CfgT<DP>::kMaxBias ? 1 : 0;
+  const int smem = CfgT<DP>::kSmem + (pp.bias_smem ? bias_bytes : 0);
+  static int configured = 0;   // largest dynamic smem size opted into so far (idempotent attribute)
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(chain_fwd_ts_kernel<DP, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return M2_ERR_LAUNCH;
+    configured = smem;
+  }
+  LaunchScope scope("chain_fwd", s);
+  chain_fwd_ts_kernel<DP, kDrop><<<ceil_div(p.M, kRows), kThreads, smem, s>>>(t1, t2, pp);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+template <int DP, bool kDrop, bool kStoreGH>
+int launch_bwd(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p, cudaStream_t s) {
+  const int bias_bytes = ceil_div(p.C, kCc) * kCc * 4;
+  TsParams pp = p;
+  pp.bias_smem = bias_bytes <= CfgB<DP>::kMaxBias ? 1 : 0;
+  const int smem = CfgB<DP>::kSmem + (pp.bias_smem ? bias_bytes : 0);
+  static int configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(chain_bwd_ts_kernel<DP, kDrop, kStoreGH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return M2_ERR_LAUNCH;
+    configured = smem;
+  }
+  LaunchScope scope("chain_bwd", s);
+  chain_bwd_ts_kernel<DP, kDrop, kStoreGH><<<ceil_div(p.M, kRows), kThreads, smem, s>>>(t1, t2, pp);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+template <int DP>
+int launch_bwd_d(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p, cudaStream_t s) {
+  const bool drop = p.dh.thresh || p.dout.thresh;
+  const bool store = p.g_b != nullptr;
+  if (drop) return store ? launch_bwd<DP, true, true>(t1, t2, p, s) : launch_bwd<DP, true, false>(t1, t2, p, s);
+  return store ? launch_bwd<DP, false, true>(t1, t2, p, s) : launch_bwd<DP, false, false>(t1, t2, p, s);
+}
+
+}  // namespace
+
+bool chain_fwd_ts_supported(int D) { return D >= 16 && D <= 128 && D % 8 == 0; }
+
+int chain_fwd_ts(const float* u, const float* ln_w, const float* ln_b, const void* w1b, const float* b1, const void* w2b,
+                 int ldw2, const float* b2, float* y, int M, int D, int C, float drop_p, unsigned long long seed,
+                 cudaStream_t s) {
+  if (!chain_fwd_ts_supported(D) || ldw2 % 8 || ldw2 < C) return M2_ERR_ARG;
+  const int DP = D <= 64 ? 64 : 128;
+  CUtensorMap t1, t2;
+  // W1 bf16 [C][D] (ld = D): box 64 c-rows x 64 d.   W2 bf16 [D][ldw2] (cols >= C zero): box DP d-rows x 64 c.
+  int rc = make_tmap_bf16(&t1, w1b, C, D, D, kCc, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&t2, w2b, D, ldw2, ldw2, DP, kCc);
+  if (rc) return rc;
+  TsParams p = {};
+  p.u = u; p.ln_w = ln_w; p.ln_b = ln_b; p.b1 = b1; p.b2 = b2; p.y = y;
+  p.M = M; p.D = D; p.C = C; p.ldh = (C + 7) & ~7;
+  p.dh = make_drop(drop_p, seed, kSiteChannelHidden); p.dout = make_drop(drop_p, seed, kSiteChannelOut);
+  const bool drop = p.dh.thresh || p.dout.thresh;
+  if (DP == 64) return drop ? launch_fwd<64, true>(t1, t2, p, s) : launch_fwd<64, false>(t1, t2, p, s);
+  return drop ? launch_fwd<128, true>(t1, t2, p, s) : launch_fwd<128, false>(t1, t2, p, s);
+}
+
+// Backward dgrad chain + fused LayerNorm backward.  du = dy + LN'(dXn); dln_w, dln_b, db2 accumulate (atomics).
+// xn_b / dy_b (bf16 [M][D]) are always written; g_b / dh_b (bf16 [M][ldh]) only when non-null.
+int chain_bwd_ts(const float* u, const float* ln_w, const float* ln_b, const void* w1b, const float* b1, const void* w2b,
+                 int ldw2, const float* dy, float* du, float* dln_w, float* dln_b, float* db2, void* xn_b, void* dy_b,
+                 void* g_b, void* dh_b, int ldh, int M, int D, int C, float drop_p, unsigned long long seed, cudaStream_t s) {
+  if (!chain_fwd_ts_supported(D) || ldw2 % 8 || ldw2 < C || ldh % 8 || ldh < C) return M2_ERR_ARG;
+  if ((g_b == nullptr) != (dh_b == nullptr)) return M2_ERR_ARG;
+  const int DP = D <= 64 ? 64 : 128;
+  CUtensorMap t1, t2;
+  int rc = make_tmap_bf16(&t1, w1b, C, D, D, kCc, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&t2, w2b, D, ldw2, ldw2, DP, kCc);
+  if (rc) return rc;
+  TsParams p = {};
+  p.u = u; p.ln_w = ln_w; p.ln_b = ln_b; p.b1 = b1; p.dy = dy; p.du = du;
+  p.dln_w = dln_w; p.dln_b = dln_b; p.db2 = db2;
+  p.xn_b = static_cast<__nv_bfloat16*>(xn_b); p.dy_b = static_cast<__nv_bfloat16*>(dy_b);
+  p.g_b = static_cast<__nv_bfloat16*>(g_b); p.dh_b = static_cast<__nv_bfloat16*>(dh_b);
+  p.M = M; p.D = D; p.C = C; p.ldh = ldh;
+  p.dh = make_drop(drop_p, seed, kSiteChannelHidden); p.dout = make_drop(drop_p, seed, kSiteChannelOut);
+  if (DP == 64) return launch_bwd_d<64>(t1, t2, p, s);
+  return launch_bwd_d<128>(t1, t2, p, s);
+}
+
+}  // namespace m2

@@ -40,6 +40,17 @@ int chain_bwd(const float* u, const float* ln_w, const float* ln_b, const void* 
               int ldw2, const float* dy, void* xn_b, void* dy_b, void* g_b, void* dh_b, int ldh, float* dxn, int M, int D,
               int C, int exact_gelu, float drop_p, unsigned long long seed, cudaStream_t s);
 
+// generation 2 (chain_ts.cu): row-tile operands in tensor memory, D <= 128
+bool chain_fwd_ts_supported(int D);
+int chain_fwd_ts(const float* u, const float* ln_w, const float* ln_b, const void* w1b, const float* b1, const void* w2b,
+                 int ldw2, const float* b2, float* y, int M, int D, int C, float drop_p, unsigned long long seed,
+                 cudaStream_t s);
+int chain_bwd_ts(const float* u, const float* ln_w, const float* ln_b, const void* w1b, const float* b1, const void* w2b,
+                 int ldw2, const float* dy, float* du, float* dln_w, float* dln_b, float* db2, void* xn_b, void* dy_b,
+                 void* g_b, void* dh_b, int ldh, int M, int D, int C, float drop_p, unsigned long long seed, cudaStream_t s);
+// 1 = generation-1 kernels only (env M2B200_CHAIN_GEN=1): A/B measurements, never needed for correctness
+int chain_generation();
+
 // ---- row kernels (rowops.cu)
 int cast_pad_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols, cudaStream_t s);
 int ln_fwd(const float* x, const float* w, const float* b, void* out, int out_bf16, int rows, int D, int N,
