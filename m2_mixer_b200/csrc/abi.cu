@@ -237,7 +237,18 @@ int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, c
   __nv_bfloat16* g_b = ws.take<__nv_bfloat16>(mc8);
   __nv_bfloat16* dh_b = ws.take<__nv_bfloat16>(mc8);
   float* dxn = ws.take<float>(md);
-  if (path == kPathFused) {
+  const bool gen2 = path == kPathFused && chain_generation() != 1 && chain_fwd_ts_supported(D);
+  if (gen2) {
+    // generation 2: dgrad chain with the LayerNorm backward, dln_w / dln_b / db2 fused in (chain_ts.cu)
+    if (!ws.ok) return M2_ERR_WORKSPACE;
+    if (chain_generation() != 3) {   // no G / dH spill: the weight-gradient kernel recomputes them (wgrad_fused.cu)
+      M2_TRY(chain_bwd_ts(u, ln_w, ln_b, w1b, b1, w2b, ldw2, dy, du, dln_w, dln_b, db2, xn_b, dy_b, nullptr, nullptr, c8, M, D,
+                          C, dropout_p, seed, s));
+      return wgrad_fused(xn_b, dy_b, w1b, w2b, ldw2, b1, dw1, db1, dw2, M, D, C, dropout_p, seed, s);
+    }
+    M2_TRY(chain_bwd_ts(u, ln_w, ln_b, w1b, b1, w2b, ldw2, dy, du, dln_w, dln_b, db2, xn_b, dy_b, g_b, dh_b, c8, M, D, C,
+                        dropout_p, seed, s));
+  } else if (path == kPathFused) {
     if (!ws.ok) return M2_ERR_WORKSPACE;
     M2_TRY(chain_bwd(u, ln_w, ln_b, w1b, b1, w2b, ldw2, dy, xn_b, dy_b, g_b, dh_b, c8, dxn, M, D, C, 0, dropout_p, seed, s));
   } else {
@@ -269,6 +280,7 @@ int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, c
   if (gw1.splitk == 1) gw1.accumulate = 1;
   M2_TRY(gemm_bf16_umma(gw1, s));
   M2_TRY(colsum_bf16(dh_b, c8, M, C, db1, s));
+  if (gen2) return M2_OK;
   if (drop) M2_TRY(colsum_bf16(dy_b, D, M, D, db2, s));   // the masked gradient only exists as the bf16 operand copy
   else M2_TRY(colsum_f32(dy, D, M, D, db2, s));
   return ln_bwd(dxn, static_cast<long long>(M) * D, M, u, ln_w, dy, du, dln_w, dln_b, M, D, s);

@@ -10,11 +10,15 @@
 //   * LN(u) is written ONCE per CTA into TMEM (bf16, DP/2 columns) and is the TMEM A operand of every GEMM1,
 //   * the epilogue writes G = GELU(H + b1) back to TMEM with tcgen05.st (4 rotating 32-column buffers) and GEMM2
 //     consumes it as a TMEM A operand (.kind::f16 "TS" form): shared memory only carries the weight tiles,
-//   * H has 3 accumulator buffers, GEMM1 runs 3 chunks ahead of the epilogue, the two epilogue groups never wait
-//     for a GEMM2 round trip,
+//   * H has 5 accumulator buffers and GEMM1 runs 5 chunks ahead of the epilogue; G(j) overwrites the first 32 columns
+//     of its own H buffer (a thread only touches its own lane; the tensor pipe executes GEMM2(j) before the GEMM1 of
+//     chunk j + 5 that reuses the buffer), so no "empty" barriers exist at all,
+//   * TMEM reads are the scarce resource of the epilogue (tcgen05.ld moves 16 B/clk per lane quadrant, 512 clk per
+//     [128 x 64] fp32 chunk): the accumulator is read in 16-column pieces, the load of piece t + 1 is in flight while
+//     piece t goes through the GELU,
 //   * the output tile is staged through the (then idle) weight ring so that u is read and y written coalesced.
 //
-// TMEM map (512 columns): [0,DP) Y accumulator | [DP, DP+DP/2) LN(u) bf16 | 3 x 64 H accumulators | 4 x 32 G bf16.
+// TMEM map (512 columns): [0,DP) Y accumulator | [DP, DP+DP/2) LN(u) bf16 | 5 x 64 H accumulators (G aliased).
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap.cuh"
@@ -32,8 +36,7 @@ struct CfgT {
   static constexpr int kW1Bytes = kCc * DP * 2;      // [64 c-rows][DP d]
   static constexpr int kW2Bytes = DP * kCc * 2;      // [DP d-rows][64 c]
   static constexpr int S1 = 4, S2 = 4;               // weight ring depths
-  static constexpr int NB = 3;                       // H accumulator buffers (GEMM1 lookahead)
-  static constexpr int NG = 4;                       // G operand buffers
+  static constexpr int NB = 5;                       // H accumulator buffers (GEMM1 lookahead); G(j) aliases H(j)[0:32)
   static constexpr int kRingBytes = S1 * kW1Bytes + S2 * kW2Bytes;
   static constexpr int kXPitch = DP * 2 + 16;        // bf16 LN(u) staging row pitch (conflict-free row reads)
   static constexpr int kXStage = kRows * kXPitch;
@@ -45,8 +48,7 @@ struct CfgT {
   static constexpr int kColY = 0;
   static constexpr int kColX = DP;
   static constexpr int kColH = DP + DP / 2;
-  static constexpr int kColG = kColH + NB * kCc;
-  static_assert(kColG + NG * (kCc / 2) <= 512, "TMEM budget");
+  static_assert(kColH + NB * kCc <= 512, "TMEM budget");
 };
 
 struct TsParams {
@@ -89,6 +91,20 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// explicit ld.shared (the bias pointer is derived from an aligned-up dynamic smem base: ptxas falls back to generic LD)
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -101,8 +117,9 @@ __device__ __forceinline__ void ln_rows_to_stage(const TsParams& p, int m0, uint
                                                  float* s_rstd = nullptr, __nv_bfloat16* xn_b = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kV = DP / 128 > 0 ? DP / 128 : 1;   // float4 per lane per row
-  constexpr int kB = 4;                             // rows in flight
+  constexpr int kB = 13;                            // rows in flight: one batch covers the warp's share of the tile
   constexpr int kW = kThreads / 32;
+  static_assert(kB * kW >= kRows && kV == 1, "LayerNorm prologue layout");
   float4 gw[kV], gb[kV];
 #pragma unroll
   for (int i = 0; i < kV; ++i) {
@@ -161,6 +178,34 @@ __device__ __forceinline__ void ln_rows_to_stage(const TsParams& p, int m0, uint
   }
 }
 
+// b1 -> shared memory (zero padded to whole chunks), 16-byte loads, all loads of a thread in flight together.
+__device__ __forceinline__ void stage_bias(const float* __restrict__ b1, int C, int n_pad, float* sBias) {
+  const int nv = n_pad >> 2;
+  for (int i0 = threadIdx.x; i0 < nv; i0 += 4 * kThreads) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * kThreads;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < nv) {
+        const int c = i * 4;
+        if (c + 3 < C && (reinterpret_cast<uintptr_t>(b1) & 15) == 0) v[k] = *reinterpret_cast<const float4*>(b1 + c);
+        else {
+          if (c < C) v[k].x = b1[c];
+          if (c + 1 < C) v[k].y = b1[c + 1];
+          if (c + 2 < C) v[k].z = b1[c + 2];
+          if (c + 3 < C) v[k].w = b1[c + 3];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * kThreads;
+      if (i < nv) *reinterpret_cast<float4*>(sBias + i * 4) = v[k];
+    }
+  }
+}
+
 // One epilogue thread copies (its row) x (32 TMEM columns = 64 bf16) of a padded row-major bf16 staging tile into TMEM.
 __device__ __forceinline__ void stage_row_to_tmem(const uint8_t* stage_row, uint32_t taddr) {
   uint32_t v[32];
@@ -190,7 +235,7 @@ template <int DP, bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1)
 chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TsParams p) {
   using C = CfgT<DP>;
-  constexpr int S1 = C::S1, S2 = C::S2, NB = C::NB, NG = C::NG;
+  constexpr int S1 = C::S1, S2 = C::S2, NB = C::NB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW1 = smem;
@@ -203,10 +248,8 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   uint64_t* w2full = w1empty + S1;    // [S2]
   uint64_t* w2empty = w2full + S2;    // [S2]  GEMM2 done -> TMA
   uint64_t* hfull = w2empty + S2;     // [NB]  GEMM1 done -> epilogue
-  uint64_t* hempty = hfull + NB;      // [NB]  epilogue has read Hacc -> MMA
-  uint64_t* gfull = hempty + NB;      // [NG]  epilogue wrote G to TMEM -> MMA
-  uint64_t* gempty = gfull + NG;      // [NG]  GEMM2 done reading G -> epilogue
-  uint64_t* yfull = gempty + NG;      // [1]
+  uint64_t* gfull = hfull + NB;       // [NB]  epilogue wrote G (bf16) over the first 32 columns of the buffer -> MMA
+  uint64_t* yfull = gfull + NB;       // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 1);
   float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);
 
@@ -217,16 +260,14 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < S1; ++i) { mbar_init(&w1full[i], 1); mbar_init(&w1empty[i], 1); }
     for (int i = 0; i < S2; ++i) { mbar_init(&w2full[i], 1); mbar_init(&w2empty[i], 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 128); }
-    for (int i = 0; i < NG; ++i) { mbar_init(&gfull[i], 128); mbar_init(&gempty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&hfull[i], 1); mbar_init(&gfull[i], 128); }
     mbar_init(yfull, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
-  if (p.bias_smem)
-    for (int i = threadIdx.x; i < nch * kCc; i += kThreads) sBias[i] = i < p.C ? p.b1[i] : 0.f;
+  if (p.bias_smem) stage_bias(p.b1, p.C, nch * kCc, sBias);
   __syncthreads();   // barriers initialised before the producer's early prefetch below
 
   // The weight rings do not depend on the activations: start filling them before the LayerNorm prologue.
@@ -256,111 +297,129 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   tc_fence_after();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // Refill both rings in the order the MMA issuer frees the slots: the prologue GEMM1s free W1 slots first, then
-      // iteration `it` of the issuer completes GEMM2(it) (frees a W2 slot) and GEMM1(it + NB) (frees a W1 slot).
-      auto refill_w1 = [&](int x) {
-        mbar_wait(&w1empty[x % S1], ((x / S1) & 1) ^ 1);
-        load_w1<DP>(sW1 + (x % S1) * C::kW1Bytes, &tmW1, &w1full[x % S1], x * kCc);
-      };
-      auto refill_w2 = [&](int y) {
-        mbar_wait(&w2empty[y % S2], ((y / S2) & 1) ^ 1);
-        load_w2<DP>(sW2 + (y % S2) * C::kW2Bytes, &tmW2, &w2full[y % S2], y * kCc);
-      };
-      int x = S1;   // next W1 chunk to load
-      for (; x < S1 + NB && x < nch; ++x) refill_w1(x);
-      for (int it = 0; it < nch; ++it) {
-        if (it + S2 < nch) refill_w2(it + S2);
-        if (x < nch) { refill_w1(x); ++x; }
-      }
+    // Refill both rings in the order the MMA issuer frees the slots: the prologue GEMM1s free W1 slots first, then
+    // iteration `it` of the issuer completes GEMM2(it) (frees a W2 slot) and GEMM1(it + NB) (frees a W1 slot).
+    auto refill_w1 = [&](int x) {
+      mbar_wait(&w1empty[x % S1], ((x / S1) & 1) ^ 1);
+      if (elect_one()) load_w1<DP>(sW1 + (x % S1) * C::kW1Bytes, &tmW1, &w1full[x % S1], x * kCc);
+      __syncwarp();
+    };
+    auto refill_w2 = [&](int y) {
+      mbar_wait(&w2empty[y % S2], ((y / S2) & 1) ^ 1);
+      if (elect_one()) load_w2<DP>(sW2 + (y % S2) * C::kW2Bytes, &tmW2, &w2full[y % S2], y * kCc);
+      __syncwarp();
+    };
+    int x = S1;   // next W1 chunk to load
+    for (; x < S1 + NB && x < nch; ++x) refill_w1(x);
+    for (int it = 0; it < nch; ++it) {
+      if (it + S2 < nch) refill_w2(it + S2);
+      if (x < nch) { refill_w1(x); ++x; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = umma_idesc_bf16(kRows, kCc, 0, 0);
-      constexpr uint32_t idesc2 = umma_idesc_bf16(kRows, DP, 0, 0);
-      auto gemm1 = [&](int j) {   // Hacc[j % NB] = LN(u) . W1_j^T      (A from TMEM)
-        const int s = j % S1, hb = j % NB;
-        mbar_wait(&w1full[s], (j / S1) & 1);
-        mbar_wait(&hempty[hb], ((j / NB) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t w1_addr = smem_u32(sW1 + s * C::kW1Bytes);
+    // The whole warp walks the loop (waits are warp-wide), one elected lane issues: see elect_one().
+    constexpr uint32_t idesc1 = umma_idesc_bf16(kRows, kCc, 0, 0);
+    constexpr uint32_t idesc2 = umma_idesc_bf16(kRows, DP, 0, 0);
+    const uint64_t w1_desc0 = umma_desc_sw128(smem_u32(sW1), 16, 1024);
+    const uint64_t w2_desc0 = umma_desc_sw128(smem_u32(sW2), 16, 1024);
+    auto gemm1 = [&](int j) {   // Hacc[j % NB] = LN(u) . W1_j^T      (A from TMEM)
+      const int s = j % S1, hb = j % NB;
+      mbar_wait(&w1full[s], (j / S1) & 1);   // buffer reuse is ordered by the tensor pipe: GEMM2(j - NB) was issued before
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t bd = w1_desc0 + static_cast<uint64_t>((s * C::kW1Bytes) >> 4);
         const uint32_t tH = tmem_base + C::kColH + hb * kCc;
 #pragma unroll
         for (int kk = 0; kk < DP / 16; ++kk)
-          umma_bf16_ts(tH, tX + kk * 8, umma_desc_sw128(w1_addr + (kk >> 2) * (kCc * 128) + (kk & 3) * 32, 16, 1024), idesc1,
-                       kk > 0 ? 1u : 0u);
+          umma_bf16_ts(tH, tX + kk * 8, bd + (((kk >> 2) * (kCc * 128) + (kk & 3) * 32) >> 4), idesc1, kk > 0 ? 1u : 0u);
         umma_commit(&w1empty[s]);
         umma_commit(&hfull[hb]);
-      };
-      for (int j = 0; j < (nch < NB ? nch : NB); ++j) gemm1(j);
-      for (int j = 0; j < nch; ++j) {   // Yacc += G_j . W2_j^T (A from TMEM), then run GEMM1 NB chunks ahead
-        const int s = j % S2, gb = j % NG;
-        mbar_wait(&w2full[s], (j / S2) & 1);
-        mbar_wait(&gfull[gb], (j / NG) & 1);
-        tc_fence_after();
-        const uint32_t w2_addr = smem_u32(sW2 + s * C::kW2Bytes);
-        const uint32_t tG = tmem_base + C::kColG + gb * (kCc / 2);
+      }
+      __syncwarp();
+    };
+    for (int j = 0; j < (nch < NB ? nch : NB); ++j) gemm1(j);
+    for (int j = 0; j < nch; ++j) {   // Yacc += G_j . W2_j^T (A from TMEM), then run GEMM1 NB chunks ahead
+      const int s = j % S2, gb = j % NB;
+      mbar_wait(&w2full[s], (j / S2) & 1);
+      mbar_wait(&gfull[gb], (j / NB) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t bd = w2_desc0 + static_cast<uint64_t>((s * C::kW2Bytes) >> 4);
+        const uint32_t tG = tmem_base + C::kColH + gb * kCc;
 #pragma unroll
         for (int kk = 0; kk < kCc / 16; ++kk)
-          umma_bf16_ts(tY, tG + kk * 8, umma_desc_sw128(w2_addr + kk * 32, 16, 1024), idesc2, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_ts(tY, tG + kk * 8, bd + ((kk * 32) >> 4), idesc2, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&w2empty[s]);
-        umma_commit(&gempty[gb]);
-        if (j + NB < nch) gemm1(j + NB);
       }
-      umma_commit(yfull);
+      __syncwarp();
+      if (j + NB < nch) gemm1(j + NB);
     }
+    if (elect_one()) umma_commit(yfull);
+    __syncwarp();
   } else {
     const int q = warp & 3;                // TMEM lane quadrant this warp may access (warp id % 4)
     const int grp = (warp - 2) >> 2;       // epilogue group: chunks j = grp (mod 2)
     const int r = q * 32 + lane;           // row inside the tile == TMEM lane
     const int row = m0 + r;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    for (int j = grp; j < nch; j += 2) {
-      const int hb = j % NB, gb = j % NG;
-      mbar_wait(&hfull[hb], (j / NB) & 1);
-      tc_fence_after();
-      uint32_t h[64];
-      {
-        uint32_t (&h0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&h[0]);
-        uint32_t (&h1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&h[32]);
-        tmem_ld32(tmem_base + C::kColH + lane_addr + hb * kCc, h0);
-        tmem_ld32(tmem_base + C::kColH + lane_addr + hb * kCc + 32, h1);
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&hempty[hb]);
-      const int c0 = j * kCc;
-      uint32_t g[32];
+    // Software pipeline over 16-column pieces: the tcgen05.ld of piece t + 1 is in flight while piece t is computed.
+    auto ld_piece = [&](int j, int pc, uint32_t (&dst)[16]) {
+      tmem_ld16(tmem_base + C::kColH + lane_addr + (j % NB) * kCc + pc * 16, dst);
+    };
+    auto gelu_piece = [&](const uint32_t (&h)[16], int c, uint32_t* gout) {   // 16 columns starting at channel c
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int hh = 0; hh < 2; ++hh) {
         float b[8];
         if (p.bias_smem) {
-          const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0 + ch * 8);
-          const float4 b1v = *reinterpret_cast<const float4*>(sBias + c0 + ch * 8 + 4);
+          const float4 b0 = lds_f4(sBias + c + hh * 8);
+          const float4 b1v = lds_f4(sBias + c + hh * 8 + 4);
           b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1v.x; b[5] = b1v.y; b[6] = b1v.z; b[7] = b1v.w;
         } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) b[e] = (c0 + ch * 8 + e < p.C) ? __ldg(p.b1 + c0 + ch * 8 + e) : 0.f;
+          for (int e = 0; e < 8; ++e) b[e] = (c + hh * 8 + e < p.C) ? __ldg(p.b1 + c + hh * 8 + e) : 0.f;
         }
         float2 v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          v[e] = gelu2(__fadd2_rn(make_float2(__uint_as_float(h[ch * 8 + 2 * e]), __uint_as_float(h[ch * 8 + 2 * e + 1])),
+          v[e] = gelu2(__fadd2_rn(make_float2(__uint_as_float(h[hh * 8 + 2 * e]), __uint_as_float(h[hh * 8 + 2 * e + 1])),
                                   make_float2(b[2 * e], b[2 * e + 1])));
         if (kDrop) {
-          const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + c0 + ch * 8;
+          const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + c + hh * 8;
 #pragma unroll
           for (int e = 0; e < 4; ++e) drop_apply2(p.dh, v[e].x, v[e].y, i0 + 2 * e);
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) g[ch * 4 + e] = pack_bf16(v[e].x, v[e].y);
+        for (int e = 0; e < 4; ++e) gout[hh * 4 + e] = pack_bf16(v[e].x, v[e].y);
       }
-      mbar_wait(&gempty[gb], ((j / NG) & 1) ^ 1);   // GEMM2(j - NG) has consumed this buffer
+    };
+    uint32_t hA[16], hB[16];
+    if (grp < nch) {
+      mbar_wait(&hfull[grp % NB], 0);
       tc_fence_after();
-      tmem_st32(tmem_base + C::kColG + lane_addr + gb * (kCc / 2), g);
+      ld_piece(grp, 0, hA);
+      tmem_ld_wait();
+    }
+    for (int j = grp; j < nch; j += 2) {
+      const int c0 = j * kCc;
+      uint32_t g[32];
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc) {
+        uint32_t (&cur)[16] = (pc & 1) ? hB : hA;
+        uint32_t (&nxt)[16] = (pc & 1) ? hA : hB;
+        if (pc < 3) {
+          ld_piece(j, pc + 1, nxt);
+        } else if (j + 2 < nch) {
+          mbar_wait(&hfull[(j + 2) % NB], ((j + 2) / NB) & 1);
+          tc_fence_after();
+          ld_piece(j + 2, 0, nxt);
+        }
+        gelu_piece(cur, c0 + pc * 16, g + pc * 8);
+        tmem_ld_wait();
+      }
+      // every column of H(j) has been read: G(j) (bf16, 32 columns) goes over the head of the same buffer
+      tmem_st32(tmem_base + C::kColH + lane_addr + (j % NB) * kCc, g);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&gfull[gb]);
+      mbar_arrive(&gfull[j % NB]);
     }
     // final: y = u + Drop(Yacc + b2).  Pass 1: accumulator rows -> padded fp32 staging (each group half the columns).
     mbar_wait(yfull, 0);
@@ -494,15 +553,14 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < S1; ++i) { mbar_init(&w1full[i], 1); mbar_init(&w1empty[i], 1); }
     for (int i = 0; i < S2; ++i) { mbar_init(&w2full[i], 1); mbar_init(&w2empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&hfull[i], 1); mbar_init(&dhfull[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&hfull[i], 1); mbar_init(&dhfull[i], 256); }
     mbar_init(yfull, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
-  if (p.bias_smem)
-    for (int i = threadIdx.x; i < nch * kCc; i += kThreads) sBias[i] = i < p.C ? p.b1[i] : 0.f;
+  if (p.bias_smem) stage_bias(p.b1, p.C, nch * kCc, sBias);
   for (int i = threadIdx.x; i < 3 * DP; i += kThreads) sCol[i] = 0.f;
   __syncthreads();
   if (warp == 0 && lane == 0) {
@@ -534,133 +592,155 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   tc_fence_after();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // Slot release order of the MMA issuer: hg(0), hg(1), then per iteration k: dx(k) frees W1 chunk k, hg(k + 2)
-      // frees W2 chunk k + 2.
-      auto refill_w1 = [&](int x) {
-        if (x >= nch) return;
-        mbar_wait(&w1empty[x % S1], ((x / S1) & 1) ^ 1);
-        load_w1<DP>(sW1 + (x % S1) * C::kW1Bytes, &tmW1, &w1full[x % S1], x * kCc);
-      };
-      auto refill_w2 = [&](int y) {
-        if (y >= nch) return;
-        mbar_wait(&w2empty[y % S2], ((y / S2) & 1) ^ 1);
-        load_w2<DP>(sW2 + (y % S2) * C::kW2Bytes, &tmW2, &w2full[y % S2], y * kCc);
-      };
-      refill_w2(S2);
-      refill_w2(S2 + 1);
-      for (int k = 0; S1 + k < nch || S2 + 2 + k < nch; ++k) {
-        refill_w1(S1 + k);
-        refill_w2(S2 + 2 + k);
-      }
+    // Slot release order of the MMA issuer: hg(0), hg(1), then per iteration k: dx(k) frees W1 chunk k, hg(k + 2)
+    // frees W2 chunk k + 2.
+    auto refill_w1 = [&](int x) {
+      if (x >= nch) return;
+      mbar_wait(&w1empty[x % S1], ((x / S1) & 1) ^ 1);
+      if (elect_one()) load_w1<DP>(sW1 + (x % S1) * C::kW1Bytes, &tmW1, &w1full[x % S1], x * kCc);
+      __syncwarp();
+    };
+    auto refill_w2 = [&](int y) {
+      if (y >= nch) return;
+      mbar_wait(&w2empty[y % S2], ((y / S2) & 1) ^ 1);
+      if (elect_one()) load_w2<DP>(sW2 + (y % S2) * C::kW2Bytes, &tmW2, &w2full[y % S2], y * kCc);
+      __syncwarp();
+    };
+    refill_w2(S2);
+    refill_w2(S2 + 1);
+    for (int k = 0; S1 + k < nch || S2 + 2 + k < nch; ++k) {
+      refill_w1(S1 + k);
+      refill_w2(S2 + 2 + k);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idescH = umma_idesc_bf16(kRows, kCc, 0, 0);    // B (W1 chunk) K-major
-      constexpr uint32_t idescG = umma_idesc_bf16(kRows, kCc, 0, 1);    // B (W2 tile)  MN-major
-      constexpr uint32_t idescX = umma_idesc_bf16(kRows, DP, 0, 1);     // B (W1 chunk) MN-major
-      auto hg = [&](int j) {   // H[j&1] = LN(u) . W1_j^T ; dG[j&1] = dY . W2_j     (A operands from TMEM)
-        const int s1 = j % S1, s2 = j % S2, b = j & 1;
-        mbar_wait(&w1full[s1], (j / S1) & 1);
-        mbar_wait(&w2full[s2], (j / S2) & 1);
-        tc_fence_after();
-        const uint32_t w1_addr = smem_u32(sW1 + s1 * C::kW1Bytes);
-        const uint32_t w2_addr = smem_u32(sW2 + s2 * C::kW2Bytes);
+    // The whole warp walks the loop (waits are warp-wide), one elected lane issues: see elect_one().
+    constexpr uint32_t idescH = umma_idesc_bf16(kRows, kCc, 0, 0);    // B (W1 chunk) K-major
+    constexpr uint32_t idescG = umma_idesc_bf16(kRows, kCc, 0, 1);    // B (W2 tile)  MN-major
+    constexpr uint32_t idescX = umma_idesc_bf16(kRows, DP, 0, 1);     // B (W1 chunk) MN-major
+    const uint64_t w1k_desc0 = umma_desc_sw128(smem_u32(sW1), 16, 1024);          // W1 chunk as K-major B (H GEMM)
+    const uint64_t w1m_desc0 = umma_desc_sw128(smem_u32(sW1), kCc * 128, 1024);   // W1 chunk as MN-major B (dXn GEMM)
+    const uint64_t w2m_desc0 = umma_desc_sw128(smem_u32(sW2), 8192, 1024);        // W2 tile as MN-major B (dG GEMM)
+    auto hg = [&](int j) {   // H[j&1] = LN(u) . W1_j^T ; dG[j&1] = dY . W2_j     (A operands from TMEM)
+      const int s1 = j % S1, s2 = j % S2, b = j & 1;
+      mbar_wait(&w1full[s1], (j / S1) & 1);
+      mbar_wait(&w2full[s2], (j / S2) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t bd1 = w1k_desc0 + static_cast<uint64_t>((s1 * C::kW1Bytes) >> 4);
+        const uint64_t bd2 = w2m_desc0 + static_cast<uint64_t>((s2 * C::kW2Bytes) >> 4);
         const uint32_t tH = tmem_base + C::kColH + b * kCc;
         const uint32_t tG = tmem_base + C::kColG + b * kCc;
 #pragma unroll
         for (int kk = 0; kk < DP / 16; ++kk)
-          umma_bf16_ts(tH, tX + kk * 8, umma_desc_sw128(w1_addr + (kk >> 2) * (kCc * 128) + (kk & 3) * 32, 16, 1024), idescH,
-                       kk > 0 ? 1u : 0u);
+          umma_bf16_ts(tH, tX + kk * 8, bd1 + (((kk >> 2) * (kCc * 128) + (kk & 3) * 32) >> 4), idescH, kk > 0 ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < DP / 16; ++kk)    // B = W2 tile [DP d-rows][64 c]: 16 d-rows per step = 2048 B
-          umma_bf16_ts(tG, tDY + kk * 8, umma_desc_sw128(w2_addr + kk * 2048, 8192, 1024), idescG, kk > 0 ? 1u : 0u);
+          umma_bf16_ts(tG, tDY + kk * 8, bd2 + ((kk * 2048) >> 4), idescG, kk > 0 ? 1u : 0u);
         umma_commit(&w2empty[s2]);
         umma_commit(&hfull[b]);
-      };
-      hg(0);
-      if (nch > 1) hg(1);
-      for (int j = 0; j < nch; ++j) {   // dXn += dH_j . W1_j   (contraction over the 64 channels of the chunk)
-        const int s1 = j % S1, b = j & 1;
-        mbar_wait(&dhfull[b], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t w1_addr = smem_u32(sW1 + s1 * C::kW1Bytes);
+      }
+      __syncwarp();
+    };
+    hg(0);
+    if (nch > 1) hg(1);
+    for (int j = 0; j < nch; ++j) {   // dXn += dH_j . W1_j   (contraction over the 64 channels of the chunk)
+      const int s1 = j % S1, b = j & 1;
+      mbar_wait(&dhfull[b], (j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t bd = w1m_desc0 + static_cast<uint64_t>((s1 * C::kW1Bytes) >> 4);
         const uint32_t tDH = tmem_base + C::kColG + b * kCc;
 #pragma unroll
         for (int kk = 0; kk < kCc / 16; ++kk)   // B: 16 c-rows per step = 2048 B; d panels 8 KB apart (LBO)
-          umma_bf16_ts(tDX, tDH + kk * 8, umma_desc_sw128(w1_addr + kk * 2048, kCc * 128, 1024), idescX,
-                       (j > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_ts(tDX, tDH + (kk >> 1) * 32 + (kk & 1) * 8, bd + ((kk * 2048) >> 4), idescX, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&w1empty[s1]);
-        if (j + 2 < nch) hg(j + 2);
       }
-      umma_commit(yfull);
+      __syncwarp();
+      if (j + 2 < nch) hg(j + 2);
     }
+    if (elect_one()) umma_commit(yfull);
+    __syncwarp();
   } else {
     const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;       // group g owns chunks j = g (mod 2) and accumulator buffer g
+    const int grp = (warp - 2) >> 2;       // both groups work on every chunk: group g owns columns [32 g, 32 g + 32)
     const int r = q * 32 + lane;
     const int row = m0 + r;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tH = tmem_base + C::kColH + lane_addr + grp * kCc;
-    const uint32_t tG = tmem_base + C::kColG + lane_addr + grp * kCc;
-    for (int j = grp; j < nch; j += 2) {
-      mbar_wait(&hfull[grp], (j >> 1) & 1);
-      tc_fence_after();
-      const int c0 = j * kCc;
-      uint32_t dhp[32];
+    // Software pipeline over 16-column pieces (2 per chunk and group): the tcgen05.ld of the next piece (H and dG) is in
+    // flight while the current one goes through GELU / GELU'.
+    auto ld_piece = [&](int j, int pc, uint32_t (&hd)[16], uint32_t (&gd)[16]) {
+      const uint32_t off = lane_addr + (j & 1) * kCc + grp * 32 + pc * 16;
+      tmem_ld16(tmem_base + C::kColH + off, hd);
+      tmem_ld16(tmem_base + C::kColG + off, gd);
+    };
+    auto grad_piece = [&](const uint32_t (&h)[16], const uint32_t (&dg)[16], int c, uint32_t* dhout) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t h[32], dg[32];
-        tmem_ld32(tH + half * 32, h);
-        tmem_ld32(tG + half * 32, dg);
-        tmem_ld_wait();
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cc = c + hh * 8;
+        float bias[8];
+        if (p.bias_smem) {
+          const float4 b0 = lds_f4(sBias + cc);
+          const float4 b1v = lds_f4(sBias + cc + 4);
+          bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+          bias[4] = b1v.x; bias[5] = b1v.y; bias[6] = b1v.z; bias[7] = b1v.w;
+        } else {
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int cc = c0 + half * 32 + ch * 8;
-          float bias[8];
-          if (p.bias_smem) {
-            const float4 b0 = *reinterpret_cast<const float4*>(sBias + cc);
-            const float4 b1v = *reinterpret_cast<const float4*>(sBias + cc + 4);
-            bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
-            bias[4] = b1v.x; bias[5] = b1v.y; bias[6] = b1v.z; bias[7] = b1v.w;
-          } else {
+          for (int e = 0; e < 8; ++e) bias[e] = (cc + e < p.C) ? __ldg(p.b1 + cc + e) : 0.f;
+        }
+        float2 gv[4], dv[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) bias[e] = (cc + e < p.C) ? __ldg(p.b1 + cc + e) : 0.f;
-          }
-          float2 gv[4], dv[4];
+        for (int e = 0; e < 4; ++e) {
+          float2 dgelu;
+          gv[e] = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[hh * 8 + 2 * e]), __uint_as_float(h[hh * 8 + 2 * e + 1])),
+                                        make_float2(bias[2 * e], bias[2 * e + 1])), dgelu);
+          dv[e] = __fmul2_rn(make_float2(__uint_as_float(dg[hh * 8 + 2 * e]), __uint_as_float(dg[hh * 8 + 2 * e + 1])), dgelu);
+        }
+        if (kDrop) {   // G' = m*s*G ; dH = dG' * m*s*gelu'(h)
+          const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + cc;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float2 dgelu;
-            gv[e] = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[ch * 8 + 2 * e]), __uint_as_float(h[ch * 8 + 2 * e + 1])),
-                                          make_float2(bias[2 * e], bias[2 * e + 1])), dgelu);
-            dv[e] = __fmul2_rn(make_float2(__uint_as_float(dg[ch * 8 + 2 * e]), __uint_as_float(dg[ch * 8 + 2 * e + 1])), dgelu);
+            if (kStoreGH) drop_apply2(p.dh, gv[e].x, gv[e].y, i0 + 2 * e);
+            drop_apply2(p.dh, dv[e].x, dv[e].y, i0 + 2 * e);
           }
-          if (kDrop) {   // G' = m*s*G ; dH = dG' * m*s*gelu'(h)
-            const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + cc;
+        }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (kStoreGH) drop_apply2(p.dh, gv[e].x, gv[e].y, i0 + 2 * e);
-              drop_apply2(p.dh, dv[e].x, dv[e].y, i0 + 2 * e);
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) dhp[half * 16 + ch * 4 + e] = pack_bf16(dv[e].x, dv[e].y);
-          if (kStoreGH) {
-            if (row < p.M && cc < p.ldh) {   // ldh is a multiple of 8 >= C: whole 16-byte chunks only
-              *reinterpret_cast<uint4*>(p.g_b + static_cast<long long>(row) * p.ldh + cc) =
-                  make_uint4(pack_bf16(gv[0].x, gv[0].y), pack_bf16(gv[1].x, gv[1].y), pack_bf16(gv[2].x, gv[2].y),
-                             pack_bf16(gv[3].x, gv[3].y));
-              *reinterpret_cast<uint4*>(p.dh_b + static_cast<long long>(row) * p.ldh + cc) =
-                  make_uint4(dhp[half * 16 + ch * 4], dhp[half * 16 + ch * 4 + 1], dhp[half * 16 + ch * 4 + 2],
-                             dhp[half * 16 + ch * 4 + 3]);
-            }
+        for (int e = 0; e < 4; ++e) dhout[hh * 4 + e] = pack_bf16(dv[e].x, dv[e].y);
+        if (kStoreGH) {
+          if (row < p.M && cc < p.ldh) {   // ldh is a multiple of 8 >= C: whole 16-byte chunks only
+            *reinterpret_cast<uint4*>(p.g_b + static_cast<long long>(row) * p.ldh + cc) =
+                make_uint4(pack_bf16(gv[0].x, gv[0].y), pack_bf16(gv[1].x, gv[1].y), pack_bf16(gv[2].x, gv[2].y),
+                           pack_bf16(gv[3].x, gv[3].y));
+            *reinterpret_cast<uint4*>(p.dh_b + static_cast<long long>(row) * p.ldh + cc) =
+                make_uint4(dhout[hh * 4], dhout[hh * 4 + 1], dhout[hh * 4 + 2], dhout[hh * 4 + 3]);
           }
         }
       }
-      tmem_st32(tG, dhp);           // dH (bf16) over columns 0..31 of this chunk's dG buffer
+    };
+    uint32_t hA[16], gA[16], hB[16], gB[16];
+    mbar_wait(&hfull[0], 0);
+    tc_fence_after();
+    ld_piece(0, 0, hA, gA);
+    tmem_ld_wait();
+    for (int j = 0; j < nch; ++j) {
+      const int b = j & 1;
+      const int c0 = j * kCc + grp * 32;
+      uint32_t dhp[16];
+      ld_piece(j, 1, hB, gB);
+      grad_piece(hA, gA, c0, dhp);
+      tmem_ld_wait();
+      if (j + 1 < nch) {
+        mbar_wait(&hfull[b ^ 1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        ld_piece(j + 1, 0, hA, gA);
+      }
+      grad_piece(hB, gB, c0 + 16, dhp + 8);
+      // dH (bf16, 16 columns) over the first half of the dG columns this thread has read: the two groups never touch
+      // each other's columns, the tensor pipe reads them (dXn GEMM) before chunk j + 2 overwrites the buffer.
+      tmem_st16(tmem_base + C::kColG + lane_addr + b * kCc + grp * 32, dhp);
       tmem_st_wait();
+      tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&dhfull[grp]);
+      mbar_arrive(&dhfull[b]);
     }
     // ---- final: LayerNorm backward fused on the accumulator.  Pass 1: dXn rows -> padded fp32 staging.
     mbar_wait(yfull, 0);

@@ -204,6 +204,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a CONVERGED warp (the lowest).  Roles that issue tcgen05.mma / TMA from a single thread walk their loop
+// with the whole warp and predicate only the issue on this: inside an `if (lane == 0)` region ptxas cannot prove
+// warp-uniformity and wraps every UTCHMMA in an elect / R2UR.BROADCAST / BRA.U.ANY serialisation loop (~250 clk per
+// MMA measured, profiles/r01_ncu_chain_v6.md), with it the operands stay in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");

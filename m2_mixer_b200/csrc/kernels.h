@@ -48,7 +48,11 @@ int chain_fwd_ts(const float* u, const float* ln_w, const float* ln_b, const voi
 int chain_bwd_ts(const float* u, const float* ln_w, const float* ln_b, const void* w1b, const float* b1, const void* w2b,
                  int ldw2, const float* dy, float* du, float* dln_w, float* dln_b, float* db2, void* xn_b, void* dy_b,
                  void* g_b, void* dh_b, int ldh, int M, int D, int C, float drop_p, unsigned long long seed, cudaStream_t s);
-// 1 = generation-1 kernels only (env M2B200_CHAIN_GEN=1): A/B measurements, never needed for correctness
+// fused recompute weight gradients (wgrad_fused.cu): dw1 / db1 / dw2 accumulate; xn_b / dy_b from chain_bwd_ts
+int wgrad_fused(const void* xn_b, const void* dy_b, const void* w1b, const void* w2b, int ldw2, const float* b1, float* dw1,
+                float* db1, float* dw2, int M, int D, int C, float drop_p, unsigned long long seed, cudaStream_t s);
+// env M2B200_CHAIN_GEN: 1 = generation-1 kernels, 3 = generation-2 dgrad + G/dH spill + GEMM weight gradients,
+// default 2 = generation-2 dgrad + fused recompute weight gradients.  A/B measurements only.
 int chain_generation();
 
 // ---- row kernels (rowops.cu)

@@ -68,13 +68,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and issuer walk their loops with the whole warp; one elected lane issues (see elect_one()).
   if (warp == 0) {
-    if (lane == 0) {
-      const int a_row0 = batch * p.a_batch_rows, b_row0 = batch * p.b_batch_rows;
-      for (int it = 0; it < nkt; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+    const int a_row0 = batch * p.a_batch_rows, b_row0 = batch * p.b_batch_rows;
+    for (int it = 0; it < nkt; ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full[s], 2 * kTileBytes);
         const int k0 = (kt_begin + it) * kBK;
         uint8_t* a = sA + s * kTileBytes;
@@ -92,27 +93,31 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_load_2d(b + kTileBytes / 2, &tmB, &full[s], n0 + 64, b_row0 + k0);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, kAMn ? 1 : 0, kBMn ? 1 : 0);
-      for (int it = 0; it < nkt; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t a = smem_u32(sA + s * kTileBytes), b = smem_u32(sB + s * kTileBytes);
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, kAMn ? 1 : 0, kBMn ? 1 : 0);
+    // K-major: +16 elements = +32 B inside the 128-B swizzled row.  MN-major: +16 k-rows = +2048 B.
+    const uint64_t a_desc0 = kAMn ? umma_desc_sw128(smem_u32(sA), kTileBytes / 2, 1024) : umma_desc_sw128(smem_u32(sA), 16, 1024);
+    const uint64_t b_desc0 = kBMn ? umma_desc_sw128(smem_u32(sB), kTileBytes / 2, 1024) : umma_desc_sw128(smem_u32(sB), 16, 1024);
+    for (int it = 0; it < nkt; ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t ad = a_desc0 + static_cast<uint64_t>((s * kTileBytes) >> 4);
+        const uint64_t bd = b_desc0 + static_cast<uint64_t>((s * kTileBytes) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < kBK / 16; ++kk) {
-          // K-major: +16 elements = +32 B inside the 128-B swizzled row.  MN-major: +16 k-rows = +2048 B.
-          const uint64_t ad = kAMn ? umma_desc_sw128(a + kk * 2048, kTileBytes / 2, 1024) : umma_desc_sw128(a + kk * 32, 16, 1024);
-          const uint64_t bd = kBMn ? umma_desc_sw128(b + kk * 2048, kTileBytes / 2, 1024) : umma_desc_sw128(b + kk * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-        }
+        for (int kk = 0; kk < kBK / 16; ++kk)
+          umma_bf16(tmem_base, ad + ((kk * (kAMn ? 2048 : 32)) >> 4), bd + ((kk * (kBMn ? 2048 : 32)) >> 4), idesc,
+                    (it > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&empty[s]);
       }
-      umma_commit(acc_full);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
   } else {
     mbar_wait(acc_full, 0);
     tc_fence_after();
