@@ -102,7 +102,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 // explicit ld.shared (the bias pointer is derived from an aligned-up dynamic smem base: ptxas falls back to generic LD)
 __device__ __forceinline__ float4 lds_f4(const float* p) {
   float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
   return v;
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -666,17 +666,20 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     const int r = q * 32 + lane;
     const int row = m0 + r;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    // Software pipeline over 16-column pieces (2 per chunk and group): the tcgen05.ld of the next piece (H and dG) is in
-    // flight while the current one goes through GELU / GELU'.
-    auto ld_piece = [&](int j, int pc, uint32_t (&hd)[16], uint32_t (&gd)[16]) {
-      const uint32_t off = lane_addr + (j & 1) * kCc + grp * 32 + pc * 16;
-      tmem_ld16(tmem_base + C::kColH + off, hd);
-      tmem_ld16(tmem_base + C::kColG + off, gd);
-    };
-    auto grad_piece = [&](const uint32_t (&h)[16], const uint32_t (&dg)[16], int c, uint32_t* dhout) {
+    for (int j = 0; j < nch; ++j) {
+      const int b = j & 1;
+      const uint32_t tH = tmem_base + C::kColH + lane_addr + b * kCc + grp * 32;
+      const uint32_t tG = tmem_base + C::kColG + lane_addr + b * kCc + grp * 32;
+      mbar_wait(&hfull[b], (j >> 1) & 1);
+      tc_fence_after();
+      const int c0 = j * kCc + grp * 32;
+      uint32_t h[32], dg[32], dhp[16];
+      tmem_ld32(tH, h);
+      tmem_ld32(tG, dg);
+      tmem_ld_wait();
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int cc = c + hh * 8;
+      for (int ch = 0; ch < 4; ++ch) {
+        const int cc = c0 + ch * 8;
         float bias[8];
         if (p.bias_smem) {
           const float4 b0 = lds_f4(sBias + cc);
@@ -691,9 +694,9 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float2 dgelu;
-          gv[e] = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[hh * 8 + 2 * e]), __uint_as_float(h[hh * 8 + 2 * e + 1])),
+          gv[e] = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[ch * 8 + 2 * e]), __uint_as_float(h[ch * 8 + 2 * e + 1])),
                                         make_float2(bias[2 * e], bias[2 * e + 1])), dgelu);
-          dv[e] = __fmul2_rn(make_float2(__uint_as_float(dg[hh * 8 + 2 * e]), __uint_as_float(dg[hh * 8 + 2 * e + 1])), dgelu);
+          dv[e] = __fmul2_rn(make_float2(__uint_as_float(dg[ch * 8 + 2 * e]), __uint_as_float(dg[ch * 8 + 2 * e + 1])), dgelu);
         }
         if (kDrop) {   // G' = m*s*G ; dH = dG' * m*s*gelu'(h)
           const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + cc;
@@ -704,41 +707,21 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
           }
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) dhout[hh * 4 + e] = pack_bf16(dv[e].x, dv[e].y);
+        for (int e = 0; e < 4; ++e) dhp[ch * 4 + e] = pack_bf16(dv[e].x, dv[e].y);
         if (kStoreGH) {
           if (row < p.M && cc < p.ldh) {   // ldh is a multiple of 8 >= C: whole 16-byte chunks only
             *reinterpret_cast<uint4*>(p.g_b + static_cast<long long>(row) * p.ldh + cc) =
                 make_uint4(pack_bf16(gv[0].x, gv[0].y), pack_bf16(gv[1].x, gv[1].y), pack_bf16(gv[2].x, gv[2].y),
                            pack_bf16(gv[3].x, gv[3].y));
             *reinterpret_cast<uint4*>(p.dh_b + static_cast<long long>(row) * p.ldh + cc) =
-                make_uint4(dhout[hh * 4], dhout[hh * 4 + 1], dhout[hh * 4 + 2], dhout[hh * 4 + 3]);
+                make_uint4(dhp[ch * 4], dhp[ch * 4 + 1], dhp[ch * 4 + 2], dhp[ch * 4 + 3]);
           }
         }
       }
-    };
-    uint32_t hA[16], gA[16], hB[16], gB[16];
-    mbar_wait(&hfull[0], 0);
-    tc_fence_after();
-    ld_piece(0, 0, hA, gA);
-    tmem_ld_wait();
-    for (int j = 0; j < nch; ++j) {
-      const int b = j & 1;
-      const int c0 = j * kCc + grp * 32;
-      uint32_t dhp[16];
-      ld_piece(j, 1, hB, gB);
-      grad_piece(hA, gA, c0, dhp);
-      tmem_ld_wait();
-      if (j + 1 < nch) {
-        mbar_wait(&hfull[b ^ 1], ((j + 1) >> 1) & 1);
-        tc_fence_after();
-        ld_piece(j + 1, 0, hA, gA);
-      }
-      grad_piece(hB, gB, c0 + 16, dhp + 8);
-      // dH (bf16, 16 columns) over the first half of the dG columns this thread has read: the two groups never touch
-      // each other's columns, the tensor pipe reads them (dXn GEMM) before chunk j + 2 overwrites the buffer.
-      tmem_st16(tmem_base + C::kColG + lane_addr + b * kCc + grp * 32, dhp);
+      // dH (bf16, 16 columns) over the first half of the dG columns this thread has just read: the two groups never
+      // touch each other's columns, the tensor pipe reads them (dXn GEMM) before chunk j + 2 overwrites the buffer.
+      tmem_st16(tG, dhp);
       tmem_st_wait();
-      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&dhfull[b]);
     }

@@ -22,10 +22,15 @@
 namespace m2 {
 namespace {
 
-constexpr int kRows = 128;      // token rows per tile (UMMA M of the recompute GEMMs, K of the gradient GEMMs)
+// Row tiles are 96 rows: three 48 KB ring stages fit beside the resident weight slices, and a third stage is what hides
+// the TMA latency (with two, the load of tile i + 2 can only start when the gradient GEMMs of tile i retire and the
+// in-order MMA issuer stalls on it: 5200 clk per tile measured, profiles/r01_ncu_chain_v9.md).  The recompute GEMMs
+// still run as M = 128 instructions; accumulator rows 96..127 are garbage that no gradient GEMM (K = 96) ever reads.
+constexpr int kRows = 96;       // token rows per tile (K of the gradient GEMMs)
+constexpr int kMmaM = 128;      // UMMA M of the recompute GEMMs
 constexpr int kCc = 64;         // channels per CTA
 constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (group g = column half g of the chunk)
-constexpr int kNS = 2;          // row-tile ring depth
+constexpr int kNS = 3;          // row-tile ring depth
 
 template <int DP>
 struct CfgW {
@@ -34,7 +39,7 @@ struct CfgW {
   static constexpr int kStage = 2 * kTile;
   static constexpr int kW1Bytes = kCc * DP * 2;         // [64 c][DP d]
   static constexpr int kW2Bytes = DP * kCc * 2;         // [DP d][64 c]
-  static constexpr int kGBytes = kRows * kCc * 2;       // [128 rows][64 c]
+  static constexpr int kGBytes = kMmaM * kCc * 2;       // [128 rows][64 c] (rows >= 96 are written but never read)
   static constexpr int kSmem = kNS * kStage + kW1Bytes + kW2Bytes + 2 * kGBytes + 1024 + 1024;
   static constexpr int kTmemCols = 512;
   static constexpr int kColW1 = 0, kColW2 = 64, kColH = 128, kColG = 256;
@@ -128,9 +133,9 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
   } else if (warp == 1) {
     // ---- MMA issuer
-    constexpr uint32_t idescH = umma_idesc_bf16(kRows, kCc, 0, 0);   // A row tile K-major,  B = W1c K-major
-    constexpr uint32_t idescG = umma_idesc_bf16(kRows, kCc, 0, 1);   // A row tile K-major,  B = W2c MN-major
-    constexpr uint32_t idescW = umma_idesc_bf16(kRows, kCc, 1, 1);   // A row tile MN-major, B = sdH / sG MN-major
+    constexpr uint32_t idescH = umma_idesc_bf16(kMmaM, kCc, 0, 0);   // A row tile K-major,  B = W1c K-major
+    constexpr uint32_t idescG = umma_idesc_bf16(kMmaM, kCc, 0, 1);   // A row tile K-major,  B = W2c MN-major
+    constexpr uint32_t idescW = umma_idesc_bf16(kMmaM, kCc, 1, 1);   // A row tile MN-major (M = d), B = sdH / sG MN-major
     constexpr uint32_t kLboA = DP == 128 ? C::kPanel : 0;            // DP = 64: M rows 64..127 alias the only panel
     const uint64_t xk0 = umma_desc_sw128(smem_u32(sStage), 16, 1024);
     const uint64_t xm0 = umma_desc_sw128(smem_u32(sStage), kLboA, 1024);
@@ -194,57 +199,43 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
     for (int k = 0; k < 32; ++k) dbp[k] = 0.f;
     const uint32_t bias_addr = smem_u32(sB1 + grp * 32);
-    // Software pipeline over 16-column pieces (2 per tile and group): the tcgen05.ld of the next piece is in flight
-    // while the current one goes through GELU / GELU'.
-    auto ld_piece = [&](int i, int pc, uint32_t (&hd)[16], uint32_t (&gd)[16]) {
-      const uint32_t off = lane_addr + (i & 1) * kCc + grp * 32 + pc * 16;
-      tmem_ld16(tmem_base + C::kColH + off, hd);
-      tmem_ld16(tmem_base + C::kColG + off, gd);
-    };
-    auto grad_piece = [&](const uint32_t (&h)[16], const uint32_t (&dg)[16], int pc, unsigned long long i0, uint32_t* gp,
-                          uint32_t* dp) {
-      float bias[16];
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(bias[4 * e]), "=f"(bias[4 * e + 1]), "=f"(bias[4 * e + 2]), "=f"(bias[4 * e + 3])
-                     : "r"(bias_addr + (pc * 16 + 4 * e) * 4));
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = pc * 16 + 2 * e;
-        float2 dgelu;
-        float2 gv = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[2 * e]), __uint_as_float(h[2 * e + 1])),
-                                          make_float2(bias[2 * e], bias[2 * e + 1])), dgelu);
-        float2 dv = __fmul2_rn(make_float2(__uint_as_float(dg[2 * e]), __uint_as_float(dg[2 * e + 1])), dgelu);
-        if (kDrop) {
-          drop_apply2(p.dh, gv.x, gv.y, i0 + k);
-          drop_apply2(p.dh, dv.x, dv.y, i0 + k);
-        }
-        dbp[k] += dv.x; dbp[k + 1] += dv.y;
-        gp[e] = pack_bf16(gv.x, gv.y);
-        dp[e] = pack_bf16(dv.x, dv.y);
-      }
-    };
-    uint32_t hA[16], gA[16], hB[16], gB[16];
-    mbar_wait(&hfull[0], 0);
-    tc_fence_after();
-    ld_piece(0, 0, hA, gA);
-    tmem_ld_wait();
+    const bool live = r < kRows;
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
-      const unsigned long long i0 = static_cast<unsigned long long>((t_lo + i) * kRows + r) * p.ldh + cg;
-      uint32_t gp[16], dp[16];
-      ld_piece(i, 1, hB, gB);
-      grad_piece(hA, gA, 0, i0, gp, dp);
+      mbar_wait(&hfull[b], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t h[32], dg[32];
+      tmem_ld32(tmem_base + C::kColH + lane_addr + b * kCc + grp * 32, h);
+      tmem_ld32(tmem_base + C::kColG + lane_addr + b * kCc + grp * 32, dg);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&hempty[b]);          // both pieces of H[b] / dG[b] are in registers
-      if (i + 1 < nt) {
-        mbar_wait(&hfull[b ^ 1], ((i + 1) >> 1) & 1);
-        tc_fence_after();
-        ld_piece(i + 1, 0, hA, gA);
+      mbar_arrive(&hempty[b]);
+      uint32_t gp[16], dp[16];
+      const unsigned long long i0 = static_cast<unsigned long long>((t_lo + i) * kRows + r) * p.ldh + cg;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        float bias[8];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+              : "=f"(bias[4 * e]), "=f"(bias[4 * e + 1]), "=f"(bias[4 * e + 2]), "=f"(bias[4 * e + 3])
+              : "r"(bias_addr + (ch * 8 + 4 * e) * 4));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = ch * 8 + 2 * e;
+          float2 dgelu;
+          float2 gv = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[k]), __uint_as_float(h[k + 1])),
+                                            make_float2(bias[2 * e], bias[2 * e + 1])), dgelu);
+          float2 dv = __fmul2_rn(make_float2(__uint_as_float(dg[k]), __uint_as_float(dg[k + 1])), dgelu);
+          if (kDrop) {
+            drop_apply2(p.dh, gv.x, gv.y, i0 + k);
+            drop_apply2(p.dh, dv.x, dv.y, i0 + k);
+          }
+          if (live) { dbp[k] += dv.x; dbp[k + 1] += dv.y; }
+          gp[ch * 4 + e] = pack_bf16(gv.x, gv.y);
+          dp[ch * 4 + e] = pack_bf16(dv.x, dv.y);
+        }
       }
-      grad_piece(hB, gB, 1, i0, gp + 8, dp + 8);
       mbar_wait(gempty, (i & 1) ^ 1);   // gradient GEMMs of tile i - 1 have consumed sG / sdH
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -253,7 +244,6 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
       fence_proxy_async();
       mbar_arrive(gfull);
-      tmem_ld_wait();
     }
     // db1: reduce the per-row partials over the 32 rows of the warp, then over the warps (shared-memory atomics)
     float mine = 0.f;
