@@ -28,7 +28,12 @@ namespace {
 
 constexpr int kRows = 128;      // token rows per CTA (UMMA M)
 constexpr int kCc = 64;         // channels per chunk
-constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue: two groups of 4 warps
+constexpr int kThreads = 320;   // forward: warp0 TMA, warp1 MMA, warps 2-9 epilogue (two groups of 4 warps)
+// backward: FOUR epilogue groups (16 warps, 4 per scheduler).  With two, the GELU' epilogue ran at 0.46 IPC per
+// scheduler - dependent FMA chains and MUFU latency, no pipe above 40 % (profiles/r01_ncu_chain_v9.md): latency bound,
+// so the cure is more warps in flight, each on a quarter (16 columns) of the chunk.
+constexpr int kGroupsB = 4;
+constexpr int kThreadsB = 64 + 128 * kGroupsB;
 constexpr int kBarBytes = 512;
 
 template <int DP>
@@ -50,6 +55,20 @@ struct CfgT {
   static constexpr int kColH = DP + DP / 2;
   static_assert(kColH + NB * kCc <= 512, "TMEM budget");
 };
+
+// Optional in-kernel timeline (debug builds: -DM2_TRACE): CTA 0 records (tag, chunk, clock) triples of its MMA warp
+// and first epilogue warp; tools/trace_chain.py prints them.  Compiled out by default.
+#ifdef M2_TRACE
+__device__ long long g_trace[4096];
+__device__ __forceinline__ void trace_evt(int slot, int tag, int j) {
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && slot < 1360) {
+    g_trace[3 * slot] = tag; g_trace[3 * slot + 1] = j; g_trace[3 * slot + 2] = clock64();
+  }
+}
+#define M2_TR(slot, tag, j) trace_evt(slot, tag, j)
+#else
+#define M2_TR(slot, tag, j)
+#endif
 
 struct TsParams {
   const float* u;        // [M][D] block input (pre-LN residual stream)
@@ -99,6 +118,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 // explicit ld.shared (the bias pointer is derived from an aligned-up dynamic smem base: ptxas falls back to generic LD)
 __device__ __forceinline__ float4 lds_f4(const float* p) {
   float4 v;
@@ -112,14 +136,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // LayerNorm the tile's rows (warp per row, kB rows in flight) into a padded row-major bf16 staging tile.
-template <int DP>
+template <int DP, int kB = 13>   // kB rows in flight per warp: one batch must cover the warp's share of the tile
 __device__ __forceinline__ void ln_rows_to_stage(const TsParams& p, int m0, uint8_t* stage, float* s_mean = nullptr,
                                                  float* s_rstd = nullptr, __nv_bfloat16* xn_b = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kV = DP / 128 > 0 ? DP / 128 : 1;   // float4 per lane per row
-  constexpr int kB = 13;                            // rows in flight: one batch covers the warp's share of the tile
-  constexpr int kW = kThreads / 32;
-  static_assert(kB * kW >= kRows && kV == 1, "LayerNorm prologue layout");
+  const int kW = blockDim.x >> 5;
+  static_assert(kV == 1, "LayerNorm prologue layout");
   float4 gw[kV], gb[kV];
 #pragma unroll
   for (int i = 0; i < kV; ++i) {
@@ -181,11 +204,11 @@ __device__ __forceinline__ void ln_rows_to_stage(const TsParams& p, int m0, uint
 // b1 -> shared memory (zero padded to whole chunks), 16-byte loads, all loads of a thread in flight together.
 __device__ __forceinline__ void stage_bias(const float* __restrict__ b1, int C, int n_pad, float* sBias) {
   const int nv = n_pad >> 2;
-  for (int i0 = threadIdx.x; i0 < nv; i0 += 4 * kThreads) {
+  for (int i0 = threadIdx.x; i0 < nv; i0 += 4 * blockDim.x) {
     float4 v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * kThreads;
+      const int i = i0 + k * blockDim.x;
       v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < nv) {
         const int c = i * 4;
@@ -200,7 +223,7 @@ __device__ __forceinline__ void stage_bias(const float* __restrict__ b1, int C, 
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * kThreads;
+      const int i = i0 + k * blockDim.x;
       if (i < nv) *reinterpret_cast<float4*>(sBias + i * 4) = v[k];
     }
   }
@@ -253,7 +276,12 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 1);
   float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Roles by LOGICAL warp id (0 = TMA producer, 1 = MMA issuer, 2.. = epilogue).  Physically the epilogue warps come
+  // first and the two single-thread roles LAST: the warp scheduler prefers the highest warp id on its sub-partition,
+  // and the latency-critical issuer starved behind the busy epilogue warps when it was warp 1 (724-clk gaps between a
+  // commit and the next wait in the in-kernel timeline, profiles/r01_trace_dgrad.md).
+  const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = pwarp < 8 ? pwarp + 2 : pwarp - 8;
   const int m0 = blockIdx.x * kRows;
   const int nch = ceil_div(p.C, kCc);
 
@@ -285,7 +313,7 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
 
   // staging -> TMEM (the A operand of every GEMM1): epilogue thread = TMEM lane = tile row; DP/2 columns
   if (warp >= 2) {
-    const int q = warp & 3, grp = (warp - 2) >> 2;
+    const int q = pwarp & 3, grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     for (int cb = grp; cb < DP / 64; cb += 2)   // 32 TMEM columns (= 64 bf16 = 128 B of the staging row) per step
@@ -337,10 +365,16 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
       __syncwarp();
     };
     for (int j = 0; j < (nch < NB ? nch : NB); ++j) gemm1(j);
-    for (int j = 0; j < nch; ++j) {   // Yacc += G_j . W2_j^T (A from TMEM), then run GEMM1 NB chunks ahead
+    // Steady state: ONE burst per chunk - GEMM2(j) and GEMM1(j + NB) are issued together after all their waits.  Every
+    // wake-up of the issuer costs ~200 clk of start-up plus ~100-200 clk per mbarrier wait (in-kernel timeline,
+    // profiles/r01_trace_dgrad.md), so the serial issue path, not the tensor pipe, paced the loop when they were separate.
+    for (int j = 0; j < nch; ++j) {   // Yacc += G_j . W2_j^T (A from TMEM) ; Hacc[(j+NB) % NB] = LN(u) . W1_{j+NB}^T
       const int s = j % S2, gb = j % NB;
-      mbar_wait(&w2full[s], (j / S2) & 1);
+      const int jn = j + NB, sn = jn % S1;
+      const bool more = jn < nch;
       mbar_wait(&gfull[gb], (j / NB) & 1);
+      mbar_wait(&w2full[s], (j / S2) & 1);
+      if (more) mbar_wait(&w1full[sn], (jn / S1) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t bd = w2_desc0 + static_cast<uint64_t>((s * C::kW2Bytes) >> 4);
@@ -349,14 +383,21 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         for (int kk = 0; kk < kCc / 16; ++kk)
           umma_bf16_ts(tY, tG + kk * 8, bd + ((kk * 32) >> 4), idesc2, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&w2empty[s]);
+        if (more) {   // same buffer gb: the tensor pipe runs GEMM2(j) (reads G) before this GEMM1 overwrites it
+          const uint64_t bd1 = w1_desc0 + static_cast<uint64_t>((sn * C::kW1Bytes) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < DP / 16; ++kk)
+            umma_bf16_ts(tG, tX + kk * 8, bd1 + (((kk >> 2) * (kCc * 128) + (kk & 3) * 32) >> 4), idesc1, kk > 0 ? 1u : 0u);
+          umma_commit(&w1empty[sn]);
+          umma_commit(&hfull[gb]);
+        }
       }
       __syncwarp();
-      if (j + NB < nch) gemm1(j + NB);
     }
     if (elect_one()) umma_commit(yfull);
     __syncwarp();
   } else {
-    const int q = warp & 3;                // TMEM lane quadrant this warp may access (warp id % 4)
+    const int q = pwarp & 3;               // TMEM lane quadrant this warp may access (physical warp id % 4)
     const int grp = (warp - 2) >> 2;       // epilogue group: chunks j = grp (mod 2)
     const int r = q * 32 + lane;           // row inside the tile == TMEM lane
     const int row = m0 + r;
@@ -502,7 +543,7 @@ __device__ __forceinline__ void dy_rows_to_stage(const TsParams& p, int m0, uint
   constexpr int kLanes = DP / 4;                 // lanes that cover one row
   constexpr int kRowsPerIter = 32 / kLanes;      // 1 (DP = 128) or 2 (DP = 64)
   const int c = (lane % kLanes) * 4;
-  for (int r0 = warp * kRowsPerIter; r0 < kRows; r0 += (kThreads / 32) * kRowsPerIter) {
+  for (int r0 = warp * kRowsPerIter; r0 < kRows; r0 += (blockDim.x >> 5) * kRowsPerIter) {
     const int r = r0 + lane / kLanes, row = m0 + r;
     uint2 o = make_uint2(0u, 0u);
     if (row < p.M && c < p.D) {
@@ -521,7 +562,7 @@ __device__ __forceinline__ void dy_rows_to_stage(const TsParams& p, int m0, uint
 }
 
 template <int DP, bool kDrop, bool kStoreGH>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsB, 1)
 chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TsParams p) {
   using C = CfgB<DP>;
   constexpr int S1 = C::S1, S2 = C::S2;
@@ -546,14 +587,19 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 1);
   float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Roles by LOGICAL warp id (0 = TMA producer, 1 = MMA issuer, 2.. = epilogue).  Physically the epilogue warps come
+  // first and the two single-thread roles LAST: the warp scheduler prefers the highest warp id on its sub-partition,
+  // and the latency-critical issuer starved behind the busy epilogue warps when it was warp 1 (724-clk gaps between a
+  // commit and the next wait in the in-kernel timeline, profiles/r01_trace_dgrad.md).
+  const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = pwarp < 4 * kGroupsB ? pwarp + 2 : pwarp - 4 * kGroupsB;
   const int m0 = blockIdx.x * kRows;
   const int nch = ceil_div(p.C, kCc);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S1; ++i) { mbar_init(&w1full[i], 1); mbar_init(&w1empty[i], 1); }
     for (int i = 0; i < S2; ++i) { mbar_init(&w2full[i], 1); mbar_init(&w2empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&hfull[i], 1); mbar_init(&dhfull[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&hfull[i], 1); mbar_init(&dhfull[i], 128 * kGroupsB); }
     mbar_init(yfull, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmW1);
@@ -561,13 +607,13 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
   if (p.bias_smem) stage_bias(p.b1, p.C, nch * kCc, sBias);
-  for (int i = threadIdx.x; i < 3 * DP; i += kThreads) sCol[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * DP; i += blockDim.x) sCol[i] = 0.f;
   __syncthreads();
   if (warp == 0 && lane == 0) {
     for (int j = 0; j < (nch < S1 ? nch : S1); ++j) load_w1<DP>(sW1 + j * C::kW1Bytes, &tmW1, &w1full[j], j * kCc);
     for (int j = 0; j < (nch < S2 ? nch : S2); ++j) load_w2<DP>(sW2 + j * C::kW2Bytes, &tmW2, &w2full[j], j * kCc);
   }
-  ln_rows_to_stage<DP>(p, m0, sStageX, sMean, sRstd, p.xn_b);
+  ln_rows_to_stage<DP, 8>(p, m0, sStageX, sMean, sRstd, p.xn_b);   // 18 warps x 8 rows >= 128
   dy_rows_to_stage<DP, kDrop>(p, m0, sStageDY);
   tc_fence_before();
   __syncthreads();
@@ -577,14 +623,16 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   const uint32_t tX = tmem_base + C::kColX;
   const uint32_t tDY = tmem_base + C::kColDY;
 
-  if (warp >= 2) {   // staging -> TMEM: group 0 copies LN(u), group 1 copies dY
-    const int q = warp & 3, grp = (warp - 2) >> 2;
+  if (warp >= 2) {   // staging -> TMEM: groups 0/1 copy the two 32-column halves of LN(u), groups 2/3 those of dY
+    const int q = pwarp & 3, grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const uint8_t* src = (grp == 0 ? sStageX : sStageDY) + r * C::kXPitch;
-    const uint32_t dst = (grp == 0 ? tX : tDY) + lane_addr;
-#pragma unroll
-    for (int cb = 0; cb < DP / 64; ++cb) stage_row_to_tmem(src + cb * 128, dst + cb * 32);
+    const int mat = grp >> 1, cb = grp & 1;
+    if (cb < DP / 64) {
+      const uint8_t* src = (mat == 0 ? sStageX : sStageDY) + r * C::kXPitch;
+      const uint32_t dst = (mat == 0 ? tX : tDY) + lane_addr;
+      stage_row_to_tmem(src + cb * 128, dst + cb * 32);
+    }
     tmem_st_wait();
   }
   tc_fence_before();
@@ -643,42 +691,68 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     };
     hg(0);
     if (nch > 1) hg(1);
-    for (int j = 0; j < nch; ++j) {   // dXn += dH_j . W1_j   (contraction over the 64 channels of the chunk)
+    // Steady state: ONE burst per chunk - dXn(j) and the H / dG GEMMs of chunk j + 2 (which reuse buffer j & 1) are issued
+    // together after all their waits (see the forward kernel for why).
+    for (int j = 0; j < nch; ++j) {   // dXn += dH_j . W1_j ; H[j&1] = LN(u) . W1_{j+2}^T ; dG[j&1] = dY . W2_{j+2}
       const int s1 = j % S1, b = j & 1;
+      const int jn = j + 2, s1n = jn % S1, s2n = jn % S2;
+      const bool more = jn < nch;
+      M2_TR(4 * j + 0, 1, j);
       mbar_wait(&dhfull[b], (j >> 1) & 1);
+      if (more) {
+        mbar_wait(&w1full[s1n], (jn / S1) & 1);
+        mbar_wait(&w2full[s2n], (jn / S2) & 1);
+      }
+      M2_TR(4 * j + 1, 2, j);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t bd = w1m_desc0 + static_cast<uint64_t>((s1 * C::kW1Bytes) >> 4);
-        const uint32_t tDH = tmem_base + C::kColG + b * kCc;
+        const uint32_t tH = tmem_base + C::kColH + b * kCc;
+        const uint32_t tG = tmem_base + C::kColG + b * kCc;
 #pragma unroll
-        for (int kk = 0; kk < kCc / 16; ++kk)   // B: 16 c-rows per step = 2048 B; d panels 8 KB apart (LBO)
-          umma_bf16_ts(tDX, tDH + (kk >> 1) * 32 + (kk & 1) * 8, bd + ((kk * 2048) >> 4), idescX, (j > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < kCc / 16; ++kk)   // B: 16 c-rows per step = 2048 B; d panels 8 KB apart (LBO); A: group kk's dH
+          umma_bf16_ts(tDX, tG + kk * 16, bd + ((kk * 2048) >> 4), idescX, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&w1empty[s1]);
+        if (more) {
+          const uint64_t bd1 = w1k_desc0 + static_cast<uint64_t>((s1n * C::kW1Bytes) >> 4);
+          const uint64_t bd2 = w2m_desc0 + static_cast<uint64_t>((s2n * C::kW2Bytes) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < DP / 16; ++kk)
+            umma_bf16_ts(tH, tX + kk * 8, bd1 + (((kk >> 2) * (kCc * 128) + (kk & 3) * 32) >> 4), idescH, kk > 0 ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < DP / 16; ++kk)
+            umma_bf16_ts(tG, tDY + kk * 8, bd2 + ((kk * 2048) >> 4), idescG, kk > 0 ? 1u : 0u);
+          umma_commit(&w2empty[s2n]);
+          umma_commit(&hfull[b]);
+        }
+        M2_TR(4 * j + 2, 10, j);
       }
       __syncwarp();
-      if (j + 2 < nch) hg(j + 2);
     }
     if (elect_one()) umma_commit(yfull);
     __syncwarp();
   } else {
-    const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;       // both groups work on every chunk: group g owns columns [32 g, 32 g + 32)
+    const int q = pwarp & 3;
+    const int grp = (warp - 2) >> 2;       // every group works on every chunk: group g owns columns [16 g, 16 g + 16)
     const int r = q * 32 + lane;
     const int row = m0 + r;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     for (int j = 0; j < nch; ++j) {
       const int b = j & 1;
-      const uint32_t tH = tmem_base + C::kColH + lane_addr + b * kCc + grp * 32;
-      const uint32_t tG = tmem_base + C::kColG + lane_addr + b * kCc + grp * 32;
+      const uint32_t tH = tmem_base + C::kColH + lane_addr + b * kCc + grp * 16;
+      const uint32_t tG = tmem_base + C::kColG + lane_addr + b * kCc + grp * 16;
+      if (warp == 2) M2_TR(400 + 4 * j + 0, 5, j);   // epilogue: about to wait for H / dG
       mbar_wait(&hfull[b], (j >> 1) & 1);
+      if (warp == 2) M2_TR(400 + 4 * j + 1, 6, j);   // epilogue: accumulators ready
       tc_fence_after();
-      const int c0 = j * kCc + grp * 32;
-      uint32_t h[32], dg[32], dhp[16];
-      tmem_ld32(tH, h);
-      tmem_ld32(tG, dg);
+      const int c0 = j * kCc + grp * 16;
+      uint32_t h[16], dg[16], dhp[8];
+      tmem_ld16(tH, h);
+      tmem_ld16(tG, dg);
       tmem_ld_wait();
+      if (warp == 2) M2_TR(400 + 4 * j + 2, 7, j);   // epilogue: TMEM loads done
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < 2; ++ch) {
         const int cc = c0 + ch * 8;
         float bias[8];
         if (p.bias_smem) {
@@ -718,18 +792,19 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
           }
         }
       }
-      // dH (bf16, 16 columns) over the first half of the dG columns this thread has just read: the two groups never
-      // touch each other's columns, the tensor pipe reads them (dXn GEMM) before chunk j + 2 overwrites the buffer.
-      tmem_st16(tG, dhp);
+      // dH (bf16, 8 columns) over the first half of the dG columns this thread has just read: the groups never touch
+      // each other's columns, the tensor pipe reads them (dXn GEMM) before chunk j + 2 overwrites the buffer.
+      tmem_st8(tG, dhp);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&dhfull[b]);
+      if (warp == 2) M2_TR(400 + 4 * j + 3, 8, j);   // epilogue: dH stored, arrived
     }
     // ---- final: LayerNorm backward fused on the accumulator.  Pass 1: dXn rows -> padded fp32 staging.
     mbar_wait(yfull, 0);
     tc_fence_after();
-#pragma unroll 1
-    for (int d0 = grp * (DP / 2); d0 < (grp + 1) * (DP / 2); d0 += 32) {
+    if (grp * 32 < DP) {   // 32 accumulator columns per group
+      const int d0 = grp * 32;
       uint32_t a[32];
       tmem_ld32(tDX + lane_addr + d0, a);
       tmem_ld_wait();
@@ -739,7 +814,7 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         *reinterpret_cast<float4*>(o + e) = make_float4(__uint_as_float(a[e]), __uint_as_float(a[e + 1]),
                                                         __uint_as_float(a[e + 2]), __uint_as_float(a[e + 3]));
     }
-    named_bar_sync(1, 256);
+    named_bar_sync(1, 128 * kGroupsB);
     // Pass 2: kLanes lanes per row along d (coalesced u / dy reads, du writes):
     //   g = dXn * gamma ; du = dy + rstd * (g - mean_d(g) - xhat * mean_d(g * xhat))
     //   dln_w += sum_rows dXn * xhat ; dln_b += sum_rows dXn ; db2 += sum_rows dY(masked)
@@ -753,7 +828,7 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     const float4 gam = dok ? *reinterpret_cast<const float4*>(p.ln_w + d2) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 aw = make_float4(0.f, 0.f, 0.f, 0.f), ab = aw, a2 = aw;
 #pragma unroll 2
-    for (int rr = ew * kRowsPerIter; rr < kRows; rr += 8 * kRowsPerIter) {
+    for (int rr = ew * kRowsPerIter; rr < kRows; rr += 4 * kGroupsB * kRowsPerIter) {
       const int r2 = rr + rsub;
       const int grow = m0 + r2;
       const bool ok = dok && grow < p.M;
@@ -797,8 +872,8 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
       atomicAdd(&sCol[DP + d2], ab.x); atomicAdd(&sCol[DP + d2 + 1], ab.y); atomicAdd(&sCol[DP + d2 + 2], ab.z); atomicAdd(&sCol[DP + d2 + 3], ab.w);
       atomicAdd(&sCol[2 * DP + d2], a2.x); atomicAdd(&sCol[2 * DP + d2 + 1], a2.y); atomicAdd(&sCol[2 * DP + d2 + 2], a2.z); atomicAdd(&sCol[2 * DP + d2 + 3], a2.w);
     }
-    named_bar_sync(1, 256);
-    for (int i = threadIdx.x - 64; i < 3 * DP; i += 256) {
+    named_bar_sync(1, 128 * kGroupsB);
+    for (int i = (warp - 2) * 32 + lane; i < 3 * DP; i += 128 * kGroupsB) {
       const int which = i / DP, d = i % DP;
       if (d < p.D) atomicAdd((which == 0 ? p.dln_w : which == 1 ? p.dln_b : p.db2) + d, sCol[i]);
     }
@@ -840,7 +915,7 @@ int launch_bwd(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p, 
     configured = smem;
   }
   LaunchScope scope("chain_bwd", s);
-  chain_bwd_ts_kernel<DP, kDrop, kStoreGH><<<ceil_div(p.M, kRows), kThreads, smem, s>>>(t1, t2, pp);
+  chain_bwd_ts_kernel<DP, kDrop, kStoreGH><<<ceil_div(p.M, kRows), kThreadsB, smem, s>>>(t1, t2, pp);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }
@@ -854,6 +929,12 @@ int launch_bwd_d(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p
 }
 
 }  // namespace
+
+#ifdef M2_TRACE
+int chain_trace_read(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * n) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 bool chain_fwd_ts_supported(int D) { return D >= 16 && D <= 128 && D % 8 == 0; }
 

@@ -46,7 +46,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* acc_full = empty + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // logical roles 0 = TMA, 1 = MMA, 2-5 = epilogue; physically the epilogue warps come first (see chain_ts.cu)
+  const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = pwarp < 4 ? pwarp + 2 : pwarp - 4;
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
   const int batch = blockIdx.z / p.splitk, split = blockIdx.z % p.splitk;
   const int k_tiles = ceil_div(p.K, kBK);
@@ -121,7 +123,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int q = warp & 3;
+    const int q = pwarp & 3;
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < p.M;
     const bool lead = (split == 0);

@@ -80,7 +80,9 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   float* sDb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);   // [64] db1 partials (16-byte aligned)
   float* sB1 = sDb + kCc;                                  // [64] b1 of the chunk
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // logical roles 0 = TMA, 1 = MMA, 2.. = epilogue; physically the epilogue warps come first (see chain_ts.cu)
+  const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = pwarp < 8 ? pwarp + 2 : pwarp - 8;
   const int c0 = blockIdx.x * kCc;
   const int t_lo = static_cast<int>(static_cast<long long>(p.ntiles) * blockIdx.y / p.R);
   const int t_hi = static_cast<int>(static_cast<long long>(p.ntiles) * (blockIdx.y + 1) / p.R);
@@ -167,9 +169,17 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     mbar_wait(wfull, 0);
     hg(0);
     if (nt > 1) hg(1);
-    for (int i = 0; i < nt; ++i) {   // dW1c^T += Xn_i^T . dH_i ; dW2c += dY_i^T . G_i   (contraction over the 128 rows)
+    // Steady state: ONE burst per tile - the gradient GEMMs of tile i and the recompute GEMMs of tile i + 2 are issued
+    // together after all their waits (every wake-up of the issuer costs several hundred cycles, chain_ts.cu).
+    for (int i = 0; i < nt; ++i) {   // dW1c^T += Xn_i^T . dH_i ; dW2c += dY_i^T . G_i   (contraction over the rows)
       const int s = i % kNS;
+      const int in = i + 2, sn = in % kNS, b = i & 1;
+      const bool more = in < nt;
       mbar_wait(gfull, i & 1);
+      if (more) {
+        mbar_wait(&full[sn], (in / kNS) & 1);
+        mbar_wait(&hempty[b], ((in >> 1) & 1) ^ 1);
+      }
       tc_fence_after();
       if (elect_one()) {
         const uint64_t xa = xm0 + static_cast<uint64_t>((s * C::kStage) >> 4);
@@ -182,15 +192,28 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           umma_bf16(tmem_base + C::kColW2, ya + ((kk * 2048) >> 4), gd + ((kk * 2048) >> 4), idescW, (i > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&empty[s]);
         umma_commit(gempty);
+        if (more) {
+          const uint64_t xk = xk0 + static_cast<uint64_t>((sn * C::kStage) >> 4);
+          const uint64_t yk = xk + static_cast<uint64_t>(C::kTile >> 4);
+          const uint32_t tH = tmem_base + C::kColH + b * kCc;
+          const uint32_t tG = tmem_base + C::kColG + b * kCc;
+#pragma unroll
+          for (int kk = 0; kk < DP / 16; ++kk)
+            umma_bf16(tH, xk + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4), w1d + (((kk >> 2) * (kCc * 128) + (kk & 3) * 32) >> 4),
+                      idescH, kk > 0 ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < DP / 16; ++kk)
+            umma_bf16(tG, yk + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4), w2d + ((kk * 2048) >> 4), idescG, kk > 0 ? 1u : 0u);
+          umma_commit(&hfull[b]);
+        }
       }
       __syncwarp();
-      if (i + 2 < nt) hg(i + 2);
     }
     if (elect_one()) umma_commit(accfull);
     __syncwarp();
   } else {
     // ---- epilogue: thread = row of the tile (TMEM lane), group g = columns [32 g, 32 g + 32) of the chunk
-    const int q = warp & 3;
+    const int q = pwarp & 3;
     const int grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -284,7 +307,7 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const int t = threadIdx.x - 64;
+    const int t = (warp - 2) * 32 + lane;
     if (t < kCc && c0 + t < p.C) atomicAdd(p.db1 + c0 + t, sDb[t]);
   }
   tc_fence_before();

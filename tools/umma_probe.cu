@@ -55,9 +55,10 @@ __global__ void probe(int rounds, long long* out) {
     }
     long long t1 = clock64();
     umma_commit(&bar);
+    long long tc = clock64();
     mbar_wait(&bar, 0);
     long long t2 = clock64();
-    if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; out[2] = tc - t1; }
   }
   tc_fence_before();
   __syncthreads();
@@ -70,19 +71,32 @@ void run(int grid, long long* dout) {
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int rounds = 512 / (NACC * CHAIN) > 0 ? 512 / (NACC * CHAIN) : 1;
   const int nmma = rounds * NACC * CHAIN;
-  long long h[2];
+  long long h[3];
   for (int rep = 0; rep < 2; ++rep) {
     k<<<grid, 128, 64 * 1024>>>(rounds, dout);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return; }
   }
   cudaMemcpy(h, dout, sizeof(h), cudaMemcpyDeviceToHost);
-  printf("N=%3d %s B=%s grid=%3d nmma=%4d nacc=%d chain=%3d : issue %7lld clk, total %7lld clk, %6.1f clk/MMA (floor %d)\n", N,
-         MODE ? "TS" : "SS", B_MN ? "MN" : "K ", grid, nmma, NACC, CHAIN, h[0], h[1], double(h[1]) / nmma, N / 2);
+  printf("N=%3d %s B=%s grid=%3d nmma=%4d nacc=%d chain=%3d : issue %7lld clk, commit %5lld clk, total %7lld clk, %6.1f clk/MMA (floor %d)\n", N,
+         MODE ? "TS" : "SS", B_MN ? "MN" : "K ", grid, nmma, NACC, CHAIN, h[0], h[2], h[1], double(h[1]) / nmma, N / 2);
+}
+
+template <int N, int MODE, int NACC, int CHAIN, int B_MN>
+void run_short(int grid, long long* dout) {
+  auto k = probe<N, MODE, NACC, CHAIN, B_MN>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  long long h[3];
+  for (int rep = 0; rep < 2; ++rep) { k<<<grid, 128, 64 * 1024>>>(1, dout); cudaDeviceSynchronize(); }
+  cudaMemcpy(h, dout, sizeof(h), cudaMemcpyDeviceToHost);
+  printf("SHORT N=%3d %s nmma=%3d : issue %6lld clk, commit %5lld clk, total %6lld clk\n", N, MODE ? "TS" : "SS", NACC * CHAIN, h[0], h[2], h[1]);
 }
 
 template <int MODE>
 void sweep(int grid, long long* dout) {
+  run_short<128, MODE, 1, 4, 1>(grid, dout);
+  run_short<64, MODE, 2, 8, 0>(grid, dout);
+  run_short<64, MODE, 1, 1, 0>(grid, dout);
   run<64, MODE, 1, 64, 0>(grid, dout);
   run<64, MODE, 1, 8, 0>(grid, dout);
   run<64, MODE, 2, 8, 0>(grid, dout);
@@ -99,8 +113,8 @@ void sweep(int grid, long long* dout) {
 
 int main() {
   long long* dout;
-  cudaMalloc(&dout, 16);
-  for (int grid : {1, 148}) {
+  cudaMalloc(&dout, 32);
+  for (int grid : {148}) {
     sweep<0>(grid, dout);
     sweep<1>(grid, dout);
   }
