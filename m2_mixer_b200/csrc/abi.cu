@@ -113,6 +113,9 @@ int m2b200_token_mix_bwd(const float* du, const float* x, const float* ln_w, con
                          uint64_t seed, void* workspace, size_t workspace_bytes, void* stream) {
   if (!du || !x || !ln_w || !ln_b || !wt1 || !bt1 || !wt2 || !dx || !dln_w || !dln_b || !dwt1 || !dbt1 || !dwt2 || !dbt2)
     return M2_ERR_ARG;
+  if (precision != M2B200_FP32 && token_generation() != 1 && token_mix_mma_supported(N, D, T))   // LN backward fused in
+    return token_mix_mma_bwd(du, x, ln_w, ln_b, wt1, bt1, wt2, dx, dln_w, dln_b, dwt1, dbt1, dwt2, dbt2, B, N, D, T, dropout_p,
+                             seed, S(stream));
   Carver ws(workspace, workspace_bytes);
   float* dxn = ws.take<float>(static_cast<size_t>(B) * N * D);
   if (!ws.ok) return M2_ERR_WORKSPACE;

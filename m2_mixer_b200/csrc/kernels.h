@@ -87,6 +87,16 @@ int token_mix_bwd(const float* du, const float* x, const float* ln_w, const floa
                   const float* w2, float* dxn, float* dw1, float* db1, float* dw2, float* db2,
                   int B, int N, int D, int T, int exact_gelu, float drop_p, unsigned long long seed, cudaStream_t s);
 
+// warp-level tensor-core path (token_mix_mma.cu): bf16 mode, N <= 16, T <= 32, D in {32,64,128,256}
+bool token_mix_mma_supported(int N, int D, int T);
+int token_mix_mma_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1, const float* w2,
+                      const float* b2, float* u, int B, int N, int D, int T, float drop_p, unsigned long long seed,
+                      cudaStream_t s);
+int token_mix_mma_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
+                      const float* w2, float* dx, float* dln_w, float* dln_b, float* dw1, float* db1, float* dw2, float* db2,
+                      int B, int N, int D, int T, float drop_p, unsigned long long seed, cudaStream_t s);
+int token_generation();   // env M2B200_TOKEN_GEN: 1 = CUDA-core kernels only (A/B measurements)
+
 // ---- heads + multi-head loss (heads.cu)
 struct HeadsArgs {
   const float* tok[3]; long long tok_bstride[3]; int ntok[3]; int dim[3];   // pooled inputs per head

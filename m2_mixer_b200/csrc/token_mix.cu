@@ -7,6 +7,8 @@
 // a tensor-core tile would be >90 % padding, so this path keeps the [N x D] sample tile in shared memory and runs
 // FP32 FMAs, reading x once and writing u once.  One CTA handles a slice of `dt` hidden columns of one sample and
 // loops over samples; weights are read through L1 (warp-uniform addresses).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -465,10 +467,20 @@ constexpr size_t kMaxSmem = 220 * 1024;
 
 }  // namespace
 
+int token_generation() {
+  static const int gen = []() {
+    const char* e = getenv("M2B200_TOKEN_GEN");
+    return e ? atoi(e) : 2;
+  }();
+  return gen;
+}
+
 int token_mix_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1, const float* w2,
                   const float* b2, float* u, int B, int N, int D, int T, int exact_gelu, float drop_p,
                   unsigned long long seed, cudaStream_t s) {
   if (B <= 0 || N <= 0 || D <= 0 || T <= 0) return M2_ERR_ARG;
+  if (!exact_gelu && token_generation() != 1 && token_mix_mma_supported(N, D, T))
+    return token_mix_mma_fwd(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, D, T, drop_p, seed, s);
   if (small_ok(N, D, T)) {
     const Drop dh = make_drop(drop_p, seed, kSiteTokenHidden), dout = make_drop(drop_p, seed, kSiteTokenOut);
     const int spb = kThreads / D, Tp = (T + 1) & ~1;

@@ -1,0 +1,566 @@
+// Token-mixing half of a Mixer block on the warp-level tensor cores (mma.sync m16n8k16, bf16 x bf16 -> fp32).
+//
+// Reference arithmetic: MixerBlock.token_mix, modules/mixer.py:30-35,43, transpose-free:
+//     H^T[d,t] = sum_n LN(x)[n,d] W1[t,n] + b1[t]      U^T[d,n'] = sum_t Drop(GELU(H^T))[d,t] W2[n',t] + b2[n']
+//     u[b,n',d] = x[b,n',d] + Drop(U^T[d,n'])
+// The contraction lengths of the shipped configs are tiny (N = 4 or 8 tokens, T <= 32: SURVEY D2), so a tcgen05 tile would
+// be >90 % padding and TMEM round trips per 4 KB sample; but on the CUDA cores the 2 x N x T FMAs per (sample, column)
+// cost 3x the GELU they surround (token_mix.cu: 40-130 us per launch at B = 4096).  Here one WARP owns one sample:
+//   * its [N x D] tile lives in registers in mma A-fragment order (rows = hidden columns d, k = tokens n), LayerNorm
+//     statistics are reduced with three shuffles per row,
+//   * GEMM1 (K = N zero-padded to 16) -> fp32 C fragments -> GELU -> packed straight into the A fragments of GEMM2
+//     (the flash-attention register hand-off: two adjacent n8 C tiles are one k16 A tile), no shared memory at all,
+//   * MMA row r of a 16-row tile is hidden column d0 + 2r (r < 8) / d0 + 2(r-8) + 1, so every lane owns PAIRS of adjacent
+//     columns: 8-byte global accesses, and one dropout hash per pair.
+// Backward (token_mix_mma_bwd_kernel): recomputes H, forms dG = dU W2, dH = dG * GELU'(H), dXn = dH W1 the same way,
+// finishes the LayerNorm backward in the warp (dx = du + LN'(dXn): no dXn buffer, no separate ln_bwd launch), and gets
+// the weight gradients (contractions over d) from movmatrix-transposed fragments accumulated in registers across samples.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace m2 {
+namespace {
+
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// transpose an 8x8 b16 matrix held one row-pair per thread (thread 4r+q holds row r, cols 2q..2q+1)
+__device__ __forceinline__ uint32_t movmatrix_t(uint32_t v) {
+  uint32_t r;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+// sum over the 8 lanes that share (lane & 3)
+__device__ __forceinline__ float group_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+// D = 16 * DM, T <= TP (multiple of 16), N <= NP (8 or 16).
+template <int DM, int TP, int NP, bool kDrop>
+__global__ void __launch_bounds__(kWarps * 32)
+token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                         const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                         const float* __restrict__ b2, float* __restrict__ u, int B, int N, int T, const Drop dh,
+                         const Drop dout) {
+  constexpr int D = 16 * DM;
+  constexpr int KN = NP / 8;      // 8-token groups (k halves of GEMM1 / n tiles of GEMM2)
+  constexpr int NT1 = TP / 8;     // n tiles of GEMM1
+  constexpr int KS2 = TP / 16;    // k steps of GEMM2
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+
+  // ---- constant B fragments and biases (registers, loaded once per warp)
+  uint32_t w1f[NT1][KN];          // B1[k = n][col = t] = W1[t][n]
+  float b1f[NT1][2];
+#pragma unroll
+  for (int j = 0; j < NT1; ++j) {
+    const int t = 8 * j + g;
+#pragma unroll
+    for (int kh = 0; kh < KN; ++kh) {
+      const int n0 = 2 * tq + 8 * kh;
+      const float v0 = (t < T && n0 < N) ? w1[t * N + n0] : 0.f;
+      const float v1 = (t < T && n0 + 1 < N) ? w1[t * N + n0 + 1] : 0.f;
+      w1f[j][kh] = pack_bf16(v0, v1);
+    }
+    b1f[j][0] = (8 * j + 2 * tq < T) ? b1[8 * j + 2 * tq] : 0.f;
+    b1f[j][1] = (8 * j + 2 * tq + 1 < T) ? b1[8 * j + 2 * tq + 1] : 0.f;
+  }
+  uint32_t w2f[KS2][KN][2];       // B2[k = t][col = n'] = W2[n'][t]
+  float b2f[KN][2];
+#pragma unroll
+  for (int jn = 0; jn < KN; ++jn) {
+    const int n = 8 * jn + g;
+#pragma unroll
+    for (int ks = 0; ks < KS2; ++ks)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int t0 = 16 * ks + 2 * tq + 8 * hh;
+        const float v0 = (n < N && t0 < T) ? w2[n * T + t0] : 0.f;
+        const float v1 = (n < N && t0 + 1 < T) ? w2[n * T + t0 + 1] : 0.f;
+        w2f[ks][jn][hh] = pack_bf16(v0, v1);
+      }
+    b2f[jn][0] = (8 * jn + 2 * tq < N) ? b2[8 * jn + 2 * tq] : 0.f;
+    b2f[jn][1] = (8 * jn + 2 * tq + 1 < N) ? b2[8 * jn + 2 * tq + 1] : 0.f;
+  }
+  const float inv_d = 1.f / D;
+
+  for (int b = blockIdx.x * kWarps + warp; b < B; b += gridDim.x * kWarps) {
+    const float* xb = x + static_cast<long long>(b) * N * D;
+    // raw tile: xr[mt][kh][nn] = x[n = 8 kh + 2 tq + nn][d = 16 mt + 2 g .. +1]
+    float2 xr[DM][KN][2];
+    float s[KN][2];
+#pragma unroll
+    for (int kh = 0; kh < KN; ++kh)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        const int n = 8 * kh + 2 * tq + nn;
+        float acc = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < DM; ++mt) {
+          xr[mt][kh][nn] = n < N ? *reinterpret_cast<const float2*>(xb + n * D + 16 * mt + 2 * g) : make_float2(0.f, 0.f);
+          acc += xr[mt][kh][nn].x + xr[mt][kh][nn].y;
+        }
+        s[kh][nn] = acc;
+      }
+    float mean[KN][2], rstd[KN][2];
+#pragma unroll
+    for (int kh = 0; kh < KN; ++kh)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        mean[kh][nn] = group_sum(s[kh][nn]) * inv_d;
+        float ss = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < DM; ++mt) {
+          const float a = xr[mt][kh][nn].x - mean[kh][nn], c = xr[mt][kh][nn].y - mean[kh][nn];
+          ss += a * a + c * c;
+        }
+        rstd[kh][nn] = rsqrtf(group_sum(ss) * inv_d + kLnEps);
+      }
+
+#pragma unroll
+    for (int mt = 0; mt < DM; ++mt) {
+      const int d_lo = 16 * mt + 2 * g;
+      const float2 gm = *reinterpret_cast<const float2*>(ln_w + d_lo);
+      const float2 bt = *reinterpret_cast<const float2*>(ln_b + d_lo);
+      // A1: a0 = (row g = d_lo, k = 2tq..+1), a1 = (row g+8 = d_hi, same k), a2 / a3 = k + 8
+      uint32_t a1f[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int kh = 0; kh < KN; ++kh) {
+        const float x00 = (xr[mt][kh][0].x - mean[kh][0]) * rstd[kh][0] * gm.x + bt.x;
+        const float x01 = (xr[mt][kh][1].x - mean[kh][1]) * rstd[kh][1] * gm.x + bt.x;
+        const float x10 = (xr[mt][kh][0].y - mean[kh][0]) * rstd[kh][0] * gm.y + bt.y;
+        const float x11 = (xr[mt][kh][1].y - mean[kh][1]) * rstd[kh][1] * gm.y + bt.y;
+        const int n = 8 * kh + 2 * tq;
+        a1f[2 * kh] = pack_bf16(n < N ? x00 : 0.f, n + 1 < N ? x01 : 0.f);
+        a1f[2 * kh + 1] = pack_bf16(n < N ? x10 : 0.f, n + 1 < N ? x11 : 0.f);
+      }
+      float c[NT1][4];
+#pragma unroll
+      for (int j = 0; j < NT1; ++j) {
+        c[j][0] = c[j][2] = b1f[j][0];
+        c[j][1] = c[j][3] = b1f[j][1];
+        mma_bf16(c[j], a1f[0], a1f[1], a1f[2], a1f[3], w1f[j][0], KN > 1 ? w1f[j][KN - 1] : 0u);
+      }
+      // GELU (+ dropout) -> A2 fragments; C tile j: c0 = (d_lo, t), c1 = (d_lo, t+1), c2 = (d_hi, t), c3 = (d_hi, t+1)
+      uint32_t a2f[KS2][4];
+#pragma unroll
+      for (int j = 0; j < NT1; ++j) {
+        float2 lo = gelu2(make_float2(c[j][0], c[j][1]));
+        float2 hi = gelu2(make_float2(c[j][2], c[j][3]));
+        if (kDrop) {   // hidden-site index (b T + t) D + d: (d_lo, d_hi) is one hash pair
+          const int t = 8 * j + 2 * tq;
+          const unsigned long long i0 = (static_cast<unsigned long long>(b) * T + t) * D + d_lo;
+          drop_apply2(dh, lo.x, hi.x, i0);
+          drop_apply2(dh, lo.y, hi.y, i0 + D);
+        }
+        a2f[j >> 1][(j & 1) * 2] = pack_bf16(lo.x, lo.y);
+        a2f[j >> 1][(j & 1) * 2 + 1] = pack_bf16(hi.x, hi.y);
+      }
+      float o[KN][4];
+#pragma unroll
+      for (int jn = 0; jn < KN; ++jn) {
+        o[jn][0] = o[jn][2] = b2f[jn][0];
+        o[jn][1] = o[jn][3] = b2f[jn][1];
+#pragma unroll
+        for (int ks = 0; ks < KS2; ++ks)
+          mma_bf16(o[jn], a2f[ks][0], a2f[ks][1], a2f[ks][2], a2f[ks][3], w2f[ks][jn][0], w2f[ks][jn][1]);
+      }
+      // o[jn]: c0 = (d_lo, n'), c1 = (d_lo, n'+1), c2 = (d_hi, n'), c3 = (d_hi, n'+1),  n' = 8 jn + 2 tq
+#pragma unroll
+      for (int jn = 0; jn < KN; ++jn)
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) {
+          const int n = 8 * jn + 2 * tq + nn;
+          if (n < N) {
+            float v_lo = o[jn][nn], v_hi = o[jn][2 + nn];
+            const long long off = (static_cast<long long>(b) * N + n) * D + d_lo;
+            if (kDrop) drop_apply2(dout, v_lo, v_hi, static_cast<unsigned long long>(off));
+            *reinterpret_cast<float2*>(u + off) = make_float2(xr[mt][jn][nn].x + v_lo, xr[mt][jn][nn].y + v_hi);
+          }
+        }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward.  dx = du + LN'(dXn);  dln_w, dln_b, dw1, db1, dw2, db2 are accumulated (per-CTA shared-memory partials, then
+// one global atomic per element and CTA).  kW warps per CTA; sDxn is the lane-private spill of the dXn tile that the
+// LayerNorm backward needs after the per-row sums over the whole hidden axis are known.
+template <int DM, int TP, int NP, bool kDrop, int kW, int kMinB>
+__global__ void __launch_bounds__(kW * 32, kMinB)
+token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__ x, const float* __restrict__ ln_w,
+                         const float* __restrict__ ln_b, const float* __restrict__ w1, const float* __restrict__ b1,
+                         const float* __restrict__ w2, float* __restrict__ dx, float* __restrict__ dln_w,
+                         float* __restrict__ dln_b, float* __restrict__ dw1, float* __restrict__ db1,
+                         float* __restrict__ dw2, float* __restrict__ db2, int B, int N, int T, const Drop dh, const Drop dout) {
+  constexpr int D = 16 * DM;
+  constexpr int KN = NP / 8;      // 8-token groups
+  constexpr int NT1 = TP / 8;     // 8-wide hidden-unit tiles
+  constexpr int KS2 = TP / 16;    // 16-wide hidden-unit steps (k steps of the dXn GEMM, m tiles of the weight-gradient GEMMs)
+  constexpr int DQ = (DM + 3) / 4;
+  extern __shared__ float smem_f[];
+  float* sAcc = smem_f;                               // [2][TP][NP] dw1^T / dw2^T partials, [TP] db1, [NP] db2, [2][D] dln_w / dln_b
+  float* sDxn = sAcc + 2 * TP * NP + TP + NP + 2 * D; // [kW][DM * KN * 4][32] lane-private
+  constexpr int kAcc = 2 * TP * NP + TP + NP + 2 * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  for (int i = threadIdx.x; i < kAcc; i += kW * 32) sAcc[i] = 0.f;
+  float* myDxn = sDxn + warp * (DM * KN * 4 * 32) + lane;
+
+  // ---- constant B fragments
+  uint32_t w1f[NT1][KN];          // GEMM1  B[k = n][col = t]  = W1[t][n]
+  uint32_t w2g[NT1][KN];          // GEMM3  B[k = n'][col = t] = W2[n'][t]
+  float b1f[NT1][2];
+#pragma unroll
+  for (int j = 0; j < NT1; ++j) {
+    const int t = 8 * j + g;
+#pragma unroll
+    for (int kh = 0; kh < KN; ++kh) {
+      const int n0 = 2 * tq + 8 * kh;
+      w1f[j][kh] = pack_bf16((t < T && n0 < N) ? w1[t * N + n0] : 0.f, (t < T && n0 + 1 < N) ? w1[t * N + n0 + 1] : 0.f);
+      w2g[j][kh] = pack_bf16((t < T && n0 < N) ? w2[n0 * T + t] : 0.f, (t < T && n0 + 1 < N) ? w2[(n0 + 1) * T + t] : 0.f);
+    }
+    b1f[j][0] = (8 * j + 2 * tq < T) ? b1[8 * j + 2 * tq] : 0.f;
+    b1f[j][1] = (8 * j + 2 * tq + 1 < T) ? b1[8 * j + 2 * tq + 1] : 0.f;
+  }
+  uint32_t w1g[KS2][KN][2];       // GEMM4  B[k = t][col = n]  = W1[t][n]
+#pragma unroll
+  for (int jn = 0; jn < KN; ++jn) {
+    const int n = 8 * jn + g;
+#pragma unroll
+    for (int ks = 0; ks < KS2; ++ks)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int t0 = 16 * ks + 2 * tq + 8 * hh;
+        w1g[ks][jn][hh] = pack_bf16((n < N && t0 < T) ? w1[t0 * N + n] : 0.f, (n < N && t0 + 1 < T) ? w1[(t0 + 1) * N + n] : 0.f);
+      }
+  }
+  // ---- accumulators that live across samples
+  float gw1[KS2][KN][4], gw2[KS2][KN][4];   // C fragments of dW1[t][n], dW2^T[t][n']
+  float db1a[NT1][2], db2a[KN][2], dgam[DQ][2], dbet[DQ][2];
+#pragma unroll
+  for (int a = 0; a < KS2; ++a)
+#pragma unroll
+    for (int c = 0; c < KN; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { gw1[a][c][e] = 0.f; gw2[a][c][e] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < NT1; ++j) { db1a[j][0] = 0.f; db1a[j][1] = 0.f; }
+#pragma unroll
+  for (int c = 0; c < KN; ++c) { db2a[c][0] = 0.f; db2a[c][1] = 0.f; }
+#pragma unroll
+  for (int q = 0; q < DQ; ++q) { dgam[q][0] = dgam[q][1] = dbet[q][0] = dbet[q][1] = 0.f; }
+  const float inv_d = 1.f / D;
+  __syncthreads();
+
+  for (int b = blockIdx.x * kW + warp; b < B; b += gridDim.x * kW) {
+    const long long sbase = static_cast<long long>(b) * N * D;
+    const float* xb = x + sbase;
+    const float* dub = du + sbase;
+    float2 xr[DM][KN][2];
+    float mean[KN][2], rstd[KN][2];
+#pragma unroll
+    for (int kh = 0; kh < KN; ++kh)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        const int n = 8 * kh + 2 * tq + nn;
+        float acc = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < DM; ++mt) {
+          xr[mt][kh][nn] = n < N ? *reinterpret_cast<const float2*>(xb + n * D + 16 * mt + 2 * g) : make_float2(0.f, 0.f);
+          acc += xr[mt][kh][nn].x + xr[mt][kh][nn].y;
+        }
+        mean[kh][nn] = group_sum(acc) * inv_d;
+        float ss = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < DM; ++mt) {
+          const float a = xr[mt][kh][nn].x - mean[kh][nn], c = xr[mt][kh][nn].y - mean[kh][nn];
+          ss += a * a + c * c;
+        }
+        rstd[kh][nn] = rsqrtf(group_sum(ss) * inv_d + kLnEps);
+      }
+    float s1[KN][2], s2[KN][2];   // per-token sums over d of gamma dXn and gamma dXn xhat
+#pragma unroll
+    for (int kh = 0; kh < KN; ++kh) { s1[kh][0] = s1[kh][1] = s2[kh][0] = s2[kh][1] = 0.f; }
+
+#pragma unroll
+    for (int mt = 0; mt < DM; ++mt) {
+      const int d_lo = 16 * mt + 2 * g;
+      const float2 gm = *reinterpret_cast<const float2*>(ln_w + d_lo);
+      const float2 bt = *reinterpret_cast<const float2*>(ln_b + d_lo);
+      uint32_t a1f[4] = {0u, 0u, 0u, 0u}, a3f[4] = {0u, 0u, 0u, 0u};
+      float2 xh[KN][2];            // xhat of this tile
+#pragma unroll
+      for (int kh = 0; kh < KN; ++kh) {
+        const int n = 8 * kh + 2 * tq;
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) {
+          xh[kh][nn].x = (xr[mt][kh][nn].x - mean[kh][nn]) * rstd[kh][nn];
+          xh[kh][nn].y = (xr[mt][kh][nn].y - mean[kh][nn]) * rstd[kh][nn];
+        }
+        const bool v0 = n < N, v1 = n + 1 < N;
+        a1f[2 * kh] = pack_bf16(v0 ? xh[kh][0].x * gm.x + bt.x : 0.f, v1 ? xh[kh][1].x * gm.x + bt.x : 0.f);
+        a1f[2 * kh + 1] = pack_bf16(v0 ? xh[kh][0].y * gm.y + bt.y : 0.f, v1 ? xh[kh][1].y * gm.y + bt.y : 0.f);
+        float2 u0 = v0 ? *reinterpret_cast<const float2*>(dub + n * D + d_lo) : make_float2(0.f, 0.f);
+        float2 u1 = v1 ? *reinterpret_cast<const float2*>(dub + (n + 1) * D + d_lo) : make_float2(0.f, 0.f);
+        if (kDrop) {   // gradient of the dropped branch output
+          drop_apply2(dout, u0.x, u0.y, static_cast<unsigned long long>(sbase + n * D + d_lo));
+          drop_apply2(dout, u1.x, u1.y, static_cast<unsigned long long>(sbase + (n + 1) * D + d_lo));
+        }
+        db2a[kh][0] += u0.x + u0.y;
+        db2a[kh][1] += u1.x + u1.y;
+        a3f[2 * kh] = pack_bf16(u0.x, u1.x);
+        a3f[2 * kh + 1] = pack_bf16(u0.y, u1.y);
+      }
+      float c1[NT1][4], c3[NT1][4];
+#pragma unroll
+      for (int j = 0; j < NT1; ++j) {
+        c1[j][0] = c1[j][2] = b1f[j][0];
+        c1[j][1] = c1[j][3] = b1f[j][1];
+        c3[j][0] = c3[j][1] = c3[j][2] = c3[j][3] = 0.f;
+        mma_bf16(c1[j], a1f[0], a1f[1], a1f[2], a1f[3], w1f[j][0], KN > 1 ? w1f[j][KN - 1] : 0u);
+        mma_bf16(c3[j], a3f[0], a3f[1], a3f[2], a3f[3], w2g[j][0], KN > 1 ? w2g[j][KN - 1] : 0u);
+      }
+      // G = Drop(GELU(H)), dH = dG * Drop'(.) * GELU'(H); packs: lo = (rows 0-7 = d_lo set), hi = (rows 8-15 = d_hi set)
+      uint32_t pG[NT1][2], pH[NT1][2];
+#pragma unroll
+      for (int j = 0; j < NT1; ++j) {
+        float2 dg_lo, dg_hi;
+        float2 g_lo = gelu2_grad(make_float2(c1[j][0], c1[j][1]), dg_lo);
+        float2 g_hi = gelu2_grad(make_float2(c1[j][2], c1[j][3]), dg_hi);
+        float2 h_lo = __fmul2_rn(make_float2(c3[j][0], c3[j][1]), dg_lo);
+        float2 h_hi = __fmul2_rn(make_float2(c3[j][2], c3[j][3]), dg_hi);
+        if (kDrop) {
+          const int t = 8 * j + 2 * tq;
+          const unsigned long long i0 = (static_cast<unsigned long long>(b) * T + t) * D + d_lo;
+          drop_apply2(dh, g_lo.x, g_hi.x, i0);
+          drop_apply2(dh, g_lo.y, g_hi.y, i0 + D);
+          drop_apply2(dh, h_lo.x, h_hi.x, i0);
+          drop_apply2(dh, h_lo.y, h_hi.y, i0 + D);
+        }
+        db1a[j][0] += h_lo.x + h_hi.x;
+        db1a[j][1] += h_lo.y + h_hi.y;
+        pG[j][0] = pack_bf16(g_lo.x, g_lo.y); pG[j][1] = pack_bf16(g_hi.x, g_hi.y);
+        pH[j][0] = pack_bf16(h_lo.x, h_lo.y); pH[j][1] = pack_bf16(h_hi.x, h_hi.y);
+      }
+      // dXn^T[d, n] = sum_t dH[d,t] W1[t,n]
+      float c4[KN][4];
+#pragma unroll
+      for (int jn = 0; jn < KN; ++jn) {
+        c4[jn][0] = c4[jn][1] = c4[jn][2] = c4[jn][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS2; ++ks)
+          mma_bf16(c4[jn], pH[2 * ks][0], pH[2 * ks][1], pH[2 * ks + 1][0], pH[2 * ks + 1][1], w1g[ks][jn][0], w1g[ks][jn][1]);
+      }
+      // LayerNorm backward partials; c4[jn]: c0 = (d_lo, n), c1 = (d_lo, n+1), c2 = (d_hi, n), c3 = (d_hi, n+1)
+      float pgl = 0.f, pgh = 0.f, pbl = 0.f, pbh = 0.f;
+#pragma unroll
+      for (int jn = 0; jn < KN; ++jn)
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) {
+          const float dlo = c4[jn][nn], dhi = c4[jn][2 + nn];
+          s1[jn][nn] += gm.x * dlo + gm.y * dhi;
+          s2[jn][nn] += gm.x * dlo * xh[jn][nn].x + gm.y * dhi * xh[jn][nn].y;
+          pgl += dlo * xh[jn][nn].x; pgh += dhi * xh[jn][nn].y;
+          pbl += dlo; pbh += dhi;
+          myDxn[((mt * KN + jn) * 4 + nn * 2) * 32] = dlo;
+          myDxn[((mt * KN + jn) * 4 + nn * 2 + 1) * 32] = dhi;
+        }
+      // dln_w / dln_b: sum over the tokens held by the 4 lanes of this row group; lane tq keeps the tiles with mt % 4 == tq
+      pgl += __shfl_xor_sync(0xffffffffu, pgl, 1); pgl += __shfl_xor_sync(0xffffffffu, pgl, 2);
+      pgh += __shfl_xor_sync(0xffffffffu, pgh, 1); pgh += __shfl_xor_sync(0xffffffffu, pgh, 2);
+      pbl += __shfl_xor_sync(0xffffffffu, pbl, 1); pbl += __shfl_xor_sync(0xffffffffu, pbl, 2);
+      pbh += __shfl_xor_sync(0xffffffffu, pbh, 1); pbh += __shfl_xor_sync(0xffffffffu, pbh, 2);
+      if ((mt & 3) == tq) {
+        dgam[mt >> 2][0] += pgl; dgam[mt >> 2][1] += pgh;
+        dbet[mt >> 2][0] += pbl; dbet[mt >> 2][1] += pbh;
+      }
+      // weight gradients: contraction over the 16 hidden columns of the tile -> transposed fragments
+      uint32_t bx[KN][2], bu[KN][2];
+#pragma unroll
+      for (int jn = 0; jn < KN; ++jn) {
+        bx[jn][0] = movmatrix_t(a1f[2 * jn]); bx[jn][1] = movmatrix_t(a1f[2 * jn + 1]);
+        bu[jn][0] = movmatrix_t(a3f[2 * jn]); bu[jn][1] = movmatrix_t(a3f[2 * jn + 1]);
+      }
+#pragma unroll
+      for (int m5 = 0; m5 < KS2; ++m5) {
+        const uint32_t h0 = movmatrix_t(pH[2 * m5][0]), h1 = movmatrix_t(pH[2 * m5 + 1][0]);
+        const uint32_t h2 = movmatrix_t(pH[2 * m5][1]), h3 = movmatrix_t(pH[2 * m5 + 1][1]);
+        const uint32_t g0 = movmatrix_t(pG[2 * m5][0]), g1 = movmatrix_t(pG[2 * m5 + 1][0]);
+        const uint32_t g2 = movmatrix_t(pG[2 * m5][1]), g3 = movmatrix_t(pG[2 * m5 + 1][1]);
+#pragma unroll
+        for (int jn = 0; jn < KN; ++jn) {
+          mma_bf16(gw1[m5][jn], h0, h1, h2, h3, bx[jn][0], bx[jn][1]);   // dW1[t][n]   += dH^T . Xn^T
+          mma_bf16(gw2[m5][jn], g0, g1, g2, g3, bu[jn][0], bu[jn][1]);   // dW2^T[t][n'] += G^T . dU^T
+        }
+      }
+    }
+    // ---- LayerNorm backward: dx = du + rstd (gamma dXn - mean_d(gamma dXn) - xhat mean_d(gamma dXn xhat))
+#pragma unroll
+    for (int kh = 0; kh < KN; ++kh)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        s1[kh][nn] = group_sum(s1[kh][nn]) * inv_d;
+        s2[kh][nn] = group_sum(s2[kh][nn]) * inv_d;
+      }
+#pragma unroll
+    for (int mt = 0; mt < DM; ++mt) {
+      const int d_lo = 16 * mt + 2 * g;
+      const float2 gm = *reinterpret_cast<const float2*>(ln_w + d_lo);
+#pragma unroll
+      for (int kh = 0; kh < KN; ++kh)
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) {
+          const int n = 8 * kh + 2 * tq + nn;
+          if (n < N) {
+            const float dlo = myDxn[((mt * KN + kh) * 4 + nn * 2) * 32], dhi = myDxn[((mt * KN + kh) * 4 + nn * 2 + 1) * 32];
+            const float xlo = (xr[mt][kh][nn].x - mean[kh][nn]) * rstd[kh][nn];
+            const float xhi = (xr[mt][kh][nn].y - mean[kh][nn]) * rstd[kh][nn];
+            const float2 ur = *reinterpret_cast<const float2*>(dub + n * D + d_lo);
+            float2 o;
+            o.x = ur.x + rstd[kh][nn] * (gm.x * dlo - s1[kh][nn] - xlo * s2[kh][nn]);
+            o.y = ur.y + rstd[kh][nn] * (gm.y * dhi - s1[kh][nn] - xhi * s2[kh][nn]);
+            *reinterpret_cast<float2*>(dx + sbase + n * D + d_lo) = o;
+          }
+        }
+    }
+  }
+
+  // ---- per-CTA reduction of the accumulators, then one global atomic per element
+  float* sW1 = sAcc;                    // [TP][NP]
+  float* sW2 = sW1 + TP * NP;           // [TP][NP]
+  float* sB1 = sW2 + TP * NP;           // [TP]
+  float* sB2 = sB1 + TP;                // [NP]
+  float* sGam = sB2 + NP;               // [D]
+  float* sBet = sGam + D;               // [D]
+#pragma unroll
+  for (int m5 = 0; m5 < KS2; ++m5)
+#pragma unroll
+    for (int jn = 0; jn < KN; ++jn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {     // c0 = (t = 16 m5 + g, n = 8 jn + 2 tq), c1 = n + 1, c2 / c3 = t + 8
+        const int t = 16 * m5 + g + (e >> 1) * 8, n = 8 * jn + 2 * tq + (e & 1);
+        atomicAdd(&sW1[t * NP + n], gw1[m5][jn][e]);
+        atomicAdd(&sW2[t * NP + n], gw2[m5][jn][e]);
+      }
+#pragma unroll
+  for (int j = 0; j < NT1; ++j) {
+    const float v0 = group_sum(db1a[j][0]), v1 = group_sum(db1a[j][1]);
+    if (g == 0) { atomicAdd(&sB1[8 * j + 2 * tq], v0); atomicAdd(&sB1[8 * j + 2 * tq + 1], v1); }
+  }
+#pragma unroll
+  for (int kh = 0; kh < KN; ++kh) {
+    const float v0 = group_sum(db2a[kh][0]), v1 = group_sum(db2a[kh][1]);
+    if (g == 0) { atomicAdd(&sB2[8 * kh + 2 * tq], v0); atomicAdd(&sB2[8 * kh + 2 * tq + 1], v1); }
+  }
+#pragma unroll
+  for (int mt = 0; mt < DM; ++mt)
+    if ((mt & 3) == tq) {
+      const int d_lo = 16 * mt + 2 * g;
+      atomicAdd(&sGam[d_lo], dgam[mt >> 2][0]); atomicAdd(&sGam[d_lo + 1], dgam[mt >> 2][1]);
+      atomicAdd(&sBet[d_lo], dbet[mt >> 2][0]); atomicAdd(&sBet[d_lo + 1], dbet[mt >> 2][1]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TP * NP; i += kW * 32) {
+    const int t = i / NP, n = i - t * NP;
+    if (t < T && n < N) {
+      atomicAdd(dw1 + t * N + n, sW1[i]);
+      atomicAdd(dw2 + n * T + t, sW2[i]);
+    }
+  }
+  for (int i = threadIdx.x; i < TP; i += kW * 32) if (i < T) atomicAdd(db1 + i, sB1[i]);
+  for (int i = threadIdx.x; i < NP; i += kW * 32) if (i < N) atomicAdd(db2 + i, sB2[i]);
+  for (int i = threadIdx.x; i < D; i += kW * 32) { atomicAdd(dln_w + i, sGam[i]); atomicAdd(dln_b + i, sBet[i]); }
+}
+
+template <int DM, int TP, int NP, int kW = 8, int kMinB = 1>
+int launch_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
+               const float* w2, float* dx, float* dln_w, float* dln_b, float* dw1, float* db1, float* dw2, float* db2, int B,
+               int N, int T, const Drop& dh, const Drop& dout, cudaStream_t s) {
+  constexpr int D = 16 * DM, KN = NP / 8;
+  constexpr size_t smem = (2 * TP * NP + TP + NP + 2 * D + static_cast<size_t>(kW) * DM * KN * 4 * 32) * sizeof(float);
+  int grid = ceil_div(B, kW);
+  if (grid > 148 * 2 * kMinB) grid = 148 * 2 * kMinB;   // persistent: the per-CTA gradient partials cost one atomic round per CTA
+  LaunchScope scope("token_mix_mma_bwd", s);
+  auto launch = [&](auto kern) -> int {
+    static bool configured = false;   // per instantiation of this generic lambda
+    if (!configured && smem > 48 * 1024) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return M2_ERR_LAUNCH;
+      configured = true;
+    }
+    kern<<<grid, kW * 32, smem, s>>>(du, x, ln_w, ln_b, w1, b1, w2, dx, dln_w, dln_b, dw1, db1, dw2, db2, B, N, T, dh, dout);
+    return M2_OK;
+  };
+  int rc;
+  if (dh.thresh || dout.thresh) rc = launch(token_mix_mma_bwd_kernel<DM, TP, NP, true, kW, kMinB>);
+  else rc = launch(token_mix_mma_bwd_kernel<DM, TP, NP, false, kW, kMinB>);
+  if (rc) return rc;
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+template <int DM, int TP, int NP>
+int launch_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1, const float* w2,
+               const float* b2, float* u, int B, int N, int T, const Drop& dh, const Drop& dout, cudaStream_t s) {
+  int grid = ceil_div(B, kWarps);
+  if (grid > 148 * 4) grid = 148 * 4;
+  LaunchScope scope("token_mix_mma_fwd", s);
+  if (dh.thresh || dout.thresh)
+    token_mix_mma_fwd_kernel<DM, TP, NP, true><<<grid, kWarps * 32, 0, s>>>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, T, dh, dout);
+  else
+    token_mix_mma_fwd_kernel<DM, TP, NP, false><<<grid, kWarps * 32, 0, s>>>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, T, dh, dout);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+}  // namespace
+
+// Shapes the warp-level tensor-core path covers (bf16 mode only): the register tile is DM * (N / 8) * 4 floats per lane.
+bool token_mix_mma_supported(int N, int D, int T) {
+  if (!(D == 32 || D == 64 || D == 128 || D == 256)) return false;
+  if (N < 1 || N > 16 || T < 1 || T > 32) return false;
+  const int kn = N <= 8 ? 1 : 2;
+  return (D / 16) * kn <= 16;
+}
+
+int token_mix_mma_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1, const float* w2,
+                      const float* b2, float* u, int B, int N, int D, int T, float drop_p, unsigned long long seed,
+                      cudaStream_t s) {
+  if (!token_mix_mma_supported(N, D, T)) return M2_ERR_ARG;
+  const Drop dh = make_drop(drop_p, seed, kSiteTokenHidden), dout = make_drop(drop_p, seed, kSiteTokenOut);
+  const int dm = D / 16, tp = T <= 16 ? 16 : 32, np = N <= 8 ? 8 : 16;
+#define M2_TMF(DM_, TP_, NP_) \
+  if (dm == DM_ && tp == TP_ && np == NP_) return launch_fwd<DM_, TP_, NP_>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, T, dh, dout, s);
+  M2_TMF(2, 16, 8) M2_TMF(2, 32, 8) M2_TMF(4, 16, 8) M2_TMF(4, 32, 8) M2_TMF(8, 16, 8) M2_TMF(8, 32, 8) M2_TMF(16, 16, 8) M2_TMF(16, 32, 8)
+  M2_TMF(2, 16, 16) M2_TMF(2, 32, 16) M2_TMF(4, 16, 16) M2_TMF(4, 32, 16) M2_TMF(8, 16, 16) M2_TMF(8, 32, 16)
+#undef M2_TMF
+  return M2_ERR_ARG;
+}
+
+// dx = du + LN'(dXn) (complete: no separate ln_bwd pass); every parameter gradient is ACCUMULATED.
+int token_mix_mma_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
+                      const float* w2, float* dx, float* dln_w, float* dln_b, float* dw1, float* db1, float* dw2, float* db2,
+                      int B, int N, int D, int T, float drop_p, unsigned long long seed, cudaStream_t s) {
+  if (!token_mix_mma_supported(N, D, T)) return M2_ERR_ARG;
+  const Drop dh = make_drop(drop_p, seed, kSiteTokenHidden), dout = make_drop(drop_p, seed, kSiteTokenOut);
+  const int dm = D / 16, tp = T <= 16 ? 16 : 32, np = N <= 8 ? 8 : 16;
+#define M2_TMB(DM_, TP_, NP_)              \
+  if (dm == DM_ && tp == TP_ && np == NP_) \
+    return launch_bwd<DM_, TP_, NP_>(du, x, ln_w, ln_b, w1, b1, w2, dx, dln_w, dln_b, dw1, db1, dw2, db2, B, N, T, dh, dout, s);
+  M2_TMB(2, 16, 8) M2_TMB(2, 32, 8) M2_TMB(4, 16, 8) M2_TMB(4, 32, 8) M2_TMB(8, 16, 8) M2_TMB(8, 32, 8) M2_TMB(16, 16, 8) M2_TMB(16, 32, 8)
+  M2_TMB(2, 16, 16) M2_TMB(2, 32, 16) M2_TMB(4, 16, 16) M2_TMB(4, 32, 16) M2_TMB(8, 16, 16) M2_TMB(8, 32, 16)
+#undef M2_TMB
+  return M2_ERR_ARG;
+}
+
+}  // namespace m2
