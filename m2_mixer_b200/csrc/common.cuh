@@ -43,70 +43,63 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// tanh-form GELU with a degree-5 odd inner polynomial fitted to the erf form (max abs error 2.6e-5 on [-8,8],
-// derivative 1.1e-4): far below bf16 rounding of the result, and one MUFU.TANH instead of erff().
-constexpr float kGa = 7.97507884e-01f, kGb = 3.70056460e-02f, kGc = -3.51516780e-04f;
+// Scalar tanh-form GELU of the bf16 mode (same cubic inner polynomial as the packed version below, so that every
+// forward / backward pair in the library differentiates the same function).
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float xc = fminf(fmaxf(x, -8.f), 8.f);
-  const float x2 = xc * xc;
-  const float u = xc * fmaf(x2, fmaf(x2, kGc, kGb), kGa);
-  const float t = tanh_approx(u);
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
+  const float u = x * fmaf(x * x, 0.03470089342f, 0.80015707848f);
+  const float w = fmaf(tanh_approx(u), 0.5f, 0.5f);
+  return x * w;
 }
 // returns GELU(x), writes d/dx
 __device__ __forceinline__ float gelu_fast_grad(float x, float& dgelu) {
-  const float xc = fminf(fmaxf(x, -8.f), 8.f);
-  const float x2 = xc * xc;
-  const float u = xc * fmaf(x2, fmaf(x2, kGc, kGb), kGa);
-  const float du = fmaf(x2, fmaf(x2, 5.f * kGc, 3.f * kGb), kGa);
-  const float t = tanh_approx(u);
-  const float hx = 0.5f * x;
-  dgelu = fmaf(hx * (1.f - t * t), du, 0.5f + 0.5f * t);
-  return fmaf(hx, t, hx);
+  const float x2 = x * x;
+  const float u = x * fmaf(x2, 0.03470089342f, 0.80015707848f);
+  const float du2 = fmaf(x2, 6.f * 0.03470089342f, 2.f * 0.80015707848f);
+  const float w = fmaf(tanh_approx(u), 0.5f, 0.5f);
+  const float g = x * w;
+  dgelu = fmaf(g * (1.f - w), du2, w);
+  return g;
 }
 
-// ---- packed fp32x2 GELU (tanh form, see common.cuh) : half the issue slots of the scalar version
+// ---- packed fp32x2 GELU used by every bf16-mode tensor-core epilogue.  The epilogues are CUDA-core ISSUE bound
+// (0.73 warp-instructions per hidden element in the weight-gradient kernel, profiles/r01_ncu_wgrad_v18.md), so the form
+// is chosen for instruction count: tanh form with a CUBIC inner polynomial u = x (a + b x^2) fitted to the erf form
+// (max abs error 2.7e-4 on the value, 8.7e-4 on the derivative: below the bf16 rounding of the result for |G| > 0.1),
+// monotonic, so no clamping and no saturation fix-ups are needed (tanh.approx saturates to +-1):
+//     w = (1 + tanh u) / 2        GELU = x w        GELU' = w + 2 (x w) (1 - w) u'
+//   forward 7 instructions per pair (FMUL2, FFMA2, FMUL2, 2 MUFU, FFMA2, FMUL2), backward 11.
+constexpr float kG3a = 0.80015707848f, kG3b = 0.03470089342f;
 __device__ __forceinline__ float tanh_ap(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float2 gelu2(float2 x) {
-  float2 x2 = __fmul2_rn(x, x);
-  x2.x = fminf(x2.x, 64.f); x2.y = fminf(x2.y, 64.f);       // |x| > 8: inner polynomial frozen, tanh saturates
-  float2 p = __ffma2_rn(x2, make_float2(kGc, kGc), make_float2(kGb, kGb));
-  p = __ffma2_rn(x2, p, make_float2(kGa, kGa));
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 p = __ffma2_rn(x2, make_float2(kG3b, kG3b), make_float2(kG3a, kG3a));
   const float2 u = __fmul2_rn(x, p);
   const float2 t = make_float2(tanh_ap(u.x), tanh_ap(u.y));
-  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-  return __ffma2_rn(hx, t, hx);
+  const float2 w = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  return __fmul2_rn(x, w);
 }
 // returns GELU(x); dg = GELU'(x)
 __device__ __forceinline__ float2 gelu2_grad(float2 x, float2& dg) {
-  float2 x2 = __fmul2_rn(x, x);
-  const bool sx = x2.x > 64.f, sy = x2.y > 64.f;
-  x2.x = fminf(x2.x, 64.f); x2.y = fminf(x2.y, 64.f);
-  float2 p = __ffma2_rn(x2, make_float2(kGc, kGc), make_float2(kGb, kGb));
-  p = __ffma2_rn(x2, p, make_float2(kGa, kGa));
-  float2 du = __ffma2_rn(x2, make_float2(5.f * kGc, 5.f * kGc), make_float2(3.f * kGb, 3.f * kGb));
-  du = __ffma2_rn(x2, du, make_float2(kGa, kGa));
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 p = __ffma2_rn(x2, make_float2(kG3b, kG3b), make_float2(kG3a, kG3a));
+  const float2 du2 = __ffma2_rn(x2, make_float2(6.f * kG3b, 6.f * kG3b), make_float2(2.f * kG3a, 2.f * kG3a));   // 2 u'
   const float2 u = __fmul2_rn(x, p);
   const float2 t = make_float2(tanh_ap(u.x), tanh_ap(u.y));
-  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-  // 0.5 (1 + t) + 0.5 x (1 - t^2) u'
-  const float2 omt2 = __ffma2_rn(make_float2(-t.x, -t.y), t, make_float2(1.f, 1.f));
-  const float2 a = __fmul2_rn(hx, omt2);
-  const float2 half1 = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
-  dg = __ffma2_rn(a, du, half1);
-  if (sx) dg.x = half1.x;    // saturated region: derivative of the frozen polynomial form
-  if (sy) dg.y = half1.y;
-  return __ffma2_rn(hx, t, hx);
+  const float2 w = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  const float2 g = __fmul2_rn(x, w);
+  const float2 omw = __ffma2_rn(w, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+  const float2 tmp = __fmul2_rn(g, omw);
+  dg = __ffma2_rn(tmp, du2, w);
+  return g;
 }
 
 // ------------------------------------------------------------------------------------------ dropout

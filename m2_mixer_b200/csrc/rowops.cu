@@ -20,6 +20,27 @@ __global__ void cast_pad_bf16_kernel(const float* __restrict__ src, long long ld
     dst[i] = __float2bfloat16(c < cols ? src[r * lds + c] : 0.f);
   }
 }
+// 8 elements per thread (two 16-byte loads, one 16-byte store); row = blockIdx.y * rows_per_block + ..: no divisions.
+// Requires lds % 4 == 0, ldd % 8 == 0 and 16-byte aligned bases; columns >= cols are written as zero.
+__global__ void __launch_bounds__(256) cast_pad_bf16_vec_kernel(const float* __restrict__ src, long long lds,
+                                                                __nv_bfloat16* __restrict__ dst, long long ldd, int rows,
+                                                                int cols) {
+  const int c = (blockIdx.x * 32 + (threadIdx.x & 31)) * 8;
+  if (c >= ldd) return;
+  for (int r = blockIdx.y * 8 + (threadIdx.x >> 5); r < rows; r += gridDim.y * 8) {
+    const float* s = src + r * lds + c;
+    float v[8];
+    if (c + 8 <= cols) {
+      const float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = c + e < cols ? s[e] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(dst + r * ldd + c) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
 
 // ------------------------------------------------------------------------------------------ LayerNorm forward
 // rows = B*N tokens; output row (b, n) goes to out + b*out_bstride + n*D  (lets an encoder's final LN write
@@ -343,7 +364,15 @@ inline int grid_for(long long n, int block) {
 int cast_pad_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols, cudaStream_t s) {
   LaunchScope scope("cast_pad_bf16", s);
   if (rows <= 0 || cols <= 0 || ldd < cols) return M2_ERR_ARG;
-  cast_pad_bf16_kernel<<<grid_for(static_cast<long long>(rows) * ldd, 256), 256, 0, s>>>(src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+  if (lds % 4 == 0 && ldd % 8 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const int gx = ceil_div(static_cast<int>(ldd), 256);
+    int gy = ceil_div(rows, 8);
+    const int cap = ceil_div(148 * 8, gx);
+    if (gy > cap) gy = cap;
+    cast_pad_bf16_vec_kernel<<<dim3(gx, gy), 256, 0, s>>>(src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+  } else {
+    cast_pad_bf16_kernel<<<grid_for(static_cast<long long>(rows) * ldd, 256), 256, 0, s>>>(src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+  }
   M2_LAUNCH_CHECK();
   return M2_OK;
 }

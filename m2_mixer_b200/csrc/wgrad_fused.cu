@@ -22,27 +22,33 @@
 namespace m2 {
 namespace {
 
-// Row tiles are 96 rows: three 48 KB ring stages fit beside the resident weight slices, and a third stage is what hides
-// the TMA latency (with two, the load of tile i + 2 can only start when the gradient GEMMs of tile i retire and the
-// in-order MMA issuer stalls on it: 5200 clk per tile measured, profiles/r01_ncu_chain_v9.md).  The recompute GEMMs
-// still run as M = 128 instructions; accumulator rows 96..127 are garbage that no gradient GEMM (K = 96) ever reads.
+// A CTA owns 128 channels and walks 96-row tiles.  Why these numbers (measured, profiles/r01_chain_tuning.md):
+//  * every wake-up of the single MMA-issuing thread costs several hundred cycles (mbarrier waits, burst start-up), so the
+//    work per wake-up must be large: 128-channel GEMMs (N = 128, 64 clk per MMA instead of 48 for N = 64: the same
+//    wake-ups now feed twice the channels, and A is read from shared memory once per 128 instead of per 64 channels);
+//  * 96-row tiles: two 48 KB ring stages + 64 KB of resident weight slices + 64 KB of G / dH operand tiles = 224 KB.  The
+//    recompute GEMMs still run as M = 128 instructions; accumulator rows 96..127 are garbage that no gradient GEMM
+//    (K = 96) ever reads.
 constexpr int kRows = 96;       // token rows per tile (K of the gradient GEMMs)
 constexpr int kMmaM = 128;      // UMMA M of the recompute GEMMs
-constexpr int kCc = 64;         // channels per CTA
-constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (group g = column half g of the chunk)
-constexpr int kNS = 3;          // row-tile ring depth
+constexpr int kCc = 128;        // channels per CTA
+constexpr int kThreads = 320;   // warps 0-7 epilogue (group g = columns [64 g, 64 g + 64)), warp 8 TMA, warp 9 MMA
+constexpr int kNS = 2;          // row-tile ring depth
 
 template <int DP>
 struct CfgW {
-  static constexpr int kPanel = kRows * 128;            // one [128 rows][64 d] SW128 panel
+  static constexpr int kPanel = kRows * 128;            // one [96 rows][64 d] SW128 panel of a row tile
   static constexpr int kTile = (DP / 64) * kPanel;      // LN(u) or dY row tile
   static constexpr int kStage = 2 * kTile;
-  static constexpr int kW1Bytes = kCc * DP * 2;         // [64 c][DP d]
-  static constexpr int kW2Bytes = DP * kCc * 2;         // [DP d][64 c]
-  static constexpr int kGBytes = kMmaM * kCc * 2;       // [128 rows][64 c] (rows >= 96 are written but never read)
-  static constexpr int kSmem = kNS * kStage + kW1Bytes + kW2Bytes + 2 * kGBytes + 1024 + 1024;
+  static constexpr int kW1Panel = kCc * 128;            // [128 c][64 d]
+  static constexpr int kW1Bytes = (DP / 64) * kW1Panel;
+  static constexpr int kW2Panel = DP * 128;             // [DP d][64 c]
+  static constexpr int kW2Bytes = 2 * kW2Panel;
+  static constexpr int kGPanel = kMmaM * 128;           // [128 rows][64 c]
+  static constexpr int kGBytes = 2 * kGPanel;
+  static constexpr int kSmem = kNS * kStage + kW1Bytes + kW2Bytes + 2 * kGBytes + 1280 + 1024;
   static constexpr int kTmemCols = 512;
-  static constexpr int kColW1 = 0, kColW2 = 64, kColH = 128, kColG = 256;
+  static constexpr int kColW1 = 0, kColW2 = 128, kColH = 256, kColG = 384;
 };
 
 struct WgParams {
@@ -71,14 +77,14 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   uint64_t* wfull = bars;             // [1]   W1c / W2c landed
   uint64_t* full = wfull + 1;         // [kNS] row tile landed
   uint64_t* empty = full + kNS;       // [kNS] gradient GEMMs done with the row tile -> TMA
-  uint64_t* hfull = empty + kNS;      // [2]   H / dG accumulators ready -> epilogue
-  uint64_t* hempty = hfull + 2;       // [2]   epilogue has read them -> MMA
-  uint64_t* gfull = hempty + 2;       // [1]   epilogue wrote sG / sdH -> MMA
+  uint64_t* hfull = empty + kNS;      // [1]   H / dG accumulators ready -> epilogue
+  uint64_t* hempty = hfull + 1;       // [1]   epilogue has them in registers -> MMA
+  uint64_t* gfull = hempty + 1;       // [1]   epilogue wrote sG / sdH -> MMA
   uint64_t* gempty = gfull + 1;       // [1]   gradient GEMMs done with sG / sdH -> epilogue
   uint64_t* accfull = gempty + 1;     // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
-  float* sDb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);   // [64] db1 partials (16-byte aligned)
-  float* sB1 = sDb + kCc;                                  // [64] b1 of the chunk
+  float* sDb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);   // [128] db1 partials (16-byte aligned)
+  float* sB1 = sDb + kCc;                                                          // [128] b1 of the chunk
 
   // logical roles 0 = TMA, 1 = MMA, 2.. = epilogue; physically the epilogue warps come first (see chain_ts.cu)
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,7 +98,8 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_init(wfull, 1);
     for (int i = 0; i < kNS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 256); }
+    mbar_init(hfull, 1);
+    mbar_init(hempty, 256);
     mbar_init(gfull, 256);
     mbar_init(gempty, 1);
     mbar_init(accfull, 1);
@@ -114,8 +121,13 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (elect_one()) {
       mbar_arrive_expect_tx(wfull, C::kW1Bytes + C::kW2Bytes);
 #pragma unroll
-      for (int pnl = 0; pnl < DP / 64; ++pnl) tma_load_2d(sW1 + pnl * (kCc * 128), &tmW1, wfull, pnl * 64, c0);
-      tma_load_2d(sW2, &tmW2, wfull, c0, 0);
+      for (int pnl = 0; pnl < DP / 64; ++pnl)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)   // [64 c][64 d] boxes: d panel pnl, channel half h
+          tma_load_2d(sW1 + pnl * C::kW1Panel + h * (64 * 128), &tmW1, wfull, pnl * 64, c0 + h * 64);
+#pragma unroll
+      for (int h = 0; h < 2; ++h)     // [DP d][64 c] boxes: channel panel h
+        tma_load_2d(sW2 + h * C::kW2Panel, &tmW2, wfull, c0 + h * 64, 0);
     }
     __syncwarp();
     for (int i = 0; i < nt; ++i) {
@@ -134,52 +146,45 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ---- MMA issuer
-    constexpr uint32_t idescH = umma_idesc_bf16(kMmaM, kCc, 0, 0);   // A row tile K-major,  B = W1c K-major
+    // ---- MMA issuer.  Per tile two bursts: hg(i + 1) as soon as the epilogue has tile i's accumulators in registers (it
+    // then overlaps the rest of that epilogue), wg(i) when the epilogue has written G / dH.
+    constexpr uint32_t idescH = umma_idesc_bf16(kMmaM, kCc, 0, 0);   // A row tile K-major,  B = W1c K-major (N = 128 rows)
     constexpr uint32_t idescG = umma_idesc_bf16(kMmaM, kCc, 0, 1);   // A row tile K-major,  B = W2c MN-major
     constexpr uint32_t idescW = umma_idesc_bf16(kMmaM, kCc, 1, 1);   // A row tile MN-major (M = d), B = sdH / sG MN-major
     constexpr uint32_t kLboA = DP == 128 ? C::kPanel : 0;            // DP = 64: M rows 64..127 alias the only panel
     const uint64_t xk0 = umma_desc_sw128(smem_u32(sStage), 16, 1024);
     const uint64_t xm0 = umma_desc_sw128(smem_u32(sStage), kLboA, 1024);
     const uint64_t w1d = umma_desc_sw128(smem_u32(sW1), 16, 1024);
-    const uint64_t w2d = umma_desc_sw128(smem_u32(sW2), 8192, 1024);
-    const uint64_t gd = umma_desc_sw128(smem_u32(sG), 8192, 1024);
-    const uint64_t dhd = umma_desc_sw128(smem_u32(sdH), 8192, 1024);
-    auto hg = [&](int i) {   // H[i&1] = Xn_i . W1c^T ; dG[i&1] = dY_i . W2c
-      const int s = i % kNS, b = i & 1;
+    const uint64_t w2d = umma_desc_sw128(smem_u32(sW2), C::kW2Panel, 1024);
+    const uint64_t gd = umma_desc_sw128(smem_u32(sG), C::kGPanel, 1024);
+    const uint64_t dhd = umma_desc_sw128(smem_u32(sdH), C::kGPanel, 1024);
+    auto hg = [&](int i) {   // H = Xn_i . W1c^T ; dG = dY_i . W2c      (N = 128)
+      const int s = i % kNS;
       mbar_wait(&full[s], (i / kNS) & 1);
-      mbar_wait(&hempty[b], ((i >> 1) & 1) ^ 1);
+      mbar_wait(hempty, (i & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t xa = xk0 + static_cast<uint64_t>((s * C::kStage) >> 4);
         const uint64_t ya = xa + static_cast<uint64_t>(C::kTile >> 4);
-        const uint32_t tH = tmem_base + C::kColH + b * kCc;
-        const uint32_t tG = tmem_base + C::kColG + b * kCc;
 #pragma unroll
         for (int kk = 0; kk < DP / 16; ++kk)
-          umma_bf16(tH, xa + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4), w1d + (((kk >> 2) * (kCc * 128) + (kk & 3) * 32) >> 4),
-                    idescH, kk > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + C::kColH, xa + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4),
+                    w1d + (((kk >> 2) * C::kW1Panel + (kk & 3) * 32) >> 4), idescH, kk > 0 ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < DP / 16; ++kk)
-          umma_bf16(tG, ya + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4), w2d + ((kk * 2048) >> 4), idescG, kk > 0 ? 1u : 0u);
-        umma_commit(&hfull[b]);
+          umma_bf16(tmem_base + C::kColG, ya + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4), w2d + ((kk * 2048) >> 4), idescG,
+                    kk > 0 ? 1u : 0u);
+        umma_commit(hfull);
       }
       __syncwarp();
     };
     mbar_wait(wfull, 0);
     hg(0);
-    if (nt > 1) hg(1);
-    // Steady state: ONE burst per tile - the gradient GEMMs of tile i and the recompute GEMMs of tile i + 2 are issued
-    // together after all their waits (every wake-up of the issuer costs several hundred cycles, chain_ts.cu).
-    for (int i = 0; i < nt; ++i) {   // dW1c^T += Xn_i^T . dH_i ; dW2c += dY_i^T . G_i   (contraction over the rows)
+    for (int i = 0; i < nt; ++i) {
+      if (i + 1 < nt) hg(i + 1);
+      // dW1c^T += Xn_i^T . dH_i ; dW2c += dY_i^T . G_i   (contraction over the 96 rows)
       const int s = i % kNS;
-      const int in = i + 2, sn = in % kNS, b = i & 1;
-      const bool more = in < nt;
       mbar_wait(gfull, i & 1);
-      if (more) {
-        mbar_wait(&full[sn], (in / kNS) & 1);
-        mbar_wait(&hempty[b], ((in >> 1) & 1) ^ 1);
-      }
       tc_fence_after();
       if (elect_one()) {
         const uint64_t xa = xm0 + static_cast<uint64_t>((s * C::kStage) >> 4);
@@ -192,90 +197,88 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           umma_bf16(tmem_base + C::kColW2, ya + ((kk * 2048) >> 4), gd + ((kk * 2048) >> 4), idescW, (i > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&empty[s]);
         umma_commit(gempty);
-        if (more) {
-          const uint64_t xk = xk0 + static_cast<uint64_t>((sn * C::kStage) >> 4);
-          const uint64_t yk = xk + static_cast<uint64_t>(C::kTile >> 4);
-          const uint32_t tH = tmem_base + C::kColH + b * kCc;
-          const uint32_t tG = tmem_base + C::kColG + b * kCc;
-#pragma unroll
-          for (int kk = 0; kk < DP / 16; ++kk)
-            umma_bf16(tH, xk + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4), w1d + (((kk >> 2) * (kCc * 128) + (kk & 3) * 32) >> 4),
-                      idescH, kk > 0 ? 1u : 0u);
-#pragma unroll
-          for (int kk = 0; kk < DP / 16; ++kk)
-            umma_bf16(tG, yk + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4), w2d + ((kk * 2048) >> 4), idescG, kk > 0 ? 1u : 0u);
-          umma_commit(&hfull[b]);
-        }
       }
       __syncwarp();
     }
     if (elect_one()) umma_commit(accfull);
     __syncwarp();
   } else {
-    // ---- epilogue: thread = row of the tile (TMEM lane), group g = columns [32 g, 32 g + 32) of the chunk
+    // ---- epilogue: thread = row of the tile (TMEM lane), group g = columns [64 g, 64 g + 64) in four 16-column quarters
     const int q = pwarp & 3;
     const int grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const int cg = c0 + grp * 32;
-    float dbp[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) dbp[k] = 0.f;
-    const uint32_t bias_addr = smem_u32(sB1 + grp * 32);
+    const int cg = c0 + grp * 64;
     const bool live = r < kRows;
+    float2 dbp[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) dbp[k] = make_float2(0.f, 0.f);
+    const uint32_t bias_addr = smem_u32(sB1 + grp * 64);
+    uint8_t* gdst = sG + grp * C::kGPanel;
+    uint8_t* hdst = sdH + grp * C::kGPanel;
+    auto ld_quarter = [&](int qt, uint32_t (&hd)[16], uint32_t (&gd2)[16]) {
+      tmem_ld16(tmem_base + C::kColH + lane_addr + grp * 64 + qt * 16, hd);
+      tmem_ld16(tmem_base + C::kColG + lane_addr + grp * 64 + qt * 16, gd2);
+    };
     for (int i = 0; i < nt; ++i) {
-      const int b = i & 1;
-      mbar_wait(&hfull[b], (i >> 1) & 1);
+      mbar_wait(hfull, i & 1);
       tc_fence_after();
-      uint32_t h[32], dg[32];
-      tmem_ld32(tmem_base + C::kColH + lane_addr + b * kCc + grp * 32, h);
-      tmem_ld32(tmem_base + C::kColG + lane_addr + b * kCc + grp * 32, dg);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&hempty[b]);
-      uint32_t gp[16], dp[16];
       const unsigned long long i0 = static_cast<unsigned long long>((t_lo + i) * kRows + r) * p.ldh + cg;
+      uint32_t hA[16], gA[16], hB[16], gB[16];
+      ld_quarter(0, hA, gA);
+      tmem_ld_wait();
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        float bias[8];
+      for (int qt = 0; qt < 4; ++qt) {
+        uint32_t (&h)[16] = (qt & 1) ? hB : hA;
+        uint32_t (&dg)[16] = (qt & 1) ? gB : gA;
+        if (qt < 3) ld_quarter(qt + 1, (qt & 1) ? hA : hB, (qt & 1) ? gA : gB);   // in flight during this quarter's math
+        float bias[16];
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
+        for (int e = 0; e < 4; ++e)
           asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
               : "=f"(bias[4 * e]), "=f"(bias[4 * e + 1]), "=f"(bias[4 * e + 2]), "=f"(bias[4 * e + 3])
-              : "r"(bias_addr + (ch * 8 + 4 * e) * 4));
+              : "r"(bias_addr + (qt * 16 + 4 * e) * 4));
+        uint32_t gp[8], dp[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = ch * 8 + 2 * e;
+        for (int e = 0; e < 8; ++e) {
+          const int k = qt * 16 + 2 * e;
           float2 dgelu;
-          float2 gv = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[k]), __uint_as_float(h[k + 1])),
+          float2 gv = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[2 * e]), __uint_as_float(h[2 * e + 1])),
                                             make_float2(bias[2 * e], bias[2 * e + 1])), dgelu);
-          float2 dv = __fmul2_rn(make_float2(__uint_as_float(dg[k]), __uint_as_float(dg[k + 1])), dgelu);
+          float2 dv = __fmul2_rn(make_float2(__uint_as_float(dg[2 * e]), __uint_as_float(dg[2 * e + 1])), dgelu);
           if (kDrop) {
             drop_apply2(p.dh, gv.x, gv.y, i0 + k);
             drop_apply2(p.dh, dv.x, dv.y, i0 + k);
           }
-          if (live) { dbp[k] += dv.x; dbp[k + 1] += dv.y; }
-          gp[ch * 4 + e] = pack_bf16(gv.x, gv.y);
-          dp[ch * 4 + e] = pack_bf16(dv.x, dv.y);
+          if (live) dbp[k >> 1] = __fadd2_rn(dbp[k >> 1], dv);
+          gp[e] = pack_bf16(gv.x, gv.y);
+          dp[e] = pack_bf16(dv.x, dv.y);
         }
-      }
-      mbar_wait(gempty, (i & 1) ^ 1);   // gradient GEMMs of tile i - 1 have consumed sG / sdH
+        if (qt == 0) mbar_wait(gempty, (i & 1) ^ 1);   // gradient GEMMs of tile i - 1 have consumed sG / sdH
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        *reinterpret_cast<uint4*>(sG + sw128_offset(r, grp * 4 + k)) = make_uint4(gp[4 * k], gp[4 * k + 1], gp[4 * k + 2], gp[4 * k + 3]);
-        *reinterpret_cast<uint4*>(sdH + sw128_offset(r, grp * 4 + k)) = make_uint4(dp[4 * k], dp[4 * k + 1], dp[4 * k + 2], dp[4 * k + 3]);
+        for (int k = 0; k < 2; ++k) {
+          *reinterpret_cast<uint4*>(gdst + sw128_offset(r, qt * 2 + k)) = make_uint4(gp[4 * k], gp[4 * k + 1], gp[4 * k + 2], gp[4 * k + 3]);
+          *reinterpret_cast<uint4*>(hdst + sw128_offset(r, qt * 2 + k)) = make_uint4(dp[4 * k], dp[4 * k + 1], dp[4 * k + 2], dp[4 * k + 3]);
+        }
+        if (qt < 3) tmem_ld_wait();
+        if (qt == 2) {   // the last quarter is in registers: the accumulators may be overwritten by hg(i + 1)
+          tc_fence_before();
+          mbar_arrive(hempty);
+        }
       }
       fence_proxy_async();
       mbar_arrive(gfull);
     }
     // db1: reduce the per-row partials over the 32 rows of the warp, then over the warps (shared-memory atomics)
-    float mine = 0.f;
+    float mine0 = 0.f, mine1 = 0.f;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float sres = warp_sum(dbp[k]);
-      if (lane == k) mine = sres;
+    for (int k = 0; k < 32; ++k) {   // column k of the group's first / second 32 columns
+      const float s0 = warp_sum((k & 1) ? dbp[k >> 1].y : dbp[k >> 1].x);
+      const float s1 = warp_sum((k & 1) ? dbp[16 + (k >> 1)].y : dbp[16 + (k >> 1)].x);
+      if (lane == k) { mine0 = s0; mine1 = s1; }
     }
-    atomicAdd(&sDb[grp * 32 + lane], mine);
+    atomicAdd(&sDb[grp * 64 + lane], mine0);
+    atomicAdd(&sDb[grp * 64 + 32 + lane], mine1);
     // accumulators: TMEM lane = d.  group 0: dW1^T slice -> dw1[c][d] (lanes contiguous in d: coalesced reductions);
     //                               group 1: dW2 slice   -> dw2[d][c]
     mbar_wait(accfull, 0);
@@ -343,9 +346,9 @@ int wgrad_fused(const void* xn_b, const void* dy_b, const void* w1b, const void*
   if (rc) return rc;
   rc = make_tmap_bf16(&ty, dy_b, M, D, D, kRows, 64);
   if (rc) return rc;
-  rc = make_tmap_bf16(&t1, w1b, C, D, D, kCc, 64);
+  rc = make_tmap_bf16(&t1, w1b, C, D, D, 64, 64);
   if (rc) return rc;
-  rc = make_tmap_bf16(&t2, w2b, D, ldw2, ldw2, DP, kCc);
+  rc = make_tmap_bf16(&t2, w2b, D, ldw2, ldw2, DP, 64);
   if (rc) return rc;
   WgParams p = {};
   p.b1 = b1; p.dw1 = dw1; p.dw2 = dw2; p.db1 = db1;
