@@ -111,18 +111,29 @@ def run_reference(args, cfg):
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi polled every 20 ms from BEFORE the warm-up (its start-up alone takes ~100 ms, longer than a short timed
+    region); stop(t0, t1) keeps the samples whose timestamps fall inside the timed region [t0, t1] (host wall clock) and
+    falls back to every sample taken while the GPU was busy (warm-up included) if the region was too short to catch one."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
-    def stop(self) -> dict:
+    @staticmethod
+    def _ts(txt: str):
+        import datetime
+        try:
+            return datetime.datetime.strptime(txt.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0: float = None, t1: float = None) -> dict:
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -131,21 +142,24 @@ class ClockSampler:
         except Exception:
             self.p.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for ln in out.strip().splitlines():
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                rows.append((self._ts(f[0]), float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+        inside = [r for r in rows if t0 is not None and r[0] is not None and t0 <= r[0] <= t1]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for r in rows if t1 is None or r[0] is None or r[0] <= t1], "warm-up + timed region (region shorter than the sampling period)"
+        sm, mx = [r[1] for r in inside], [r[2] for r in inside]
+        reasons = sorted({n for r in inside for n in r[3]})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -203,13 +217,16 @@ def run_ours(args, cfg):
         barrier()
         return float(ms)
 
+    clocks = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
         step(batches[i % NB])
-    clocks = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()
+    torch.cuda.synchronize()
+    w0 = time.time()
     ms = timed(lambda i: step(batches[i % NB]), args.steps)
+    w1 = time.time()
     launches = _lib.launch_count() - l0
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(w0, w1) if clocks else None
 
     # ---- end to end through the public API from pinned host memory: the batch of EVERY step is copied host -> device
     # inside the timed region (m2_mixer_b200.data.DevicePrefetcher double-buffers it on a side stream, one batch ahead)
@@ -274,20 +291,26 @@ def run_ours(args, cfg):
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
         if peak is None:
             peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
-        cands = {k: v for k, v in table.items() if k in ("chain_fwd", "chain_bwd")}
+        # the three tcgen05 kernels of a channel-mixing block; each carries 4*M*D*C ALGORITHMIC FLOPs per launch:
+        #   chain_fwd   : the two forward GEMMs
+        #   chain_bwd   : dG = dY W2 and dXn = dH W1            (its recomputed H GEMM is not counted)
+        #   wgrad_fused : dW1 = dH^T LN(u) and dW2 = dY^T G      (its recomputed H and dG GEMMs are not counted)
+        cands = {k: v for k, v in table.items() if k in ("chain_fwd", "chain_bwd", "wgrad_fused")}
         if cands:
             name = max(cands, key=lambda k: cands[k][1])
             n, tot_ms = cands[name]
-            # both chains carry 4*M*D*C algorithmic FLOPs per launch (fwd: two GEMMs; bwd: dG and dXn; the recomputed
-            # H GEMM of the backward chain is NOT counted)
             flops = per_sample_chain * B * 3                            # 3 profiled steps
             ach = flops / (tot_ms / 1e3) / 1e12
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tpath):
                 traffic = json.load(open(tpath)).get(name)
+            chain_ms = sum(v[1] for v in cands.values())
             roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": traffic, "launches": n, "avg_launch_ms": tot_ms / n, "peak_source": peak_src,
+                    "algorithmic_flops_per_launch": "4*M*D*C (recomputed GEMMs not counted)",
+                    "all_chain_kernels": {"achieved": 3 * flops / (chain_ms / 1e3) / 1e12, "frac": 3 * flops / (chain_ms / 1e3) / 1e12 / peak,
+                                          "note": "fwd + dgrad + wgrad together: 12*M*D*C algorithmic FLOPs over their summed time"},
                     "step_share": {k: round(v[1] / 3, 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])}}
 
     cpu = None

@@ -406,6 +406,7 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     auto ld_piece = [&](int j, int pc, uint32_t (&dst)[16]) {
       tmem_ld16(tmem_base + C::kColH + lane_addr + (j % NB) * kCc + pc * 16, dst);
     };
+    const float hs = kDrop ? 0.5f * p.dh.scale : 0.5f;   // dropout scale folded into the GELU
     auto gelu_piece = [&](const uint32_t (&h)[16], int c, uint32_t* gout) {   // 16 columns starting at channel c
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -422,11 +423,11 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           v[e] = gelu2(__fadd2_rn(make_float2(__uint_as_float(h[hh * 8 + 2 * e]), __uint_as_float(h[hh * 8 + 2 * e + 1])),
-                                  make_float2(b[2 * e], b[2 * e + 1])));
+                                  make_float2(b[2 * e], b[2 * e + 1])), hs);
         if (kDrop) {
           const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + c + hh * 8;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) drop_apply2(p.dh, v[e].x, v[e].y, i0 + 2 * e);
+          for (int e = 0; e < 4; ++e) drop_zero2(p.dh, v[e].x, v[e].y, i0 + 2 * e);   // the scale is already in v (hs)
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) gout[hh * 4 + e] = pack_bf16(v[e].x, v[e].y);
@@ -737,6 +738,8 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     const int r = q * 32 + lane;
     const int row = m0 + r;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const float hs = kDrop ? 0.5f * p.dh.scale : 0.5f;          // dropout scale folded into GELU / GELU'
+    const float ninv_s = kDrop ? -1.f / p.dh.scale : -1.f;
     for (int j = 0; j < nch; ++j) {
       const int b = j & 1;
       const uint32_t tH = tmem_base + C::kColH + lane_addr + b * kCc + grp * 16;
@@ -769,16 +772,13 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         for (int e = 0; e < 4; ++e) {
           float2 dgelu;
           gv[e] = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[ch * 8 + 2 * e]), __uint_as_float(h[ch * 8 + 2 * e + 1])),
-                                        make_float2(bias[2 * e], bias[2 * e + 1])), dgelu);
+                                        make_float2(bias[2 * e], bias[2 * e + 1])), dgelu, hs, ninv_s);
           dv[e] = __fmul2_rn(make_float2(__uint_as_float(dg[ch * 8 + 2 * e]), __uint_as_float(dg[ch * 8 + 2 * e + 1])), dgelu);
         }
         if (kDrop) {   // G' = m*s*G ; dH = dG' * m*s*gelu'(h)
           const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + cc;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (kStoreGH) drop_apply2(p.dh, gv[e].x, gv[e].y, i0 + 2 * e);
-            drop_apply2(p.dh, dv[e].x, dv[e].y, i0 + 2 * e);
-          }
+          for (int e = 0; e < 4; ++e) drop_zero2x2(p.dh, gv[e].x, gv[e].y, dv[e].x, dv[e].y, i0 + 2 * e);   // scale folded in
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) dhp[ch * 4 + e] = pack_bf16(dv[e].x, dv[e].y);

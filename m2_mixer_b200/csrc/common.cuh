@@ -79,26 +79,28 @@ __device__ __forceinline__ float tanh_ap(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float2 gelu2(float2 x) {
+// `hs` = s / 2 folds the dropout scale s = 1 / (1 - p) of the following nn.Dropout into the result for free
+// (the epilogue then only SELECTS kept values, drop_zero2): returns s * GELU(x).
+__device__ __forceinline__ float2 gelu2(float2 x, float hs = 0.5f) {
   const float2 x2 = __fmul2_rn(x, x);
   const float2 p = __ffma2_rn(x2, make_float2(kG3b, kG3b), make_float2(kG3a, kG3a));
   const float2 u = __fmul2_rn(x, p);
   const float2 t = make_float2(tanh_ap(u.x), tanh_ap(u.y));
-  const float2 w = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  const float2 w = __ffma2_rn(t, make_float2(hs, hs), make_float2(hs, hs));
   return __fmul2_rn(x, w);
 }
-// returns GELU(x); dg = GELU'(x)
-__device__ __forceinline__ float2 gelu2_grad(float2 x, float2& dg) {
+// returns s * GELU(x); dg = s * GELU'(x)   (s = 2 hs, ninv_s = -1 / s; defaults: s = 1)
+__device__ __forceinline__ float2 gelu2_grad(float2 x, float2& dg, float hs = 0.5f, float ninv_s = -1.f) {
   const float2 x2 = __fmul2_rn(x, x);
   const float2 p = __ffma2_rn(x2, make_float2(kG3b, kG3b), make_float2(kG3a, kG3a));
   const float2 du2 = __ffma2_rn(x2, make_float2(6.f * kG3b, 6.f * kG3b), make_float2(2.f * kG3a, 2.f * kG3a));   // 2 u'
   const float2 u = __fmul2_rn(x, p);
   const float2 t = make_float2(tanh_ap(u.x), tanh_ap(u.y));
-  const float2 w = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
-  const float2 g = __fmul2_rn(x, w);
-  const float2 omw = __ffma2_rn(w, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+  const float2 w = __ffma2_rn(t, make_float2(hs, hs), make_float2(hs, hs));           // s w0
+  const float2 g = __fmul2_rn(x, w);                                                  // s GELU
+  const float2 omw = __ffma2_rn(w, make_float2(ninv_s, ninv_s), make_float2(1.f, 1.f));   // 1 - w0
   const float2 tmp = __fmul2_rn(g, omw);
-  dg = __ffma2_rn(tmp, du2, w);
+  dg = __ffma2_rn(tmp, du2, w);                                                       // s (w0 + 2 GELU (1 - w0) u')
   return g;
 }
 
@@ -113,23 +115,42 @@ struct Drop {
   uint32_t thresh;   // 0 = dropout off
   float scale;
 };
+// Two-round multiply / xorshift finisher (the first two rounds of lowbias32).  The epilogues are instruction-issue bound
+// and with dropout on the mask arithmetic was ~20 of ~45 instructions per element pair (ALU pipe 42-48 % busy,
+// profiles/r01_ncu_final.md), so it is kept short: the key is already a full-avalanche splitmix64 of (seed, site).
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15;
   return x;
 }
+// Only the LOW 32 bits of the element index enter the hash (the mask of a tensor with more than 2^32 elements repeats with
+// that period): all index arithmetic at the call sites narrows to 32-bit integer instructions.
 __device__ __forceinline__ uint32_t drop_pair_bits(uint32_t key, uint32_t pair_idx) { return mix32(pair_idx * 0x9E3779B9U + key); }
 __device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
-  const uint32_t h = drop_pair_bits(d.key, static_cast<uint32_t>(idx >> 1));
-  return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) >= d.thresh;
+  const uint32_t lo = static_cast<uint32_t>(idx);
+  const uint32_t h = drop_pair_bits(d.key, lo >> 1);
+  return ((lo & 1) ? (h >> 16) : (h & 0xFFFFu)) >= d.thresh;
 }
 __device__ __forceinline__ float drop_apply(const Drop& d, float v, unsigned long long idx) {
   return drop_keep(d, idx) ? v * d.scale : 0.f;
 }
 // two consecutive elements starting at an EVEN index: one hash
 __device__ __forceinline__ void drop_apply2(const Drop& d, float& v0, float& v1, unsigned long long even_idx) {
-  const uint32_t h = drop_pair_bits(d.key, static_cast<uint32_t>(even_idx >> 1));
+  const uint32_t h = drop_pair_bits(d.key, static_cast<uint32_t>(even_idx) >> 1);
   v0 = (h & 0xFFFFu) >= d.thresh ? v0 * d.scale : 0.f;
   v1 = (h >> 16) >= d.thresh ? v1 * d.scale : 0.f;
+}
+// same mask, values already carry the scale (gelu2 / gelu2_grad with hs = scale / 2): select only
+__device__ __forceinline__ void drop_zero2(const Drop& d, float& v0, float& v1, unsigned long long even_idx) {
+  const uint32_t h = drop_pair_bits(d.key, static_cast<uint32_t>(even_idx) >> 1);
+  v0 = (h & 0xFFFFu) >= d.thresh ? v0 : 0.f;
+  v1 = (h >> 16) >= d.thresh ? v1 : 0.f;
+}
+// the same hash masks TWO value pairs (G and dH of the backward kernels)
+__device__ __forceinline__ void drop_zero2x2(const Drop& d, float& a0, float& a1, float& b0, float& b1, unsigned long long even_idx) {
+  const uint32_t h = drop_pair_bits(d.key, static_cast<uint32_t>(even_idx) >> 1);
+  const bool k0 = (h & 0xFFFFu) >= d.thresh, k1 = (h >> 16) >= d.thresh;
+  a0 = k0 ? a0 : 0.f; b0 = k0 ? b0 : 0.f;
+  a1 = k1 ? a1 : 0.f; b1 = k1 ? b1 : 0.f;
 }
 inline Drop make_drop(float p, unsigned long long seed, uint32_t site) {
   Drop d;

@@ -93,6 +93,7 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
     b2f[jn][1] = (8 * jn + 2 * tq + 1 < N) ? b2[8 * jn + 2 * tq + 1] : 0.f;
   }
   const float inv_d = 1.f / D;
+  const float hs = kDrop ? 0.5f * dh.scale : 0.5f;   // dropout scale folded into the GELU
 
   for (int b = blockIdx.x * kWarps + warp; b < B; b += gridDim.x * kWarps) {
     const float* xb = x + static_cast<long long>(b) * N * D;
@@ -155,13 +156,13 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
       uint32_t a2f[KS2][4];
 #pragma unroll
       for (int j = 0; j < NT1; ++j) {
-        float2 lo = gelu2(make_float2(c[j][0], c[j][1]));
-        float2 hi = gelu2(make_float2(c[j][2], c[j][3]));
+        float2 lo = gelu2(make_float2(c[j][0], c[j][1]), hs);
+        float2 hi = gelu2(make_float2(c[j][2], c[j][3]), hs);
         if (kDrop) {   // hidden-site index (b T + t) D + d: (d_lo, d_hi) is one hash pair
           const int t = 8 * j + 2 * tq;
           const unsigned long long i0 = (static_cast<unsigned long long>(b) * T + t) * D + d_lo;
-          drop_apply2(dh, lo.x, hi.x, i0);
-          drop_apply2(dh, lo.y, hi.y, i0 + D);
+          drop_zero2(dh, lo.x, hi.x, i0);   // scale folded into the GELU (hs)
+          drop_zero2(dh, lo.y, hi.y, i0 + D);
         }
         a2f[j >> 1][(j & 1) * 2] = pack_bf16(lo.x, lo.y);
         a2f[j >> 1][(j & 1) * 2 + 1] = pack_bf16(hi.x, hi.y);
@@ -261,6 +262,8 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
 #pragma unroll
   for (int q = 0; q < DQ; ++q) { dgam[q][0] = dgam[q][1] = dbet[q][0] = dbet[q][1] = 0.f; }
   const float inv_d = 1.f / D;
+  const float hs = kDrop ? 0.5f * dh.scale : 0.5f;          // dropout scale folded into GELU / GELU'
+  const float ninv_s = kDrop ? -1.f / dh.scale : -1.f;
   __syncthreads();
 
   for (int b = blockIdx.x * kW + warp; b < B; b += gridDim.x * kW) {
@@ -336,17 +339,15 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
 #pragma unroll
       for (int j = 0; j < NT1; ++j) {
         float2 dg_lo, dg_hi;
-        float2 g_lo = gelu2_grad(make_float2(c1[j][0], c1[j][1]), dg_lo);
-        float2 g_hi = gelu2_grad(make_float2(c1[j][2], c1[j][3]), dg_hi);
+        float2 g_lo = gelu2_grad(make_float2(c1[j][0], c1[j][1]), dg_lo, hs, ninv_s);
+        float2 g_hi = gelu2_grad(make_float2(c1[j][2], c1[j][3]), dg_hi, hs, ninv_s);
         float2 h_lo = __fmul2_rn(make_float2(c3[j][0], c3[j][1]), dg_lo);
         float2 h_hi = __fmul2_rn(make_float2(c3[j][2], c3[j][3]), dg_hi);
         if (kDrop) {
           const int t = 8 * j + 2 * tq;
           const unsigned long long i0 = (static_cast<unsigned long long>(b) * T + t) * D + d_lo;
-          drop_apply2(dh, g_lo.x, g_hi.x, i0);
-          drop_apply2(dh, g_lo.y, g_hi.y, i0 + D);
-          drop_apply2(dh, h_lo.x, h_hi.x, i0);
-          drop_apply2(dh, h_lo.y, h_hi.y, i0 + D);
+          drop_zero2x2(dh, g_lo.x, g_hi.x, h_lo.x, h_hi.x, i0);   // scale folded into gelu2_grad
+          drop_zero2x2(dh, g_lo.y, g_hi.y, h_lo.y, h_hi.y, i0 + D);
         }
         db1a[j][0] += h_lo.x + h_hi.x;
         db1a[j][1] += h_lo.y + h_hi.y;

@@ -214,6 +214,8 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
     for (int k = 0; k < 32; ++k) dbp[k] = make_float2(0.f, 0.f);
     const uint32_t bias_addr = smem_u32(sB1 + grp * 64);
+    const float hs = kDrop ? 0.5f * p.dh.scale : 0.5f;          // dropout scale folded into GELU / GELU'
+    const float ninv_s = kDrop ? -1.f / p.dh.scale : -1.f;
     uint8_t* gdst = sG + grp * C::kGPanel;
     uint8_t* hdst = sdH + grp * C::kGPanel;
     auto ld_quarter = [&](int qt, uint32_t (&hd)[16], uint32_t (&gd2)[16]) {
@@ -244,12 +246,9 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           const int k = qt * 16 + 2 * e;
           float2 dgelu;
           float2 gv = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[2 * e]), __uint_as_float(h[2 * e + 1])),
-                                            make_float2(bias[2 * e], bias[2 * e + 1])), dgelu);
+                                            make_float2(bias[2 * e], bias[2 * e + 1])), dgelu, hs, ninv_s);
           float2 dv = __fmul2_rn(make_float2(__uint_as_float(dg[2 * e]), __uint_as_float(dg[2 * e + 1])), dgelu);
-          if (kDrop) {
-            drop_apply2(p.dh, gv.x, gv.y, i0 + k);
-            drop_apply2(p.dh, dv.x, dv.y, i0 + k);
-          }
+          if (kDrop) drop_zero2x2(p.dh, gv.x, gv.y, dv.x, dv.y, i0 + k);   // scale folded into gelu2_grad
           if (live) dbp[k >> 1] = __fadd2_rn(dbp[k >> 1], dv);
           gp[e] = pack_bf16(gv.x, gv.y);
           dp[e] = pack_bf16(dv.x, dv.y);
