@@ -48,6 +48,11 @@ const char* m2b200_status_string(int status);
  * fp32 master weights in the reference's [out,in] state-dict layout and refresh this cache after every
  * optimiser step. */
 int m2b200_cast_bf16(const float* src, int64_t lds, void* dst_bf16, int64_t ldd, int rows, int cols, void* stream);
+/* The same for every GEMM weight of a model in ONE launch.  table_dev: n sextuples {src ptr, dst ptr, rows, cols, lds,
+ * ldd} of int64 in DEVICE memory (built once by the caller; the pointers are stable because FusedAdam keeps the
+ * parameters in one flat buffer).  Replaces the per-matrix refresh after each optimiser step (reference: the weights
+ * are nn.Linear / nn.Conv2d parameters, modules/mixer.py:13-19,143-146). */
+int m2b200_cast_bf16_multi(const int64_t* table_dev, int n, void* stream);
 
 /* Generic GEMM  C[b] = act(A[b] (x) B[b] + bias) + residual  (see csrc/kernels.h GemmArgs for the full contract).
  * precision FP32: A,B are fp32; BF16: A,B are bf16 (tcgen05 + TMA).  a_mn/b_mn = 1 means the operand is stored

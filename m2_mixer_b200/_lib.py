@@ -25,6 +25,7 @@ PROTOTYPES = {
     "m2b200_abi_version": (i32, []),
     "m2b200_status_string": (C.c_char_p, [i32]),
     "m2b200_cast_bf16": (i32, [vp, i64, vp, i64, i32, i32, vp]),
+    "m2b200_cast_bf16_multi": (i32, [vp, i32, vp]),
     "m2b200_gemm": (i32, [i32, vp, i32, i64, vp, i32, i64, i32, i32, i32, i32, i64, i64, vp, i32, i32, vp, i64, i64, vp,
                           i32, i64, i64, i32, i32, vp]),
     "m2b200_token_mix_fwd": (i32, [vp] * 8 + [i32] * 5 + [f32, u64, vp]),

@@ -79,6 +79,10 @@ int m2b200_cast_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int 
   return cast_pad_bf16(src, lds, dst, ldd, rows, cols, S(stream));
 }
 
+int m2b200_cast_bf16_multi(const int64_t* table_dev, int n, void* stream) {
+  return cast_pad_bf16_multi(reinterpret_cast<const long long*>(table_dev), n, S(stream));
+}
+
 int m2b200_gemm(int precision, const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, int M, int N,
                 int K, int batch, int64_t a_batch_rows, int64_t b_batch_rows, const float* bias, int bias_mode, int act,
                 const float* residual, int64_t ldr, int64_t r_batch_stride, void* C, int c_bf16, int64_t ldc,

@@ -57,6 +57,8 @@ int chain_generation();
 
 // ---- row kernels (rowops.cu)
 int cast_pad_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols, cudaStream_t s);
+// table_dev: n x {src ptr, dst ptr, rows, cols, lds, ldd} as int64 in device memory
+int cast_pad_bf16_multi(const long long* table_dev, int n, cudaStream_t s);
 int ln_fwd(const float* x, const float* w, const float* b, void* out, int out_bf16, int rows, int D, int N,
            long long out_bstride, float* mean, float* rstd, cudaStream_t s);
 int ln_bwd(const float* dy, long long dy_bstride, int N, const float* x, const float* w, const float* dres, float* dx,

@@ -42,6 +42,44 @@ __global__ void __launch_bounds__(256) cast_pad_bf16_vec_kernel(const float* __r
   }
 }
 
+// All bf16 operand copies of a model in ONE launch: table[e] = {src, dst, rows, cols, lds, ldd} (device int64 sextuples),
+// blockIdx.y = entry.  Replaces one small launch per weight matrix (22 per M2-Mixer-B step, 0.17 ms).
+__global__ void __launch_bounds__(256) cast_pad_bf16_multi_kernel(const long long* __restrict__ table) {
+  const long long* e = table + 6 * blockIdx.y;
+  const float* __restrict__ src = reinterpret_cast<const float*>(e[0]);
+  __nv_bfloat16* __restrict__ dst = reinterpret_cast<__nv_bfloat16*>(e[1]);
+  const int rows = static_cast<int>(e[2]), cols = static_cast<int>(e[3]);
+  const long long lds = e[4], ldd = e[5];
+  const bool vec = (lds % 4 == 0) && (ldd % 8 == 0) && (((e[0] | e[1]) & 15) == 0);
+  if (vec) {
+    const int gpr = static_cast<int>(ldd / 8);
+    const long long total = static_cast<long long>(rows) * gpr;
+    for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < total;
+         g += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int r = static_cast<int>(g / gpr), c = static_cast<int>(g - static_cast<long long>(r) * gpr) * 8;
+      const float* sp = src + r * lds + c;
+      float v[8];
+      if (c + 8 <= cols) {
+        const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = c + k < cols ? sp[k] : 0.f;
+      }
+      *reinterpret_cast<uint4*>(dst + r * ldd + c) =
+          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+  } else {
+    const long long total = static_cast<long long>(rows) * ldd;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long r = i / ldd;
+      const int c = static_cast<int>(i - r * ldd);
+      dst[i] = __float2bfloat16(c < cols ? src[r * lds + c] : 0.f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ LayerNorm forward
 // rows = B*N tokens; output row (b, n) goes to out + b*out_bstride + n*D  (lets an encoder's final LN write
 // straight into its slice of the fused-token buffer: zero-copy ConcatFusion, reference modules/fusion.py:117).
@@ -373,6 +411,14 @@ int cast_pad_bf16(const float* src, long long lds, void* dst, long long ldd, int
   } else {
     cast_pad_bf16_kernel<<<grid_for(static_cast<long long>(rows) * ldd, 256), 256, 0, s>>>(src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
   }
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int cast_pad_bf16_multi(const long long* table_dev, int n, cudaStream_t s) {
+  LaunchScope scope("cast_pad_bf16_multi", s);
+  if (!table_dev || n <= 0 || n > 65535) return M2_ERR_ARG;
+  cast_pad_bf16_multi_kernel<<<dim3(ceil_div(148 * 4, n) < 1 ? 1 : ceil_div(148 * 4, n), n), 256, 0, s>>>(table_dev);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }

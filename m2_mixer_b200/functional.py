@@ -235,6 +235,70 @@ def _drop_args(p: float, seed):
     return p, int(next_dropout_seed() if seed is None else seed)
 
 
+class _Bf16WeightCache:
+    """bf16 operand copies of the GEMM weights (fp32 masters stay in the reference's [out, in] state-dict layout).
+
+    An entry is stale when its parameter's storage pointer or autograd version changed (load_state_dict, torch optimizers and
+    any other in-place update of the parameter bump the version) or when ``invalidate_bf16_weights()`` was called since -
+    FusedAdam.step() does that, because it updates the flat buffer the parameters are views of, which does NOT touch the
+    parameters' own version counters.  Writes through ``.data`` are invisible: call ``invalidate_bf16_weights()`` after them.
+    The first stale lookup refreshes EVERY registered copy in one launch (m2b200_cast_bf16_multi) - after an optimiser step
+    the weights all changed together - instead of one small launch per matrix and forward."""
+
+    def __init__(self):
+        self.entries = {}          # id(param) -> [param weakref, rows, cols, ld, dst, data_ptr, version, epoch]
+        self.epoch = 0
+        self.table = None
+        self.table_key = None
+
+    def get(self, param: torch.Tensor, rows: int, cols: int, ld: int) -> torch.Tensor:
+        import weakref
+        e = self.entries.get(id(param))
+        if e is not None and (e[0]() is not param or e[1:4] != [rows, cols, ld] or e[4].device != param.device):
+            e = None
+        if e is None:
+            if not (param.is_cuda and param.dtype == torch.float32 and param.is_contiguous()):
+                raise RuntimeError("bf16 weight cache expects contiguous float32 CUDA parameters")
+            dst = torch.empty(rows, ld, dtype=torch.bfloat16, device=param.device)
+            key = id(param)
+            e = [weakref.ref(param, lambda _r, k=key: self.entries.pop(k, None)), rows, cols, ld, dst, 0, -1, -1]
+            self.entries[key] = e
+        if e[5] != param.data_ptr() or e[6] != param._version or e[7] != self.epoch:
+            self._refresh(param.device)
+        return e[4]
+
+    def _refresh(self, device) -> None:
+        live = []
+        for e in list(self.entries.values()):
+            p = e[0]()
+            if p is not None and p.device == device:
+                live.append((e, p))
+        key = tuple((p.data_ptr(), e[4].data_ptr()) for e, p in live)
+        if key != self.table_key or self.table is None or self.table.device != device:
+            rows = [[p.data_ptr(), e[4].data_ptr(), e[1], e[2], e[2], e[3]] for e, p in live]
+            self.table = torch.tensor(rows, dtype=torch.int64).to(device)
+            self.table_key = key
+        with torch.no_grad():
+            ops.cast_bf16_multi(self.table, len(live))
+        for e, p in live:
+            e[5], e[6], e[7] = p.data_ptr(), p._version, self.epoch
+
+
+_WCACHE = _Bf16WeightCache()
+
+
+def invalidate_bf16_weights() -> None:
+    """Mark every cached bf16 weight copy stale (the next forward refreshes them all in one launch)."""
+    _WCACHE.epoch += 1
+
+
+def bf16_weight(param: torch.Tensor, rows: Optional[int] = None, cols: Optional[int] = None) -> torch.Tensor:
+    """bf16 [rows][up8(cols)] operand copy of a weight parameter viewed as [rows][cols] (default: its first axis x the rest)."""
+    rows = param.shape[0] if rows is None else rows
+    cols = param.numel() // rows if cols is None else cols
+    return _WCACHE.get(param, rows, cols, _up8(cols))
+
+
 def token_mix(x, ln_w, ln_b, w1, b1, w2, b2, precision, dropout_p: float = 0.0, seed=None) -> torch.Tensor:
     p, seed = _drop_args(dropout_p, seed)
     return _TokenMix.apply(x, ln_w, ln_b, w1, b1, w2, b2, precision_code(precision), p, seed)
@@ -245,9 +309,12 @@ def channel_mix(u, ln_w, ln_b, w1, b1, w2, b2, precision, w1b=None, w2b=None, dr
     prec = precision_code(precision)
     p, seed = _drop_args(dropout_p, seed)
     if prec == BF16 and (w1b is None or w2b is None):
-        with torch.no_grad():
-            w1b = _O.cast_bf16(w1, w1.shape[1])
-            w2b = _O.cast_bf16(w2, _up8(w2.shape[1]))
+        if isinstance(w1, torch.nn.Parameter) and isinstance(w2, torch.nn.Parameter) and w1.shape[1] % 8 == 0:
+            w1b, w2b = bf16_weight(w1), bf16_weight(w2)          # cached, refreshed together after an optimiser step
+        else:
+            with torch.no_grad():
+                w1b = _O.cast_bf16(w1, w1.shape[1])
+                w2b = _O.cast_bf16(w2, _up8(w2.shape[1]))
     return _ChannelMix.apply(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, prec, p, seed)
 
 
@@ -259,8 +326,11 @@ def linear(x, w, bias=None, act: int = ACT_NONE, precision="bf16", wb=None, drop
     prec = precision_code(precision)
     p, seed = _drop_args(dropout_p, seed)
     if prec == BF16 and wb is None:
-        with torch.no_grad():
-            wb = _O.cast_bf16(w.reshape(w.shape[0], -1), _up8(w[0].numel()))
+        if isinstance(w, torch.nn.Parameter):
+            wb = bf16_weight(w)
+        else:
+            with torch.no_grad():
+                wb = _O.cast_bf16(w.reshape(w.shape[0], -1), _up8(w[0].numel()))
     return _Linear.apply(x, w.reshape(w.shape[0], -1), bias, wb, act, prec, p, seed)
 
 
@@ -269,8 +339,11 @@ def patch_embed(img, conv_w, conv_b, patch: int, precision="bf16") -> torch.Tens
     prec = precision_code(precision)
     wb = None
     if prec == BF16:
-        with torch.no_grad():
-            wb = _O.cast_bf16(conv_w.reshape(conv_w.shape[0], -1), _up8(conv_w[0].numel()))
+        if isinstance(conv_w, torch.nn.Parameter):
+            wb = bf16_weight(conv_w)
+        else:
+            with torch.no_grad():
+                wb = _O.cast_bf16(conv_w.reshape(conv_w.shape[0], -1), _up8(conv_w[0].numel()))
     return _PatchEmbed.apply(img, conv_w, conv_b, wb, patch, prec)
 
 

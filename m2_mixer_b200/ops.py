@@ -74,6 +74,13 @@ def cast_bf16(w: torch.Tensor, ld: int) -> torch.Tensor:
 _define("cast_bf16", "(Tensor w, int ld) -> Tensor", cast_bf16)
 
 
+def cast_bf16_multi(table: torch.Tensor, n: int) -> None:
+    """table: int64 CUDA tensor [n, 6] of {src ptr, dst ptr, rows, cols, lds, ldd}: every bf16 weight copy in one launch."""
+    if not (table.is_cuda and table.dtype == torch.int64 and table.is_contiguous() and table.numel() >= 6 * n):
+        raise RuntimeError("m2b200::cast_bf16_multi expects a contiguous int64 CUDA table [n, 6]")
+    check(_L().m2b200_cast_bf16_multi(table.data_ptr(), n, _stream()), "cast_bf16_multi")
+
+
 # ------------------------------------------------------------------------------------------------ token mixing
 def token_mix_fwd(x, ln_w, ln_b, w1, b1, w2, b2, precision: int, dropout_p: float = 0.0, seed: int = 0):
     x = _f32c(x, "x")

@@ -69,4 +69,6 @@ class FusedAdam(torch.optim.Optimizer):
         self.step_count += 1
         _O.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, float(g["lr"]), g["betas"][0],
                      g["betas"][1], g["eps"], g["weight_decay"], self.step_count, float(self.grad_scale), self._state_dev)
+        from .functional import invalidate_bf16_weights   # the parameters are views of flat_param: their versions did not move
+        invalidate_bf16_weights()
         return loss

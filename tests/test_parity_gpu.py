@@ -249,8 +249,11 @@ def test_channel_mix_dropout_matches_oracle_with_exported_mask(precision, tol, M
         assert rel_err(pt[k].grad, pd[k].grad) < gtol, k
 
 
-@pytest.mark.parametrize("B,N,D,T", [(9, 4, 128, 32), (3, 40, 48, 16)])
-def test_token_mix_dropout_matches_oracle_with_exported_mask(B, N, D, T):
+@pytest.mark.parametrize("precision,B,N,D,T", [("fp32", 9, 4, 128, 32), ("fp32", 3, 40, 48, 16),
+                                               ("bf16", 37, 4, 128, 32), ("bf16", 19, 8, 64, 16), ("bf16", 5, 12, 64, 32)])
+def test_token_mix_dropout_matches_oracle_with_exported_mask(precision, B, N, D, T):
+    """fp32: CUDA-core kernels; bf16: the warp-level tensor-core kernels (token_mix_mma.cu), whose lanes own column PAIRS and
+    regenerate the hidden-site and output-site masks from the same (b, t / n, d) element indices."""
     from m2_mixer_b200 import functional as F, ops
     from oracle import m2mixer_oracle as O
     torch.manual_seed(1)
@@ -268,14 +271,16 @@ def test_token_mix_dropout_matches_oracle_with_exported_mask(B, N, D, T):
     ur = xd + (torch.einsum("nt,btd->bnd", pd["w2"], h) + pd["b2"][None, :, None]) * mo
     pt = {k: v.clone().requires_grad_(True) for k, v in prm.items()}
     xt = x.clone().requires_grad_(True)
-    u = F.token_mix(xt, pt["ln_w"], pt["ln_b"], pt["w1"], pt["b1"], pt["w2"], pt["b2"], "fp32", dropout_p=p, seed=seed)
+    u = F.token_mix(xt, pt["ln_w"], pt["ln_b"], pt["w1"], pt["b1"], pt["w2"], pt["b2"], precision, dropout_p=p, seed=seed)
     du = torch.randn(B, N, D, device=dev)
     ur.backward(du.double())
     u.backward(du)
-    assert rel_err(u, ur) < 1e-5
-    assert rel_err(xt.grad, xd.grad) < 1e-4
+    tol, gtol = (1e-5, 1e-4) if precision == "fp32" else (2e-2, 3e-2)
+    assert rel_err(u, ur) < tol
+    assert rel_err(u - xt, ur - xd) < (1e-4 if precision == "fp32" else 3e-2)      # the branch alone (the residual dominates u)
+    assert rel_err(xt.grad, xd.grad) < gtol
     for k in prm:
-        assert rel_err(pt[k].grad, pd[k].grad) < 1e-4, k
+        assert rel_err(pt[k].grad, pd[k].grad) < gtol, k
 
 
 def test_dropout_statistics_and_modes():
