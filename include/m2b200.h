@@ -70,7 +70,8 @@ int m2b200_gemm(int precision, const void* A, int a_mn, int64_t lda, const void*
  * m2b200_dropout_mask exports the exact keep-mask (1/0) of a site for testing: index = r*ld + c with
  *   site 0 token hidden   rows = B*T, ld = D        site 1 token out     rows = B*N, ld = D
  *   site 2 channel hidden rows = M,   ld = up8(C)   site 3 channel out   rows = M,   ld = D      site 4 linear ld = N
- * kept values are scaled by 65536 / (65536 - round(p*65536)).                                                        */
+ * The drop probability is quantised to t/128, t = round(p*128) (one hash per 4 consecutive elements, 7 bits each);
+ * kept values are scaled by 128 / (128 - t), the inverse of the realised keep probability.                            */
 int m2b200_dropout_mask(float* out, int rows, int cols, int64_t ld, float dropout_p, uint64_t seed, int site, void* stream);
 
 /* ---- MixerBlock.token_mix + residual: modules/mixer.py:30-35,43

@@ -19,6 +19,8 @@
 //   * the output tile is staged through the (then idle) weight ring so that u is read and y written coalesced.
 //
 // TMEM map (512 columns): [0,DP) Y accumulator | [DP, DP+DP/2) LN(u) bf16 | 5 x 64 H accumulators (G aliased).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap.cuh"
@@ -28,12 +30,12 @@ namespace {
 
 constexpr int kRows = 128;      // token rows per CTA (UMMA M)
 constexpr int kCc = 64;         // channels per chunk
-constexpr int kThreads = 320;   // forward: warp0 TMA, warp1 MMA, warps 2-9 epilogue (two groups of 4 warps)
+// forward: 96 + 128 kG threads (TMA warp, two MMA-issuing warps, kG epilogue groups of 4 warps), see chain_fwd_ts_kernel
 // backward: FOUR epilogue groups (16 warps, 4 per scheduler).  With two, the GELU' epilogue ran at 0.46 IPC per
 // scheduler - dependent FMA chains and MUFU latency, no pipe above 40 % (profiles/r01_ncu_chain_v9.md): latency bound,
 // so the cure is more warps in flight, each on a quarter (16 columns) of the chunk.
 constexpr int kGroupsB = 4;
-constexpr int kThreadsB = 64 + 128 * kGroupsB;
+constexpr int kThreadsB = 96 + 128 * kGroupsB;
 constexpr int kBarBytes = 512;
 
 template <int DP>
@@ -164,33 +166,52 @@ __device__ __forceinline__ void ln_rows_to_stage(const TsParams& p, int m0, uint
                       : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+    // Statistics of all kB rows together: the butterfly steps of different rows are independent, so their shuffle
+    // latencies overlap (row after row this prologue took 6900 clk of a 62 k clk kernel, profiles/r01_trace_fwd_*.log).
+    float mean[kB], rstd[kB];
+#pragma unroll
+    for (int b = 0; b < kB; ++b) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < kV; ++i) s += v[b][i].x + v[b][i].y + v[b][i].z + v[b][i].w;
+      mean[b] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int b = 0; b < kB; ++b) mean[b] += __shfl_xor_sync(0xffffffffu, mean[b], o);
+#pragma unroll
+    for (int b = 0; b < kB; ++b) {
+      mean[b] *= inv_d;
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < kV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < p.D) {
+          const float a = v[b][i].x - mean[b], bb = v[b][i].y - mean[b], cc = v[b][i].z - mean[b], d = v[b][i].w - mean[b];
+          ss += a * a + bb * bb + cc * cc + d * d;
+        }
+      }
+      rstd[b] = ss;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int b = 0; b < kB; ++b) rstd[b] += __shfl_xor_sync(0xffffffffu, rstd[b], o);
 #pragma unroll
     for (int b = 0; b < kB; ++b) {
       const int r = r0 + b, row = m0 + r;
       if (r < kRows) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < kV; ++i) s += v[b][i].x + v[b][i].y + v[b][i].z + v[b][i].w;
-        const float mean = warp_sum(s) * inv_d;
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < kV; ++i) {
-          const int c = (i * 32 + lane) * 4;
-          if (c < p.D) {
-            const float a = v[b][i].x - mean, bb = v[b][i].y - mean, cc = v[b][i].z - mean, d = v[b][i].w - mean;
-            ss += a * a + bb * bb + cc * cc + d * d;
-          }
-        }
-        const float rstd = rsqrtf(warp_sum(ss) * inv_d + kLnEps);
-        if (s_mean && lane == 0) { s_mean[r] = mean; s_rstd[r] = rstd; }
+        const float mu = mean[b], rs = rsqrtf(rstd[b] * inv_d + kLnEps);
+        if (s_mean && lane == 0) { s_mean[r] = mu; s_rstd[r] = rs; }
 #pragma unroll
         for (int i = 0; i < kV; ++i) {
           const int c = (i * 32 + lane) * 4;
           if (c < DP) {
             uint2 o = make_uint2(0u, 0u);
             if (row < p.M && c < p.D) {
-              o.x = pack_bf16((v[b][i].x - mean) * rstd * gw[i].x + gb[i].x, (v[b][i].y - mean) * rstd * gw[i].y + gb[i].y);
-              o.y = pack_bf16((v[b][i].z - mean) * rstd * gw[i].z + gb[i].z, (v[b][i].w - mean) * rstd * gw[i].w + gb[i].w);
+              o.x = pack_bf16((v[b][i].x - mu) * rs * gw[i].x + gb[i].x, (v[b][i].y - mu) * rs * gw[i].y + gb[i].y);
+              o.y = pack_bf16((v[b][i].z - mu) * rs * gw[i].z + gb[i].z, (v[b][i].w - mu) * rs * gw[i].w + gb[i].w);
               if (xn_b) *reinterpret_cast<uint2*>(xn_b + static_cast<long long>(row) * p.D + c) = o;
             }
             *reinterpret_cast<uint2*>(stage + r * CfgT<DP>::kXPitch + c * 2) = o;
@@ -201,31 +222,36 @@ __device__ __forceinline__ void ln_rows_to_stage(const TsParams& p, int m0, uint
   }
 }
 
-// b1 -> shared memory (zero padded to whole chunks), 16-byte loads, all loads of a thread in flight together.
-__device__ __forceinline__ void stage_bias(const float* __restrict__ b1, int C, int n_pad, float* sBias) {
+// b1 -> shared memory (zero padded to whole chunks), 16-byte loads.  Split into a load half and a store half so that the
+// loads are in flight during the LayerNorm prologue (back to back they cost 640 clk of load latency,
+// profiles/r01_trace_fwd_*.log).  One round covers 16 * blockDim floats (the launchers check it).
+struct BiasRegs { float4 v[4]; };
+__device__ __forceinline__ BiasRegs bias_load(const float* __restrict__ b1, int C, int n_pad) {
+  BiasRegs br;
   const int nv = n_pad >> 2;
-  for (int i0 = threadIdx.x; i0 < nv; i0 += 4 * blockDim.x) {
-    float4 v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * blockDim.x;
-      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < nv) {
-        const int c = i * 4;
-        if (c + 3 < C && (reinterpret_cast<uintptr_t>(b1) & 15) == 0) v[k] = *reinterpret_cast<const float4*>(b1 + c);
-        else {
-          if (c < C) v[k].x = b1[c];
-          if (c + 1 < C) v[k].y = b1[c + 1];
-          if (c + 2 < C) v[k].z = b1[c + 2];
-          if (c + 3 < C) v[k].w = b1[c + 3];
-        }
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.x + k * blockDim.x;
+    br.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nv) {
+      const int c = i * 4;
+      if (c + 3 < C && (reinterpret_cast<uintptr_t>(b1) & 15) == 0) br.v[k] = *reinterpret_cast<const float4*>(b1 + c);
+      else {
+        if (c < C) br.v[k].x = b1[c];
+        if (c + 1 < C) br.v[k].y = b1[c + 1];
+        if (c + 2 < C) br.v[k].z = b1[c + 2];
+        if (c + 3 < C) br.v[k].w = b1[c + 3];
       }
     }
+  }
+  return br;
+}
+__device__ __forceinline__ void bias_store(const BiasRegs& br, int n_pad, float* sBias) {
+  const int nv = n_pad >> 2;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * blockDim.x;
-      if (i < nv) *reinterpret_cast<float4*>(sBias + i * 4) = v[k];
-    }
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.x + k * blockDim.x;
+    if (i < nv) *reinterpret_cast<float4*>(sBias + i * 4) = br.v[k];
   }
 }
 
@@ -254,8 +280,11 @@ __device__ __forceinline__ void load_w2(uint8_t* slot, const CUtensorMap* tmW2, 
 }
 
 // ============================================================================================ forward
-template <int DP, bool kDrop>
-__global__ void __launch_bounds__(kThreads, 1)
+// kG epilogue groups of 4 warps (group g owns chunks j = g mod kG).  With two groups (2 warps per scheduler) the epilogue
+// issued 34 % of the time with no pipe above 30 % (profiles/r01_ncu_final.md): latency bound, like the backward before
+// it went to four groups.
+template <int DP, bool kDrop, int kG>
+__global__ void __launch_bounds__(96 + 128 * kG, 1)
 chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TsParams p) {
   using C = CfgT<DP>;
   constexpr int S1 = C::S1, S2 = C::S2, NB = C::NB;
@@ -273,40 +302,57 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   uint64_t* hfull = w2empty + S2;     // [NB]  GEMM1 done -> epilogue
   uint64_t* gfull = hfull + NB;       // [NB]  epilogue wrote G (bf16) over the first 32 columns of the buffer -> MMA
   uint64_t* yfull = gfull + NB;       // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 1);
+  uint64_t* g2done = yfull + 1;       // [NB]  GEMM2(j) has read G(j): the GEMM1 issuer may overwrite the buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g2done + NB);
   float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);
 
-  // Roles by LOGICAL warp id (0 = TMA producer, 1 = MMA issuer, 2.. = epilogue).  Physically the epilogue warps come
-  // first and the two single-thread roles LAST: the warp scheduler prefers the highest warp id on its sub-partition,
-  // and the latency-critical issuer starved behind the busy epilogue warps when it was warp 1 (724-clk gaps between a
-  // commit and the next wait in the in-kernel timeline, profiles/r01_trace_dgrad.md).
+  // Roles by LOGICAL warp id (0 = TMA producer, 1 = GEMM2 issuer, 2.. = epilogue, -1 = GEMM1 issuer).  Physically the
+  // epilogue warps come first and the single-thread roles LAST: the warp scheduler prefers the highest warp id on its
+  // sub-partition, and a latency-critical issuer starved behind the busy epilogue warps when it was warp 1 (724-clk gaps
+  // between a commit and the next wait in the in-kernel timeline, profiles/r01_trace_dgrad.md).
+  //
+  // TWO issuing warps: tcgen05.mma issue blocks at the execution rate (the queue holds only a few MMAs:
+  // tools/umma_probe.cu, issue time == execution time) and every wait on an mbarrier costs the issuer ~200 clk even
+  // when the phase completed long ago, so ONE issuer that waits for G(j), W2(j), W1(j+NB) and then issues 12 MMAs keeps
+  // the tensor pipe idle during its waits: 1378 clk per chunk for 620 clk of tensor work, the epilogue starved for H
+  // (in-kernel timeline, profiles/r01_trace_fwd_*.log).  With the GEMM1s and the GEMM2s on different warps one issuer's
+  // waits overlap the other's MMAs.  Each accumulator has ONE writer (Y: GEMM2 warp, H buffers: GEMM1 warp); the only
+  // cross-warp hazard is the G(j) -> H(j + NB) buffer reuse, ordered by the g2done barrier (tcgen05.commit of GEMM2(j)).
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp = pwarp < 8 ? pwarp + 2 : pwarp - 8;
+  const int warp = pwarp < 4 * kG ? pwarp + 2 : (pwarp == 4 * kG + 2 ? -1 : pwarp - 4 * kG);
   const int m0 = blockIdx.x * kRows;
   const int nch = ceil_div(p.C, kCc);
+  if (pwarp == 0) M2_TR(1300, 20, 0);   // kernel entry
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S1; ++i) { mbar_init(&w1full[i], 1); mbar_init(&w1empty[i], 1); }
     for (int i = 0; i < S2; ++i) { mbar_init(&w2full[i], 1); mbar_init(&w2empty[i], 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(&hfull[i], 1); mbar_init(&gfull[i], 128); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&hfull[i], 1); mbar_init(&gfull[i], 64 * kG); mbar_init(&g2done[i], 1); }
     mbar_init(yfull, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
-  if (p.bias_smem) stage_bias(p.b1, p.C, nch * kCc, sBias);
   __syncthreads();   // barriers initialised before the producer's early prefetch below
+  if (pwarp == 0) M2_TR(1301, 21, 0);   // barriers / TMEM allocated
 
   // The weight rings do not depend on the activations: start filling them before the LayerNorm prologue.
   if (warp == 0 && lane == 0) {
     for (int j = 0; j < (nch < S1 ? nch : S1); ++j) load_w1<DP>(sW1 + j * C::kW1Bytes, &tmW1, &w1full[j], j * kCc);
     for (int j = 0; j < (nch < S2 ? nch : S2); ++j) load_w2<DP>(sW2 + j * C::kW2Bytes, &tmW2, &w2full[j], j * kCc);
   }
-  ln_rows_to_stage<DP>(p, m0, sStage);
+  if (pwarp == 0) M2_TR(1308, 28, 0);
+  BiasRegs br;
+  if (p.bias_smem) br = bias_load(p.b1, p.C, nch * kCc);      // in flight during the LayerNorm
+  ln_rows_to_stage<DP, kG == 2 ? 13 : 8>(p, m0, sStage);
+  if (pwarp == 0) M2_TR(1309, 29, 0);
+  if (p.bias_smem) bias_store(br, nch * kCc, sBias);          // first read by the epilogue, two block barriers later
+  if (pwarp == 0) M2_TR(1310, 30, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (pwarp == 0) M2_TR(1302, 22, 0);   // LayerNorm rows staged
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tY = tmem_base + C::kColY;
   const uint32_t tX = tmem_base + C::kColX;
@@ -316,13 +362,14 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     const int q = pwarp & 3, grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    for (int cb = grp; cb < DP / 64; cb += 2)   // 32 TMEM columns (= 64 bf16 = 128 B of the staging row) per step
+    for (int cb = grp; cb < DP / 64; cb += kG)   // 32 TMEM columns (= 64 bf16 = 128 B of the staging row) per step
       stage_row_to_tmem(sStage + r * C::kXPitch + cb * 128, tX + lane_addr + cb * 32);
     tmem_st_wait();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (pwarp == 0) M2_TR(1303, 23, 0);   // LN(u) in TMEM: roles start
 
   if (warp == 0) {
     // Refill both rings in the order the MMA issuer frees the slots: the prologue GEMM1s free W1 slots first, then
@@ -343,15 +390,16 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
       if (it + S2 < nch) refill_w2(it + S2);
       if (x < nch) { refill_w1(x); ++x; }
     }
-  } else if (warp == 1) {
+  } else if (warp == -1) {
+    // ---- GEMM1 issuer: Hacc[j % NB] = LN(u) . W1_j^T (A from TMEM), NB chunks ahead of the epilogue.
     // The whole warp walks the loop (waits are warp-wide), one elected lane issues: see elect_one().
     constexpr uint32_t idesc1 = umma_idesc_bf16(kRows, kCc, 0, 0);
-    constexpr uint32_t idesc2 = umma_idesc_bf16(kRows, DP, 0, 0);
     const uint64_t w1_desc0 = umma_desc_sw128(smem_u32(sW1), 16, 1024);
-    const uint64_t w2_desc0 = umma_desc_sw128(smem_u32(sW2), 16, 1024);
-    auto gemm1 = [&](int j) {   // Hacc[j % NB] = LN(u) . W1_j^T      (A from TMEM)
+    for (int j = 0; j < nch; ++j) {
       const int s = j % S1, hb = j % NB;
-      mbar_wait(&w1full[s], (j / S1) & 1);   // buffer reuse is ordered by the tensor pipe: GEMM2(j - NB) was issued before
+      // GEMM2(j - NB) must have consumed the G that aliases this buffer
+      if (j >= NB) mbar_wait2(&w1full[s], (j / S1) & 1, &g2done[hb], ((j / NB) - 1) & 1);
+      else mbar_wait(&w1full[s], (j / S1) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t bd = w1_desc0 + static_cast<uint64_t>((s * C::kW1Bytes) >> 4);
@@ -363,34 +411,27 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         umma_commit(&hfull[hb]);
       }
       __syncwarp();
-    };
-    for (int j = 0; j < (nch < NB ? nch : NB); ++j) gemm1(j);
-    // Steady state: ONE burst per chunk - GEMM2(j) and GEMM1(j + NB) are issued together after all their waits.  Every
-    // wake-up of the issuer costs ~200 clk of start-up plus ~100-200 clk per mbarrier wait (in-kernel timeline,
-    // profiles/r01_trace_dgrad.md), so the serial issue path, not the tensor pipe, paced the loop when they were separate.
-    for (int j = 0; j < nch; ++j) {   // Yacc += G_j . W2_j^T (A from TMEM) ; Hacc[(j+NB) % NB] = LN(u) . W1_{j+NB}^T
+    }
+  } else if (warp == 1) {
+    // ---- GEMM2 issuer: Yacc += G_j . W2_j^T (A from TMEM)
+    constexpr uint32_t idesc2 = umma_idesc_bf16(kRows, DP, 0, 0);
+    const uint64_t w2_desc0 = umma_desc_sw128(smem_u32(sW2), 16, 1024);
+    for (int j = 0; j < nch; ++j) {
       const int s = j % S2, gb = j % NB;
-      const int jn = j + NB, sn = jn % S1;
-      const bool more = jn < nch;
-      mbar_wait(&gfull[gb], (j / NB) & 1);
-      mbar_wait(&w2full[s], (j / S2) & 1);
-      if (more) mbar_wait(&w1full[sn], (jn / S1) & 1);
+      M2_TR(4 * j + 0, 1, j);                         // issuer: about to wait
+      mbar_wait2(&gfull[gb], (j / NB) & 1, &w2full[s], (j / S2) & 1);
+      M2_TR(4 * j + 2, 3, j);                         // issuer: G(j) and the weights there
       tc_fence_after();
       if (elect_one()) {
         const uint64_t bd = w2_desc0 + static_cast<uint64_t>((s * C::kW2Bytes) >> 4);
         const uint32_t tG = tmem_base + C::kColH + gb * kCc;
 #pragma unroll
-        for (int kk = 0; kk < kCc / 16; ++kk)
-          umma_bf16_ts(tY, tG + kk * 8, bd + ((kk * 32) >> 4), idesc2, (j > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < kCc / 16; ++kk)   // A: k-step kk of G(j); kG = 4: the halves sit at columns 0 and 32 of the buffer
+          umma_bf16_ts(tY, tG + (kG == 4 ? (kk >> 1) * 32 + (kk & 1) * 8 : kk * 8), bd + ((kk * 32) >> 4), idesc2,
+                       (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&w2empty[s]);
-        if (more) {   // same buffer gb: the tensor pipe runs GEMM2(j) (reads G) before this GEMM1 overwrites it
-          const uint64_t bd1 = w1_desc0 + static_cast<uint64_t>((sn * C::kW1Bytes) >> 4);
-#pragma unroll
-          for (int kk = 0; kk < DP / 16; ++kk)
-            umma_bf16_ts(tG, tX + kk * 8, bd1 + (((kk >> 2) * (kCc * 128) + (kk & 3) * 32) >> 4), idesc1, kk > 0 ? 1u : 0u);
-          umma_commit(&w1empty[sn]);
-          umma_commit(&hfull[gb]);
-        }
+        umma_commit(&g2done[gb]);
+        M2_TR(4 * j + 3, 4, j);                       // issuer: burst issued
       }
       __syncwarp();
     }
@@ -398,7 +439,7 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     __syncwarp();
   } else {
     const int q = pwarp & 3;               // TMEM lane quadrant this warp may access (physical warp id % 4)
-    const int grp = (warp - 2) >> 2;       // epilogue group: chunks j = grp (mod 2)
+    const int grp = (warp - 2) >> 2;       // epilogue group: chunks j = grp (mod kG)
     const int r = q * 32 + lane;           // row inside the tile == TMEM lane
     const int row = m0 + r;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -407,7 +448,10 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
       tmem_ld16(tmem_base + C::kColH + lane_addr + (j % NB) * kCc + pc * 16, dst);
     };
     const float hs = kDrop ? 0.5f * p.dh.scale : 0.5f;   // dropout scale folded into the GELU
+    // dropout: hash input of the quad at channel 0 of this thread's row (quad index = (row * ldh + c) / 4)
+    const uint32_t hrow = (static_cast<uint32_t>(row) * static_cast<uint32_t>(p.ldh) >> 2) * kDropGolden + p.dh.key;
     auto gelu_piece = [&](const uint32_t (&h)[16], int c, uint32_t* gout) {   // 16 columns starting at channel c
+      const uint32_t hin = hrow + static_cast<uint32_t>(c >> 2) * kDropGolden;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float b[8];
@@ -419,55 +463,95 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
 #pragma unroll
           for (int e = 0; e < 8; ++e) b[e] = (c + hh * 8 + e < p.C) ? __ldg(p.b1 + c + hh * 8 + e) : 0.f;
         }
-        float2 v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          v[e] = gelu2(__fadd2_rn(make_float2(__uint_as_float(h[hh * 8 + 2 * e]), __uint_as_float(h[hh * 8 + 2 * e + 1])),
-                                  make_float2(b[2 * e], b[2 * e + 1])), hs);
-        if (kDrop) {
-          const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + c + hh * 8;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) drop_zero2(p.dh, v[e].x, v[e].y, i0 + 2 * e);   // the scale is already in v (hs)
+        for (int e = 0; e < 4; ++e) {
+          const float2 v = gelu2(__fadd2_rn(make_float2(__uint_as_float(h[hh * 8 + 2 * e]), __uint_as_float(h[hh * 8 + 2 * e + 1])),
+                                            make_float2(b[2 * e], b[2 * e + 1])), hs);
+          gout[hh * 4 + e] = pack_bf16(v.x, v.y);
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) gout[hh * 4 + e] = pack_bf16(v[e].x, v[e].y);
+        if (kDrop) {   // the scale is already in the values (hs): AND the packed pairs with the keep masks
+          const uint32_t f0 = drop_flags_from_hash_input(p.dh, hin + (2 * hh) * kDropGolden);
+          const uint32_t f1 = drop_flags_from_hash_input(p.dh, hin + (2 * hh + 1) * kDropGolden);
+          gout[hh * 4 + 0] &= drop_mask_bf16x2<0>(f0); gout[hh * 4 + 1] &= drop_mask_bf16x2<1>(f0);
+          gout[hh * 4 + 2] &= drop_mask_bf16x2<0>(f1); gout[hh * 4 + 3] &= drop_mask_bf16x2<1>(f1);
+        }
       }
     };
+    // kG = 2: group g owns the chunks j = g (mod 2), four 16-column pieces per thread.
+    // kG = 4: TWO groups share a chunk (chunks j = g / 2 (mod 2)); group half h = g & 1 owns columns [32 h, 32 h + 32),
+    //         two pieces per thread.  At most two chunks are in the epilogue either way (that is what the 5-buffer ring
+    //         sustains: with four chunks in flight every group starved for H, profiles/r01_trace_fwd_*.log), but a chunk
+    //         is finished by 8 warps.  A group writes its bf16 G over the head of ITS OWN columns: G columns
+    //         [32 h, 32 h + 16) of the buffer (the GEMM2 issuer picks its A operand k-steps from there).
+    constexpr int kSplit = kG / 2;             // groups per chunk
+    constexpr int kPieces = 4 / kSplit;        // 16-column pieces per thread and chunk
+    const int cgrp = grp / kSplit, half = grp % kSplit;
+    const int pc0 = half * kPieces;            // first piece of this group
+    const bool tr = pwarp == 0 || pwarp == 4 * kSplit;   // first warp of the first group of each chunk parity (M2_TRACE)
     uint32_t hA[16], hB[16];
-    if (grp < nch) {
-      mbar_wait(&hfull[grp % NB], 0);
+    if (cgrp < nch) {
+      mbar_wait(&hfull[cgrp % NB], 0);
       tc_fence_after();
-      ld_piece(grp, 0, hA);
+      ld_piece(cgrp, pc0, hA);
       tmem_ld_wait();
     }
-    for (int j = grp; j < nch; j += 2) {
+    for (int j = cgrp; j < nch; j += 2) {
       const int c0 = j * kCc;
-      uint32_t g[32];
+      const uint32_t tGj = tmem_base + C::kColH + lane_addr + (j % NB) * kCc + half * 32;
+      uint32_t g[8];
+      if (tr) M2_TR(400 + 4 * j + 0, 5, j);      // epilogue: chunk start (first piece loaded)
 #pragma unroll
-      for (int pc = 0; pc < 4; ++pc) {
-        uint32_t (&cur)[16] = (pc & 1) ? hB : hA;
-        uint32_t (&nxt)[16] = (pc & 1) ? hA : hB;
-        if (pc < 3) {
+      for (int pl = 0; pl < kPieces; ++pl) {
+        const int pc = pc0 + pl;
+        uint32_t (&cur)[16] = (pl & 1) ? hB : hA;
+        uint32_t (&nxt)[16] = (pl & 1) ? hA : hB;
+        if (pl < kPieces - 1) {
           ld_piece(j, pc + 1, nxt);
         } else if (j + 2 < nch) {
+          if (tr) M2_TR(400 + 4 * j + 1, 6, j);  // epilogue: about to wait for the next H
           mbar_wait(&hfull[(j + 2) % NB], ((j + 2) / NB) & 1);
+          if (tr) M2_TR(400 + 4 * j + 2, 7, j);  // epilogue: next H ready
           tc_fence_after();
-          ld_piece(j + 2, 0, nxt);
+          ld_piece(j + 2, pc0, nxt);
         }
-        gelu_piece(cur, c0 + pc * 16, g + pc * 8);
+        // G piece pl (8 bf16x2 columns) goes over columns [8 pl, 8 pl + 8) of the group's part of the buffer: all read
+        // already (the piece in flight starts at column 16 (pl + 1))
+        gelu_piece(cur, c0 + pc * 16, g);
+        tmem_st8(tGj + pl * 8, *reinterpret_cast<const uint32_t (*)[8]>(g));
         tmem_ld_wait();
       }
-      // every column of H(j) has been read: G(j) (bf16, 32 columns) goes over the head of the same buffer
-      tmem_st32(tmem_base + C::kColH + lane_addr + (j % NB) * kCc, g);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&gfull[j % NB]);
+      if (tr) M2_TR(400 + 4 * j + 3, 8, j);      // epilogue: G stored, arrived
     }
     // final: y = u + Drop(Yacc + b2).  Pass 1: accumulator rows -> padded fp32 staging (each group half the columns).
+    if (pwarp == 0) M2_TR(1304, 24, 0);   // epilogue loop done
+    // final: y = u + Drop(Yacc + b2).  The u rows of pass 2 (warp per row, lanes along d) are fetched NOW, while the last
+    // GEMM2s drain (the loads were the critical path of the 4200-clk tail, profiles/r01_trace_fwd_*.log).
+    const int ew = warp - 2;
+    constexpr int kRowsPerIter = DP == 128 ? 1 : 2;   // DP = 64: 16 lanes cover a row, two rows per warp step
+    constexpr int kIters = kRows / (4 * kG * kRowsPerIter);
+    const int d2 = DP == 128 ? lane * 4 : (lane & 15) * 4;
+    const int rsub = DP == 128 ? 0 : (lane >> 4);
+    float4 upre[kIters];
+    float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d2 < p.D) {
+      bq = *reinterpret_cast<const float4*>(p.b2 + d2);
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int grow = m0 + (ew + it * 4 * kG) * kRowsPerIter + rsub;
+        upre[it] = grow < p.M ? *reinterpret_cast<const float4*>(p.u + static_cast<long long>(grow) * p.D + d2)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     mbar_wait(yfull, 0);
     tc_fence_after();
+    if (pwarp == 0) M2_TR(1305, 25, 0);   // Y accumulator complete
+    // Pass 1: accumulator rows -> padded fp32 staging (each group its share of the columns).
+    constexpr int kColsPerGrp = DP / kG < 32 ? 32 : DP / kG;
 #pragma unroll 1
-    for (int d0 = grp * (DP / 2); d0 < (grp + 1) * (DP / 2); d0 += 32) {
+    for (int d0 = grp * kColsPerGrp; d0 < (grp + 1) * kColsPerGrp && d0 < DP; d0 += 32) {
       uint32_t a[32];
       tmem_ld32(tY + lane_addr + d0, a);
       tmem_ld_wait();
@@ -477,33 +561,25 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         *reinterpret_cast<float4*>(o + e) = make_float4(__uint_as_float(a[e]), __uint_as_float(a[e + 1]),
                                                         __uint_as_float(a[e + 2]), __uint_as_float(a[e + 3]));
     }
-    named_bar_sync(1, 256);
-    // Pass 2: warp per row, lanes along d: coalesced u read / y write, bias and dropout applied here.
-    const int ew = warp - 2;
-    constexpr int kRowsPerIter = DP == 128 ? 1 : 2;   // DP = 64: 16 lanes cover a row, two rows per warp step
-    const int d2 = DP == 128 ? lane * 4 : (lane & 15) * 4;
-    const int rsub = DP == 128 ? 0 : (lane >> 4);
+    named_bar_sync(1, 128 * kG);
+    if (pwarp == 0) M2_TR(1306, 26, 0);   // Y staged in shared memory
+    // Pass 2: warp per row, lanes along d: coalesced y write, bias and dropout applied here.
     if (d2 < p.D) {
-      const float4 bq = *reinterpret_cast<const float4*>(p.b2 + d2);
-#pragma unroll 4
-      for (int rr = ew * kRowsPerIter; rr < kRows; rr += 8 * kRowsPerIter) {
-        const int r2 = rr + rsub;
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int r2 = (ew + it * 4 * kG) * kRowsPerIter + rsub;
         const int grow = m0 + r2;
         if (grow < p.M) {
           const float4 acc = *reinterpret_cast<const float4*>(sOut + r2 * C::kOPitch + d2 * 4);
           float4 o = make_float4(acc.x + bq.x, acc.y + bq.y, acc.z + bq.z, acc.w + bq.w);
-          if (kDrop) {
-            const unsigned long long i0 = static_cast<unsigned long long>(grow) * p.D + d2;
-            drop_apply2(p.dout, o.x, o.y, i0);
-            drop_apply2(p.dout, o.z, o.w, i0 + 2);
-          }
-          const float4 uu = *reinterpret_cast<const float4*>(p.u + static_cast<long long>(grow) * p.D + d2);
-          o.x += uu.x; o.y += uu.y; o.z += uu.z; o.w += uu.w;
+          if (kDrop) drop_apply4(p.dout, o, static_cast<unsigned long long>(grow) * p.D + d2);
+          o.x += upre[it].x; o.y += upre[it].y; o.z += upre[it].z; o.w += upre[it].w;
           *reinterpret_cast<float4*>(p.y + static_cast<long long>(grow) * p.D + d2) = o;
         }
       }
     }
   }
+  if (pwarp == 0) M2_TR(1307, 27, 0);     // output written
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
@@ -549,11 +625,7 @@ __device__ __forceinline__ void dy_rows_to_stage(const TsParams& p, int m0, uint
     uint2 o = make_uint2(0u, 0u);
     if (row < p.M && c < p.D) {
       float4 v = *reinterpret_cast<const float4*>(p.dy + static_cast<long long>(row) * p.D + c);
-      if (kDrop) {   // gradient of the dropped branch output: dY * mask * scale
-        const unsigned long long i0 = static_cast<unsigned long long>(row) * p.D + c;
-        drop_apply2(p.dout, v.x, v.y, i0);
-        drop_apply2(p.dout, v.z, v.w, i0 + 2);
-      }
+      if (kDrop) drop_apply4(p.dout, v, static_cast<unsigned long long>(row) * p.D + c);   // dY * mask * scale
       o.x = pack_bf16(v.x, v.y);
       o.y = pack_bf16(v.z, v.w);
       if (p.dy_b) *reinterpret_cast<uint2*>(p.dy_b + static_cast<long long>(row) * p.D + c) = o;
@@ -585,37 +657,40 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   uint64_t* hfull = w2empty + S2;     // [2]   H and dG accumulators of a chunk ready -> epilogue
   uint64_t* dhfull = hfull + 2;       // [2]   epilogue wrote dH (bf16, TMEM) -> MMA
   uint64_t* yfull = dhfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yfull + 1);
+  uint64_t* dxdone = yfull + 1;       // [2]   dXn GEMM has read dH: the H / dG issuer may overwrite the buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dxdone + 2);
   float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);
 
-  // Roles by LOGICAL warp id (0 = TMA producer, 1 = MMA issuer, 2.. = epilogue).  Physically the epilogue warps come
-  // first and the two single-thread roles LAST: the warp scheduler prefers the highest warp id on its sub-partition,
-  // and the latency-critical issuer starved behind the busy epilogue warps when it was warp 1 (724-clk gaps between a
-  // commit and the next wait in the in-kernel timeline, profiles/r01_trace_dgrad.md).
+  // Roles by LOGICAL warp id (0 = TMA producer, 1 = dXn issuer, 2.. = epilogue, -1 = H / dG issuer); physically the
+  // epilogue warps come first and the single-thread roles last, and the MMAs are issued by TWO warps so that one
+  // issuer's barrier waits overlap the other's MMAs (see chain_fwd_ts_kernel).  One writer per accumulator: dXn <- warp 1,
+  // H / dG buffers <- warp -1; the dH -> (H, dG)(j + 2) buffer reuse is ordered by the dxdone barrier.
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp = pwarp < 4 * kGroupsB ? pwarp + 2 : pwarp - 4 * kGroupsB;
+  const int warp = pwarp < 4 * kGroupsB ? pwarp + 2 : (pwarp == 4 * kGroupsB + 2 ? -1 : pwarp - 4 * kGroupsB);
   const int m0 = blockIdx.x * kRows;
   const int nch = ceil_div(p.C, kCc);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S1; ++i) { mbar_init(&w1full[i], 1); mbar_init(&w1empty[i], 1); }
     for (int i = 0; i < S2; ++i) { mbar_init(&w2full[i], 1); mbar_init(&w2empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&hfull[i], 1); mbar_init(&dhfull[i], 128 * kGroupsB); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&hfull[i], 1); mbar_init(&dhfull[i], 128 * kGroupsB); mbar_init(&dxdone[i], 1); }
     mbar_init(yfull, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
-  if (p.bias_smem) stage_bias(p.b1, p.C, nch * kCc, sBias);
   for (int i = threadIdx.x; i < 3 * DP; i += blockDim.x) sCol[i] = 0.f;
   __syncthreads();
   if (warp == 0 && lane == 0) {
     for (int j = 0; j < (nch < S1 ? nch : S1); ++j) load_w1<DP>(sW1 + j * C::kW1Bytes, &tmW1, &w1full[j], j * kCc);
     for (int j = 0; j < (nch < S2 ? nch : S2); ++j) load_w2<DP>(sW2 + j * C::kW2Bytes, &tmW2, &w2full[j], j * kCc);
   }
-  ln_rows_to_stage<DP, 8>(p, m0, sStageX, sMean, sRstd, p.xn_b);   // 18 warps x 8 rows >= 128
+  BiasRegs br;
+  if (p.bias_smem) br = bias_load(p.b1, p.C, nch * kCc);           // in flight during the row prologue
+  ln_rows_to_stage<DP, 8>(p, m0, sStageX, sMean, sRstd, p.xn_b);   // 19 warps x 8 rows >= 128
   dy_rows_to_stage<DP, kDrop>(p, m0, sStageDY);
+  if (p.bias_smem) bias_store(br, nch * kCc, sBias);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -661,18 +736,18 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
       refill_w1(S1 + k);
       refill_w2(S2 + 2 + k);
     }
-  } else if (warp == 1) {
+  } else if (warp == -1) {
+    // ---- H / dG issuer: H[j&1] = LN(u) . W1_j^T ; dG[j&1] = dY . W2_j  (A operands from TMEM), two chunks ahead.
     // The whole warp walks the loop (waits are warp-wide), one elected lane issues: see elect_one().
     constexpr uint32_t idescH = umma_idesc_bf16(kRows, kCc, 0, 0);    // B (W1 chunk) K-major
     constexpr uint32_t idescG = umma_idesc_bf16(kRows, kCc, 0, 1);    // B (W2 tile)  MN-major
-    constexpr uint32_t idescX = umma_idesc_bf16(kRows, DP, 0, 1);     // B (W1 chunk) MN-major
     const uint64_t w1k_desc0 = umma_desc_sw128(smem_u32(sW1), 16, 1024);          // W1 chunk as K-major B (H GEMM)
-    const uint64_t w1m_desc0 = umma_desc_sw128(smem_u32(sW1), kCc * 128, 1024);   // W1 chunk as MN-major B (dXn GEMM)
     const uint64_t w2m_desc0 = umma_desc_sw128(smem_u32(sW2), 8192, 1024);        // W2 tile as MN-major B (dG GEMM)
-    auto hg = [&](int j) {   // H[j&1] = LN(u) . W1_j^T ; dG[j&1] = dY . W2_j     (A operands from TMEM)
+    for (int j = 0; j < nch; ++j) {
       const int s1 = j % S1, s2 = j % S2, b = j & 1;
-      mbar_wait(&w1full[s1], (j / S1) & 1);
-      mbar_wait(&w2full[s2], (j / S2) & 1);
+      // chunk j - 2's dXn GEMM must have consumed the dH that aliases this buffer
+      if (j >= 2) mbar_wait3(&w1full[s1], (j / S1) & 1, &w2full[s2], (j / S2) & 1, &dxdone[b], ((j >> 1) - 1) & 1);
+      else mbar_wait2(&w1full[s1], (j / S1) & 1, &w2full[s2], (j / S2) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t bd1 = w1k_desc0 + static_cast<uint64_t>((s1 * C::kW1Bytes) >> 4);
@@ -689,43 +764,26 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         umma_commit(&hfull[b]);
       }
       __syncwarp();
-    };
-    hg(0);
-    if (nch > 1) hg(1);
-    // Steady state: ONE burst per chunk - dXn(j) and the H / dG GEMMs of chunk j + 2 (which reuse buffer j & 1) are issued
-    // together after all their waits (see the forward kernel for why).
-    for (int j = 0; j < nch; ++j) {   // dXn += dH_j . W1_j ; H[j&1] = LN(u) . W1_{j+2}^T ; dG[j&1] = dY . W2_{j+2}
+    }
+  } else if (warp == 1) {
+    // ---- dXn issuer: dXn += dH_j . W1_j  (A = dH from TMEM, the W1 chunk consumed MN-major).  W1_j is known to have landed:
+    // the H GEMM of the chunk waited for it, and its completion reached this warp through hfull -> epilogue -> dhfull.
+    constexpr uint32_t idescX = umma_idesc_bf16(kRows, DP, 0, 1);     // B (W1 chunk) MN-major
+    const uint64_t w1m_desc0 = umma_desc_sw128(smem_u32(sW1), kCc * 128, 1024);   // W1 chunk as MN-major B (dXn GEMM)
+    for (int j = 0; j < nch; ++j) {
       const int s1 = j % S1, b = j & 1;
-      const int jn = j + 2, s1n = jn % S1, s2n = jn % S2;
-      const bool more = jn < nch;
       M2_TR(4 * j + 0, 1, j);
       mbar_wait(&dhfull[b], (j >> 1) & 1);
-      if (more) {
-        mbar_wait(&w1full[s1n], (jn / S1) & 1);
-        mbar_wait(&w2full[s2n], (jn / S2) & 1);
-      }
       M2_TR(4 * j + 1, 2, j);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t bd = w1m_desc0 + static_cast<uint64_t>((s1 * C::kW1Bytes) >> 4);
-        const uint32_t tH = tmem_base + C::kColH + b * kCc;
         const uint32_t tG = tmem_base + C::kColG + b * kCc;
 #pragma unroll
         for (int kk = 0; kk < kCc / 16; ++kk)   // B: 16 c-rows per step = 2048 B; d panels 8 KB apart (LBO); A: group kk's dH
           umma_bf16_ts(tDX, tG + kk * 16, bd + ((kk * 2048) >> 4), idescX, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&w1empty[s1]);
-        if (more) {
-          const uint64_t bd1 = w1k_desc0 + static_cast<uint64_t>((s1n * C::kW1Bytes) >> 4);
-          const uint64_t bd2 = w2m_desc0 + static_cast<uint64_t>((s2n * C::kW2Bytes) >> 4);
-#pragma unroll
-          for (int kk = 0; kk < DP / 16; ++kk)
-            umma_bf16_ts(tH, tX + kk * 8, bd1 + (((kk >> 2) * (kCc * 128) + (kk & 3) * 32) >> 4), idescH, kk > 0 ? 1u : 0u);
-#pragma unroll
-          for (int kk = 0; kk < DP / 16; ++kk)
-            umma_bf16_ts(tG, tDY + kk * 8, bd2 + ((kk * 2048) >> 4), idescG, kk > 0 ? 1u : 0u);
-          umma_commit(&w2empty[s2n]);
-          umma_commit(&hfull[b]);
-        }
+        umma_commit(&dxdone[b]);
         M2_TR(4 * j + 2, 10, j);
       }
       __syncwarp();
@@ -740,6 +798,7 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const float hs = kDrop ? 0.5f * p.dh.scale : 0.5f;          // dropout scale folded into GELU / GELU'
     const float ninv_s = kDrop ? -1.f / p.dh.scale : -1.f;
+    const uint32_t hrow = (static_cast<uint32_t>(row) * static_cast<uint32_t>(p.ldh) >> 2) * kDropGolden + p.dh.key;
     for (int j = 0; j < nch; ++j) {
       const int b = j & 1;
       const uint32_t tH = tmem_base + C::kColH + lane_addr + b * kCc + grp * 16;
@@ -767,26 +826,28 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
 #pragma unroll
           for (int e = 0; e < 8; ++e) bias[e] = (cc + e < p.C) ? __ldg(p.b1 + cc + e) : 0.f;
         }
-        float2 gv[4], dv[4];
+        uint32_t gpk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float2 dgelu;
-          gv[e] = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[ch * 8 + 2 * e]), __uint_as_float(h[ch * 8 + 2 * e + 1])),
-                                        make_float2(bias[2 * e], bias[2 * e + 1])), dgelu, hs, ninv_s);
-          dv[e] = __fmul2_rn(make_float2(__uint_as_float(dg[ch * 8 + 2 * e]), __uint_as_float(dg[ch * 8 + 2 * e + 1])), dgelu);
+          const float2 gv = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[ch * 8 + 2 * e]), __uint_as_float(h[ch * 8 + 2 * e + 1])),
+                                                  make_float2(bias[2 * e], bias[2 * e + 1])), dgelu, hs, ninv_s);
+          const float2 dv = __fmul2_rn(make_float2(__uint_as_float(dg[ch * 8 + 2 * e]), __uint_as_float(dg[ch * 8 + 2 * e + 1])), dgelu);
+          dhp[ch * 4 + e] = pack_bf16(dv.x, dv.y);
+          if (kStoreGH) gpk[e] = pack_bf16(gv.x, gv.y);
         }
-        if (kDrop) {   // G' = m*s*G ; dH = dG' * m*s*gelu'(h)
-          const unsigned long long i0 = static_cast<unsigned long long>(row) * p.ldh + cc;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) drop_zero2x2(p.dh, gv[e].x, gv[e].y, dv[e].x, dv[e].y, i0 + 2 * e);   // scale folded in
+        if (kDrop) {   // G' = m*s*G ; dH = dG' * m*s*gelu'(h): the scale is folded in, AND the packed pairs with the keep masks
+          const uint32_t hin = hrow + static_cast<uint32_t>(cc >> 2) * kDropGolden;
+          const uint32_t f0 = drop_flags_from_hash_input(p.dh, hin);
+          const uint32_t f1 = drop_flags_from_hash_input(p.dh, hin + kDropGolden);
+          const uint32_t m0 = drop_mask_bf16x2<0>(f0), m1 = drop_mask_bf16x2<1>(f0);
+          const uint32_t m2 = drop_mask_bf16x2<0>(f1), m3 = drop_mask_bf16x2<1>(f1);
+          dhp[ch * 4 + 0] &= m0; dhp[ch * 4 + 1] &= m1; dhp[ch * 4 + 2] &= m2; dhp[ch * 4 + 3] &= m3;
+          if (kStoreGH) { gpk[0] &= m0; gpk[1] &= m1; gpk[2] &= m2; gpk[3] &= m3; }
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) dhp[ch * 4 + e] = pack_bf16(dv[e].x, dv[e].y);
         if (kStoreGH) {
           if (row < p.M && cc < p.ldh) {   // ldh is a multiple of 8 >= C: whole 16-byte chunks only
-            *reinterpret_cast<uint4*>(p.g_b + static_cast<long long>(row) * p.ldh + cc) =
-                make_uint4(pack_bf16(gv[0].x, gv[0].y), pack_bf16(gv[1].x, gv[1].y), pack_bf16(gv[2].x, gv[2].y),
-                           pack_bf16(gv[3].x, gv[3].y));
+            *reinterpret_cast<uint4*>(p.g_b + static_cast<long long>(row) * p.ldh + cc) = make_uint4(gpk[0], gpk[1], gpk[2], gpk[3]);
             *reinterpret_cast<uint4*>(p.dh_b + static_cast<long long>(row) * p.ldh + cc) =
                 make_uint4(dhp[ch * 4], dhp[ch * 4 + 1], dhp[ch * 4 + 2], dhp[ch * 4 + 3]);
           }
@@ -857,11 +918,7 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         o4.z = dyv.z + rstd * (g.z - s1 - xh.z * s2);
         o4.w = dyv.w + rstd * (g.w - s1 - xh.w * s2);
         *reinterpret_cast<float4*>(p.du + static_cast<long long>(grow) * p.D + d2) = o4;
-        if (kDrop) {
-          const unsigned long long i0 = static_cast<unsigned long long>(grow) * p.D + d2;
-          drop_apply2(p.dout, dyv.x, dyv.y, i0);
-          drop_apply2(p.dout, dyv.z, dyv.w, i0 + 2);
-        }
+        if (kDrop) drop_apply4(p.dout, dyv, static_cast<unsigned long long>(grow) * p.D + d2);
         aw.x += acc.x * xh.x; aw.y += acc.y * xh.y; aw.z += acc.z * xh.z; aw.w += acc.w * xh.w;
         ab.x += acc.x; ab.y += acc.y; ab.z += acc.z; ab.w += acc.w;
         a2.x += dyv.x; a2.y += dyv.y; a2.z += dyv.z; a2.w += dyv.w;
@@ -883,29 +940,41 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
-template <int DP, bool kDrop>
-int launch_fwd(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p, cudaStream_t s) {
+template <int DP, bool kDrop, int kG>
+int launch_fwd_g(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p, cudaStream_t s) {
   const int bias_bytes = ceil_div(p.C, kCc) * kCc * 4;
   TsParams pp = p;
-  pp.bias_smem = bias_bytes <= CfgT<DP>::kMaxBias ? 1 : 0;
+  pp.bias_smem = (bias_bytes <= CfgT<DP>::kMaxBias && bias_bytes / 4 <= 16 * (96 + 128 * kG)) ? 1 : 0;   // one bias_load round
   const int smem = CfgT<DP>::kSmem + (pp.bias_smem ? bias_bytes : 0);
   static int configured = 0;   // largest dynamic smem size opted into so far (idempotent attribute)
   if (smem > configured) {
-    if (cudaFuncSetAttribute(chain_fwd_ts_kernel<DP, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(chain_fwd_ts_kernel<DP, kDrop, kG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return M2_ERR_LAUNCH;
     configured = smem;
   }
   LaunchScope scope("chain_fwd", s);
-  chain_fwd_ts_kernel<DP, kDrop><<<ceil_div(p.M, kRows), kThreads, smem, s>>>(t1, t2, pp);
+  chain_fwd_ts_kernel<DP, kDrop, kG><<<ceil_div(p.M, kRows), 96 + 128 * kG, smem, s>>>(t1, t2, pp);
   M2_LAUNCH_CHECK();
   return M2_OK;
+}
+// M2B200_FWD_GROUPS = 2 | 4 selects the number of epilogue groups (A/B runs); default 4.
+inline int fwd_groups() {
+  static const int g = [] {
+    const char* e = getenv("M2B200_FWD_GROUPS");
+    return (e && e[0] == '2') ? 2 : 4;
+  }();
+  return g;
+}
+template <int DP, bool kDrop>
+int launch_fwd(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p, cudaStream_t s) {
+  return fwd_groups() == 2 ? launch_fwd_g<DP, kDrop, 2>(t1, t2, p, s) : launch_fwd_g<DP, kDrop, 4>(t1, t2, p, s);
 }
 
 template <int DP, bool kDrop, bool kStoreGH>
 int launch_bwd(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p, cudaStream_t s) {
   const int bias_bytes = ceil_div(p.C, kCc) * kCc * 4;
   TsParams pp = p;
-  pp.bias_smem = bias_bytes <= CfgB<DP>::kMaxBias ? 1 : 0;
+  pp.bias_smem = (bias_bytes <= CfgB<DP>::kMaxBias && bias_bytes / 4 <= 16 * kThreadsB) ? 1 : 0;   // one bias_load round
   const int smem = CfgB<DP>::kSmem + (pp.bias_smem ? bias_bytes : 0);
   static int configured = 0;
   if (smem > configured) {

@@ -106,51 +106,87 @@ __device__ __forceinline__ float2 gelu2_grad(float2 x, float2& dg, float hs = 0.
 
 // ------------------------------------------------------------------------------------------ dropout
 // Counter-based mask shared by every kernel (forward and the recomputing backward evaluate the same function):
-// one 32-bit hash per PAIR of consecutive elements, 16 random bits per element, keep iff bits >= thresh
-// (thresh = round(p * 65536), scale = 65536 / (65536 - thresh): unbiased for the realised keep probability).
-// Not bit-compatible with torch's Philox stream by design: tested statistically and through
-// m2b200_dropout_mask(), which exports exactly this function.
+// one 32-bit hash per QUAD of consecutive elements, 7 random bits per element (one byte each, top bit unused), keep iff
+// bits >= thresh with thresh = round(p * 128): the drop probability is quantised to 1/128 (exact for p = 0.5, 0.25, ...;
+// 0.1 -> 0.1016, 0.3 -> 0.2969) and scale = 128 / (128 - thresh) is the inverse of the REALISED keep probability, so
+// the estimator stays unbiased.  The four compares are ONE add: (h & 0x7f7f7f7f) + (0x80 - thresh per byte) leaves
+// each element's keep flag in bit 7 of its byte, and a sign-replicating PRMT turns two flags into an AND mask for a
+// packed bf16x2 pair.  With the previous layout (16 bits per element, one hash per pair, ISETP + FSEL per element) the
+// mask arithmetic was HALF of the dgrad epilogue's instructions (56 of 114 per 8 hidden elements in the SASS of
+// chain_bwd_ts_kernel); this form costs 11 per quad.  Not bit-compatible with torch's Philox stream by design
+// (SURVEY H7): tested statistically and through m2b200_dropout_mask(), which exports exactly this function.
 struct Drop {
   uint32_t key;      // per call-site key derived from (seed, site) on the host
-  uint32_t thresh;   // 0 = dropout off
-  float scale;
+  uint32_t thresh;   // round(p * 128), 0 = dropout off
+  float scale;       // 128 / (128 - thresh)
+  uint32_t kadd;     // 0x80808080 - thresh * 0x01010101
 };
-// Two-round multiply / xorshift finisher (the first two rounds of lowbias32).  The epilogues are instruction-issue bound
-// and with dropout on the mask arithmetic was ~20 of ~45 instructions per element pair (ALU pipe 42-48 % busy,
-// profiles/r01_ncu_final.md), so it is kept short: the key is already a full-avalanche splitmix64 of (seed, site).
+// Two-round multiply / xorshift finisher (the first two rounds of lowbias32); the key is already a full-avalanche
+// splitmix64 of (seed, site).
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15;
   return x;
 }
+constexpr uint32_t kDropGolden = 0x9E3779B9U;
 // Only the LOW 32 bits of the element index enter the hash (the mask of a tensor with more than 2^32 elements repeats with
 // that period): all index arithmetic at the call sites narrows to 32-bit integer instructions.
-__device__ __forceinline__ uint32_t drop_pair_bits(uint32_t key, uint32_t pair_idx) { return mix32(pair_idx * 0x9E3779B9U + key); }
+// Keep flags of elements 4q .. 4q+3: bit 7 of byte i <=> element 4q + i is kept.
+__device__ __forceinline__ uint32_t drop_flags_from_hash_input(const Drop& d, uint32_t hin) {
+  return (mix32(hin) & 0x7f7f7f7fU) + d.kadd;
+}
+__device__ __forceinline__ uint32_t drop_quad_flags(const Drop& d, uint32_t quad_idx) {
+  return drop_flags_from_hash_input(d, quad_idx * kDropGolden + d.key);
+}
+// AND masks from the flags (prmt with the sign-replicate bit set in every selector nibble).
+template <int kPair>   // elements 2 kPair, 2 kPair + 1 of the quad as the two halves of a packed bf16x2
+__device__ __forceinline__ uint32_t drop_mask_bf16x2(uint32_t flags) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(m) : "r"(flags), "n"(kPair ? 0xBBAA : 0x9988));
+  return m;
+}
+template <int kElem>   // element kElem of the quad as a full 32-bit mask
+__device__ __forceinline__ uint32_t drop_mask_b32(uint32_t flags) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(m) : "r"(flags), "n"(0x8888 + 0x1111 * kElem));
+  return m;
+}
+__device__ __forceinline__ float drop_and(float v, uint32_t m) { return __uint_as_float(__float_as_uint(v) & m); }
+
 __device__ __forceinline__ bool drop_keep(const Drop& d, unsigned long long idx) {
   const uint32_t lo = static_cast<uint32_t>(idx);
-  const uint32_t h = drop_pair_bits(d.key, lo >> 1);
-  return ((lo & 1) ? (h >> 16) : (h & 0xFFFFu)) >= d.thresh;
+  return (drop_quad_flags(d, lo >> 2) >> (8 * (lo & 3u) + 7)) & 1u;
 }
 __device__ __forceinline__ float drop_apply(const Drop& d, float v, unsigned long long idx) {
   return drop_keep(d, idx) ? v * d.scale : 0.f;
 }
 // two consecutive elements starting at an EVEN index: one hash
+__device__ __forceinline__ uint32_t drop_pair_flags(const Drop& d, unsigned long long even_idx) {   // bits 7 and 15
+  const uint32_t lo = static_cast<uint32_t>(even_idx);
+  return drop_quad_flags(d, lo >> 2) >> ((lo & 2u) << 3);
+}
 __device__ __forceinline__ void drop_apply2(const Drop& d, float& v0, float& v1, unsigned long long even_idx) {
-  const uint32_t h = drop_pair_bits(d.key, static_cast<uint32_t>(even_idx) >> 1);
-  v0 = (h & 0xFFFFu) >= d.thresh ? v0 * d.scale : 0.f;
-  v1 = (h >> 16) >= d.thresh ? v1 * d.scale : 0.f;
+  const uint32_t f = drop_pair_flags(d, even_idx);
+  v0 = (f & 0x80u) ? v0 * d.scale : 0.f;
+  v1 = (f & 0x8000u) ? v1 * d.scale : 0.f;
 }
 // same mask, values already carry the scale (gelu2 / gelu2_grad with hs = scale / 2): select only
 __device__ __forceinline__ void drop_zero2(const Drop& d, float& v0, float& v1, unsigned long long even_idx) {
-  const uint32_t h = drop_pair_bits(d.key, static_cast<uint32_t>(even_idx) >> 1);
-  v0 = (h & 0xFFFFu) >= d.thresh ? v0 : 0.f;
-  v1 = (h >> 16) >= d.thresh ? v1 : 0.f;
+  const uint32_t f = drop_pair_flags(d, even_idx);
+  v0 = (f & 0x80u) ? v0 : 0.f;
+  v1 = (f & 0x8000u) ? v1 : 0.f;
 }
 // the same hash masks TWO value pairs (G and dH of the backward kernels)
 __device__ __forceinline__ void drop_zero2x2(const Drop& d, float& a0, float& a1, float& b0, float& b1, unsigned long long even_idx) {
-  const uint32_t h = drop_pair_bits(d.key, static_cast<uint32_t>(even_idx) >> 1);
-  const bool k0 = (h & 0xFFFFu) >= d.thresh, k1 = (h >> 16) >= d.thresh;
+  const uint32_t f = drop_pair_flags(d, even_idx);
+  const bool k0 = f & 0x80u, k1 = f & 0x8000u;
   a0 = k0 ? a0 : 0.f; b0 = k0 ? b0 : 0.f;
   a1 = k1 ? a1 : 0.f; b1 = k1 ? b1 : 0.f;
+}
+// four consecutive elements starting at a multiple of 4 (fp32 values, scale applied)
+__device__ __forceinline__ void drop_apply4(const Drop& d, float4& v, unsigned long long idx4) {
+  const uint32_t f = drop_quad_flags(d, static_cast<uint32_t>(idx4) >> 2);
+  v.x = drop_and(v.x * d.scale, drop_mask_b32<0>(f)); v.y = drop_and(v.y * d.scale, drop_mask_b32<1>(f));
+  v.z = drop_and(v.z * d.scale, drop_mask_b32<2>(f)); v.w = drop_and(v.w * d.scale, drop_mask_b32<3>(f));
 }
 inline Drop make_drop(float p, unsigned long long seed, uint32_t site) {
   Drop d;
@@ -159,10 +195,12 @@ inline Drop make_drop(float p, unsigned long long seed, uint32_t site) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
   z ^= z >> 31;
   d.key = static_cast<uint32_t>(z ^ (z >> 32));
-  long t = p > 0.f ? static_cast<long>(p * 65536.0f + 0.5f) : 0;
-  if (t > 65535) t = 65535;
+  long t = p > 0.f ? static_cast<long>(p * 128.0f + 0.5f) : 0;
+  if (p > 0.f && t < 1) t = 1;
+  if (t > 127) t = 127;
   d.thresh = static_cast<uint32_t>(t);
-  d.scale = 65536.0f / (65536.0f - static_cast<float>(t));
+  d.scale = 128.0f / (128.0f - static_cast<float>(t));
+  d.kadd = 0x80808080U - d.thresh * 0x01010101U;
   return d;
 }
 enum DropSite { kSiteTokenHidden = 0, kSiteTokenOut = 1, kSiteChannelHidden = 2, kSiteChannelOut = 3, kSiteLinear = 4 };
@@ -216,6 +254,47 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) __trap();
   }
+}
+
+// Two barriers at once.  A wait costs ~120-150 clk even when the phase completed long ago (tools/wait_probe.cu: the
+// SYNCS.TRYWAIT round trip); issuing both probes back to back overlaps the two round trips.
+__device__ __forceinline__ bool mbar_try_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+      "and.pred p, p, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar_a)), "r"(parity_a), "r"(smem_u32(bar_b)), "r"(parity_b)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait2(bar_a, parity_a, bar_b, parity_b)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
+__device__ __forceinline__ void mbar_wait3(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b, uint64_t* bar_c,
+                                           uint32_t parity_c) {
+  uint32_t spins = 0, ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p, q, r;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 r, [%5], %6;\n\t"
+        "and.pred p, p, q;\n\t"
+        "and.pred p, p, r;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar_a)), "r"(parity_a), "r"(smem_u32(bar_b)), "r"(parity_b), "r"(smem_u32(bar_c)), "r"(parity_c)
+        : "memory");
+    if (++spins > (1u << 26)) __trap();
+  } while (!ok);
 }
 
 // One lane of a CONVERGED warp (the lowest).  Roles that issue tcgen05.mma / TMA from a single thread walk their loop

@@ -32,7 +32,13 @@ namespace {
 constexpr int kRows = 96;       // token rows per tile (K of the gradient GEMMs)
 constexpr int kMmaM = 128;      // UMMA M of the recompute GEMMs
 constexpr int kCc = 128;        // channels per CTA
-constexpr int kThreads = 320;   // warps 0-7 epilogue (group g = columns [64 g, 64 g + 64)), warp 8 TMA, warp 9 MMA
+// 16 warps = 4 column groups (group g = columns [32 g, 32 g + 32)) x 4 TMEM lane quadrants.  A warp may only touch the
+// TMEM lanes of quadrant (warp id % 4), which is also its scheduler: with 96-row tiles quadrant 3 (rows 96..127) holds
+// garbage, so its four warps do no epilogue work - three of them are the TMA producer (warp 3) and the two MMA issuers
+// (warps 7, 11), which then have scheduler 3 to themselves (no busy epilogue warp delays an MMA burst), and the twelve live warps
+// put four warps on each of the other three schedulers (two before: the GELU' epilogue was latency bound at 0.5 IPC).
+constexpr int kThreads = 512;
+constexpr int kLiveThreads = 384;
 constexpr int kNS = 2;          // row-tile ring depth
 
 template <int DP>
@@ -86,9 +92,10 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   float* sDb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);   // [128] db1 partials (16-byte aligned)
   float* sB1 = sDb + kCc;                                                          // [128] b1 of the chunk
 
-  // logical roles 0 = TMA, 1 = MMA, 2.. = epilogue; physically the epilogue warps come first (see chain_ts.cu)
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp = pwarp < 8 ? pwarp + 2 : pwarp - 8;
+  const int q = pwarp & 3;             // TMEM lane quadrant (= scheduler)
+  const int grp = pwarp >> 2;          // column group
+  const bool is_tma = pwarp == 3, is_mma_hg = pwarp == 7, is_mma_wg = pwarp == 11;
   const int c0 = blockIdx.x * kCc;
   const int t_lo = static_cast<int>(static_cast<long long>(p.ntiles) * blockIdx.y / p.R);
   const int t_hi = static_cast<int>(static_cast<long long>(p.ntiles) * (blockIdx.y + 1) / p.R);
@@ -99,14 +106,14 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     mbar_init(wfull, 1);
     for (int i = 0; i < kNS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(hfull, 1);
-    mbar_init(hempty, 256);
-    mbar_init(gfull, 256);
+    mbar_init(hempty, kLiveThreads);
+    mbar_init(gfull, kLiveThreads);
     mbar_init(gempty, 1);
     mbar_init(accfull, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDY); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
   }
-  if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (pwarp == 0) tmem_alloc(tmem_slot, C::kTmemCols);
   if (threadIdx.x < kCc) {
     sDb[threadIdx.x] = 0.f;
     sB1[threadIdx.x] = (c0 + threadIdx.x < p.C) ? p.b1[c0 + threadIdx.x] : 0.f;
@@ -116,7 +123,7 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (is_tma) {
     // ---- TMA producer (whole warp walks the loop, one elected lane issues)
     if (elect_one()) {
       mbar_arrive_expect_tx(wfull, C::kW1Bytes + C::kW2Bytes);
@@ -145,23 +152,20 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ---- MMA issuer.  Per tile two bursts: hg(i + 1) as soon as the epilogue has tile i's accumulators in registers (it
-    // then overlaps the rest of that epilogue), wg(i) when the epilogue has written G / dH.
+  } else if (is_mma_hg) {
+    // ---- recompute issuer: H = Xn_i . W1c^T ; dG = dY_i . W2c   (N = 128), as soon as the epilogue has tile i - 1's
+    // accumulators in registers.  Two issuing warps (this one and the gradient issuer below) so that one's barrier waits
+    // overlap the other's MMAs (tcgen05.mma issue blocks at the execution rate and a completed-barrier wait costs ~130 clk:
+    // see chain_fwd_ts_kernel); each accumulator has one writer, and every hand-over goes through the epilogue's barriers.
     constexpr uint32_t idescH = umma_idesc_bf16(kMmaM, kCc, 0, 0);   // A row tile K-major,  B = W1c K-major (N = 128 rows)
     constexpr uint32_t idescG = umma_idesc_bf16(kMmaM, kCc, 0, 1);   // A row tile K-major,  B = W2c MN-major
-    constexpr uint32_t idescW = umma_idesc_bf16(kMmaM, kCc, 1, 1);   // A row tile MN-major (M = d), B = sdH / sG MN-major
-    constexpr uint32_t kLboA = DP == 128 ? C::kPanel : 0;            // DP = 64: M rows 64..127 alias the only panel
     const uint64_t xk0 = umma_desc_sw128(smem_u32(sStage), 16, 1024);
-    const uint64_t xm0 = umma_desc_sw128(smem_u32(sStage), kLboA, 1024);
     const uint64_t w1d = umma_desc_sw128(smem_u32(sW1), 16, 1024);
     const uint64_t w2d = umma_desc_sw128(smem_u32(sW2), C::kW2Panel, 1024);
-    const uint64_t gd = umma_desc_sw128(smem_u32(sG), C::kGPanel, 1024);
-    const uint64_t dhd = umma_desc_sw128(smem_u32(sdH), C::kGPanel, 1024);
-    auto hg = [&](int i) {   // H = Xn_i . W1c^T ; dG = dY_i . W2c      (N = 128)
+    mbar_wait(wfull, 0);
+    for (int i = 0; i < nt; ++i) {
       const int s = i % kNS;
-      mbar_wait(&full[s], (i / kNS) & 1);
-      mbar_wait(hempty, (i & 1) ^ 1);
+      mbar_wait2(&full[s], (i / kNS) & 1, hempty, (i & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t xa = xk0 + static_cast<uint64_t>((s * C::kStage) >> 4);
@@ -177,12 +181,17 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         umma_commit(hfull);
       }
       __syncwarp();
-    };
-    mbar_wait(wfull, 0);
-    hg(0);
+    }
+  } else if (is_mma_wg) {
+    // ---- gradient issuer: dW1c^T += Xn_i^T . dH_i ; dW2c += dY_i^T . G_i   (contraction over the 96 rows), when the
+    // epilogue has written G / dH.  The row tile is known to have landed (full[s] -> recompute issuer -> hfull -> epilogue
+    // -> gfull).
+    constexpr uint32_t idescW = umma_idesc_bf16(kMmaM, kCc, 1, 1);   // A row tile MN-major (M = d), B = sdH / sG MN-major
+    constexpr uint32_t kLboA = DP == 128 ? C::kPanel : 0;            // DP = 64: M rows 64..127 alias the only panel
+    const uint64_t xm0 = umma_desc_sw128(smem_u32(sStage), kLboA, 1024);
+    const uint64_t gd = umma_desc_sw128(smem_u32(sG), C::kGPanel, 1024);
+    const uint64_t dhd = umma_desc_sw128(smem_u32(sdH), C::kGPanel, 1024);
     for (int i = 0; i < nt; ++i) {
-      if (i + 1 < nt) hg(i + 1);
-      // dW1c^T += Xn_i^T . dH_i ; dW2c += dY_i^T . G_i   (contraction over the 96 rows)
       const int s = i % kNS;
       mbar_wait(gfull, i & 1);
       tc_fence_after();
@@ -202,65 +211,73 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
     if (elect_one()) umma_commit(accfull);
     __syncwarp();
-  } else {
-    // ---- epilogue: thread = row of the tile (TMEM lane), group g = columns [64 g, 64 g + 64) in four 16-column quarters
-    const int q = pwarp & 3;
-    const int grp = (warp - 2) >> 2;
+  } else if (q < 3) {
+    // ---- epilogue: thread = row of the tile (TMEM lane), group g = columns [32 g, 32 g + 32) in two 16-column pieces
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const int cg = c0 + grp * 64;
-    const bool live = r < kRows;
-    float2 dbp[32];
+    const int cg = c0 + grp * 32;
+    float2 dbp[16];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) dbp[k] = make_float2(0.f, 0.f);
-    const uint32_t bias_addr = smem_u32(sB1 + grp * 64);
+    for (int k = 0; k < 16; ++k) dbp[k] = make_float2(0.f, 0.f);
+    const uint32_t bias_addr = smem_u32(sB1 + grp * 32);
     const float hs = kDrop ? 0.5f * p.dh.scale : 0.5f;          // dropout scale folded into GELU / GELU'
     const float ninv_s = kDrop ? -1.f / p.dh.scale : -1.f;
-    uint8_t* gdst = sG + grp * C::kGPanel;
-    uint8_t* hdst = sdH + grp * C::kGPanel;
-    auto ld_quarter = [&](int qt, uint32_t (&hd)[16], uint32_t (&gd2)[16]) {
-      tmem_ld16(tmem_base + C::kColH + lane_addr + grp * 64 + qt * 16, hd);
-      tmem_ld16(tmem_base + C::kColG + lane_addr + grp * 64 + qt * 16, gd2);
+    uint8_t* gdst = sG + (grp >> 1) * C::kGPanel;               // [128 rows][64 c] SW128 panel; this group: 16-byte chunks
+    uint8_t* hdst = sdH + (grp >> 1) * C::kGPanel;              //   4 (grp & 1) .. 4 (grp & 1) + 3 of the row
+    const int chunk0 = (grp & 1) * 4;
+    auto ld_piece = [&](int pc, uint32_t (&hd)[16], uint32_t (&gd2)[16]) {
+      tmem_ld16(tmem_base + C::kColH + lane_addr + grp * 32 + pc * 16, hd);
+      tmem_ld16(tmem_base + C::kColG + lane_addr + grp * 32 + pc * 16, gd2);
     };
     for (int i = 0; i < nt; ++i) {
       mbar_wait(hfull, i & 1);
       tc_fence_after();
-      const unsigned long long i0 = static_cast<unsigned long long>((t_lo + i) * kRows + r) * p.ldh + cg;
+      // dropout: hash input of the quad at this thread's (row, first channel of the group)
+      const uint32_t hin = ((static_cast<uint32_t>((t_lo + i) * kRows + r) * static_cast<uint32_t>(p.ldh) + static_cast<uint32_t>(cg)) >> 2) * kDropGolden + p.dh.key;
       uint32_t hA[16], gA[16], hB[16], gB[16];
-      ld_quarter(0, hA, gA);
+      ld_piece(0, hA, gA);
       tmem_ld_wait();
+      ld_piece(1, hB, gB);                                      // in flight during the first piece's math
 #pragma unroll
-      for (int qt = 0; qt < 4; ++qt) {
-        uint32_t (&h)[16] = (qt & 1) ? hB : hA;
-        uint32_t (&dg)[16] = (qt & 1) ? gB : gA;
-        if (qt < 3) ld_quarter(qt + 1, (qt & 1) ? hA : hB, (qt & 1) ? gA : gB);   // in flight during this quarter's math
+      for (int pc = 0; pc < 2; ++pc) {
+        uint32_t (&h)[16] = pc ? hB : hA;
+        uint32_t (&dg)[16] = pc ? gB : gA;
         float bias[16];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
               : "=f"(bias[4 * e]), "=f"(bias[4 * e + 1]), "=f"(bias[4 * e + 2]), "=f"(bias[4 * e + 3])
-              : "r"(bias_addr + (qt * 16 + 4 * e) * 4));
+              : "r"(bias_addr + (pc * 16 + 4 * e) * 4));
         uint32_t gp[8], dp[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int k = qt * 16 + 2 * e;
-          float2 dgelu;
-          float2 gv = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[2 * e]), __uint_as_float(h[2 * e + 1])),
-                                            make_float2(bias[2 * e], bias[2 * e + 1])), dgelu, hs, ninv_s);
-          float2 dv = __fmul2_rn(make_float2(__uint_as_float(dg[2 * e]), __uint_as_float(dg[2 * e + 1])), dgelu);
-          if (kDrop) drop_zero2x2(p.dh, gv.x, gv.y, dv.x, dv.y, i0 + k);   // scale folded into gelu2_grad
-          if (live) dbp[k >> 1] = __fadd2_rn(dbp[k >> 1], dv);
-          gp[e] = pack_bf16(gv.x, gv.y);
-          dp[e] = pack_bf16(dv.x, dv.y);
+        for (int qd = 0; qd < 4; ++qd) {   // quads of channels: one mask hash each
+          uint32_t flags = 0;
+          if (kDrop) flags = drop_flags_from_hash_input(p.dh, hin + static_cast<uint32_t>(pc * 4 + qd) * kDropGolden);
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int e = qd * 2 + e2;
+            float2 dgelu;
+            const float2 gv = gelu2_grad(__fadd2_rn(make_float2(__uint_as_float(h[2 * e]), __uint_as_float(h[2 * e + 1])),
+                                                    make_float2(bias[2 * e], bias[2 * e + 1])), dgelu, hs, ninv_s);
+            float2 dv = __fmul2_rn(make_float2(__uint_as_float(dg[2 * e]), __uint_as_float(dg[2 * e + 1])), dgelu);
+            gp[e] = pack_bf16(gv.x, gv.y);
+            if (kDrop) {   // scale folded into gelu2_grad: G is masked packed, dH in fp32 (db1 accumulates it)
+              gp[e] &= e2 ? drop_mask_bf16x2<1>(flags) : drop_mask_bf16x2<0>(flags);
+              dv.x = drop_and(dv.x, e2 ? drop_mask_b32<2>(flags) : drop_mask_b32<0>(flags));
+              dv.y = drop_and(dv.y, e2 ? drop_mask_b32<3>(flags) : drop_mask_b32<1>(flags));
+            }
+            dbp[pc * 8 + e] = __fadd2_rn(dbp[pc * 8 + e], dv);
+            dp[e] = pack_bf16(dv.x, dv.y);
+          }
         }
-        if (qt == 0) mbar_wait(gempty, (i & 1) ^ 1);   // gradient GEMMs of tile i - 1 have consumed sG / sdH
+        if (pc == 0) mbar_wait(gempty, (i & 1) ^ 1);   // gradient GEMMs of tile i - 1 have consumed sG / sdH
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          *reinterpret_cast<uint4*>(gdst + sw128_offset(r, qt * 2 + k)) = make_uint4(gp[4 * k], gp[4 * k + 1], gp[4 * k + 2], gp[4 * k + 3]);
-          *reinterpret_cast<uint4*>(hdst + sw128_offset(r, qt * 2 + k)) = make_uint4(dp[4 * k], dp[4 * k + 1], dp[4 * k + 2], dp[4 * k + 3]);
+          *reinterpret_cast<uint4*>(gdst + sw128_offset(r, chunk0 + pc * 2 + k)) = make_uint4(gp[4 * k], gp[4 * k + 1], gp[4 * k + 2], gp[4 * k + 3]);
+          *reinterpret_cast<uint4*>(hdst + sw128_offset(r, chunk0 + pc * 2 + k)) = make_uint4(dp[4 * k], dp[4 * k + 1], dp[4 * k + 2], dp[4 * k + 3]);
         }
-        if (qt < 3) tmem_ld_wait();
-        if (qt == 2) {   // the last quarter is in registers: the accumulators may be overwritten by hg(i + 1)
+        if (pc == 0) {   // the last piece is in registers: the accumulators may be overwritten by hg(i + 1)
+          tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(hempty);
         }
@@ -269,27 +286,31 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       mbar_arrive(gfull);
     }
     // db1: reduce the per-row partials over the 32 rows of the warp, then over the warps (shared-memory atomics)
-    float mine0 = 0.f, mine1 = 0.f;
+    float mine = 0.f;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {   // column k of the group's first / second 32 columns
+    for (int k = 0; k < 32; ++k) {   // column k of the group's 32 columns
       const float s0 = warp_sum((k & 1) ? dbp[k >> 1].y : dbp[k >> 1].x);
-      const float s1 = warp_sum((k & 1) ? dbp[16 + (k >> 1)].y : dbp[16 + (k >> 1)].x);
-      if (lane == k) { mine0 = s0; mine1 = s1; }
+      if (lane == k) mine = s0;
     }
-    atomicAdd(&sDb[grp * 64 + lane], mine0);
-    atomicAdd(&sDb[grp * 64 + 32 + lane], mine1);
-    // accumulators: TMEM lane = d.  group 0: dW1^T slice -> dw1[c][d] (lanes contiguous in d: coalesced reductions);
-    //                               group 1: dW2 slice   -> dw2[d][c]
-    mbar_wait(accfull, 0);
-    tc_fence_after();
-    const int d = r;
+    atomicAdd(&sDb[grp * 32 + lane], mine);
+  }
+  // ---- all 16 warps: accumulators -> global.  TMEM lane = d.  groups 0 / 1: dW1^T columns [0,64) / [64,128) -> dw1[c][d]
+  // (lanes contiguous in d: coalesced reductions); groups 2 / 3: dW2 columns likewise -> dw2[d][c]
+  __syncwarp();
+  mbar_wait(accfull, 0);
+  tc_fence_after();
+  {
+    const int d = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const bool first = grp < 2;
+    const int cbase = (grp & 1) * 64;
 #pragma unroll 1
-    for (int cb = 0; cb < kCc; cb += 32) {
+    for (int cb = cbase; cb < cbase + 64; cb += 32) {
       uint32_t a[32];
-      tmem_ld32(tmem_base + (grp == 0 ? C::kColW1 : C::kColW2) + lane_addr + cb, a);
+      tmem_ld32(tmem_base + (first ? C::kColW1 : C::kColW2) + lane_addr + cb, a);
       tmem_ld_wait();
       if (d < p.D) {
-        if (grp == 0) {
+        if (first) {
 #pragma unroll
           for (int k = 0; k < 32; ++k)
             if (c0 + cb + k < p.C) atomicAdd(p.dw1 + static_cast<long long>(c0 + cb + k) * p.D + d, __uint_as_float(a[k]));
@@ -308,13 +329,11 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
       }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const int t = (warp - 2) * 32 + lane;
-    if (t < kCc && c0 + t < p.C) atomicAdd(p.db1 + c0 + t, sDb[t]);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (threadIdx.x < kCc && c0 + threadIdx.x < p.C) atomicAdd(p.db1 + c0 + threadIdx.x, sDb[threadIdx.x]);
+  if (pwarp == 0) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 template <int DP, bool kDrop>

@@ -287,9 +287,14 @@ def dropout_mask(rows: int, cols: int, ld: int, dropout_p: float, seed: int, sit
     return out
 
 
+def dropout_threshold(p: float) -> int:
+    """round(p * 128) clamped to [1, 127] (0 when dropout is off): the kernels quantise the drop probability to 1/128."""
+    return min(max(int(p * 128.0 + 0.5), 1), 127) if p > 0 else 0
+
+
 def dropout_scale(p: float) -> float:
-    t = min(int(p * 65536.0 + 0.5), 65535) if p > 0 else 0
-    return 65536.0 / (65536.0 - t)
+    """Inverse of the REALISED keep probability (csrc/common.cuh make_drop)."""
+    return 128.0 / (128.0 - dropout_threshold(p))
 
 
 # ------------------------------------------------------------------------------------------------ fusion

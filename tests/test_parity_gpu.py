@@ -288,10 +288,18 @@ def test_dropout_statistics_and_modes():
     for p in (0.1, 0.3, 0.5):
         m = ops.dropout_mask(2048, 512, 512, p, 7, 2)
         n = m.numel()
-        assert abs(float(m.mean()) - (1 - p)) < 5 * (p * (1 - p) / n) ** 0.5 + 2e-5, p
-        assert abs(ops.dropout_scale(p) * (1 - round(p * 65536) / 65536) - 1) < 1e-6
+        pr = ops.dropout_threshold(p) / 128.0                 # realised drop probability (quantised to 1/128)
+        assert abs(pr - p) <= 1 / 256 + 1e-9
+        assert abs(float(m.mean()) - (1 - pr)) < 5 * (pr * (1 - pr) / n) ** 0.5 + 2e-5, p
+        assert abs(ops.dropout_scale(p) * (1 - pr) - 1) < 1e-6
         # neighbouring elements and different seeds / sites are uncorrelated
         a, b = m[:, 0::2].flatten(), m[:, 1::2].flatten()
+        assert abs(float(((a - a.mean()) * (b - b.mean())).mean())) < 5e-3
+        for i in range(4):                                    # the four elements of a hash quad, and neighbouring quads / rows
+            for j in range(i + 1, 8):
+                a, b = m[:, i::8].flatten(), m[:, j::8].flatten()
+                assert abs(float(((a - a.mean()) * (b - b.mean())).mean())) < 5e-3, (i, j)
+        a, b = m[0::2].flatten(), m[1::2].flatten()
         assert abs(float(((a - a.mean()) * (b - b.mean())).mean())) < 5e-3
         m2 = ops.dropout_mask(2048, 512, 512, p, 8, 2)
         assert abs(float(((m - m.mean()) * (m2 - m2.mean())).mean())) < 5e-3

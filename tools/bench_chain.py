@@ -45,12 +45,15 @@ def main():
     run(lambda: ops.channel_mix_fwd(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, BF16), "channel_mix_fwd", f)
     run(lambda: ops.channel_mix_fwd(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, BF16, 0.5, 1234), "channel_mix_fwd dropout .5", f)
     run(lambda: ops.channel_mix_bwd(dy, u, ln_w, ln_b, w1, b1, w2, w1b, w2b, BF16), "channel_mix_bwd (all)", 2 * f)
-    with _lib.profile() as p:
-        for _ in range(5):
-            ops.channel_mix_bwd(dy, u, ln_w, ln_b, w1, b1, w2, w1b, w2b, BF16)
-        torch.cuda.synchronize()
-    for k, (n, ms) in sorted(p.table.items(), key=lambda kv: -kv[1][1]):
-        print(f"   {k:24s} {ms / n * 1e3:8.1f} us/launch x{n // 5}")
+    run(lambda: ops.channel_mix_bwd(dy, u, ln_w, ln_b, w1, b1, w2, w1b, w2b, BF16, 0.5, 1234), "channel_mix_bwd dropout .5", 2 * f)
+    for pdrop in (0.0, 0.5):
+        with _lib.profile() as p:
+            for _ in range(5):
+                ops.channel_mix_fwd(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, BF16, pdrop, 1234)
+                ops.channel_mix_bwd(dy, u, ln_w, ln_b, w1, b1, w2, w1b, w2b, BF16, pdrop, 1234)
+            torch.cuda.synchronize()
+        for k, (n, ms) in sorted(p.table.items(), key=lambda kv: -kv[1][1]):
+            print(f"   p={pdrop} {k:24s} {ms / n * 1e3:8.1f} us/launch x{n // 5}")
 
 
 if __name__ == "__main__":
