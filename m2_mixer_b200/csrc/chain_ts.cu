@@ -654,17 +654,17 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   uint64_t* w1empty = w1full + S1;    // [S1]  dXn GEMM done with the W1 chunk -> TMA
   uint64_t* w2full = w1empty + S1;    // [S2]
   uint64_t* w2empty = w2full + S2;    // [S2]  dG GEMM done -> TMA
-  uint64_t* hfull = w2empty + S2;     // [2]   H and dG accumulators of a chunk ready -> epilogue
+  uint64_t* hfull = w2empty + S2;     // [2]   H and dG accumulators of a chunk ready (one arrival per issuing warp) -> epilogue
   uint64_t* dhfull = hfull + 2;       // [2]   epilogue wrote dH (bf16, TMEM) -> MMA
   uint64_t* yfull = dhfull + 2;
-  uint64_t* dxdone = yfull + 1;       // [2]   dXn GEMM has read dH: the H / dG issuer may overwrite the buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dxdone + 2);
+  uint64_t* hloaded = yfull + 1;      // [2]   epilogue has H / dG of the chunk in registers: the H accumulator may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hloaded + 2);
   float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);
 
-  // Roles by LOGICAL warp id (0 = TMA producer, 1 = dXn issuer, 2.. = epilogue, -1 = H / dG issuer); physically the
+  // Roles by LOGICAL warp id (0 = TMA producer, 1 = dXn / dG issuer, 2.. = epilogue, -1 = H issuer); physically the
   // epilogue warps come first and the single-thread roles last, and the MMAs are issued by TWO warps so that one
-  // issuer's barrier waits overlap the other's MMAs (see chain_fwd_ts_kernel).  One writer per accumulator: dXn <- warp 1,
-  // H / dG buffers <- warp -1; the dH -> (H, dG)(j + 2) buffer reuse is ordered by the dxdone barrier.
+  // issuer's barrier waits overlap the other's MMAs (see chain_fwd_ts_kernel).  One writer per accumulator: dXn and the
+  // dG buffers <- warp 1, H buffers <- warp -1.
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = pwarp < 4 * kGroupsB ? pwarp + 2 : (pwarp == 4 * kGroupsB + 2 ? -1 : pwarp - 4 * kGroupsB);
   const int m0 = blockIdx.x * kRows;
@@ -673,7 +673,7 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < S1; ++i) { mbar_init(&w1full[i], 1); mbar_init(&w1empty[i], 1); }
     for (int i = 0; i < S2; ++i) { mbar_init(&w2full[i], 1); mbar_init(&w2empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&hfull[i], 1); mbar_init(&dhfull[i], 128 * kGroupsB); mbar_init(&dxdone[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&hfull[i], 2); mbar_init(&dhfull[i], 128 * kGroupsB); mbar_init(&hloaded[i], 128 * kGroupsB); }
     mbar_init(yfull, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmW1);
@@ -737,43 +737,62 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
       refill_w2(S2 + 2 + k);
     }
   } else if (warp == -1) {
-    // ---- H / dG issuer: H[j&1] = LN(u) . W1_j^T ; dG[j&1] = dY . W2_j  (A operands from TMEM), two chunks ahead.
+    // ---- H issuer: H[j&1] = LN(u) . W1_j^T (A from TMEM), two chunks ahead: the H accumulator is free as soon as the
+    // epilogue of chunk j - 2 has LOADED it (hloaded), so this GEMM overlaps the epilogue's math.
     // The whole warp walks the loop (waits are warp-wide), one elected lane issues: see elect_one().
     constexpr uint32_t idescH = umma_idesc_bf16(kRows, kCc, 0, 0);    // B (W1 chunk) K-major
-    constexpr uint32_t idescG = umma_idesc_bf16(kRows, kCc, 0, 1);    // B (W2 tile)  MN-major
     const uint64_t w1k_desc0 = umma_desc_sw128(smem_u32(sW1), 16, 1024);          // W1 chunk as K-major B (H GEMM)
-    const uint64_t w2m_desc0 = umma_desc_sw128(smem_u32(sW2), 8192, 1024);        // W2 tile as MN-major B (dG GEMM)
     for (int j = 0; j < nch; ++j) {
-      const int s1 = j % S1, s2 = j % S2, b = j & 1;
-      // chunk j - 2's dXn GEMM must have consumed the dH that aliases this buffer
-      if (j >= 2) mbar_wait3(&w1full[s1], (j / S1) & 1, &w2full[s2], (j / S2) & 1, &dxdone[b], ((j >> 1) - 1) & 1);
-      else mbar_wait2(&w1full[s1], (j / S1) & 1, &w2full[s2], (j / S2) & 1);
+      const int s1 = j % S1, b = j & 1;
+      M2_TR(800 + 4 * j + 0, 11, j);
+      if (j >= 2) mbar_wait2(&w1full[s1], (j / S1) & 1, &hloaded[b], ((j >> 1) - 1) & 1);
+      else mbar_wait(&w1full[s1], (j / S1) & 1);
+      M2_TR(800 + 4 * j + 1, 12, j);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t bd1 = w1k_desc0 + static_cast<uint64_t>((s1 * C::kW1Bytes) >> 4);
-        const uint64_t bd2 = w2m_desc0 + static_cast<uint64_t>((s2 * C::kW2Bytes) >> 4);
         const uint32_t tH = tmem_base + C::kColH + b * kCc;
-        const uint32_t tG = tmem_base + C::kColG + b * kCc;
 #pragma unroll
         for (int kk = 0; kk < DP / 16; ++kk)
           umma_bf16_ts(tH, tX + kk * 8, bd1 + (((kk >> 2) * (kCc * 128) + (kk & 3) * 32) >> 4), idescH, kk > 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < DP / 16; ++kk)    // B = W2 tile [DP d-rows][64 c]: 16 d-rows per step = 2048 B
-          umma_bf16_ts(tG, tDY + kk * 8, bd2 + ((kk * 2048) >> 4), idescG, kk > 0 ? 1u : 0u);
-        umma_commit(&w2empty[s2]);
-        umma_commit(&hfull[b]);
+        umma_commit(&hfull[b]);     // hfull counts two arrivals: this one and the dG GEMM's
+        M2_TR(800 + 4 * j + 3, 14, j);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ---- dXn issuer: dXn += dH_j . W1_j  (A = dH from TMEM, the W1 chunk consumed MN-major).  W1_j is known to have landed:
-    // the H GEMM of the chunk waited for it, and its completion reached this warp through hfull -> epilogue -> dhfull.
+    // ---- dXn / dG issuer: dXn += dH_j . W1_j (A = dH from TMEM, the W1 chunk consumed MN-major), then in the SAME burst
+    // dG[j&1] = dY . W2_{j+2}, which overwrites the accumulator whose head held dH_j: the tensor pipe executes one thread's
+    // MMAs in issue order, so no completion round trip sits in the epilogue -> dXn -> dG -> epilogue ring (with the dG GEMM
+    // on the other warp that ring cost 2 x ~300 clk of commit -> barrier -> wait latency per chunk,
+    // profiles/r01_trace_bwd_two_issuers.log).  W1_j is known to have landed: the H GEMM of the chunk waited for it, and its
+    // completion reached this warp through hfull -> epilogue -> dhfull.
     constexpr uint32_t idescX = umma_idesc_bf16(kRows, DP, 0, 1);     // B (W1 chunk) MN-major
+    constexpr uint32_t idescG = umma_idesc_bf16(kRows, kCc, 0, 1);    // B (W2 tile)  MN-major
     const uint64_t w1m_desc0 = umma_desc_sw128(smem_u32(sW1), kCc * 128, 1024);   // W1 chunk as MN-major B (dXn GEMM)
+    const uint64_t w2m_desc0 = umma_desc_sw128(smem_u32(sW2), 8192, 1024);        // W2 tile as MN-major B (dG GEMM)
+    auto issue_dg = [&](int jn) {   // elected lane only
+      const int s2 = jn % S2, b = jn & 1;
+      const uint64_t bd2 = w2m_desc0 + static_cast<uint64_t>((s2 * C::kW2Bytes) >> 4);
+      const uint32_t tG = tmem_base + C::kColG + b * kCc;
+#pragma unroll
+      for (int kk = 0; kk < DP / 16; ++kk)    // B = W2 tile [DP d-rows][64 c]: 16 d-rows per step = 2048 B
+        umma_bf16_ts(tG, tDY + kk * 8, bd2 + ((kk * 2048) >> 4), idescG, kk > 0 ? 1u : 0u);
+      umma_commit(&w2empty[s2]);
+      umma_commit(&hfull[b]);
+    };
+    for (int jn = 0; jn < 2 && jn < nch; ++jn) {
+      mbar_wait(&w2full[jn % S2], 0);
+      tc_fence_after();
+      if (elect_one()) issue_dg(jn);
+      __syncwarp();
+    }
     for (int j = 0; j < nch; ++j) {
       const int s1 = j % S1, b = j & 1;
+      const int jn = j + 2;
       M2_TR(4 * j + 0, 1, j);
-      mbar_wait(&dhfull[b], (j >> 1) & 1);
+      if (jn < nch) mbar_wait2(&dhfull[b], (j >> 1) & 1, &w2full[jn % S2], (jn / S2) & 1);
+      else mbar_wait(&dhfull[b], (j >> 1) & 1);
       M2_TR(4 * j + 1, 2, j);
       tc_fence_after();
       if (elect_one()) {
@@ -783,7 +802,7 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         for (int kk = 0; kk < kCc / 16; ++kk)   // B: 16 c-rows per step = 2048 B; d panels 8 KB apart (LBO); A: group kk's dH
           umma_bf16_ts(tDX, tG + kk * 16, bd + ((kk * 2048) >> 4), idescX, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&w1empty[s1]);
-        umma_commit(&dxdone[b]);
+        if (jn < nch) issue_dg(jn);
         M2_TR(4 * j + 2, 10, j);
       }
       __syncwarp();
@@ -812,6 +831,8 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
       tmem_ld16(tH, h);
       tmem_ld16(tG, dg);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&hloaded[b]);                      // the H accumulator of this buffer may be overwritten
       if (warp == 2) M2_TR(400 + 4 * j + 2, 7, j);   // epilogue: TMEM loads done
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {

@@ -34,12 +34,12 @@ constexpr int kMmaM = 128;      // UMMA M of the recompute GEMMs
 constexpr int kCc = 128;        // channels per CTA
 // 16 warps = 4 column groups (group g = columns [32 g, 32 g + 32)) x 4 TMEM lane quadrants.  A warp may only touch the
 // TMEM lanes of quadrant (warp id % 4), which is also its scheduler: with 96-row tiles quadrant 3 (rows 96..127) holds
-// garbage, so its four warps do no epilogue work - three of them are the TMA producer (warp 3) and the two MMA issuers
+// garbage, so its four warps do no epilogue work - they are the two TMA producers (warps 3, 15) and the two MMA issuers
 // (warps 7, 11), which then have scheduler 3 to themselves (no busy epilogue warp delays an MMA burst), and the twelve live warps
 // put four warps on each of the other three schedulers (two before: the GELU' epilogue was latency bound at 0.5 IPC).
 constexpr int kThreads = 512;
 constexpr int kLiveThreads = 384;
-constexpr int kNS = 2;          // row-tile ring depth
+constexpr int kNS = 2;          // row-tile buffers: [0] feeds the recompute GEMMs, [1] the gradient GEMMs (see the kernel)
 
 template <int DP>
 struct CfgW {
@@ -56,6 +56,19 @@ struct CfgW {
   static constexpr int kTmemCols = 512;
   static constexpr int kColW1 = 0, kColW2 = 128, kColH = 256, kColG = 384;
 };
+
+// Optional in-kernel timeline (debug builds: -DM2_TRACE, tools/trace_wgrad.cu): CTA (0,0) records (tag, tile, clock).
+#ifdef M2_TRACE
+__device__ long long g_wtrace[4096];
+__device__ __forceinline__ void wtrace_evt(int slot, int tag, int j) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && slot < 1360) {
+    g_wtrace[3 * slot] = tag; g_wtrace[3 * slot + 1] = j; g_wtrace[3 * slot + 2] = clock64();
+  }
+}
+#define M2_WTR(slot, tag, j) wtrace_evt(slot, tag, j)
+#else
+#define M2_WTR(slot, tag, j)
+#endif
 
 struct WgParams {
   const float* b1;
@@ -95,7 +108,7 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = pwarp & 3;             // TMEM lane quadrant (= scheduler)
   const int grp = pwarp >> 2;          // column group
-  const bool is_tma = pwarp == 3, is_mma_hg = pwarp == 7, is_mma_wg = pwarp == 11;
+  const bool is_tma = pwarp == 3, is_mma_hg = pwarp == 7, is_mma_wg = pwarp == 11, is_tma_b = pwarp == 15;
   const int c0 = blockIdx.x * kCc;
   const int t_lo = static_cast<int>(static_cast<long long>(p.ntiles) * blockIdx.y / p.R);
   const int t_hi = static_cast<int>(static_cast<long long>(p.ntiles) * (blockIdx.y + 1) / p.R);
@@ -137,17 +150,35 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tma_load_2d(sW2 + h * C::kW2Panel, &tmW2, wfull, c0 + h * 64, 0);
     }
     __syncwarp();
+    // Row tile i is needed twice: by the recompute GEMMs (early) and by the gradient GEMMs (after the epilogue of the tile).
+    // Held in one 2-slot ring it stayed resident for two tile periods and the ring (wg(i) done -> TMA of tile i + 2 ->
+    // hg(i + 2) -> epilogue -> wg(i + 2)) paced the kernel at 3400-3700 clk per tile for a 3100-clk epilogue
+    // (profiles/r01_trace_wgrad.log).  So the tile is fetched TWICE from L2 into two single buffers with independent
+    // lifetimes: buffer 0 (this warp) is refilled as soon as hg(i) completes, buffer 1 (warp 15) as soon as wg(i) completes.
     for (int i = 0; i < nt; ++i) {
-      const int s = i % kNS;
-      mbar_wait(&empty[s], ((i / kNS) & 1) ^ 1);
+      mbar_wait(&empty[0], (i & 1) ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full[s], C::kStage);
-        uint8_t* dst = sStage + s * C::kStage;
+        mbar_arrive_expect_tx(&full[0], C::kStage);
         const int row0 = (t_lo + i) * kRows;
 #pragma unroll
         for (int pnl = 0; pnl < DP / 64; ++pnl) {
-          tma_load_2d(dst + pnl * C::kPanel, &tmX, &full[s], pnl * 64, row0);
-          tma_load_2d(dst + C::kTile + pnl * C::kPanel, &tmDY, &full[s], pnl * 64, row0);
+          tma_load_2d(sStage + pnl * C::kPanel, &tmX, &full[0], pnl * 64, row0);
+          tma_load_2d(sStage + C::kTile + pnl * C::kPanel, &tmDY, &full[0], pnl * 64, row0);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (is_tma_b) {
+    for (int i = 0; i < nt; ++i) {
+      mbar_wait(&empty[1], (i & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[1], C::kStage);
+        uint8_t* dst = sStage + C::kStage;
+        const int row0 = (t_lo + i) * kRows;
+#pragma unroll
+        for (int pnl = 0; pnl < DP / 64; ++pnl) {
+          tma_load_2d(dst + pnl * C::kPanel, &tmX, &full[1], pnl * 64, row0);
+          tma_load_2d(dst + C::kTile + pnl * C::kPanel, &tmDY, &full[1], pnl * 64, row0);
         }
       }
       __syncwarp();
@@ -164,8 +195,10 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const uint64_t w2d = umma_desc_sw128(smem_u32(sW2), C::kW2Panel, 1024);
     mbar_wait(wfull, 0);
     for (int i = 0; i < nt; ++i) {
-      const int s = i % kNS;
-      mbar_wait2(&full[s], (i / kNS) & 1, hempty, (i & 1) ^ 1);
+      constexpr int s = 0;
+      M2_WTR(4 * i + 0, 1, i);
+      mbar_wait2(&full[0], i & 1, hempty, (i & 1) ^ 1);
+      M2_WTR(4 * i + 1, 2, i);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t xa = xk0 + static_cast<uint64_t>((s * C::kStage) >> 4);
@@ -178,22 +211,25 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (int kk = 0; kk < DP / 16; ++kk)
           umma_bf16(tmem_base + C::kColG, ya + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4), w2d + ((kk * 2048) >> 4), idescG,
                     kk > 0 ? 1u : 0u);
+        umma_commit(&empty[0]);
         umma_commit(hfull);
+        M2_WTR(4 * i + 2, 3, i);
       }
       __syncwarp();
     }
   } else if (is_mma_wg) {
     // ---- gradient issuer: dW1c^T += Xn_i^T . dH_i ; dW2c += dY_i^T . G_i   (contraction over the 96 rows), when the
-    // epilogue has written G / dH.  The row tile is known to have landed (full[s] -> recompute issuer -> hfull -> epilogue
-    // -> gfull).
+    // epilogue has written G / dH and the tile's second copy has landed in buffer 1.
     constexpr uint32_t idescW = umma_idesc_bf16(kMmaM, kCc, 1, 1);   // A row tile MN-major (M = d), B = sdH / sG MN-major
     constexpr uint32_t kLboA = DP == 128 ? C::kPanel : 0;            // DP = 64: M rows 64..127 alias the only panel
     const uint64_t xm0 = umma_desc_sw128(smem_u32(sStage), kLboA, 1024);
     const uint64_t gd = umma_desc_sw128(smem_u32(sG), C::kGPanel, 1024);
     const uint64_t dhd = umma_desc_sw128(smem_u32(sdH), C::kGPanel, 1024);
     for (int i = 0; i < nt; ++i) {
-      const int s = i % kNS;
-      mbar_wait(gfull, i & 1);
+      constexpr int s = 1;
+      M2_WTR(200 + 4 * i + 0, 4, i);
+      mbar_wait2(gfull, i & 1, &full[1], i & 1);
+      M2_WTR(200 + 4 * i + 1, 5, i);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t xa = xm0 + static_cast<uint64_t>((s * C::kStage) >> 4);
@@ -204,8 +240,9 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
         for (int kk = 0; kk < kRows / 16; ++kk)
           umma_bf16(tmem_base + C::kColW2, ya + ((kk * 2048) >> 4), gd + ((kk * 2048) >> 4), idescW, (i > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&empty[s]);
+        umma_commit(&empty[1]);
         umma_commit(gempty);
+        M2_WTR(200 + 4 * i + 2, 6, i);
       }
       __syncwarp();
     }
@@ -230,14 +267,22 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       tmem_ld16(tmem_base + C::kColG + lane_addr + grp * 32 + pc * 16, gd2);
     };
     for (int i = 0; i < nt; ++i) {
+      if (pwarp == 0) M2_WTR(400 + 4 * i + 0, 7, i);
       mbar_wait(hfull, i & 1);
+      if (pwarp == 0) M2_WTR(400 + 4 * i + 1, 8, i);
       tc_fence_after();
       // dropout: hash input of the quad at this thread's (row, first channel of the group)
       const uint32_t hin = ((static_cast<uint32_t>((t_lo + i) * kRows + r) * static_cast<uint32_t>(p.ldh) + static_cast<uint32_t>(cg)) >> 2) * kDropGolden + p.dh.key;
       uint32_t hA[16], gA[16], hB[16], gB[16];
+      // Both pieces are fetched before any math and the accumulators handed back at once: hg(i + 1) (1000 clk of MMAs plus the
+      // commit round trip) then runs under this tile's ~3000 clk of epilogue math.  When hempty was only signalled after the
+      // first piece's math the recompute GEMMs and the epilogue alternated (profiles/r01_trace_wgrad.log: 3700 clk per tile).
       ld_piece(0, hA, gA);
+      ld_piece(1, hB, gB);
       tmem_ld_wait();
-      ld_piece(1, hB, gB);                                      // in flight during the first piece's math
+      tc_fence_before();
+      mbar_arrive(hempty);
+      if (pwarp == 0) M2_WTR(400 + 4 * i + 2, 9, i);
 #pragma unroll
       for (int pc = 0; pc < 2; ++pc) {
         uint32_t (&h)[16] = pc ? hB : hA;
@@ -276,14 +321,10 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           *reinterpret_cast<uint4*>(gdst + sw128_offset(r, chunk0 + pc * 2 + k)) = make_uint4(gp[4 * k], gp[4 * k + 1], gp[4 * k + 2], gp[4 * k + 3]);
           *reinterpret_cast<uint4*>(hdst + sw128_offset(r, chunk0 + pc * 2 + k)) = make_uint4(dp[4 * k], dp[4 * k + 1], dp[4 * k + 2], dp[4 * k + 3]);
         }
-        if (pc == 0) {   // the last piece is in registers: the accumulators may be overwritten by hg(i + 1)
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(hempty);
-        }
       }
       fence_proxy_async();
       mbar_arrive(gfull);
+      if (pwarp == 0) M2_WTR(400 + 4 * i + 3, 10, i);
     }
     // db1: reduce the per-row partials over the 32 rows of the warp, then over the warps (shared-memory atomics)
     float mine = 0.f;
@@ -353,6 +394,12 @@ int launch_wg(const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& t
 }
 
 }  // namespace
+
+#ifdef M2_TRACE
+int wgrad_trace_read(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, g_wtrace, sizeof(long long) * n) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // dw1 [C][D], dw2 [D][C], db1 [C] are ACCUMULATED (fp32 reductions).  xn_b / dy_b: bf16 [M][D] written by chain_bwd_ts.
 int wgrad_fused(const void* xn_b, const void* dy_b, const void* w1b, const void* w2b, int ldw2, const float* b1, float* dw1,

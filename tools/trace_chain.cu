@@ -32,7 +32,7 @@ int main() {
   }
   std::vector<long long> t(4096);
   m2::chain_trace_read(t.data(), 4096);
-  const char* names[] = {"", "dx wait", "dx issue", "hg wait", "hg issue", "epi wait", "epi ready", "epi loaded", "epi arrived", "mma", "commit"};
+  const char* names[] = {"", "dx wait", "dx go", "hg wait", "hg issue", "epi wait", "epi ready", "epi loaded", "epi arrived", "mma", "dx issued"};
   long long t0 = t[3 * 0 + 2];
   for (int s = 0; s < 1360; ++s) if (t[3 * s + 2] && (t0 == 0 || t[3 * s + 2] < t0)) t0 = t[3 * s + 2];
   for (int j = 0; j < 48; ++j) {
@@ -40,8 +40,8 @@ int main() {
     for (int k = 0; k < 4; ++k) printf(" %s=%lld", names[t[3 * (4 * j + k)]], t[3 * (4 * j + k) + 2] - t0);
     printf(" |");
     for (int k = 0; k < 4; ++k) printf(" %s=%lld", names[t[3 * (400 + 4 * j + k)]], t[3 * (400 + 4 * j + k) + 2] - t0);
-    printf(" | dx mma clocks:");
-    for (int k = 0; k < 5; ++k) printf(" %lld", t[3 * (800 + 6 * j + k) + 2] - t0);
+    printf(" | hg: top / H go / dG go / issued:");
+    for (int k = 0; k < 4; ++k) printf(" %lld", t[3 * (800 + 4 * j + k) + 2] - t0);
     printf("\n");
   }
   return 0;
