@@ -73,6 +73,12 @@ int m2b200_gemm(int precision, const void* A, int a_mn, int64_t lda, const void*
  * The drop probability is quantised to t/128, t = round(p*128) (one hash per 4 consecutive elements, 7 bits each);
  * kept values are scaled by 128 / (128 - t), the inverse of the realised keep probability.                            */
 int m2b200_dropout_mask(float* out, int rows, int cols, int64_t ld, float dropout_p, uint64_t seed, int site, void* stream);
+/* CUDA-graph support for the dropout sites: (dropout_p, seed) are launch parameters, so a captured graph would replay the
+ * same masks.  After m2b200_set_dropout_epoch_ptr(p) (p: one uint32 in device memory, NULL switches it off again) every
+ * subsequently LAUNCHED kernel folds *p into its mask key at run time; m2b200_dropout_epoch_advance(p, stream) increments
+ * it (one tiny launch, capturable).  Process-global setting, read at launch time.                                         */
+void m2b200_set_dropout_epoch_ptr(const void* dev_u32);
+int m2b200_dropout_epoch_advance(void* dev_u32, void* stream);
 
 /* ---- MixerBlock.token_mix + residual: modules/mixer.py:30-35,43
  *   u[b] = x[b] + Wt2 . GELU(Wt1 . LN(x[b]) + bt1) + bt2,   x,u [B][N][D], wt1 [T][N], wt2 [N][T]            */

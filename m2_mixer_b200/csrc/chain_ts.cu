@@ -449,7 +449,7 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     };
     const float hs = kDrop ? 0.5f * p.dh.scale : 0.5f;   // dropout scale folded into the GELU
     // dropout: hash input of the quad at channel 0 of this thread's row (quad index = (row * ldh + c) / 4)
-    const uint32_t hrow = (static_cast<uint32_t>(row) * static_cast<uint32_t>(p.ldh) >> 2) * kDropGolden + p.dh.key;
+    const uint32_t hrow = (static_cast<uint32_t>(row) * static_cast<uint32_t>(p.ldh) >> 2) * kDropGolden + drop_key(p.dh);
     auto gelu_piece = [&](const uint32_t (&h)[16], int c, uint32_t* gout) {   // 16 columns starting at channel c
       const uint32_t hin = hrow + static_cast<uint32_t>(c >> 2) * kDropGolden;
 #pragma unroll
@@ -817,7 +817,7 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const float hs = kDrop ? 0.5f * p.dh.scale : 0.5f;          // dropout scale folded into GELU / GELU'
     const float ninv_s = kDrop ? -1.f / p.dh.scale : -1.f;
-    const uint32_t hrow = (static_cast<uint32_t>(row) * static_cast<uint32_t>(p.ldh) >> 2) * kDropGolden + p.dh.key;
+    const uint32_t hrow = (static_cast<uint32_t>(row) * static_cast<uint32_t>(p.ldh) >> 2) * kDropGolden + drop_key(p.dh);
     for (int j = 0; j < nch; ++j) {
       const int b = j & 1;
       const uint32_t tH = tmem_base + C::kColH + lane_addr + b * kCc + grp * 16;

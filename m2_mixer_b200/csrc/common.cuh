@@ -120,7 +120,15 @@ struct Drop {
   uint32_t thresh;   // round(p * 128), 0 = dropout off
   float scale;       // 128 / (128 - thresh)
   uint32_t kadd;     // 0x80808080 - thresh * 0x01010101
+  const uint32_t* epoch;   // optional device counter folded into the key at run time (nullptr: off), see drop_key()
 };
+// The (seed, site) key is a launch PARAMETER, so a captured CUDA graph would replay the same masks for ever.  When the host
+// has registered a device-resident epoch counter (m2b200_set_dropout_epoch_ptr; the graphed training step advances it once
+// per replay) every kernel folds it into its key: same kernels, same parameters, fresh masks per replay.
+extern const uint32_t* g_drop_epoch_ptr;   // profile.cu
+__device__ __forceinline__ uint32_t drop_key(const Drop& d) {
+  return d.epoch ? d.key + __ldg(d.epoch) * 0x85EBCA6BU : d.key;
+}
 // Two-round multiply / xorshift finisher (the first two rounds of lowbias32); the key is already a full-avalanche
 // splitmix64 of (seed, site).
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
@@ -135,7 +143,7 @@ __device__ __forceinline__ uint32_t drop_flags_from_hash_input(const Drop& d, ui
   return (mix32(hin) & 0x7f7f7f7fU) + d.kadd;
 }
 __device__ __forceinline__ uint32_t drop_quad_flags(const Drop& d, uint32_t quad_idx) {
-  return drop_flags_from_hash_input(d, quad_idx * kDropGolden + d.key);
+  return drop_flags_from_hash_input(d, quad_idx * kDropGolden + drop_key(d));
 }
 // AND masks from the flags (prmt with the sign-replicate bit set in every selector nibble).
 template <int kPair>   // elements 2 kPair, 2 kPair + 1 of the quad as the two halves of a packed bf16x2
@@ -201,6 +209,7 @@ inline Drop make_drop(float p, unsigned long long seed, uint32_t site) {
   d.thresh = static_cast<uint32_t>(t);
   d.scale = 128.0f / (128.0f - static_cast<float>(t));
   d.kadd = 0x80808080U - d.thresh * 0x01010101U;
+  d.epoch = g_drop_epoch_ptr;
   return d;
 }
 enum DropSite { kSiteTokenHidden = 0, kSiteTokenOut = 1, kSiteChannelHidden = 2, kSiteChannelOut = 3, kSiteLinear = 4 };

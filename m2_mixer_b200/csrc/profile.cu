@@ -15,7 +15,9 @@
 #include "kernels.h"
 
 namespace m2 {
+const uint32_t* g_drop_epoch_ptr = nullptr;   // device counter folded into every dropout key (common.cuh drop_key)
 namespace {
+__global__ void epoch_advance_kernel(uint32_t* e) { *e += 1u; }
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_enabled{0};
 struct Rec { const char* name; cudaEvent_t a, b; };
@@ -45,6 +47,16 @@ LaunchScope::~LaunchScope() {
 }  // namespace m2
 
 extern "C" {
+
+void m2b200_set_dropout_epoch_ptr(const void* dev_u32) { m2::g_drop_epoch_ptr = static_cast<const uint32_t*>(dev_u32); }
+
+int m2b200_dropout_epoch_advance(void* dev_u32, void* stream) {
+  if (!dev_u32) return M2_ERR_ARG;
+  m2::LaunchScope scope("epoch_advance", static_cast<cudaStream_t>(stream));
+  m2::epoch_advance_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint32_t*>(dev_u32));
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
 
 unsigned long long m2b200_launch_count(void) { return m2::g_launches.load(); }
 

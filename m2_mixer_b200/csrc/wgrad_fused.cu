@@ -266,13 +266,14 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       tmem_ld16(tmem_base + C::kColH + lane_addr + grp * 32 + pc * 16, hd);
       tmem_ld16(tmem_base + C::kColG + lane_addr + grp * 32 + pc * 16, gd2);
     };
+    const uint32_t dkey = drop_key(p.dh);
     for (int i = 0; i < nt; ++i) {
       if (pwarp == 0) M2_WTR(400 + 4 * i + 0, 7, i);
       mbar_wait(hfull, i & 1);
       if (pwarp == 0) M2_WTR(400 + 4 * i + 1, 8, i);
       tc_fence_after();
       // dropout: hash input of the quad at this thread's (row, first channel of the group)
-      const uint32_t hin = ((static_cast<uint32_t>((t_lo + i) * kRows + r) * static_cast<uint32_t>(p.ldh) + static_cast<uint32_t>(cg)) >> 2) * kDropGolden + p.dh.key;
+      const uint32_t hin = ((static_cast<uint32_t>((t_lo + i) * kRows + r) * static_cast<uint32_t>(p.ldh) + static_cast<uint32_t>(cg)) >> 2) * kDropGolden + dkey;
       uint32_t hA[16], gA[16], hB[16], gB[16];
       // Both pieces are fetched before any math and the accumulators handed back at once: hg(i + 1) (1000 clk of MMAs plus the
       // commit round trip) then runs under this tile's ~3000 clk of epilogue math.  When hempty was only signalled after the

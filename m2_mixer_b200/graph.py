@@ -1,0 +1,100 @@
+"""Whole-step CUDA graph for the launch-bound configurations.
+
+M2-Mixer-S, MIMIC-H and friends are a few MFLOP per sample: a training step is ~100-300 kernel launches of a few
+microseconds each, and the step time is the launch path (Python -> dispatcher -> ctypes -> cudaLaunch), not the GPU.
+``GraphedTrainStep`` captures ``zero_grad -> training_step -> backward -> (gradient allreduce) -> optimizer step`` once
+and replays it with one ``cudaGraphLaunch`` per step:
+
+* inputs are copied into static tensors (the graph's kernels hold raw pointers),
+* the optimizer must be ``FusedAdam(..., capturable=True)`` (lr and the step counter live in device memory),
+* dropout stays random: (p, seed) are launch parameters and would be frozen by the capture, so a device-resident epoch
+  counter is registered with the library (``ops.set_dropout_epoch``); every kernel folds it into its mask key at run time
+  and the captured step ends by advancing it.
+
+Reference behaviour covered: one iteration of the Lightning loop around ``shared_step`` (modules/train_test_module.py:77-83,
+models/avmnist.py:236-312, models/mimic.py:93-142) with ``torch.optim.Adam`` (models/avmnist.py:413-415).
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Optional
+
+import torch
+
+from . import ops
+from .optim import FusedAdam
+
+
+def _static_like(x: Any) -> Any:
+    if torch.is_tensor(x):
+        return torch.empty_like(x).copy_(x)
+    if isinstance(x, dict):
+        return {k: _static_like(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return type(x)(_static_like(v) for v in x)
+    return x
+
+
+def _copy_into(dst: Any, src: Any) -> None:
+    if torch.is_tensor(dst):
+        if dst.shape != src.shape or dst.dtype != src.dtype:
+            raise ValueError(f"GraphedTrainStep was captured for a batch of shape {tuple(dst.shape)} / {dst.dtype}, "
+                             f"got {tuple(src.shape)} / {src.dtype}")
+        dst.copy_(src, non_blocking=True)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_into(dst[k], src[k])
+    elif isinstance(dst, (list, tuple)):
+        for d, s in zip(dst, src):
+            _copy_into(d, s)
+
+
+class GraphedTrainStep:
+    """``step = GraphedTrainStep(model, opt, example_batch); loss = step(batch)`` - loss is a 0-dim device tensor that the
+    next call overwrites (clone it to keep it)."""
+
+    def __init__(self, model: torch.nn.Module, optimizer: FusedAdam, example_batch: Any, warmup: int = 3,
+                 grad_sync: Optional[Any] = None, step_fn: Optional[Callable[[Any], torch.Tensor]] = None):
+        if not isinstance(optimizer, FusedAdam) or not optimizer.capturable:
+            raise ValueError("GraphedTrainStep needs FusedAdam(..., capturable=True): lr / step must live on the device")
+        if not torch.cuda.is_available():
+            raise RuntimeError("GraphedTrainStep needs a GPU: the hot path has no CPU fallback")
+        self.model, self.opt, self.sync = model, optimizer, grad_sync
+        self._fn = step_fn or (lambda b: model.training_step(b))
+        self.batch = _static_like(example_batch)
+        dev = optimizer.flat_param.device
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        ops.set_dropout_epoch(self.epoch)
+        optimizer.sync_lr_to_device()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):          # allocator / lazy-init warm-up outside the capture
+                self._one()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._one()
+        self.opt.step_count -= 1                      # the capture ran step()'s host side without executing the kernels
+        self.replays = 0
+
+    def _one(self) -> torch.Tensor:
+        self.opt.zero_grad()
+        loss = self._fn(self.batch)
+        loss.backward()
+        if self.sync is not None:
+            self.sync.finish()
+        self.opt.step()
+        ops.dropout_epoch_advance(self.epoch)
+        return loss.detach()
+
+    def __call__(self, batch: Any) -> torch.Tensor:
+        _copy_into(self.batch, batch)
+        self.graph.replay()
+        self.replays += 1
+        self.opt.step_count += 1                      # host mirror of the device-resident step counter
+        return self.loss
+
+    def close(self) -> None:
+        """Unregister the dropout epoch (eager calls afterwards use their host seeds only)."""
+        ops.set_dropout_epoch(None)

@@ -454,3 +454,16 @@ def gemm(precision: int, A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, *
                            batch, a_batch_rows, b_batch_rows, _ptr(bias), bias_mode, act, _ptr(residual), N, M * N,
                            out.data_ptr(), int(out_bf16), N, M * N, int(accumulate), splitk, _stream()), "gemm")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ graph-safe dropout
+def set_dropout_epoch(t: Optional[torch.Tensor]) -> None:
+    """Register (or, with None, clear) the device-resident uint32/int32 counter every dropout kernel folds into its mask key
+    (include/m2b200.h: m2b200_set_dropout_epoch_ptr).  The caller keeps the tensor alive."""
+    if t is not None and not (t.is_cuda and t.numel() >= 1 and t.element_size() == 4):
+        raise RuntimeError("m2b200: the dropout epoch must be a 4-byte CUDA tensor")
+    _L().m2b200_set_dropout_epoch_ptr(None if t is None else t.data_ptr())
+
+
+def dropout_epoch_advance(t: torch.Tensor) -> None:
+    check(_L().m2b200_dropout_epoch_advance(t.data_ptr(), _stream()), "dropout_epoch_advance")

@@ -343,6 +343,74 @@ def test_training_with_reference_dropout_learns():
         assert sum(losses[-10:]) / 10 < 0.5 * sum(losses[:3]) / 3, (name, losses[:3], losses[-3:])
 
 
+def test_fp32_linear_weight_gradient_with_long_token_axis():
+    """The fp32 (CUDA-core) GEMM splits K when a weight gradient has few output tiles and a long contraction
+    (MLP encoder / proj at large batch): same result as torch to fp32 accuracy, with and without accumulation."""
+    import m2_mixer_b200.functional as F
+    torch.manual_seed(3)
+    for M, K, N in ((5000, 5, 64), (4096, 64, 64), (9000, 12, 40)):
+        x = torch.randn(M, K, device="cuda", requires_grad=True)
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).requires_grad_(True)
+        b = torch.randn(N, device="cuda", requires_grad=True)
+        dy = torch.randn(M, N, device="cuda")
+        y = F.linear(x, w, b, 0, "fp32")
+        y.backward(dy)
+        xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+        yr = torch.nn.functional.linear(xr, wr, br)
+        yr.backward(dy.double())
+        assert rel_err(y, yr) < 1e-5
+        for a, r in ((x.grad, xr.grad), (w.grad, wr.grad), (b.grad, br.grad)):
+            assert rel_err(a, r) < 1e-5, (M, K, N)
+
+
+def test_graphed_train_step_matches_eager_and_keeps_dropout_random():
+    """the whole step (zero_grad, fwd, bwd, FusedAdam) replayed as ONE CUDA graph.  Without dropout the
+    graphed loss curve equals the eager one; with dropout the masks change from replay to replay (device-resident epoch)
+    and the model still learns."""
+    from m2_mixer_b200 import models, ops, presets
+    from m2_mixer_b200.graph import GraphedTrainStep
+    from m2_mixer_b200.optim import FusedAdam
+    from oracle.seeding import synthetic_batch
+
+    def build(name, dropout, lr):
+        cfg = dict(presets.get(name), dropout=dropout)
+        torch.manual_seed(0)
+        m = models.get_model(cfg["type"])(cfg, {}).cuda().train()
+        return m, FusedAdam(m.parameters(), lr=lr, capturable=True)
+
+    def to_dev(bt):
+        return {k: v.cuda() for k, v in bt.items()} if isinstance(bt, dict) else tuple(v.cuda() for v in bt)
+
+    for name, kind in (("avmnist_S", "avmnist"), ("mimic_H", "mimic")):
+        batches = [to_dev(synthetic_batch(kind, 32, 10 + i)) for i in range(4)]
+        # ---- no dropout: graph == eager (3 warm-up steps on batch 0 inside the ctor are mirrored on the eager side)
+        m, opt = build(name, 0.0, 1e-3)
+        eager = []
+        for i in range(3 + 8):
+            bt = batches[0] if i < 3 else batches[(i - 3) % 4]
+            opt.zero_grad(); loss = m.training_step(bt); loss.backward(); opt.step()
+            eager.append(float(loss))
+        m, opt = build(name, 0.0, 1e-3)
+        step = GraphedTrainStep(m, opt, batches[0], warmup=3)
+        graphed = [float(step(batches[i % 4])) for i in range(8)]
+        step.close()
+        assert max(abs(a - b) for a, b in zip(eager[3:], graphed)) < 2e-3 * max(abs(v) for v in eager), (name, eager[3:], graphed)
+        # ---- dropout on, lr = 0: the weights never move, so the loss varies only through the masks
+        m, opt = build(name, 0.3, 0.0)
+        step = GraphedTrainStep(m, opt, batches[0], warmup=1)
+        ls = [float(step(batches[0])) for _ in range(6)]
+        assert len({round(v, 6) for v in ls}) >= 5, (name, ls)
+        assert int(step.epoch) == 1 + 6
+        step.close()
+        # ---- dropout on, training: learns
+        m, opt = build(name, presets.get(name)["dropout"], 1e-2)
+        step = GraphedTrainStep(m, opt, batches[0], warmup=1)
+        ls = [float(step(batches[0])) for _ in range(150)]
+        step.close()
+        assert sum(ls[-10:]) / 10 < 0.5 * sum(ls[:3]) / 3, (name, ls[:3], ls[-3:])
+    ops.set_dropout_epoch(None)
+
+
 def test_direct_gradient_accumulation_equals_autograd_path():
     """FusedAdam registers flat-buffer destinations; the backward kernels then accumulate in place.  Same grads."""
     from m2_mixer_b200 import models, presets
