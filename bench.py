@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dropout", type=float, default=None, help="override the cfg's dropout (default: the reference cfg's value)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying one CUDA graph per step")
     return ap.parse_args()
 
 
@@ -180,7 +181,8 @@ def run_ours(args, cfg):
     torch.manual_seed(42)                                         # cfg seed (reference cfg train.seed)
     model = models.get_model(cfg["type"])(cfg, dict(presets.AVMNIST_OPTIM)).to(dev).set_precision(args.precision)
     model.train()
-    opt = FusedAdam(model.parameters(), lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    use_graph = not args.no_graph and world == 1     # N > 1: the NCCL bucket allreduce is launched eagerly (parallel.py)
+    opt = FusedAdam(model.parameters(), lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, capturable=use_graph)
     sync = parallel.attach(opt) if world > 1 else None
 
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -218,14 +220,26 @@ def run_ours(args, cfg):
         return float(ms)
 
     clocks = ClockSampler(local) if rank == 0 else None
+    gstep = None
+    if use_graph:
+        # one captured graph per resident batch (no input copies); the launch count of a step is taken from the capture
+        from m2_mixer_b200.graph import GraphedTrainStep
+        step(batches[0])
+        lc = _lib.launch_count()
+        step(batches[0])
+        per_step_launches = _lib.launch_count() - lc
+        gstep = GraphedTrainStep(model, opt, static_batches=batches, warmup=2)
+        run = lambda i: gstep.replay(i % NB)
+    else:
+        run = lambda i: step(batches[i % NB])
     for i in range(args.warmup):
-        step(batches[i % NB])
+        run(i)
     l0 = _lib.launch_count()
     torch.cuda.synchronize()
     w0 = time.time()
-    ms = timed(lambda i: step(batches[i % NB]), args.steps)
+    ms = timed(run, args.steps)
     w1 = time.time()
-    launches = _lib.launch_count() - l0
+    launches = (per_step_launches + 1) * args.steps if use_graph else _lib.launch_count() - l0   # + the epoch-advance launch
     clk = clocks.stop(w0, w1) if clocks else None
 
     # ---- end to end through the public API from pinned host memory: the batch of EVERY step is copied host -> device
@@ -242,15 +256,25 @@ def run_ours(args, cfg):
                 yield host[i % 2]
 
         pre = DevicePrefetcher(host_stream(2), dev)
+        estep = None
         for b in pre:                                             # warm the copy path / allocator
             sink.append(float(step(b).detach()))
+        if use_graph:
+            # the prefetcher's two device buffer sets are the static inputs of two captured graphs
+            if gstep is not None:
+                gstep.close()
+            from m2_mixer_b200.graph import GraphedTrainStep
+            estep = GraphedTrainStep(model, opt, static_batches=pre.bufs, warmup=1)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pre = DevicePrefetcher(host_stream(args.steps), dev)      # first copy is issued (and waited for) inside the region
+        pre = DevicePrefetcher(host_stream(args.steps), dev, bufs=pre.bufs if use_graph else None)   # first copy is issued (and waited for) inside the region
         pending = None
         for b in pre:
-            loss = step(b).detach()
+            if estep is not None:
+                loss = estep.replay(pre.index_of(b)).clone()      # the graph's loss slot is overwritten two steps later
+            else:
+                loss = step(b).detach()
             if pending is not None:
                 sink.append(float(pending))                       # D2H read of the previous step's loss: no pipeline bubble
             pending = loss
@@ -269,6 +293,9 @@ def run_ours(args, cfg):
                "note": "H2D of each step's batch from pinned memory (double-buffered on a copy stream) + D2H of each step's loss"}
 
     # ---- per-kernel device time (CUDA events on the launching stream) for the roofline of the dominant kernel
+    if use_graph:                                                 # the profiled steps below run kernel by kernel
+        from m2_mixer_b200 import ops as _ops
+        _ops.set_dropout_epoch(None)
     roof = None
     if rank != 0:
         for i in range(3):                                        # keep the collectives of rank 0's profiled steps matched
@@ -328,6 +355,7 @@ def run_ours(args, cfg):
                            "global_batch": world * B, "parallelism": f"dp{world}",
                            "l2": f"{NB} rotating input batches of {B * (784 + 12544) * 4 >> 20} MiB each (> 126 MB L2)",
                            "dropout": f"{run_dropout} (reference cfg: {ref_dropout}; fused counter-based masks, regenerated in backward)",
+                           "launch": "one CUDA graph replay per step (m2_mixer_b200.graph.GraphedTrainStep)" if use_graph else "kernel by kernel",
                            "model_tflops_per_gpu": fl["fwd_bwd"] * value / world / 1e12,
                            "frac_of_bf16_peak_burst": fl["fwd_bwd"] * value / world / 1e12 / 1644.4},
                 "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}

@@ -22,12 +22,14 @@ class DevicePrefetcher:
     loop does naturally).
     """
 
-    def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device: torch.device, depth: int = 2):
+    def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device: torch.device, depth: int = 2, bufs=None):
         self.src: Iterator[Dict[str, torch.Tensor]] = iter(batches)
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.depth = depth
-        self.bufs = [None] * depth                      # device buffer sets
+        # device buffer sets; pass the ``bufs`` of an earlier prefetcher to keep the SAME device tensors (they are the
+        # static inputs of captured CUDA graphs, graph.GraphedTrainStep(static_batches=...))
+        self.bufs = list(bufs) if bufs is not None else [None] * depth
         self.copied = [torch.cuda.Event() for _ in range(depth)]   # copy of buffer set k finished (copy stream)
         self.released = [None] * depth                  # consumer done with buffer set k (compute stream)
         self.slot = 0
@@ -54,6 +56,13 @@ class DevicePrefetcher:
 
     def __iter__(self):
         return self
+
+    def index_of(self, batch) -> int:
+        """Which buffer set a yielded batch is (the index of the graph captured on it)."""
+        for k, b in enumerate(self.bufs):
+            if b is batch:
+                return k
+        raise ValueError("not a batch of this prefetcher")
 
     def __next__(self) -> Dict[str, torch.Tensor]:
         if self.pending is None:

@@ -16,7 +16,7 @@ models/avmnist.py:236-312, models/mimic.py:93-142) with ``torch.optim.Adam`` (mo
 """
 from __future__ import annotations
 
-from typing import Any, Callable, Optional
+from typing import Any, Callable, Optional, Sequence
 
 import torch
 
@@ -49,51 +49,67 @@ def _copy_into(dst: Any, src: Any) -> None:
 
 
 class GraphedTrainStep:
-    """``step = GraphedTrainStep(model, opt, example_batch); loss = step(batch)`` - loss is a 0-dim device tensor that the
-    next call overwrites (clone it to keep it)."""
+    """``step = GraphedTrainStep(model, opt, example_batch); loss = step(batch)`` - loss is a 0-dim device tensor that a
+    later call overwrites (clone it to keep it).
 
-    def __init__(self, model: torch.nn.Module, optimizer: FusedAdam, example_batch: Any, warmup: int = 3,
-                 grad_sync: Optional[Any] = None, step_fn: Optional[Callable[[Any], torch.Tensor]] = None):
+    ``static_batches=[b0, b1, ...]`` (device tensors the caller fills in place, e.g. the buffer sets of a
+    ``DevicePrefetcher``) captures one graph per buffer set - they share one memory pool - and ``step.replay(k)`` runs
+    the step on set k without any input copy."""
+
+    def __init__(self, model: torch.nn.Module, optimizer: FusedAdam, example_batch: Any = None, warmup: int = 3,
+                 grad_sync: Optional[Any] = None, step_fn: Optional[Callable[[Any], torch.Tensor]] = None,
+                 static_batches: Optional[Sequence[Any]] = None):
         if not isinstance(optimizer, FusedAdam) or not optimizer.capturable:
             raise ValueError("GraphedTrainStep needs FusedAdam(..., capturable=True): lr / step must live on the device")
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedTrainStep needs a GPU: the hot path has no CPU fallback")
+        if (example_batch is None) == (static_batches is None):
+            raise ValueError("pass either example_batch or static_batches")
         self.model, self.opt, self.sync = model, optimizer, grad_sync
         self._fn = step_fn or (lambda b: model.training_step(b))
-        self.batch = _static_like(example_batch)
+        self.batches = list(static_batches) if static_batches is not None else [_static_like(example_batch)]
+        self.batch = self.batches[0]
         dev = optimizer.flat_param.device
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.losses = [torch.zeros((), dtype=torch.float32, device=dev) for _ in self.batches]   # outside the graph pool
         ops.set_dropout_epoch(self.epoch)
         optimizer.sync_lr_to_device()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):          # allocator / lazy-init warm-up outside the capture
-                self._one()
+                self._one(0)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._one()
-        self.opt.step_count -= 1                      # the capture ran step()'s host side without executing the kernels
+        self.graphs = []
+        for k in range(len(self.batches)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.graphs[0].pool() if self.graphs else None):
+                self._one(k)
+            self.opt.step_count -= 1                  # the capture ran step()'s host side without executing the kernels
+            self.graphs.append(g)
+        self.graph, self.loss = self.graphs[0], self.losses[0]
         self.replays = 0
 
-    def _one(self) -> torch.Tensor:
+    def _one(self, k: int) -> None:
         self.opt.zero_grad()
-        loss = self._fn(self.batch)
+        loss = self._fn(self.batches[k])
         loss.backward()
         if self.sync is not None:
             self.sync.finish()
         self.opt.step()
         ops.dropout_epoch_advance(self.epoch)
-        return loss.detach()
+        self.losses[k].copy_(loss.detach())
 
-    def __call__(self, batch: Any) -> torch.Tensor:
-        _copy_into(self.batch, batch)
-        self.graph.replay()
+    def replay(self, k: int = 0) -> torch.Tensor:
+        self.graphs[k].replay()
         self.replays += 1
         self.opt.step_count += 1                      # host mirror of the device-resident step counter
-        return self.loss
+        return self.losses[k]
+
+    def __call__(self, batch: Any) -> torch.Tensor:
+        _copy_into(self.batches[0], batch)
+        return self.replay(0)
 
     def close(self) -> None:
         """Unregister the dropout epoch (eager calls afterwards use their host seeds only)."""
