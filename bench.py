@@ -170,7 +170,21 @@ def run_ours(args, cfg):
     from m2_mixer_b200 import _lib, models, parallel, presets
     from m2_mixer_b200.optim import FusedAdam
 
-    rank, local, world = parallel.init_from_env()
+    # NCCL writes its banner ("NCCL version ...") to STDOUT when the communicator is created: keep stdout for the one
+    # JSON line by pointing fd 1 at stderr while the process group comes up.
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, local, world = parallel.init_from_env()
+        if world > 1 and torch.cuda.is_available():
+            t = torch.zeros(1, device=torch.device("cuda", local))
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU: the hot path has no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -181,7 +195,7 @@ def run_ours(args, cfg):
     torch.manual_seed(42)                                         # cfg seed (reference cfg train.seed)
     model = models.get_model(cfg["type"])(cfg, dict(presets.AVMNIST_OPTIM)).to(dev).set_precision(args.precision)
     model.train()
-    use_graph = not args.no_graph and world == 1     # N > 1: the NCCL bucket allreduce is launched eagerly (parallel.py)
+    use_graph = not args.no_graph                    # N > 1: two graphs per step around ONE eager NCCL allreduce (graph.py)
     opt = FusedAdam(model.parameters(), lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, capturable=use_graph)
     sync = parallel.attach(opt) if world > 1 else None
 
@@ -228,7 +242,7 @@ def run_ours(args, cfg):
         lc = _lib.launch_count()
         step(batches[0])
         per_step_launches = _lib.launch_count() - lc
-        gstep = GraphedTrainStep(model, opt, static_batches=batches, warmup=2)
+        gstep = GraphedTrainStep(model, opt, static_batches=batches, warmup=2, grad_sync=sync)
         run = lambda i: gstep.replay(i % NB)
     else:
         run = lambda i: step(batches[i % NB])
@@ -241,6 +255,8 @@ def run_ours(args, cfg):
     w1 = time.time()
     launches = (per_step_launches + 1) * args.steps if use_graph else _lib.launch_count() - l0   # + the epoch-advance launch
     clk = clocks.stop(w0, w1) if clocks else None
+    if gstep is not None:
+        gstep.close()
 
     # ---- end to end through the public API from pinned host memory: the batch of EVERY step is copied host -> device
     # inside the timed region (m2_mixer_b200.data.DevicePrefetcher double-buffers it on a side stream, one batch ahead)
@@ -261,10 +277,8 @@ def run_ours(args, cfg):
             sink.append(float(step(b).detach()))
         if use_graph:
             # the prefetcher's two device buffer sets are the static inputs of two captured graphs
-            if gstep is not None:
-                gstep.close()
             from m2_mixer_b200.graph import GraphedTrainStep
-            estep = GraphedTrainStep(model, opt, static_batches=pre.bufs, warmup=1)
+            estep = GraphedTrainStep(model, opt, static_batches=pre.bufs, warmup=1, grad_sync=sync)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -286,6 +300,8 @@ def run_ours(args, cfg):
             dist.all_reduce(ems_t, op=dist.ReduceOp.MAX)
         barrier()
         ems = float(ems_t)
+        if estep is not None:
+            estep.close()
         assert len(sink) == 2 + args.steps
         h2d = sum(v.numel() * v.element_size() for v in host[0].values())
         e2e = {"value": world * B * args.steps / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -293,9 +309,6 @@ def run_ours(args, cfg):
                "note": "H2D of each step's batch from pinned memory (double-buffered on a copy stream) + D2H of each step's loss"}
 
     # ---- per-kernel device time (CUDA events on the launching stream) for the roofline of the dominant kernel
-    if use_graph:                                                 # the profiled steps below run kernel by kernel
-        from m2_mixer_b200 import ops as _ops
-        _ops.set_dropout_epoch(None)
     roof = None
     if rank != 0:
         for i in range(3):                                        # keep the collectives of rank 0's profiled steps matched

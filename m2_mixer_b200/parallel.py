@@ -56,6 +56,7 @@ class GradSync:
         self._pending = [b[2] for b in self.buckets]
         self._launched = [False] * len(self.buckets)
         self._handles = []
+        self.enabled = True       # False: the hooks do nothing (graph.GraphedTrainStep reduces the whole buffer between graphs)
         if self.world > 1:
             for i, p in enumerate(params):
                 if p.requires_grad:
@@ -71,6 +72,8 @@ class GradSync:
         b = self.bucket_of[i]
 
         def hook(_p):
+            if not self.enabled:
+                return
             self._pending[b] -= 1
             if self._pending[b] == 0:
                 self._launch(b)
@@ -90,7 +93,7 @@ class GradSync:
     def finish(self):
         """Call after backward, before optimizer.step(): flushes buckets whose hooks did not all fire (unused
         parameters) and makes the compute stream wait for the communication stream."""
-        if self.world == 1:
+        if self.world == 1 or not self.enabled:
             return
         for b in range(len(self.buckets)):
             if not self._launched[b]:
@@ -102,6 +105,13 @@ class GradSync:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         self._pending = list(self._static_pending)
         self._launched = [False] * len(self.buckets)
+
+
+    def allreduce_all(self):
+        """One sum-allreduce over the whole flat gradient buffer on the current stream (no overlap): what a graphed step
+        uses between its forward/backward graph and its optimizer graph."""
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
 
 
 def attach(optimizer, bucket_bytes: int = 8 << 20, group=None) -> GradSync:
