@@ -500,6 +500,9 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
       const uint32_t tGj = tmem_base + C::kColH + lane_addr + (j % NB) * kCc + half * 32;
       uint32_t g[8];
       if (tr) M2_TR(400 + 4 * j + 0, 5, j);      // epilogue: chunk start (first piece loaded)
+      // probe the next chunk's accumulator barrier now: in steady state GEMM1 is chunks ahead, and the wait's round trip
+      // then hides under this chunk's math
+      const bool next_ready = (j + 2 < nch) && mbar_probe(&hfull[(j + 2) % NB], ((j + 2) / NB) & 1);
 #pragma unroll
       for (int pl = 0; pl < kPieces; ++pl) {
         const int pc = pc0 + pl;
@@ -509,7 +512,8 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
           ld_piece(j, pc + 1, nxt);
         } else if (j + 2 < nch) {
           if (tr) M2_TR(400 + 4 * j + 1, 6, j);  // epilogue: about to wait for the next H
-          mbar_wait(&hfull[(j + 2) % NB], ((j + 2) / NB) & 1);
+          if (!next_ready) mbar_wait(&hfull[(j + 2) % NB], ((j + 2) / NB) & 1);
+          __syncwarp();
           if (tr) M2_TR(400 + 4 * j + 2, 7, j);  // epilogue: next H ready
           tc_fence_after();
           ld_piece(j + 2, pc0, nxt);
@@ -818,12 +822,14 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     const float hs = kDrop ? 0.5f * p.dh.scale : 0.5f;          // dropout scale folded into GELU / GELU'
     const float ninv_s = kDrop ? -1.f / p.dh.scale : -1.f;
     const uint32_t hrow = (static_cast<uint32_t>(row) * static_cast<uint32_t>(p.ldh) >> 2) * kDropGolden + drop_key(p.dh);
+    bool ready = false;                              // hfull of the chunk already observed by an early probe
     for (int j = 0; j < nch; ++j) {
       const int b = j & 1;
       const uint32_t tH = tmem_base + C::kColH + lane_addr + b * kCc + grp * 16;
       const uint32_t tG = tmem_base + C::kColG + lane_addr + b * kCc + grp * 16;
       if (warp == 2) M2_TR(400 + 4 * j + 0, 5, j);   // epilogue: about to wait for H / dG
-      mbar_wait(&hfull[b], (j >> 1) & 1);
+      if (!ready) mbar_wait(&hfull[b], (j >> 1) & 1);
+      __syncwarp();
       if (warp == 2) M2_TR(400 + 4 * j + 1, 6, j);   // epilogue: accumulators ready
       tc_fence_after();
       const int c0 = j * kCc + grp * 16;
@@ -877,6 +883,8 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
       // dH (bf16, 8 columns) over the first half of the dG columns this thread has just read: the groups never touch
       // each other's columns, the tensor pipe reads them (dXn GEMM) before chunk j + 2 overwrites the buffer.
       tmem_st8(tG, dhp);
+      // probe the next chunk's barrier (other buffer) while the store drains: its round trip hides under the store wait
+      ready = (j + 1 < nch) && mbar_probe(&hfull[b ^ 1], ((j + 1) >> 1) & 1);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&dhfull[b]);

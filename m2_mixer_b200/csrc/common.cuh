@@ -265,6 +265,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Early probe of a barrier whose result is consumed later (`if (!ready) mbar_wait(...)`): the ~130-clk SYNCS round trip of a
+// wait on an already completed phase then overlaps the math between the probe and its use.
+__device__ __forceinline__ bool mbar_probe(uint64_t* bar, uint32_t parity) { return mbar_try_wait(bar, parity); }
+
 // Two barriers at once.  A wait costs ~120-150 clk even when the phase completed long ago (tools/wait_probe.cu: the
 // SYNCS.TRYWAIT round trip); issuing both probes back to back overlaps the two round trips.
 __device__ __forceinline__ bool mbar_try_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {

@@ -267,9 +267,11 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       tmem_ld16(tmem_base + C::kColG + lane_addr + grp * 32 + pc * 16, gd2);
     };
     const uint32_t dkey = drop_key(p.dh);
+    bool ready = false;                              // hfull of the tile already observed by an early probe
     for (int i = 0; i < nt; ++i) {
       if (pwarp == 0) M2_WTR(400 + 4 * i + 0, 7, i);
-      mbar_wait(hfull, i & 1);
+      if (!ready) mbar_wait(hfull, i & 1);
+      __syncwarp();
       if (pwarp == 0) M2_WTR(400 + 4 * i + 1, 8, i);
       tc_fence_after();
       // dropout: hash input of the quad at this thread's (row, first channel of the group)
@@ -317,6 +319,7 @@ wgrad_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           }
         }
         if (pc == 0) mbar_wait(gempty, (i & 1) ^ 1);   // gradient GEMMs of tile i - 1 have consumed sG / sdH
+        else ready = (i + 1 < nt) && mbar_probe(hfull, (i + 1) & 1);   // next tile's accumulators: round trip hidden under the stores
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           *reinterpret_cast<uint4*>(gdst + sw128_offset(r, chunk0 + pc * 2 + k)) = make_uint4(gp[4 * k], gp[4 * k + 1], gp[4 * k + 2], gp[4 * k + 3]);
