@@ -142,6 +142,11 @@ int m2b200_patch_gather(const float* img, float* cols, int B, int cin, int H, in
 int m2b200_copy_tokens(const float* src, int64_t src_bstride, float* dst, int64_t dst_bstride, int B, int64_t per_batch,
                        int accumulate, void* stream);
 int m2b200_add(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* MaxFusion (modules/fusion.py:190-204, torch.maximum) and MeanFusion of two modalities (modules/fusion.py:258-272):
+ * mode 1: out = max(a, b), mode 2: out = (a + b) / 2.  Backward of max with torch's tie rule (equal inputs share the
+ * gradient evenly): da = g [a > b] + g/2 [a == b], db = g - da.  The backward of mean is g/2 for both (host side).     */
+int m2b200_fuse2_fwd(const float* a, const float* b, float* out, int64_t n, int mode, void* stream);
+int m2b200_fuse2_max_bwd(const float* a, const float* b, const float* g, float* da, float* db, int64_t n, void* stream);
 
 /* ---- token mean-pool of a standalone StandardClassifier.forward (modules/classification.py:90):
  *   out[b][d] = mean_n x[b][n][d]; the task modules use the fused heads kernel below instead.                      */

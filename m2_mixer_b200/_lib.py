@@ -49,6 +49,8 @@ PROTOTYPES = {
     "m2b200_patch_gather": (i32, [vp, vp] + [i32] * 5 + [vp]),
     "m2b200_copy_tokens": (i32, [vp, i64, vp, i64, i32, i64, i32, vp]),
     "m2b200_add": (i32, [vp, vp, vp, i64, vp]),
+    "m2b200_fuse2_fwd": (i32, [vp, vp, vp, i64, i32, vp]),
+    "m2b200_fuse2_max_bwd": (i32, [vp, vp, vp, vp, vp, i64, vp]),
     "m2b200_mean_pool_fwd": (i32, [vp, vp, i32, i32, i32, vp]),
     "m2b200_mean_pool_bwd": (i32, [vp, vp, i32, i32, i32, vp]),
     "m2b200_heads_loss_fwd": (i32, [PP, PI64, PI32, PI32, PP, PP, i32, i32, i32, i32, vp, vp, PF32, vp, vp, vp, vp]),

@@ -453,6 +453,16 @@ int m2b200_add(const float* a, const float* b, float* out, int64_t n, void* stre
   return add_f32(a, b, out, n, S(stream));
 }
 
+int m2b200_fuse2_fwd(const float* a, const float* b, float* out, int64_t n, int mode, void* stream) {
+  if (!a || !b || !out) return M2_ERR_ARG;
+  return fuse2_fwd(a, b, out, n, mode, S(stream));
+}
+
+int m2b200_fuse2_max_bwd(const float* a, const float* b, const float* g, float* da, float* db, int64_t n, void* stream) {
+  if (!a || !b || !g || !da || !db) return M2_ERR_ARG;
+  return fuse2_max_bwd(a, b, g, da, db, n, S(stream));
+}
+
 int m2b200_mean_pool_fwd(const float* x, float* out, int B, int N, int D, void* stream) {
   if (!x || !out) return M2_ERR_ARG;
   return mean_pool_fwd(x, out, B, N, D, S(stream));

@@ -337,6 +337,25 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
     o[i] = a[i] + b[i];
 }
 
+// Elementwise fusion of two token tensors (reference modules/fusion.py:190-204 MaxFusion, :258-272 MeanFusion):
+//   mode 1: o = max(a, b)      mode 2: o = (a + b) / 2
+// backward of max (torch.maximum semantics: ties split the gradient evenly): da = g * [a > b] + g/2 * [a == b], db = g - da
+__global__ void fuse2_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, long long n, int mode) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    o[i] = mode == 1 ? fmaxf(a[i], b[i]) : 0.5f * (a[i] + b[i]);
+}
+__global__ void fuse2_max_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ g,
+                                     float* __restrict__ da, float* __restrict__ db, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float x = a[i], y = b[i], gi = g[i];
+    const float ga = x > y ? gi : (x == y ? 0.5f * gi : 0.f);
+    da[i] = ga;
+    db[i] = gi - ga;
+  }
+}
+
 // pooled[b][d] = mean_n x[b][n][d]   |   dx[b][n][d] = dpooled[b][d] / N
 __global__ void mean_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int N, int D) {
   const long long total = static_cast<long long>(B) * D;
@@ -558,6 +577,22 @@ int relu_bwd(float* dy, const float* y, long long n, cudaStream_t s) {
   LaunchScope scope("relu_bwd", s);
   if (n <= 0) return M2_ERR_ARG;
   relu_bwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(dy, y, n);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int fuse2_fwd(const float* a, const float* b, float* o, long long n, int mode, cudaStream_t s) {
+  LaunchScope scope("fuse2_fwd", s);
+  if (n <= 0 || (mode != 1 && mode != 2)) return M2_ERR_ARG;
+  fuse2_fwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(a, b, o, n, mode);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int fuse2_max_bwd(const float* a, const float* b, const float* g, float* da, float* db, long long n, cudaStream_t s) {
+  LaunchScope scope("fuse2_max_bwd", s);
+  if (n <= 0) return M2_ERR_ARG;
+  fuse2_max_bwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(a, b, g, da, db, n);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }

@@ -173,6 +173,26 @@ class _Add(Function):
         return g, g
 
 
+class _Fuse2(Function):
+    """MaxFusion (mode 1) / two-input MeanFusion (mode 2), reference modules/fusion.py:190-204, 258-272."""
+
+    @staticmethod
+    def forward(ctx, a, b, mode):
+        ctx.mode = mode
+        if mode == 1:
+            ctx.save_for_backward(a, b)
+        return _O.fuse2_fwd(a, b, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.mode == 1:
+            a, b = ctx.saved_tensors
+            da, db = _O.fuse2_max_bwd(a, b, g.contiguous())
+            return da, db, None
+        h = g * 0.5
+        return h, h, None
+
+
 class _MeanPool(Function):
     @staticmethod
     def forward(ctx, x):
@@ -354,6 +374,14 @@ def mean_pool(x) -> torch.Tensor:
 
 def concat_tokens(*xs) -> torch.Tensor:
     return _Concat.apply(*xs)
+
+
+def fuse_max(a, b) -> torch.Tensor:
+    return _Fuse2.apply(a, b, 1)
+
+
+def fuse_mean(a, b) -> torch.Tensor:
+    return _Fuse2.apply(a, b, 2)
 
 
 def add(a, b) -> torch.Tensor:

@@ -357,6 +357,27 @@ _define("split_tokens", "(Tensor g, int[] sizes) -> Tensor[]", split_tokens)
 _define("add", "(Tensor a, Tensor b) -> Tensor", add)
 
 
+def fuse2_fwd(a, b, mode: int):
+    a, b = _f32c(a, "a"), _f32c(b, "b")
+    if a.shape != b.shape:
+        raise RuntimeError("m2b200::fuse2_fwd expects equal shapes")
+    out = torch.empty_like(a)
+    check(_L().m2b200_fuse2_fwd(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), mode, _stream()), "fuse2_fwd")
+    return out
+
+
+def fuse2_max_bwd(a, b, g):
+    a, b, g = _f32c(a, "a"), _f32c(b, "b"), _f32c(g, "g")
+    da, db = torch.empty_like(a), torch.empty_like(a)
+    check(_L().m2b200_fuse2_max_bwd(a.data_ptr(), b.data_ptr(), g.data_ptr(), da.data_ptr(), db.data_ptr(), a.numel(),
+                                    _stream()), "fuse2_max_bwd")
+    return da, db
+
+
+_define("fuse2_fwd", "(Tensor a, Tensor b, int mode) -> Tensor", fuse2_fwd)
+_define("fuse2_max_bwd", "(Tensor a, Tensor b, Tensor g) -> (Tensor, Tensor)", fuse2_max_bwd)
+
+
 # ------------------------------------------------------------------------------------------------ heads + loss
 def _heads_args(toks, ws, bs, head_weight):
     n = len(toks)

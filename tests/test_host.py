@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import sys
 
 import pytest
 import torch
@@ -148,3 +149,30 @@ def test_dropout_argument_validation():
         M.MixerBlock(32, 4, 8, 64, dropout=1.0)
     blk = M.MixerBlock(32, 4, 8, 64, dropout=0.5)
     assert blk.dropout_p == 0.5 and blk.token_mix[2].dropout_p == 0.5
+
+
+def test_max_and_mean_fusion_shape_contracts_match_reference():
+    """MaxFusion / MeanFusion (reference modules/fusion.py:190-204, 258-272): same get_output_shape answers and errors."""
+    from m2_mixer_b200 import modules as M
+    for cls in (M.MaxFusion, M.MeanFusion):
+        f = cls()
+        assert f.get_output_shape((4, 8, 32), (4, 8, 32)) == (4, 8, 32)
+        assert f.get_output_shape(8, 8, dim=1) == 8
+        with pytest.raises(ValueError):
+            f.get_output_shape((4, 8, 32), (4, 9, 32))
+        with pytest.raises(ValueError):
+            f.get_output_shape((4, 8, 32), (4, 8, 32), dim=1)
+    ref_root = "/root/reference"
+    if os.path.isdir(ref_root):
+        sys.path.insert(0, ref_root)
+        try:
+            import importlib
+            rf = importlib.import_module("modules.fusion")
+            for name in ("MaxFusion", "MeanFusion"):
+                a, b = getattr(rf, name)(), getattr(M, name)()
+                assert a.get_output_shape((2, 3, 4), (2, 3, 4)) == b.get_output_shape((2, 3, 4), (2, 3, 4))
+                assert a.get_output_shape(5, 5, dim=1) == b.get_output_shape(5, 5, dim=1)
+        finally:
+            sys.path.remove(ref_root)
+            for k in [k for k in sys.modules if k == "modules" or k.startswith("modules.")]:
+                del sys.modules[k]

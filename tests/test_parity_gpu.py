@@ -180,6 +180,28 @@ def test_full_size_properties_m2_mixer_b_batch_4096():
             assert rel_err(grads[k], gradsf[k]) < 5e-2, k
 
 
+def test_max_and_mean_fusion_match_torch():
+    """MaxFusion = torch.maximum, MeanFusion = torch.mean(torch.stack(args), 0) (reference modules/fusion.py:190-204, 258-272):
+    bit-exact forward, gradients incl. torch's tie rule for maximum."""
+    from m2_mixer_b200 import modules as M
+    torch.manual_seed(1)
+    a = torch.randn(64, 8, 128, device="cuda")
+    b = torch.randn(64, 8, 128, device="cuda")
+    b[:, :2] = a[:, :2]                                   # ties
+    g = torch.randn_like(a)
+    for mine, ref in ((M.MaxFusion(), lambda x, y: torch.maximum(x, y)),
+                      (M.MeanFusion(), lambda x, y: torch.mean(torch.stack((x, y)), 0))):
+        a1, b1 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        a2, b2 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        y1, y2 = mine(a1, b1), ref(a2, b2)
+        assert torch.equal(y1, y2)
+        y1.backward(g); y2.backward(g)
+        assert torch.equal(a1.grad, a2.grad) and torch.equal(b1.grad, b2.grad)
+    c = torch.randn_like(a)
+    y = M.MeanFusion()(a, b, c)
+    assert rel_err(y, torch.mean(torch.stack((a, b, c)), 0)) < 1e-6
+
+
 def test_eval_mode_and_frozen_branch():
     from m2_mixer_b200 import models, presets
     cfg = presets.get("avmnist_S")          # dropout 0.1: identity in eval mode, must run
