@@ -190,6 +190,24 @@ __device__ __forceinline__ void drop_zero2x2(const Drop& d, float& a0, float& a1
   a0 = k0 ? a0 : 0.f; b0 = k0 ? b0 : 0.f;
   a1 = k1 ? a1 : 0.f; b1 = k1 ? b1 : 0.f;
 }
+// The same pair functions for callers that keep the quad's hash input (quad_idx * kDropGolden + drop_key(d)) incrementally
+// in 32-bit registers: `sh` = 0 for the quad's first pair, 16 for its second.
+__device__ __forceinline__ void drop_zero2_hin(const Drop& d, float& v0, float& v1, uint32_t hin, uint32_t sh) {
+  const uint32_t f = drop_flags_from_hash_input(d, hin) >> sh;
+  v0 = (f & 0x80u) ? v0 : 0.f;
+  v1 = (f & 0x8000u) ? v1 : 0.f;
+}
+__device__ __forceinline__ void drop_zero2x2_hin(const Drop& d, float& a0, float& a1, float& b0, float& b1, uint32_t hin, uint32_t sh) {
+  const uint32_t f = drop_flags_from_hash_input(d, hin) >> sh;
+  const bool k0 = f & 0x80u, k1 = f & 0x8000u;
+  a0 = k0 ? a0 : 0.f; b0 = k0 ? b0 : 0.f;
+  a1 = k1 ? a1 : 0.f; b1 = k1 ? b1 : 0.f;
+}
+__device__ __forceinline__ void drop_apply2_hin(const Drop& d, float& v0, float& v1, uint32_t hin, uint32_t sh) {
+  const uint32_t f = drop_flags_from_hash_input(d, hin) >> sh;
+  v0 = (f & 0x80u) ? v0 * d.scale : 0.f;
+  v1 = (f & 0x8000u) ? v1 * d.scale : 0.f;
+}
 // four consecutive elements starting at a multiple of 4 (fp32 values, scale applied)
 __device__ __forceinline__ void drop_apply4(const Drop& d, float4& v, unsigned long long idx4) {
   const uint32_t f = drop_quad_flags(d, static_cast<uint32_t>(idx4) >> 2);

@@ -95,8 +95,17 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
   const float inv_d = 1.f / D;
   const float hs = kDrop ? 0.5f * dh.scale : 0.5f;   // dropout scale folded into the GELU
 
+  // dropout index arithmetic in 32 bits, incrementally: the hash input of the quad that holds (row, d_lo) is
+  //   ((row * D + 16 mt + 2 g) >> 2) * golden + key  =  base(row) + 4 mt * golden,   pair select shift = 16 (g & 1);
+  // rows are (b T + t) for the hidden site and (b N + n) for the output site, t / n = 2 tq + compile-time offsets.
+  constexpr uint32_t kRowG = static_cast<uint32_t>(D / 4) * kDropGolden;       // one row further
+  const uint32_t dsh = (g & 1) * 16;
+  const uint32_t lane_h = static_cast<uint32_t>(g >> 1) * kDropGolden + static_cast<uint32_t>(2 * tq) * kRowG;
+  const uint32_t key_h = kDrop ? drop_key(dh) : 0u, key_o = kDrop ? drop_key(dout) : 0u;
   for (int b = blockIdx.x * kWarps + warp; b < B; b += gridDim.x * kWarps) {
     const float* xb = x + static_cast<long long>(b) * N * D;
+    const uint32_t hin_h = static_cast<uint32_t>(b) * static_cast<uint32_t>(T) * kRowG + lane_h + key_h;   // row b T + 2 tq
+    const uint32_t hin_o = static_cast<uint32_t>(b) * static_cast<uint32_t>(N) * kRowG + lane_h + key_o;   // row b N + 2 tq
     // raw tile: xr[mt][kh][nn] = x[n = 8 kh + 2 tq + nn][d = 16 mt + 2 g .. +1]
     float2 xr[DM][KN][2];
     float s[KN][2];
@@ -158,11 +167,10 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
       for (int j = 0; j < NT1; ++j) {
         float2 lo = gelu2(make_float2(c[j][0], c[j][1]), hs);
         float2 hi = gelu2(make_float2(c[j][2], c[j][3]), hs);
-        if (kDrop) {   // hidden-site index (b T + t) D + d: (d_lo, d_hi) is one hash pair
-          const int t = 8 * j + 2 * tq;
-          const unsigned long long i0 = (static_cast<unsigned long long>(b) * T + t) * D + d_lo;
-          drop_zero2(dh, lo.x, hi.x, i0);   // scale folded into the GELU (hs)
-          drop_zero2(dh, lo.y, hi.y, i0 + D);
+        if (kDrop) {   // hidden-site index (b T + t) D + d, t = 8 j + 2 tq: (d_lo, d_hi) is one hash pair
+          const uint32_t h0 = hin_h + static_cast<uint32_t>(8 * j) * kRowG + static_cast<uint32_t>(4 * mt) * kDropGolden;
+          drop_zero2_hin(dh, lo.x, hi.x, h0, dsh);   // scale folded into the GELU (hs)
+          drop_zero2_hin(dh, lo.y, hi.y, h0 + kRowG, dsh);
         }
         a2f[j >> 1][(j & 1) * 2] = pack_bf16(lo.x, lo.y);
         a2f[j >> 1][(j & 1) * 2 + 1] = pack_bf16(hi.x, hi.y);
@@ -185,7 +193,8 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
           if (n < N) {
             float v_lo = o[jn][nn], v_hi = o[jn][2 + nn];
             const long long off = (static_cast<long long>(b) * N + n) * D + d_lo;
-            if (kDrop) drop_apply2(dout, v_lo, v_hi, static_cast<unsigned long long>(off));
+            if (kDrop)   // output-site index (b N + n) D + d, n = 8 jn + 2 tq + nn
+              drop_apply2_hin(dout, v_lo, v_hi, hin_o + static_cast<uint32_t>(8 * jn + nn) * kRowG + static_cast<uint32_t>(4 * mt) * kDropGolden, dsh);
             *reinterpret_cast<float2*>(u + off) = make_float2(xr[mt][jn][nn].x + v_lo, xr[mt][jn][nn].y + v_hi);
           }
         }
@@ -266,8 +275,15 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
   const float ninv_s = kDrop ? -1.f / dh.scale : -1.f;
   __syncthreads();
 
+  // dropout index arithmetic in 32 bits, incrementally (see the forward kernel)
+  constexpr uint32_t kRowG = static_cast<uint32_t>(D / 4) * kDropGolden;
+  const uint32_t dsh = (g & 1) * 16;
+  const uint32_t lane_h = static_cast<uint32_t>(g >> 1) * kDropGolden + static_cast<uint32_t>(2 * tq) * kRowG;
+  const uint32_t key_h = kDrop ? drop_key(dh) : 0u, key_o = kDrop ? drop_key(dout) : 0u;
   for (int b = blockIdx.x * kW + warp; b < B; b += gridDim.x * kW) {
     const long long sbase = static_cast<long long>(b) * N * D;
+    const uint32_t hin_h = static_cast<uint32_t>(b) * static_cast<uint32_t>(T) * kRowG + lane_h + key_h;   // row b T + 2 tq
+    const uint32_t hin_o = static_cast<uint32_t>(b) * static_cast<uint32_t>(N) * kRowG + lane_h + key_o;   // row b N + 2 tq
     const float* xb = x + sbase;
     const float* dub = du + sbase;
     float2 xr[DM][KN][2];
@@ -316,9 +332,10 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
         a1f[2 * kh + 1] = pack_bf16(v0 ? xh[kh][0].y * gm.y + bt.y : 0.f, v1 ? xh[kh][1].y * gm.y + bt.y : 0.f);
         float2 u0 = v0 ? *reinterpret_cast<const float2*>(dub + n * D + d_lo) : make_float2(0.f, 0.f);
         float2 u1 = v1 ? *reinterpret_cast<const float2*>(dub + (n + 1) * D + d_lo) : make_float2(0.f, 0.f);
-        if (kDrop) {   // gradient of the dropped branch output
-          drop_apply2(dout, u0.x, u0.y, static_cast<unsigned long long>(sbase + n * D + d_lo));
-          drop_apply2(dout, u1.x, u1.y, static_cast<unsigned long long>(sbase + (n + 1) * D + d_lo));
+        if (kDrop) {   // gradient of the dropped branch output: rows b N + n, n = 8 kh + 2 tq (+ 1)
+          const uint32_t h0 = hin_o + static_cast<uint32_t>(8 * kh) * kRowG + static_cast<uint32_t>(4 * mt) * kDropGolden;
+          drop_apply2_hin(dout, u0.x, u0.y, h0, dsh);
+          drop_apply2_hin(dout, u1.x, u1.y, h0 + kRowG, dsh);
         }
         db2a[kh][0] += u0.x + u0.y;
         db2a[kh][1] += u1.x + u1.y;
@@ -343,11 +360,10 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
         float2 g_hi = gelu2_grad(make_float2(c1[j][2], c1[j][3]), dg_hi, hs, ninv_s);
         float2 h_lo = __fmul2_rn(make_float2(c3[j][0], c3[j][1]), dg_lo);
         float2 h_hi = __fmul2_rn(make_float2(c3[j][2], c3[j][3]), dg_hi);
-        if (kDrop) {
-          const int t = 8 * j + 2 * tq;
-          const unsigned long long i0 = (static_cast<unsigned long long>(b) * T + t) * D + d_lo;
-          drop_zero2x2(dh, g_lo.x, g_hi.x, h_lo.x, h_hi.x, i0);   // scale folded into gelu2_grad
-          drop_zero2x2(dh, g_lo.y, g_hi.y, h_lo.y, h_hi.y, i0 + D);
+        if (kDrop) {   // rows b T + t, t = 8 j + 2 tq (+ 1)
+          const uint32_t h0 = hin_h + static_cast<uint32_t>(8 * j) * kRowG + static_cast<uint32_t>(4 * mt) * kDropGolden;
+          drop_zero2x2_hin(dh, g_lo.x, g_hi.x, h_lo.x, h_hi.x, h0, dsh);   // scale folded into gelu2_grad
+          drop_zero2x2_hin(dh, g_lo.y, g_hi.y, h_lo.y, h_hi.y, h0 + kRowG, dsh);
         }
         db1a[j][0] += h_lo.x + h_hi.x;
         db1a[j][1] += h_lo.y + h_hi.y;
