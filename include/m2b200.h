@@ -147,6 +147,12 @@ int m2b200_add(const float* a, const float* b, float* out, int64_t n, void* stre
  * gradient evenly): da = g [a > b] + g/2 [a == b], db = g - da.  The backward of mean is g/2 for both (host side).     */
 int m2b200_fuse2_fwd(const float* a, const float* b, float* out, int64_t n, int mode, void* stream);
 int m2b200_fuse2_max_bwd(const float* a, const float* b, const float* g, float* da, float* db, int64_t n, void* stream);
+/* Gate of BiModalGatedUnit.forward (modules/fusion.py:16-23): out = z tanh(h1) + (1 - z) tanh(h2), z = sigmoid(zh); the three
+ * linears around it are m2b200_linear_fwd/bwd.  Backward: dh1 = g z (1 - tanh(h1)^2), dh2 = g (1 - z)(1 - tanh(h2)^2),
+ * dzh = g (tanh(h1) - tanh(h2)) z (1 - z).                                                                              */
+int m2b200_gate_fwd(const float* h1, const float* h2, const float* zh, float* out, int64_t n, void* stream);
+int m2b200_gate_bwd(const float* h1, const float* h2, const float* zh, const float* g, float* dh1, float* dh2, float* dzh,
+                    int64_t n, void* stream);
 
 /* ---- token mean-pool of a standalone StandardClassifier.forward (modules/classification.py:90):
  *   out[b][d] = mean_n x[b][n][d]; the task modules use the fused heads kernel below instead.                      */

@@ -51,6 +51,8 @@ PROTOTYPES = {
     "m2b200_add": (i32, [vp, vp, vp, i64, vp]),
     "m2b200_fuse2_fwd": (i32, [vp, vp, vp, i64, i32, vp]),
     "m2b200_fuse2_max_bwd": (i32, [vp, vp, vp, vp, vp, i64, vp]),
+    "m2b200_gate_fwd": (i32, [vp, vp, vp, vp, i64, vp]),
+    "m2b200_gate_bwd": (i32, [vp] * 7 + [i64, vp]),
     "m2b200_mean_pool_fwd": (i32, [vp, vp, i32, i32, i32, vp]),
     "m2b200_mean_pool_bwd": (i32, [vp, vp, i32, i32, i32, vp]),
     "m2b200_heads_loss_fwd": (i32, [PP, PI64, PI32, PI32, PP, PP, i32, i32, i32, i32, vp, vp, PF32, vp, vp, vp, vp]),

@@ -463,6 +463,17 @@ int m2b200_fuse2_max_bwd(const float* a, const float* b, const float* g, float* 
   return fuse2_max_bwd(a, b, g, da, db, n, S(stream));
 }
 
+int m2b200_gate_fwd(const float* h1, const float* h2, const float* zh, float* out, int64_t n, void* stream) {
+  if (!h1 || !h2 || !zh || !out) return M2_ERR_ARG;
+  return gate_fwd(h1, h2, zh, out, n, S(stream));
+}
+
+int m2b200_gate_bwd(const float* h1, const float* h2, const float* zh, const float* g, float* dh1, float* dh2, float* dzh,
+                    int64_t n, void* stream) {
+  if (!h1 || !h2 || !zh || !g || !dh1 || !dh2 || !dzh) return M2_ERR_ARG;
+  return gate_bwd(h1, h2, zh, g, dh1, dh2, dzh, n, S(stream));
+}
+
 int m2b200_mean_pool_fwd(const float* x, float* out, int B, int N, int D, void* stream) {
   if (!x || !out) return M2_ERR_ARG;
   return mean_pool_fwd(x, out, B, N, D, S(stream));

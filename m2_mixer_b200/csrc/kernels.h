@@ -77,6 +77,9 @@ int patch_gather(const float* img, void* cols, int out_bf16, int B, int cin, int
 int concat_copy(const float* src, long long src_bstride, float* dst, long long dst_bstride, int B, long long per_batch,
                 int accumulate, cudaStream_t s);
 int add_f32(const float* a, const float* b, float* o, long long n, cudaStream_t s);
+int gate_fwd(const float* h1, const float* h2, const float* zh, float* o, long long n, cudaStream_t s);
+int gate_bwd(const float* h1, const float* h2, const float* zh, const float* g, float* dh1, float* dh2, float* dzh, long long n,
+             cudaStream_t s);
 int fuse2_fwd(const float* a, const float* b, float* o, long long n, int mode, cudaStream_t s);
 int fuse2_max_bwd(const float* a, const float* b, const float* g, float* da, float* db, long long n, cudaStream_t s);
 int relu_bwd(float* dy, const float* y, long long n, cudaStream_t s);

@@ -356,6 +356,30 @@ __global__ void fuse2_max_bwd_kernel(const float* __restrict__ a, const float* _
   }
 }
 
+// Gate of BiModalGatedUnit.forward (reference modules/fusion.py:16-23), exact tanh / sigmoid in fp32:
+//   out = z tanh(h1) + (1 - z) tanh(h2),  z = sigmoid(zh)
+//   dh1 = g z (1 - t1^2)   dh2 = g (1 - z) (1 - t2^2)   dzh = g (t1 - t2) z (1 - z)
+__global__ void gate_fwd_kernel(const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ zh,
+                                float* __restrict__ o, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float z = 1.f / (1.f + expf(-zh[i]));
+    o[i] = z * tanhf(h1[i]) + (1.f - z) * tanhf(h2[i]);
+  }
+}
+__global__ void gate_bwd_kernel(const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ zh,
+                                const float* __restrict__ g, float* __restrict__ dh1, float* __restrict__ dh2,
+                                float* __restrict__ dzh, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float z = 1.f / (1.f + expf(-zh[i]));
+    const float t1 = tanhf(h1[i]), t2 = tanhf(h2[i]), gi = g[i];
+    dh1[i] = gi * z * (1.f - t1 * t1);
+    dh2[i] = gi * (1.f - z) * (1.f - t2 * t2);
+    dzh[i] = gi * (t1 - t2) * z * (1.f - z);
+  }
+}
+
 // pooled[b][d] = mean_n x[b][n][d]   |   dx[b][n][d] = dpooled[b][d] / N
 __global__ void mean_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int N, int D) {
   const long long total = static_cast<long long>(B) * D;
@@ -593,6 +617,23 @@ int fuse2_max_bwd(const float* a, const float* b, const float* g, float* da, flo
   LaunchScope scope("fuse2_max_bwd", s);
   if (n <= 0) return M2_ERR_ARG;
   fuse2_max_bwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(a, b, g, da, db, n);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int gate_fwd(const float* h1, const float* h2, const float* zh, float* o, long long n, cudaStream_t s) {
+  LaunchScope scope("gate_fwd", s);
+  if (n <= 0) return M2_ERR_ARG;
+  gate_fwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(h1, h2, zh, o, n);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int gate_bwd(const float* h1, const float* h2, const float* zh, const float* g, float* dh1, float* dh2, float* dzh, long long n,
+             cudaStream_t s) {
+  LaunchScope scope("gate_bwd", s);
+  if (n <= 0) return M2_ERR_ARG;
+  gate_bwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(h1, h2, zh, g, dh1, dh2, dzh, n);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }

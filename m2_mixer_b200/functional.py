@@ -193,6 +193,20 @@ class _Fuse2(Function):
         return h, h, None
 
 
+class _Gate(Function):
+    """z tanh(h1) + (1 - z) tanh(h2), z = sigmoid(zh): the gate of BiModalGatedUnit (reference modules/fusion.py:16-23)."""
+
+    @staticmethod
+    def forward(ctx, h1, h2, zh):
+        ctx.save_for_backward(h1, h2, zh)
+        return _O.gate_fwd(h1, h2, zh)
+
+    @staticmethod
+    def backward(ctx, g):
+        h1, h2, zh = ctx.saved_tensors
+        return _O.gate_bwd(h1, h2, zh, g.contiguous())
+
+
 class _MeanPool(Function):
     @staticmethod
     def forward(ctx, x):
@@ -374,6 +388,10 @@ def mean_pool(x) -> torch.Tensor:
 
 def concat_tokens(*xs) -> torch.Tensor:
     return _Concat.apply(*xs)
+
+
+def gate(h1, h2, zh) -> torch.Tensor:
+    return _Gate.apply(h1, h2, zh)
 
 
 def fuse_max(a, b) -> torch.Tensor:

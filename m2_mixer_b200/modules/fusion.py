@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import torch
+from torch import nn
 
 from .. import functional as F
 
@@ -89,3 +90,34 @@ class MeanFusion:
     @staticmethod
     def get_output_shape(*args, dim=None, **kwargs):
         return _same_shape(args, dim)
+
+
+class BiModalGatedUnit(nn.Module):
+    """Gated fusion of two modalities (reference modules/fusion.py:7-55): ``z * tanh(W1 m1) + (1 - z) * tanh(W2 m2)`` with
+    ``z = sigmoid(Wz [m1, m2])``.  Same parameters (``mod1_hidden``, ``mod2_hidden``, ``z_hidden``) and
+    ``get_output_shape`` contract; the three linears run through ``m2b200_linear_*``, the gate is one kernel each way."""
+
+    def __init__(self, mod1_in, mod2_in, out_size, **kwargs):
+        super().__init__()
+        self.out_size = out_size
+        self.mod1_hidden = nn.Linear(mod1_in, out_size)
+        self.mod2_hidden = nn.Linear(mod2_in, out_size)
+        self.z_hidden = nn.Linear(mod1_in + mod2_in, out_size)
+        self.precision = "fp32"    # exact by default (the gate saturates quickly); "bf16" runs the linears on tcgen05
+
+    def forward(self, mod1, mod2):
+        h1 = F.linear(mod1, self.mod1_hidden.weight, self.mod1_hidden.bias, 0, self.precision)
+        h2 = F.linear(mod2, self.mod2_hidden.weight, self.mod2_hidden.bias, 0, self.precision)
+        zh = F.linear(torch.cat([mod1, mod2], dim=-1), self.z_hidden.weight, self.z_hidden.bias, 0, self.precision)
+        return F.gate(h1, h2, zh)
+
+    def get_output_shape(self, *args, dim=None):
+        if dim is not None:
+            if not isinstance(args[0], int):
+                raise ValueError("The dim argument is only used if the first argument is an int.")
+            if dim == -1:
+                return self.out_size
+            return args[0]
+        shape1 = list(args[0])
+        shape1[-1] = self.out_size
+        return tuple(shape1)

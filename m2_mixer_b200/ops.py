@@ -374,6 +374,25 @@ def fuse2_max_bwd(a, b, g):
     return da, db
 
 
+def gate_fwd(h1, h2, zh):
+    h1, h2, zh = _f32c(h1, "h1"), _f32c(h2, "h2"), _f32c(zh, "zh")
+    if not (h1.shape == h2.shape == zh.shape):
+        raise RuntimeError("m2b200::gate_fwd expects equal shapes")
+    out = torch.empty_like(h1)
+    check(_L().m2b200_gate_fwd(h1.data_ptr(), h2.data_ptr(), zh.data_ptr(), out.data_ptr(), h1.numel(), _stream()), "gate_fwd")
+    return out
+
+
+def gate_bwd(h1, h2, zh, g):
+    h1, h2, zh, g = _f32c(h1, "h1"), _f32c(h2, "h2"), _f32c(zh, "zh"), _f32c(g, "g")
+    d1, d2, dz = torch.empty_like(h1), torch.empty_like(h1), torch.empty_like(h1)
+    check(_L().m2b200_gate_bwd(h1.data_ptr(), h2.data_ptr(), zh.data_ptr(), g.data_ptr(), d1.data_ptr(), d2.data_ptr(),
+                               dz.data_ptr(), h1.numel(), _stream()), "gate_bwd")
+    return d1, d2, dz
+
+
+_define("gate_fwd", "(Tensor h1, Tensor h2, Tensor zh) -> Tensor", gate_fwd)
+_define("gate_bwd", "(Tensor h1, Tensor h2, Tensor zh, Tensor g) -> (Tensor, Tensor, Tensor)", gate_bwd)
 _define("fuse2_fwd", "(Tensor a, Tensor b, int mode) -> Tensor", fuse2_fwd)
 _define("fuse2_max_bwd", "(Tensor a, Tensor b, Tensor g) -> (Tensor, Tensor)", fuse2_max_bwd)
 

@@ -202,6 +202,35 @@ def test_max_and_mean_fusion_match_torch():
     assert rel_err(y, torch.mean(torch.stack((a, b, c)), 0)) < 1e-6
 
 
+def test_bimodal_gated_unit_matches_reference_formula():
+    """BiModalGatedUnit (reference modules/fusion.py:7-23): same state-dict names, forward and every gradient equal to the
+    reference arithmetic (torch, fp64) to fp32 accuracy."""
+    from m2_mixer_b200 import modules as M
+    torch.manual_seed(2)
+    g = M.BiModalGatedUnit(48, 80, 64).cuda()
+    assert sorted(g.state_dict()) == sorted(["mod1_hidden.weight", "mod1_hidden.bias", "mod2_hidden.weight", "mod2_hidden.bias",
+                                             "z_hidden.weight", "z_hidden.bias"])
+    assert g.get_output_shape((4, 49, 48), (4, 49, 80)) == (4, 49, 64) and g.get_output_shape(49, dim=1) == 49
+    assert g.get_output_shape(48, dim=-1) == 64
+    m1 = torch.randn(32, 49, 48, device="cuda", requires_grad=True)
+    m2 = torch.randn(32, 49, 80, device="cuda", requires_grad=True)
+    dy = torch.randn(32, 49, 64, device="cuda")
+    y = g(m1, m2)
+    y.backward(dy)
+    sd = {k: v.detach().double().requires_grad_(True) for k, v in g.state_dict().items()}
+    a, b = m1.detach().double().requires_grad_(True), m2.detach().double().requires_grad_(True)
+    lin = torch.nn.functional.linear
+    h1 = torch.tanh(lin(a, sd["mod1_hidden.weight"], sd["mod1_hidden.bias"]))
+    h2 = torch.tanh(lin(b, sd["mod2_hidden.weight"], sd["mod2_hidden.bias"]))
+    z = torch.sigmoid(lin(torch.cat([a, b], dim=-1), sd["z_hidden.weight"], sd["z_hidden.bias"]))
+    yr = z * h1 + (1 - z) * h2
+    yr.backward(dy.double())
+    assert rel_err(y, yr) < 1e-5
+    assert rel_err(m1.grad, a.grad) < 1e-5 and rel_err(m2.grad, b.grad) < 1e-5
+    for k, p in g.named_parameters():
+        assert rel_err(p.grad, sd[k].grad) < 1e-5, k
+
+
 def test_eval_mode_and_frozen_branch():
     from m2_mixer_b200 import models, presets
     cfg = presets.get("avmnist_S")          # dropout 0.1: identity in eval mode, must run
