@@ -81,11 +81,15 @@ void m2b200_set_dropout_epoch_ptr(const void* dev_u32);
 int m2b200_dropout_epoch_advance(void* dev_u32, void* stream);
 
 /* ---- MixerBlock.token_mix + residual: modules/mixer.py:30-35,43
- *   u[b] = x[b] + Wt2 . GELU(Wt1 . LN(x[b]) + bt1) + bt2,   x,u [B][N][D], wt1 [T][N], wt2 [N][T]            */
+ *   u[b] = x[b] + Wt2 . GELU(Wt1 . LN(x[b]) + bt1) + bt2,   x,u [B][N][D], wt1 [T][N], wt2 [N][T]
+ * Three implementations behind the same call: register-tile mma.sync kernels (N <= 16, T <= 32, bf16), batched tcgen05
+ * GEMMs with the sample tile as the MN-major operand (bf16, N * T >= 2048: MM-IMDB-shaped / Scaled configs; exact erf GELU)
+ * and CUDA-core kernels (everything else, and the fp32 parity mode).  The workspace queries return 0 where none is needed. */
+size_t m2b200_token_mix_fwd_workspace_bytes(int B, int N, int D, int T, int precision);
 int m2b200_token_mix_fwd(const float* x, const float* ln_w, const float* ln_b, const float* wt1, const float* bt1,
                          const float* wt2, const float* bt2, float* u, int B, int N, int D, int T, int precision,
-                         float dropout_p, uint64_t seed, void* stream);
-size_t m2b200_token_mix_bwd_workspace_bytes(int B, int N, int D, int T);
+                         float dropout_p, uint64_t seed, void* workspace, size_t workspace_bytes, void* stream);
+size_t m2b200_token_mix_bwd_workspace_bytes(int B, int N, int D, int T, int precision);
 int m2b200_token_mix_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* wt1,
                          const float* bt1, const float* wt2, float* dx, float* dln_w, float* dln_b, float* dwt1,
                          float* dbt1, float* dwt2, float* dbt2, int B, int N, int D, int T, int precision, float dropout_p,

@@ -28,8 +28,9 @@ PROTOTYPES = {
     "m2b200_cast_bf16_multi": (i32, [vp, i32, vp]),
     "m2b200_gemm": (i32, [i32, vp, i32, i64, vp, i32, i64, i32, i32, i32, i32, i64, i64, vp, i32, i32, vp, i64, i64, vp,
                           i32, i64, i64, i32, i32, vp]),
-    "m2b200_token_mix_fwd": (i32, [vp] * 8 + [i32] * 5 + [f32, u64, vp]),
-    "m2b200_token_mix_bwd_workspace_bytes": (sz, [i32] * 4),
+    "m2b200_token_mix_fwd_workspace_bytes": (sz, [i32] * 5),
+    "m2b200_token_mix_fwd": (i32, [vp] * 8 + [i32] * 5 + [f32, u64, vp, sz, vp]),
+    "m2b200_token_mix_bwd_workspace_bytes": (sz, [i32] * 5),
     "m2b200_token_mix_bwd": (i32, [vp] * 14 + [i32] * 5 + [f32, u64, vp, sz, vp]),
     "m2b200_channel_mix_workspace_bytes": (sz, [i32] * 5),
     "m2b200_channel_mix_fwd": (i32, [vp] * 9 + [i32, vp] + [i32] * 4 + [f32, u64, vp, sz, vp]),

@@ -97,17 +97,151 @@ int m2b200_gemm(int precision, const void* A, int a_mn, int64_t lda, const void*
   return precision == M2B200_FP32 ? gemm_f32_simt(g, S(stream)) : gemm_bf16_umma(g, S(stream));
 }
 
+}  // extern "C"
+
 // ------------------------------------------------------------------------------------------ token mixing
+namespace {
+
+// Token mixing for contraction lengths the register-tile kernels do not cover (MM-IMDB-shaped and Scaled configs: N = 196..708
+// tokens, T = 16..512): LayerNorm -> bf16, then the two contractions as BATCHED tcgen05 GEMMs with the activation tile
+// [N x D] of a sample as the MN-major B operand in its native row-major layout (no permute) and the weights as
+// the shared A operand; exact erf GELU in the first GEMM's epilogue, bias per output row, residual in the second's.
+// The backward recomputes LN and H, and reduces the per-sample weight-gradient GEMMs into ONE gradient with atomics
+// (c_batch_stride = 0).  On the CUDA-core fallback these shapes took 350-430 ms per step (profiles/r01_large_configs.json).
+bool token_mix_gemm_path(int precision, int N, int D, int T) {
+  if (precision == M2B200_FP32 || token_mix_mma_supported(N, D, T)) return false;
+  return D % 8 == 0 && static_cast<long long>(N) * T >= 2048;
+}
+
+struct TokWs {
+  __nv_bfloat16 *xn_b, *w1b, *w2b, *g_b, *du_b, *dh_b;
+  float *f1, *f2, *dxn;
+};
+size_t token_mix_gemm_ws(int B, int N, int D, int T, bool backward, TokWs* out, void* base, size_t bytes, bool* ok) {
+  Carver ws(base, bytes);
+  const size_t bn = static_cast<size_t>(B) * N * D, bt = static_cast<size_t>(B) * T * D;
+  TokWs w = {};
+  w.xn_b = ws.take<__nv_bfloat16>(bn);
+  w.w1b = ws.take<__nv_bfloat16>(static_cast<size_t>(T) * up8(N));
+  w.w2b = ws.take<__nv_bfloat16>(static_cast<size_t>(N) * up8(T));
+  w.g_b = ws.take<__nv_bfloat16>(bt);
+  w.f1 = ws.take<float>(bt);          // fwd: GELU output before the mask (dropout only) | bwd: H pre-activation
+  if (backward) {
+    w.f2 = ws.take<float>(bt);        // dG
+    w.du_b = ws.take<__nv_bfloat16>(bn);
+    w.dh_b = ws.take<__nv_bfloat16>(bt);
+    w.dxn = ws.take<float>(bn);
+  } else {
+    w.f2 = ws.take<float>(bn);        // branch output before the mask (dropout only)
+  }
+  if (out) *out = w;
+  if (ok) *ok = ws.ok;
+  return ws.off;
+}
+size_t token_mix_gemm_ws_bytes(int B, int N, int D, int T, bool backward) {
+  // dry run over a fake base: Carver only does arithmetic
+  Carver ws(reinterpret_cast<void*>(256), ~size_t(0) >> 1);
+  const size_t bn = static_cast<size_t>(B) * N * D, bt = static_cast<size_t>(B) * T * D;
+  ws.take<__nv_bfloat16>(bn); ws.take<__nv_bfloat16>(static_cast<size_t>(T) * up8(N)); ws.take<__nv_bfloat16>(static_cast<size_t>(N) * up8(T));
+  ws.take<__nv_bfloat16>(bt); ws.take<float>(bt);
+  if (backward) { ws.take<float>(bt); ws.take<__nv_bfloat16>(bn); ws.take<__nv_bfloat16>(bt); ws.take<float>(bn); }
+  else ws.take<float>(bn);
+  return ws.off;
+}
+
+int token_mix_gemm_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1, const float* w2,
+                       const float* b2, float* u, int B, int N, int D, int T, float p, uint64_t seed, void* workspace,
+                       size_t workspace_bytes, cudaStream_t s) {
+  TokWs w; bool ok;
+  token_mix_gemm_ws(B, N, D, T, false, &w, workspace, workspace_bytes, &ok);
+  if (!ok) return M2_ERR_WORKSPACE;
+  const int n8 = up8(N), t8 = up8(T);
+  const bool drop = p > 0.f;
+  M2_TRY(ln_fwd(x, ln_w, ln_b, w.xn_b, 1, B * N, D, B * N, 0, nullptr, nullptr, s));
+  M2_TRY(cast_pad_bf16(w1, N, w.w1b, n8, T, N, s));
+  M2_TRY(cast_pad_bf16(w2, T, w.w2b, t8, N, T, s));
+  // G_b [T x D] = GELU(W1 [T x N] . Xn_b [N x D] + b1 1^T)
+  GemmArgs g1 = gemm_args(w.w1b, 0, n8, w.xn_b, 1, D, T, D, N, drop ? static_cast<void*>(w.f1) : static_cast<void*>(w.g_b), drop ? 0 : 1, D);
+  g1.batch = B; g1.a_batch_rows = 0; g1.b_batch_rows = N; g1.c_batch_stride = static_cast<long long>(T) * D;
+  g1.bias = b1; g1.bias_mode = 2; g1.act = M2B200_ACT_GELU;
+  M2_TRY(gemm_bf16_umma(g1, s));
+  if (drop) M2_TRY(mask_scale(w.f1, D, w.g_b, 1, D, B * T, D, p, seed, kSiteTokenHidden, D, s));
+  // u_b [N x D] = x_b + Drop(W2 [N x T] . G_b [T x D] + b2 1^T)
+  GemmArgs g2 = gemm_args(w.w2b, 0, t8, w.g_b, 1, D, N, D, T, drop ? static_cast<void*>(w.f2) : static_cast<void*>(u), 0, D);
+  g2.batch = B; g2.a_batch_rows = 0; g2.b_batch_rows = T; g2.c_batch_stride = static_cast<long long>(N) * D;
+  g2.bias = b2; g2.bias_mode = 2;
+  if (!drop) { g2.residual = x; g2.ldr = D; g2.r_batch_stride = static_cast<long long>(N) * D; }
+  M2_TRY(gemm_bf16_umma(g2, s));
+  if (drop) {
+    M2_TRY(mask_scale(w.f2, D, w.f2, 0, D, B * N, D, p, seed, kSiteTokenOut, D, s));
+    M2_TRY(add_f32(x, w.f2, u, static_cast<long long>(B) * N * D, s));
+  }
+  return M2_OK;
+}
+
+int token_mix_gemm_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
+                       const float* w2, float* dx, float* dln_w, float* dln_b, float* dw1, float* db1, float* dw2, float* db2,
+                       int B, int N, int D, int T, float p, uint64_t seed, void* workspace, size_t workspace_bytes,
+                       cudaStream_t s) {
+  TokWs w; bool ok;
+  token_mix_gemm_ws(B, N, D, T, true, &w, workspace, workspace_bytes, &ok);
+  if (!ok) return M2_ERR_WORKSPACE;
+  const int n8 = up8(N), t8 = up8(T);
+  const long long nd = static_cast<long long>(N) * D, td = static_cast<long long>(T) * D;
+  M2_TRY(ln_fwd(x, ln_w, ln_b, w.xn_b, 1, B * N, D, B * N, 0, nullptr, nullptr, s));
+  M2_TRY(cast_pad_bf16(w1, N, w.w1b, n8, T, N, s));
+  M2_TRY(cast_pad_bf16(w2, T, w.w2b, t8, N, T, s));
+  // gradient of the dropped branch output (mask + scale), as the bf16 GEMM operand
+  if (p > 0.f) M2_TRY(mask_scale(du, D, w.du_b, 1, D, B * N, D, p, seed, kSiteTokenOut, D, s));
+  else M2_TRY(cast_pad_bf16(du, D, w.du_b, D, B * N, D, s));
+  // recompute H_b = W1 . Xn_b + b1 (pre-activation, fp32)
+  GemmArgs gh = gemm_args(w.w1b, 0, n8, w.xn_b, 1, D, T, D, N, w.f1, 0, D);
+  gh.batch = B; gh.b_batch_rows = N; gh.c_batch_stride = td; gh.bias = b1; gh.bias_mode = 2;
+  M2_TRY(gemm_bf16_umma(gh, s));
+  // dG_b [T x D] = W2^T [T x N] . dU_b [N x D]      (A = W2 [N][T] consumed MN-major)
+  GemmArgs gg = gemm_args(w.w2b, 1, t8, w.du_b, 1, D, T, D, N, w.f2, 0, D);
+  gg.batch = B; gg.b_batch_rows = N; gg.c_batch_stride = td;
+  M2_TRY(gemm_bf16_umma(gg, s));
+  // G = Drop(GELU(H)), dH = dG * Drop'(.) * GELU'(H)
+  M2_TRY(gelu_fwd_bwd(w.f1, w.f2, B * T, D, D, w.g_b, w.dh_b, D, 1, p, seed, kSiteTokenHidden, D, s));
+  // dW2 [N x T] += sum_b dU_b [N x D] . G_b^T [D x T] ;  dW1 [T x N] += sum_b dH_b [T x D] . Xn_b^T [D x N]
+  GemmArgs gw2 = gemm_args(w.du_b, 0, D, w.g_b, 0, D, N, T, D, dw2, 0, T);
+  gw2.batch = B; gw2.a_batch_rows = N; gw2.b_batch_rows = T; gw2.c_batch_stride = 0; gw2.atomic_out = 1;
+  M2_TRY(gemm_bf16_umma(gw2, s));
+  GemmArgs gw1 = gemm_args(w.dh_b, 0, D, w.xn_b, 0, D, T, N, D, dw1, 0, N);
+  gw1.batch = B; gw1.a_batch_rows = T; gw1.b_batch_rows = N; gw1.c_batch_stride = 0; gw1.atomic_out = 1;
+  M2_TRY(gemm_bf16_umma(gw1, s));
+  M2_TRY(rowsum_mod_bf16(w.dh_b, D, B * T, D, T, db1, s));
+  M2_TRY(rowsum_mod_bf16(w.du_b, D, B * N, D, N, db2, s));
+  // dXn_b [N x D] = W1^T [N x T] . dH_b [T x D]     (A = W1 [T][N] consumed MN-major)
+  GemmArgs gx = gemm_args(w.w1b, 1, n8, w.dh_b, 1, D, N, D, T, w.dxn, 0, D);
+  gx.batch = B; gx.b_batch_rows = T; gx.c_batch_stride = nd;
+  M2_TRY(gemm_bf16_umma(gx, s));
+  // dx = du (residual) + LayerNorm'(dxn);  dln_w / dln_b accumulate
+  return ln_bwd(w.dxn, nd, N, x, ln_w, du, dx, dln_w, dln_b, B * N, D, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t m2b200_token_mix_fwd_workspace_bytes(int B, int N, int D, int T, int precision) {
+  return token_mix_gemm_path(precision, N, D, T) ? token_mix_gemm_ws_bytes(B, N, D, T, false) : 0;
+}
+
 int m2b200_token_mix_fwd(const float* x, const float* ln_w, const float* ln_b, const float* wt1, const float* bt1,
                          const float* wt2, const float* bt2, float* u, int B, int N, int D, int T, int precision,
-                         float dropout_p, uint64_t seed, void* stream) {
+                         float dropout_p, uint64_t seed, void* workspace, size_t workspace_bytes, void* stream) {
   if (!x || !ln_w || !ln_b || !wt1 || !bt1 || !wt2 || !bt2 || !u) return M2_ERR_ARG;
   if (dropout_p < 0.f || dropout_p >= 1.f) return M2_ERR_ARG;
+  if (token_mix_gemm_path(precision, N, D, T))
+    return token_mix_gemm_fwd(x, ln_w, ln_b, wt1, bt1, wt2, bt2, u, B, N, D, T, dropout_p, seed, workspace, workspace_bytes,
+                              S(stream));
   return token_mix_fwd(x, ln_w, ln_b, wt1, bt1, wt2, bt2, u, B, N, D, T, precision == M2B200_FP32, dropout_p, seed, S(stream));
 }
 
-size_t m2b200_token_mix_bwd_workspace_bytes(int B, int N, int D, int T) {
-  (void)T;
+size_t m2b200_token_mix_bwd_workspace_bytes(int B, int N, int D, int T, int precision) {
+  if (token_mix_gemm_path(precision, N, D, T)) return token_mix_gemm_ws_bytes(B, N, D, T, true);
   return up256(static_cast<size_t>(B) * N * D * sizeof(float));
 }
 
@@ -117,6 +251,10 @@ int m2b200_token_mix_bwd(const float* du, const float* x, const float* ln_w, con
                          uint64_t seed, void* workspace, size_t workspace_bytes, void* stream) {
   if (!du || !x || !ln_w || !ln_b || !wt1 || !bt1 || !wt2 || !dx || !dln_w || !dln_b || !dwt1 || !dbt1 || !dwt2 || !dbt2)
     return M2_ERR_ARG;
+  if (dropout_p < 0.f || dropout_p >= 1.f) return M2_ERR_ARG;
+  if (token_mix_gemm_path(precision, N, D, T))
+    return token_mix_gemm_bwd(du, x, ln_w, ln_b, wt1, bt1, wt2, dx, dln_w, dln_b, dwt1, dbt1, dwt2, dbt2, B, N, D, T, dropout_p,
+                              seed, workspace, workspace_bytes, S(stream));
   if (precision != M2B200_FP32 && token_generation() != 1 && token_mix_mma_supported(N, D, T))   // LN backward fused in
     return token_mix_mma_bwd(du, x, ln_w, ln_b, wt1, bt1, wt2, dx, dln_w, dln_b, dwt1, dbt1, dwt2, dbt2, B, N, D, T, dropout_p,
                              seed, S(stream));

@@ -22,6 +22,7 @@ struct GemmArgs {
   const float* residual; long long ldr; long long r_batch_stride;
   void* C; int c_bf16; long long ldc; long long c_batch_stride;
   int accumulate; int splitk;
+  int atomic_out;   // fp32 C only: reduce into C with atomics even without split-K (batches that share one C: c_batch_stride = 0)
   // optional dropout applied after `act` and before `residual`; element index = m * drop_ld + n (batch ignored)
   float drop_p; unsigned long long drop_seed; int drop_site; long long drop_ld;
 };
@@ -65,6 +66,8 @@ int ln_bwd(const float* dy, long long dy_bstride, int N, const float* x, const f
            float* dw, float* db, int rows, int D, cudaStream_t s);
 int colsum_f32(const float* src, long long ld, int rows, int cols, float* out, cudaStream_t s);
 int colsum_bf16(const void* src, long long ld, int rows, int cols, float* out, cudaStream_t s);
+// out[r % period] += sum_c src[r][c]   (bf16 rows; bias gradients of the GEMM-composed token mixing)
+int rowsum_mod_bf16(const void* src, long long ld, int rows, int cols, int period, float* out, cudaStream_t s);
 int gelu_fwd_bwd(const float* h, const float* dg, int rows, int cols, long long ld_in, void* g_out, void* dh_out,
                  long long ld_out, int out_bf16, float drop_p, unsigned long long seed, int site, long long drop_ld,
                  cudaStream_t s);

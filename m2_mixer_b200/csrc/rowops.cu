@@ -248,6 +248,26 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, 
 }
 
 // ------------------------------------------------------------------------------------------ GELU fwd+bwd (unfused path)
+// out[r % period] += sum_c src[r][c]: warp per row, per-CTA shared-memory partials (period <= 1024), one atomic per slot.
+__global__ void __launch_bounds__(256) rowsum_mod_bf16_kernel(const __nv_bfloat16* __restrict__ src, long long ld, int rows,
+                                                              int cols, int period, float* __restrict__ out) {
+  extern __shared__ float part[];   // [period]
+  for (int i = threadIdx.x; i < period; i += blockDim.x) part[i] = 0.f;
+  __syncthreads();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    const __nv_bfloat16* p = src + static_cast<long long>(r) * ld;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += __bfloat162float(p[c]);
+    s = warp_sum(s);
+    if (lane == 0) atomicAdd(&part[r % period], s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < period; i += blockDim.x)
+    if (part[i] != 0.f) atomicAdd(&out[i], part[i]);
+}
+
 // h = pre-activation (bias already added). g_out = gelu(h) ; dh = dg * gelu'(h)  (dh may alias dg)
 template <typename TO>
 __global__ void gelu_fwd_bwd_kernel(const float* __restrict__ h, const float* dg, long long n, int cols,
@@ -634,6 +654,16 @@ int gate_bwd(const float* h1, const float* h2, const float* zh, const float* g, 
   LaunchScope scope("gate_bwd", s);
   if (n <= 0) return M2_ERR_ARG;
   gate_bwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(h1, h2, zh, g, dh1, dh2, dzh, n);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+int rowsum_mod_bf16(const void* src, long long ld, int rows, int cols, int period, float* out, cudaStream_t s) {
+  LaunchScope scope("rowsum_mod_bf16", s);
+  if (rows <= 0 || cols <= 0 || period <= 0 || period > 4096) return M2_ERR_ARG;
+  int grid = grid_for(static_cast<long long>(rows) * 32, 256);
+  if (grid > kNumSms * 4) grid = kNumSms * 4;
+  rowsum_mod_bf16_kernel<<<grid, 256, period * sizeof(float), s>>>(static_cast<const __nv_bfloat16*>(src), ld, rows, cols, period, out);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }

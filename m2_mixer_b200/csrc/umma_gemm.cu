@@ -31,6 +31,7 @@ struct GemmDev {
   const float* residual; long long ldr, r_batch_stride;
   void* C; int c_bf16; long long ldc, c_batch_stride;
   int accumulate;
+  int atomic;
   Drop drop; long long drop_ld;
 };
 
@@ -170,7 +171,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       } else {
         float* c = reinterpret_cast<float*>(p.C) + coff + n0 + c0;
-        if (p.splitk > 1) {
+        if (p.splitk > 1 || p.atomic) {
           if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)   // 128-bit reductions (red.global.add.v4.f32)
@@ -221,6 +222,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, dim3 
 int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
   if (!g.A || !g.B || !g.C || g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batch <= 0) return M2_ERR_ARG;
   if (g.splitk < 1 || (g.splitk > 1 && (g.c_bf16 || g.act))) return M2_ERR_ARG;
+  if (g.atomic_out && (g.c_bf16 || g.act || g.bias_mode || g.residual)) return M2_ERR_ARG;
   if (g.bias_mode && !g.bias) return M2_ERR_ARG;
   CUtensorMap ta, tb;
   int rc;
@@ -247,6 +249,7 @@ int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
   d.residual = g.residual; d.ldr = g.ldr; d.r_batch_stride = g.r_batch_stride;
   d.C = g.C; d.c_bf16 = g.c_bf16; d.ldc = g.ldc; d.c_batch_stride = g.c_batch_stride;
   d.accumulate = g.accumulate;
+  d.atomic = (g.atomic_out && !g.c_bf16) ? 1 : 0;
   d.drop = make_drop(g.drop_p, g.drop_seed, g.drop_site); d.drop_ld = g.drop_ld;
   dim3 grid(ceil_div(g.M, kBM), ceil_div(g.N, kBN), g.batch * d.splitk);
   if (grid.y > 65535 || grid.z > 65535) return M2_ERR_ARG;

@@ -87,10 +87,12 @@ def token_mix_fwd(x, ln_w, ln_b, w1, b1, w2, b2, precision: int, dropout_p: floa
     B, N, D = x.shape
     T = w1.shape[0]
     u = torch.empty_like(x)
+    nbytes = _L().m2b200_token_mix_fwd_workspace_bytes(B, N, D, T, precision)
+    ws, wsp = _ws(nbytes, x)
     check(_L().m2b200_token_mix_fwd(x.data_ptr(), _f32c(ln_w, "ln_w").data_ptr(), _f32c(ln_b, "ln_b").data_ptr(),
                                     _f32c(w1, "w1").data_ptr(), _f32c(b1, "b1").data_ptr(), _f32c(w2, "w2").data_ptr(),
                                     _f32c(b2, "b2").data_ptr(), u.data_ptr(), B, N, D, T, precision, dropout_p, seed,
-                                    _stream()),
+                                    wsp, nbytes, _stream()),
           "token_mix_fwd")
     return u
 
@@ -102,7 +104,7 @@ def token_mix_bwd(du, x, ln_w, ln_b, w1, b1, w2, precision: int, dropout_p: floa
     dx = torch.empty_like(x)
     dln_w, dln_b, dw1, db1, dw2 = (_grad_dst(grads, i, t) for i, t in enumerate((ln_w, ln_b, w1, b1, w2)))
     db2 = _grad_dst(grads, 5, w2[:, 0])
-    nbytes = _L().m2b200_token_mix_bwd_workspace_bytes(B, N, D, T)
+    nbytes = _L().m2b200_token_mix_bwd_workspace_bytes(B, N, D, T, precision)
     ws, wsp = _ws(nbytes, x)
     check(_L().m2b200_token_mix_bwd(du.data_ptr(), x.data_ptr(), _f32c(ln_w, "ln_w").data_ptr(),
                                     _f32c(ln_b, "ln_b").data_ptr(), _f32c(w1, "w1").data_ptr(), _f32c(b1, "b1").data_ptr(),

@@ -77,6 +77,24 @@ MMIMDB_TINY = mmimdb(
      "num_mixers": 1})
 
 
+# C5: SURVEY 8(d) "Scaled M2-Mixer" (Mixer-B/16-width blocks x 12 per modality, 178.6 M parameters): two 3 x 224 x 224
+# encoders through the AV-MNIST task module (dict keys 'image' / 'audio'), CE multi-head loss, K = 10.
+def _scaled_encoder():
+    return {"block_type": "MLPMixer", "in_channels": 3, "hidden_dim": 768, "patch_size": 16, "image_size": [224, 224],
+            "token_dim": 384, "channel_dim": 3072, "num_mixers": 12}
+
+
+SCALED_C5 = {
+    "type": "AVMnistMixerMultiLoss", "dropout": 0.0,
+    "modalities": {
+        "classification": {"num_classes": 10, "classifier": "StandardClassifier", "input_shape": [16, 392, 768]},
+        "image": _scaled_encoder(), "audio": _scaled_encoder(),
+        "multimodal": {"block_type": "FusionMixer", "fusion_function": "ConcatFusion", "hidden_dim": 768, "token_dim": 384,
+                       "channel_dim": 3072, "num_mixers": 12},
+    },
+}
+
+
 def get(name: str) -> dict:
     return copy.deepcopy({"avmnist_S": AVMNIST_S, "avmnist_M": AVMNIST_M, "avmnist_B": AVMNIST_B, "mimic_H": MIMIC_H, "mmimdb_C4": MMIMDB_C4,
-                          "mmimdb_tiny": MMIMDB_TINY}[name])
+                          "mmimdb_tiny": MMIMDB_TINY, "scaled_C5": SCALED_C5}[name])

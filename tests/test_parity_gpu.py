@@ -351,10 +351,12 @@ def test_channel_mix_dropout_matches_oracle_with_exported_mask(precision, tol, M
 
 
 @pytest.mark.parametrize("precision,B,N,D,T", [("fp32", 9, 4, 128, 32), ("fp32", 3, 40, 48, 16),
-                                               ("bf16", 37, 4, 128, 32), ("bf16", 19, 8, 64, 16), ("bf16", 5, 12, 64, 32)])
+                                               ("bf16", 37, 4, 128, 32), ("bf16", 19, 8, 64, 16), ("bf16", 5, 12, 64, 32),
+                                               ("bf16", 5, 196, 256, 16), ("bf16", 3, 72, 128, 200), ("bf16", 2, 130, 64, 48)])
 def test_token_mix_dropout_matches_oracle_with_exported_mask(precision, B, N, D, T):
     """fp32: CUDA-core kernels; bf16: the warp-level tensor-core kernels (token_mix_mma.cu), whose lanes own column PAIRS and
-    regenerate the hidden-site and output-site masks from the same (b, t / n, d) element indices."""
+    regenerate the hidden-site and output-site masks from the same (b, t / n, d) element indices; bf16 with N * T >= 2048:
+    the batched tcgen05 GEMM composition (ragged N / T tiles, weight gradients reduced over the batch with atomics)."""
     from m2_mixer_b200 import functional as F, ops
     from oracle import m2mixer_oracle as O
     torch.manual_seed(1)
