@@ -5,7 +5,7 @@ import sys
 from .mixer import (FeedForward, FusionMixer, MixerBlock, MLPMixer, MLPMixerNoPatching, PNLPMixer,  # noqa: F401
                     get_default_precision, set_default_precision)
 from .fusion import BiModalGatedUnit, ConcatFusion, MaxFusion, MeanFusion, SumFusion  # noqa: F401
-from .classification import StandardClassifier  # noqa: F401
+from .classification import BasicClassifier, MultilayerClassifier, StandardClassifier  # noqa: F401
 from .mlp import MLP  # noqa: F401
 
 

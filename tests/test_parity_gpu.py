@@ -231,6 +231,33 @@ def test_bimodal_gated_unit_matches_reference_formula():
         assert rel_err(p.grad, sd[k].grad) < 1e-5, k
 
 
+def test_basic_and_multilayer_classifiers_match_reference():
+    """BasicClassifier / MultilayerClassifier (reference modules/classification.py:33-47, 69-82): identical state-dict keys,
+    outputs and gradients vs the same Linear / ReLU chain in torch fp64 (note: no ReLU after the first Linear)."""
+    from m2_mixer_b200 import modules as M
+    torch.manual_seed(4)
+    for cls, attr, shape in ((M.BasicClassifier, "classifier", (16, 128)), (M.MultilayerClassifier, "classifer", (16, 3, 5, 128))):
+        m = cls((16, 49, 128), [64, 48, 32], 10).cuda()
+        keys = sorted(m.state_dict())
+        assert keys == sorted(f"{attr}.{i}.{w}" for i in (0, 1, 3, 5) for w in ("weight", "bias")), keys
+        x = torch.randn(*shape, device="cuda", requires_grad=True)
+        dy = torch.randn(16, 10, device="cuda")
+        y = m(x)
+        y.backward(dy)
+        sd = {k: v.detach().double().requires_grad_(True) for k, v in m.state_dict().items()}
+        xr = x.detach().double().requires_grad_(True)
+        h = xr.mean(dim=1).mean(dim=1) if cls is M.MultilayerClassifier else xr
+        lin = torch.nn.functional.linear
+        h = lin(h, sd[f"{attr}.0.weight"], sd[f"{attr}.0.bias"])
+        h = torch.relu(lin(h, sd[f"{attr}.1.weight"], sd[f"{attr}.1.bias"]))
+        h = torch.relu(lin(h, sd[f"{attr}.3.weight"], sd[f"{attr}.3.bias"]))
+        yr = lin(h, sd[f"{attr}.5.weight"], sd[f"{attr}.5.bias"])
+        yr.backward(dy.double())
+        assert rel_err(y, yr) < 1e-5 and rel_err(x.grad, xr.grad) < 1e-5
+        for k, p_ in m.named_parameters():
+            assert rel_err(p_.grad, sd[k].grad) < 1e-5, k
+
+
 def test_eval_mode_and_frozen_branch():
     from m2_mixer_b200 import models, presets
     cfg = presets.get("avmnist_S")          # dropout 0.1: identity in eval mode, must run
