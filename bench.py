@@ -242,7 +242,19 @@ def run_ours(args, cfg):
         lc = _lib.launch_count()
         step(batches[0])
         per_step_launches = _lib.launch_count() - lc
-        gstep = GraphedTrainStep(model, opt, static_batches=batches, warmup=2, grad_sync=sync)
+        try:
+            if os.environ.get("M2B200_BENCH_FAIL_CAPTURE"):       # test hook for the fallback below
+                raise RuntimeError("forced by M2B200_BENCH_FAIL_CAPTURE")
+            gstep = GraphedTrainStep(model, opt, static_batches=batches, warmup=2, grad_sync=sync)
+        except Exception as e:                                    # never lose the run to the launch mode: fall back, and say so
+            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running kernel by kernel", file=sys.stderr, flush=True)
+            use_graph, gstep = False, None
+            if sync is not None:
+                sync.enabled = True
+            from m2_mixer_b200 import ops as _ops
+            _ops.set_dropout_epoch(None)
+            torch.cuda.synchronize()
+    if gstep is not None:
         run = lambda i: gstep.replay(i % NB)
     else:
         run = lambda i: step(batches[i % NB])
@@ -278,11 +290,21 @@ def run_ours(args, cfg):
         if use_graph:
             # the prefetcher's two device buffer sets are the static inputs of two captured graphs
             from m2_mixer_b200.graph import GraphedTrainStep
-            estep = GraphedTrainStep(model, opt, static_batches=pre.bufs, warmup=1, grad_sync=sync)
+            try:
+                estep = GraphedTrainStep(model, opt, static_batches=pre.bufs, warmup=1, grad_sync=sync)
+            except Exception as e:
+                print(f"[bench] CUDA graph capture failed in the e2e leg ({type(e).__name__}: {e}); running kernel by kernel",
+                      file=sys.stderr, flush=True)
+                estep = None
+                if sync is not None:
+                    sync.enabled = True
+                from m2_mixer_b200 import ops as _ops
+                _ops.set_dropout_epoch(None)
+                torch.cuda.synchronize()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pre = DevicePrefetcher(host_stream(args.steps), dev, bufs=pre.bufs if use_graph else None)   # first copy is issued (and waited for) inside the region
+        pre = DevicePrefetcher(host_stream(args.steps), dev, bufs=pre.bufs if estep is not None else None)   # first copy is issued (and waited for) inside the region
         pending = None
         for b in pre:
             if estep is not None:

@@ -507,7 +507,7 @@ int ln_bwd(const float* dy, long long dy_bstride, int N, const float* x, const f
   const int per = ceil_div(D, 32);
 #define M2_LNB(P_) ln_bwd_kernel<P_><<<grid, 256, sm, s>>>(dy, dy_bstride, N, x, w, dres, dx, dw, db, rows, D)
   if (per <= 1) M2_LNB(1); else if (per <= 2) M2_LNB(2); else if (per <= 4) M2_LNB(4); else if (per <= 8) M2_LNB(8);
-  else if (per <= 16) M2_LNB(16); else M2_LNB(32);
+  else if (per <= 12) M2_LNB(12); else if (per <= 16) M2_LNB(16); else if (per <= 24) M2_LNB(24); else M2_LNB(32);
 #undef M2_LNB
   M2_LAUNCH_CHECK();
   return M2_OK;

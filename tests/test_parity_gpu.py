@@ -258,6 +258,26 @@ def test_basic_and_multilayer_classifiers_match_reference():
             assert rel_err(p_.grad, sd[k].grad) < 1e-5, k
 
 
+def test_layernorm_wide_rows_match_torch():
+    """Final / standalone LayerNorm (reference modules/mixer.py:153,161 nn.LayerNorm) at the row widths of the large configs
+    (D = 256 ... 1000: every register-tile instantiation of ln_bwd)."""
+    import m2_mixer_b200.functional as F
+    torch.manual_seed(6)
+    for D in (96, 256, 384, 520, 768, 1000):
+        x = torch.randn(37, 5, D, device="cuda", requires_grad=True)
+        w = (1 + 0.1 * torch.randn(D, device="cuda")).requires_grad_(True)
+        b = (0.1 * torch.randn(D, device="cuda")).requires_grad_(True)
+        dy = torch.randn(37, 5, D, device="cuda")
+        y = F.layer_norm(x, w, b)
+        y.backward(dy)
+        xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+        yr = torch.nn.functional.layer_norm(xr, (D,), wr, br, 1e-5)
+        yr.backward(dy.double())
+        assert rel_err(y, yr) < 1e-5, D
+        for a, r in ((x.grad, xr.grad), (w.grad, wr.grad), (b.grad, br.grad)):
+            assert rel_err(a, r) < 1e-5, D
+
+
 def test_eval_mode_and_frozen_branch():
     from m2_mixer_b200 import models, presets
     cfg = presets.get("avmnist_S")          # dropout 0.1: identity in eval mode, must run
