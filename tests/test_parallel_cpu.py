@@ -59,6 +59,21 @@ def _worker(rank, world, port, q):
     (params[0].sum() * (rank + 1)).backward()
     sync.finish()
     ok &= bool(torch.allclose(flat_g[offs[0]:offs[0] + 35], torch.full((35,), 3.0)))
+    # graphed-step mode (graph.GraphedTrainStep with a process group): the hooks are switched off, finish() is a no-op and
+    # ONE allreduce over the whole flat buffer runs between the two captured graphs
+    sync.enabled = False
+    flat_g.zero_()
+    (params[0].sum() * (rank + 1) + params[4].sum() * (2 * rank + 1)).backward()
+    sync.finish()
+    ok &= bool(torch.allclose(flat_g[offs[0]:offs[0] + 35], torch.full((35,), float(rank + 1))))     # nothing reduced yet
+    sync.allreduce_all()
+    ok &= bool(torch.allclose(flat_g[offs[0]:offs[0] + 35], torch.full((35,), 3.0)))
+    ok &= bool(torch.allclose(flat_g[offs[4]:offs[4] + 11], torch.full((11,), 4.0)))
+    sync.enabled = True                       # and back: the bucketed path works again
+    flat_g.zero_()
+    (params[2].sum() * (rank + 1)).backward()
+    sync.finish()
+    ok &= bool(torch.allclose(flat_g[offs[2]:offs[2] + 21], torch.full((21,), 3.0)))
     q.put((rank, ok))
     dist.destroy_process_group()
 
