@@ -82,3 +82,19 @@ class AVMnistMixerMultiLoss(TrainTestModule):
         if self.current_epoch >= self.loss_change_epoch:
             self.fusion_loss_weight = min(self.fusion_loss_weight + self.fusion_loss_change, 1.0)
         self.current_epoch += 1
+
+    def test_epoch_end(self, outputs, save_dir=None):
+        """Concatenate the per-batch ``test_step`` dicts and write ``test_preds.pt`` next to the checkpoint, as the reference
+        does (models/avmnist.py:382-398: same keys, same file name).  ``save_dir`` replaces the Lightning logger path the
+        reference falls back to when no checkpoint path is known."""
+        import os
+        keys = ("preds", "preds_image", "preds_audio", "labels", "image_logits", "audio_logits", "logits")
+        cat = {k: torch.cat([o[k].detach().cpu() for o in outputs]) for k in keys}
+        if save_dir is None:
+            if self.checkpoint_path is None:
+                raise ValueError("test_epoch_end needs checkpoint_path (load_from_checkpoint sets it) or save_dir")
+            save_dir = os.path.dirname(self.checkpoint_path)
+        os.makedirs(save_dir, exist_ok=True)
+        out = os.path.join(save_dir, "test_preds.pt")
+        torch.save(cat, out)
+        return out

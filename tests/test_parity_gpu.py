@@ -278,6 +278,26 @@ def test_layernorm_wide_rows_match_torch():
             assert rel_err(a, r) < 1e-5, D
 
 
+def test_test_step_and_test_preds_file(tmp_path):
+    """Forward-only test path (reference models/avmnist.py:382-398): test_step under no_grad, test_epoch_end writes
+    test_preds.pt with the reference's keys; argmax predictions agree with the logits."""
+    from m2_mixer_b200 import models, presets
+    from oracle.seeding import synthetic_batch
+    cfg = presets.get("avmnist_S")
+    m = models.AVMnistMixerMultiLoss(cfg, {}).cuda().eval()
+    outs = []
+    for i in range(3):
+        bt = {k: v.cuda() for k, v in synthetic_batch("avmnist", 8, 20 + i).items()}
+        o = m.test_step(bt)
+        assert not o["logits"].requires_grad
+        outs.append(o)
+    path = m.test_epoch_end(outs, save_dir=str(tmp_path))
+    z = torch.load(path)
+    assert sorted(z) == sorted(["preds", "preds_image", "preds_audio", "labels", "image_logits", "audio_logits", "logits"])
+    assert z["logits"].shape == (24, 10) and z["preds"].shape == (24,)
+    assert torch.equal(z["preds"], z["logits"].argmax(1)) and torch.equal(z["preds_image"], z["image_logits"].argmax(1))
+
+
 def test_eval_mode_and_frozen_branch():
     from m2_mixer_b200 import models, presets
     cfg = presets.get("avmnist_S")          # dropout 0.1: identity in eval mode, must run
