@@ -176,3 +176,22 @@ def test_max_and_mean_fusion_shape_contracts_match_reference():
             sys.path.remove(ref_root)
             for k in [k for k in sys.modules if k == "modules" or k.startswith("modules.")]:
                 del sys.modules[k]
+
+
+def test_bench_reference_arm_emits_one_json_line():
+    """`bench.py --impl reference` (the reference's algorithm on the host cores: the oracle port, no GPU involved) prints exactly
+    one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--cpu-batch", "8"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("train samples/s") and d["unit"] == "samples/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
