@@ -183,7 +183,9 @@ int m2b200_heads_loss_bwd(const float* const* tok, const int64_t* tok_bstride, c
                           const int* accumulate_dtok, float* const* dw, float* const* db, void* stream);
 
 /* ---- torch.optim.Adam as configured by the reference (models/avmnist.py:413-415) over one flat buffer.
- * state_dev (optional, device float[2] = {lr, step}) makes lr/step device-resident (graph replay, LR scheduler).   */
+ * state_dev (optional, device float[2] = {lr, step}) makes lr/step device-resident (graph replay, LR scheduler): the
+ * call first advances state_dev[1], unless step < 0 (further ranges of the same optimiser step: torch.optim.Adam skips
+ * parameters without a gradient, so a model with frozen encoders is updated range by range).                       */
 int m2b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, float grad_scale, float* state_dev, void* stream);
 

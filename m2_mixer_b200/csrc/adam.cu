@@ -58,8 +58,10 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v)) & 15)
     return M2_ERR_ALIGN;
-  LaunchScope scope("adam", s, state_dev ? 2 : 1);
-  if (state_dev) adam_tick_kernel<<<1, 1, 0, s>>>(state_dev);
+  // step < 0 with a device state: read {lr, step} as they are (further ranges of a step whose first launch advanced them)
+  const bool tick = state_dev && step >= 0;
+  LaunchScope scope("adam", s, tick ? 2 : 1);
+  if (tick) adam_tick_kernel<<<1, 1, 0, s>>>(state_dev);
   long long blocks = (n / 4 + 255) / 256;
   const int grid = static_cast<int>(blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks));
   adam_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, static_cast<float>(step), grad_scale, state_dev);

@@ -326,6 +326,14 @@ def invalidate_bf16_weights() -> None:
     _WCACHE.epoch += 1
 
 
+def refresh_bf16_weights() -> None:
+    """Re-cast every registered bf16 weight copy NOW (one launch per device) instead of at the next stale lookup.  A graphed
+    step calls this right behind its optimizer update so that no forward graph depends on having captured the refresh."""
+    devices = {e[4].device for e in _WCACHE.entries.values() if e[0]() is not None}
+    for dev in devices:
+        _WCACHE._refresh(dev)
+
+
 def bf16_weight(param: torch.Tensor, rows: Optional[int] = None, cols: Optional[int] = None) -> torch.Tensor:
     """bf16 [rows][up8(cols)] operand copy of a weight parameter viewed as [rows][cols] (default: its first axis x the rest)."""
     rows = param.shape[0] if rows is None else rows

@@ -7,11 +7,13 @@ and replays it with one ``cudaGraphLaunch`` per step:
 
 * inputs are copied into static tensors (the graph's kernels hold raw pointers),
 * the optimizer must be ``FusedAdam(..., capturable=True)`` (lr and the step counter live in device memory),
-* data parallel (``grad_sync=parallel.attach(opt)``): the step is captured as TWO graphs - (zero_grad, forward, backward)
-  and (optimizer step) - with one eager NCCL sum-allreduce of the flat gradient buffer between them; the collective is
-  deliberately not captured (NCCL inside a captured multi-stream step hung on this stack), at the price of not
-  overlapping it with the backward: 33 MB over NVLink for M2-Mixer-B, ~0.1-0.2 ms against the ~0.6 ms of launch gaps the
-  graphs remove,
+* data parallel (``grad_sync=parallel.attach(opt)``), ``comm="overlap"`` (default): ONE graph per static batch; the
+  bucketed NCCL sum-allreduces of ``parallel.GradSync`` are captured on its communication stream, forked from the
+  compute stream as soon as the last gradient of a bucket has been produced and joined before the optimizer step, so the
+  collectives run under the remaining backward kernels (the north_star's "bucketed and overlapped with backward").
+  Call ``close()`` before ``destroy_process_group``: graphs that hold NCCL kernel nodes must die before the communicator.
+  ``comm="split"`` (or ``M2B200_GRAPH_COMM=split``) is round 1's form: TWO graphs - (zero_grad, forward, backward) and
+  (optimizer step) - around one eager, un-overlapped allreduce of the whole flat gradient buffer,
 * dropout stays random: (p, seed) are launch parameters and would be frozen by the capture, so a device-resident epoch
   counter is registered with the library (``ops.set_dropout_epoch``); every kernel folds it into its mask key at run time
   and the captured step ends by advancing it.
@@ -21,12 +23,17 @@ models/avmnist.py:236-312, models/mimic.py:93-142) with ``torch.optim.Adam`` (mo
 """
 from __future__ import annotations
 
+import gc
+import os
 from typing import Any, Callable, Optional, Sequence
 
 import torch
 
+from . import functional as F
 from . import ops
 from .optim import FusedAdam
+
+_EPOCH_OWNER = None      # the live GraphedTrainStep whose epoch counter is registered with the library (process-global)
 
 
 def _static_like(x: Any) -> Any:
@@ -59,11 +66,18 @@ class GraphedTrainStep:
 
     ``static_batches=[b0, b1, ...]`` (device tensors the caller fills in place, e.g. the buffer sets of a
     ``DevicePrefetcher``) captures one graph per buffer set - they share one memory pool - and ``step.replay(k)`` runs
-    the step on set k without any input copy."""
+    the step on set k without any input copy.
+
+    Construction runs ``warmup`` real steps on the first batch (allocator / lazy-init warm-up; collectives at world > 1)
+    and then RESTORES parameters, Adam moments, step counter and dropout epoch (``restore=True``), so that the first
+    ``step(batch)`` is training step 1 of an untouched model.  Scalars captured by value (the loss weights of
+    ``shared_step``, the set of frozen parameters) need a new GraphedTrainStep when they change; lr does not - it is
+    read from device memory and ``replay`` mirrors ``param_groups[0]['lr']`` there whenever a scheduler moved it.
+    The dropout epoch pointer is process-global: the most recently constructed live instance owns it."""
 
     def __init__(self, model: torch.nn.Module, optimizer: FusedAdam, example_batch: Any = None, warmup: int = 3,
                  grad_sync: Optional[Any] = None, step_fn: Optional[Callable[[Any], torch.Tensor]] = None,
-                 static_batches: Optional[Sequence[Any]] = None):
+                 static_batches: Optional[Sequence[Any]] = None, comm: Optional[str] = None, restore: bool = True):
         if not isinstance(optimizer, FusedAdam) or not optimizer.capturable:
             raise ValueError("GraphedTrainStep needs FusedAdam(..., capturable=True): lr / step must live on the device")
         if not torch.cuda.is_available():
@@ -77,8 +91,20 @@ class GraphedTrainStep:
         dev = optimizer.flat_param.device
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
         self.losses = [torch.zeros((), dtype=torch.float32, device=dev) for _ in self.batches]   # outside the graph pool
+        global _EPOCH_OWNER
         ops.set_dropout_epoch(self.epoch)
+        _EPOCH_OWNER = self
         optimizer.sync_lr_to_device()
+        dp = self.sync is not None and getattr(self.sync, "world", 1) > 1
+        comm = comm or os.environ.get("M2B200_GRAPH_COMM", "overlap")
+        if comm not in ("overlap", "split"):
+            raise ValueError("comm must be 'overlap' or 'split'")
+        self.split = dp and comm == "split"
+        self.overlap = dp and comm == "overlap"
+        saved = None
+        if restore:
+            saved = (optimizer.flat_param.clone(), optimizer.exp_avg.clone(), optimizer.exp_avg_sq.clone(),
+                     optimizer.step_count, optimizer._state_dev.clone())
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -86,7 +112,14 @@ class GraphedTrainStep:
                 self._one(0)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.split = self.sync is not None and getattr(self.sync, "world", 1) > 1
+        if saved is not None:
+            optimizer.flat_param.copy_(saved[0]); optimizer.exp_avg.copy_(saved[1]); optimizer.exp_avg_sq.copy_(saved[2])
+            optimizer.step_count = saved[3]
+            optimizer._state_dev.copy_(saved[4])
+            self.epoch.zero_()
+            F.invalidate_bf16_weights()
+            F.refresh_bf16_weights()                  # the captured forwards then find every bf16 copy current
+            torch.cuda.synchronize(dev)
         if self.split:
             self.sync.enabled = False                 # no per-bucket collectives from the backward hooks
         self.graphs, pool = [], None
@@ -94,6 +127,8 @@ class GraphedTrainStep:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
                 self._fwd_bwd(k)
+                if self.overlap:
+                    self.sync.finish()                # joins the communication stream back into the capture
                 if not self.split:
                     self._update()
             pool = g.pool()
@@ -117,6 +152,10 @@ class GraphedTrainStep:
 
     def _update(self) -> None:
         self.opt.step()
+        # The bf16 operand copies are refreshed HERE, right behind the Adam kernel, not lazily at the next forward's first
+        # weight lookup: a lazy refresh is captured only by the graph whose capture happened to find the cache stale, and
+        # with several static batches (or the split form) the other graphs would replay on weights 1..K-1 steps old.
+        F.refresh_bf16_weights()
         ops.dropout_epoch_advance(self.epoch)
 
     def _one(self, k: int) -> None:                   # eager warm-up step
@@ -126,6 +165,8 @@ class GraphedTrainStep:
         self._update()
 
     def replay(self, k: int = 0) -> torch.Tensor:
+        if self.opt.lr_changed():                     # an LR scheduler moved param_groups[0]['lr'] (host side, no capture)
+            self.opt.sync_lr_to_device()
         self.graphs[k].replay()
         if self.split:
             self.sync.allreduce_all()
@@ -139,7 +180,14 @@ class GraphedTrainStep:
         return self.replay(0)
 
     def close(self) -> None:
-        """Unregister the dropout epoch (eager calls afterwards use their host seeds only) and hand the gradient hooks back."""
-        ops.set_dropout_epoch(None)
+        """Destroy the graphs (before any ``destroy_process_group``: they may hold NCCL kernel nodes), unregister the dropout
+        epoch if this instance owns it (eager calls afterwards use their host seeds only) and hand the gradient hooks back."""
+        global _EPOCH_OWNER
+        torch.cuda.synchronize()
+        self.graphs, self.opt_graph, self.graph = [], None, None
+        gc.collect()
+        if _EPOCH_OWNER is self:
+            ops.set_dropout_epoch(None)
+            _EPOCH_OWNER = None
         if self.split:
             self.sync.enabled = True

@@ -143,12 +143,20 @@ def run(model, batch, seed, dtype):
 
 
 def pack(out, grads, full_grads):
+    """full_grads: False = norm + first 16 elements; True = every element as float32; "f16" = every element as float16
+    after a per-tensor power-of-two scale (8.3 M gradient elements of M2-Mixer-B in ~15 MB: 2^-11 relative steps, finer
+    than the bf16 bar they are compared under; the fp32 bar uses the exact norms + heads next to them)."""
     d = {"out." + k: v.double().numpy() for k, v in out.items()}
     for k, g in grads.items():
         g = g.double()
         d["gnorm." + k] = np.array(float(g.norm()))
         d["ghead." + k] = g.flatten()[:16].numpy()
-        if full_grads:
+        if full_grads == "f16":
+            amax = float(g.abs().max())
+            e = 0 if amax == 0.0 else int(np.floor(np.log2(amax)))
+            d["gexp." + k] = np.array(e)
+            d["grad16." + k] = (g * 2.0 ** (-e)).numpy().astype(np.float16)
+        elif full_grads:
             d["grad." + k] = g.numpy().astype(np.float32)
     return d
 
@@ -158,7 +166,7 @@ def cast_batch(b, dtype):
     return {k: f(v) for k, v in b.items()} if isinstance(b, dict) else tuple(f(v) for v in b)
 
 
-def main():
+def main(only=None):
     torch.set_num_threads(8)
     jobs = []
     # name, builder, batch kind, B, full grads?
@@ -170,6 +178,7 @@ def main():
     jobs.append(("avmnist_S_sum_b8", lambda: RefAVMnist(cfgS, "SumFusion"), "avmnist", 8, False))
     jobs.append(("avmnist_M_b4", lambda: RefAVMnist(cfgM), "avmnist", 4, False))
     jobs.append(("avmnist_B_b16", lambda: RefAVMnist(cfgB), "avmnist", 16, False))
+    jobs.append(("avmnist_B_b2", lambda: RefAVMnist(cfgB), "avmnist", 2, "f16"))   # EVERY gradient element of M2-Mixer-B
     jobs.append(("mimic_H_b16", lambda: RefMimic(cfgH), "mimic", 16, True))
     img = dict(block_type="MLPMixer", in_channels=3, hidden_dim=64, patch_size=16, image_size=[64, 48], token_dim=16,
                channel_dim=96, num_mixers=1)
@@ -181,6 +190,8 @@ def main():
     jobs.append(("mmimdb_tiny_b6", lambda: RefMMIMDB(img, txt, mm, 23, pw), ("mmimdb", img, txt), 6, True))
 
     for name, build, kind, bsz, full in jobs:
+        if only is not None and name != only:
+            continue
         seed = 1234
         res = {}
         for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
@@ -203,6 +214,8 @@ def main():
         print(name, "loss", float(res["f64"][0]["loss"]), "f32 logit err", float(d["f32err.logits"]),
               "bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
 
+    if only is not None:
+        return
     # single MixerBlock at awkward sizes (C not a multiple of anything, N odd) incl. input grad
     for name, (B, N, D, T, C) in {"block_odd": (5, 7, 48, 10, 70), "block_b": (6, 8, 128, 32, 3078)}.items():
         blk = modules.MixerBlock(D, N, T, C, dropout=0.0).double()
@@ -224,5 +237,44 @@ def main():
         print(name, "bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+    big_blocks()
+
+
+def big_blocks():
+    """One MixerBlock at the layer shapes of BASELINE configs 4 and 5: these are the shapes that leave the
+    fused small-N kernels - token mixing as a real [T x N] contraction, channel mixing at D = 256 / 768.
+    x / dy are regenerated from the seed by the tests (not stored); y, dx as float32; per-parameter gradient norms
+    (fp64) + a strided sample of 4096 elements of every gradient."""
+    shapes = {"block_c5": (1, 196, 768, 384, 3072),        # Scaled C5 encoder block (Mixer-B/16 width)
+              "block_c4text": (1, 512, 256, 512, 512),     # C4 PNLPMixer text block: T = C = 512, 512 tokens
+              "block_c4fus": (1, 708, 256, 16, 512)}       # C4 fusion block: 708 tokens, T = 16
+    for name, (B, N, D, T, C) in shapes.items():
+        blk = modules.MixerBlock(D, N, T, C, dropout=0.0).double()
+        sd = seeded_state_dict({k: tuple(v.shape) for k, v in blk.state_dict().items()}, 77, torch.float64)
+        blk.load_state_dict(sd)
+        g = torch.Generator().manual_seed(78)
+        x = torch.randn(B, N, D, generator=g, dtype=torch.float64).requires_grad_(True)
+        dy = torch.randn(B, N, D, generator=g, dtype=torch.float64)
+        y = blk(x)
+        y.backward(dy)
+        d = {"y": y.detach().numpy().astype(np.float32), "dx": x.grad.numpy().astype(np.float32),
+             "ynorm": np.array(float(y.norm())), "dxnorm": np.array(float(x.grad.norm()))}
+        for k, p in blk.named_parameters():
+            gflat = p.grad.flatten()
+            stride = max(1, gflat.numel() // 4096)
+            d["gnorm." + k] = np.array(float(p.grad.norm()))
+            d["gsamp." + k] = gflat[::stride][:4096].numpy()
+            d["gstride." + k] = np.array(stride)
+        d["meta.dims"] = np.array([B, N, D, T, C])
+        d["meta.regen"] = np.array(1)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+        print(name, "bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "big_blocks":
+        big_blocks()
+    elif len(sys.argv) > 1 and sys.argv[1] == "b_full":
+        main(only="avmnist_B_b2")
+    else:
+        main()

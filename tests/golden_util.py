@@ -19,7 +19,7 @@ POS_WEIGHT = [4.57642832, 7.38544978, 10.79846869, 13.23391421, 15.59020924, 18.
               67.3890785, 84.92473118, 58.33087149, 62.68253968, 114.13294798, 141.54121864, 116.83431953]
 
 KIND = {"avmnist_S_b8": "avmnist", "avmnist_S_sum_b8": "avmnist", "avmnist_M_b4": "avmnist",
-        "avmnist_B_b16": "avmnist", "mimic_H_b16": "mimic", "mmimdb_tiny_b6": ("mmimdb", IMG_TINY, TXT_TINY)}
+        "avmnist_B_b16": "avmnist", "avmnist_B_b2": "avmnist", "mimic_H_b16": "mimic", "mmimdb_tiny_b6": ("mmimdb", IMG_TINY, TXT_TINY)}
 
 
 def load(name):
@@ -42,3 +42,31 @@ def rel_err(a, b):
     a = torch.as_tensor(a).detach().double().cpu()
     b = torch.as_tensor(b).detach().double().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def full_grad(z, name):
+    """Every element of the gradient `name` of a golden record: stored as float32 ("grad.") or as scaled float16 ("grad16." +
+    power-of-two exponent "gexp.", tests/golden/make_golden.py pack()).  None when the record only has norm + head."""
+    if "grad." + name in z:
+        return torch.as_tensor(z["grad." + name]).double()
+    if "grad16." + name in z:
+        return torch.as_tensor(z["grad16." + name].astype("float32")).double() * 2.0 ** int(z["gexp." + name])
+    return None
+
+
+BLOCK_KEYS = lambda N, D, T, C: {  # noqa: E731  state-dict layout of one reference MixerBlock (modules/mixer.py:25-40)
+    "token_mix.0.weight": (D,), "token_mix.0.bias": (D,), "token_mix.2.net.0.weight": (T, N),
+    "token_mix.2.net.0.bias": (T,), "token_mix.2.net.3.weight": (N, T), "token_mix.2.net.3.bias": (N,),
+    "channel_mix.0.weight": (D,), "channel_mix.0.bias": (D,), "channel_mix.1.net.0.weight": (C, D),
+    "channel_mix.1.net.0.bias": (C,), "channel_mix.1.net.3.weight": (D, C), "channel_mix.1.net.3.bias": (D,)}
+
+
+def block_inputs(z, dtype=torch.float64):
+    """(x, dy) of a block golden: stored, or regenerated from the generator seed the record was made with."""
+    B, N, D, T, C = (int(v) for v in z["meta.dims"])
+    if "x" in z:
+        return torch.tensor(z["x"]).to(dtype), torch.tensor(z["dy"]).to(dtype)
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(B, N, D, generator=g, dtype=torch.float64)
+    dy = torch.randn(B, N, D, generator=g, dtype=torch.float64)
+    return x.to(dtype), dy.to(dtype)

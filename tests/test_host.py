@@ -195,3 +195,26 @@ def test_bench_reference_arm_emits_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cfg"), reason="reference mount absent (GPU box)")
+@pytest.mark.parametrize("rel", ["cfg/avmnist/avmnist_m2-mixer_S.yml", "cfg/avmnist/avmnist_m2-mixer_M.yml",
+                                 "cfg/avmnist/avmnist_m2-mixer_B.yml", "cfg/mimic/mimic_m2-mixer_H.yml"])
+def test_reference_yaml_files_build_the_drop_in_models(rel):
+    """The reference's own cfg/*.yml (run.py:28: OmegaConf.load) through config.load_yaml into the drop-in task modules:
+    same class name as cfg model.type, and the SAME state-dict keys / shapes as the reference modules assembled from the
+    same file (reference models/avmnist.py:178-196, models/mimic.py:36-52 via tests/golden/make_golden.py)."""
+    import importlib
+    from m2_mixer_b200 import models
+    from m2_mixer_b200.config import load_yaml
+    cfg = load_yaml(os.path.join("/root/reference", rel))
+    assert isinstance(cfg.train.optimizer.lr, float)          # '1e-2' style strings are coerced like OmegaConf does
+    m = models.get_model(cfg.model.type)(cfg.model, cfg.train.optimizer)
+    assert type(m).__name__ == cfg.model.type
+    mg = importlib.import_module("tests.golden.make_golden")
+    ref = mg.RefMimic(mg.load_cfg(rel)["model"]) if "mimic" in rel else mg.RefAVMnist(mg.load_cfg(rel)["model"])
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    theirs = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert ours == theirs
+    ref.load_state_dict(m.state_dict(), strict=True)          # and the tensors move across in both directions
+    m.load_state_dict(ref.state_dict(), strict=True)

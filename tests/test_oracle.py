@@ -5,9 +5,9 @@ import pytest
 import torch
 
 from oracle import m2mixer_oracle as O
-from tests.golden_util import POS_WEIGHT, load, rebuild, rel_err
+from tests.golden_util import BLOCK_KEYS, POS_WEIGHT, block_inputs, full_grad, load, rebuild, rel_err
 
-AV = ["avmnist_S_b8", "avmnist_S_sum_b8", "avmnist_M_b4", "avmnist_B_b16"]
+AV = ["avmnist_S_b8", "avmnist_S_sum_b8", "avmnist_M_b4", "avmnist_B_b16", "avmnist_B_b2"]
 
 
 def _check(z, out, grads, tol):
@@ -25,6 +25,8 @@ def _check(z, out, grads, tol):
         assert rel_err(g.flatten()[:16], z["ghead." + name]) < max(tol, 1e-5) * 10, k
         if "grad." + name in z:
             assert rel_err(g, z["grad." + name]) < max(tol, 2e-6), k
+        if "grad16." + name in z:     # every element, stored as scaled float16 (2^-11 steps)
+            assert rel_err(g, full_grad(z, name)) < 5e-4, k
 
 
 @pytest.mark.parametrize("name", AV)
@@ -69,6 +71,28 @@ def test_mixer_block_matches_reference(name):
         assert abs(float(g.norm()) - float(z["gnorm." + k])) < 1e-10 * (1 + float(z["gnorm." + k]))
         if "grad." + k in z:
             assert rel_err(g, z["grad." + k]) < 1e-11
+
+
+@pytest.mark.parametrize("name", ["block_c5", "block_c4text", "block_c4fus"])
+def test_large_config_blocks_match_reference(name):
+    """One MixerBlock at the C4 / C5 layer shapes (BASELINE configs 4, 5; reference modules/mixer.py:25-47, 232-264)."""
+    from oracle.seeding import seeded_state_dict
+    z = load(name)
+    B, N, D, T, C = (int(v) for v in z["meta.dims"])
+    sd = {k: v.requires_grad_(True) for k, v in seeded_state_dict(BLOCK_KEYS(N, D, T, C), 77, torch.float64).items()}
+    x, dy = block_inputs(z)
+    x.requires_grad_(True)
+    y = O.mixer_block(x, sd, "")
+    assert abs(float(y.norm()) - float(z["ynorm"])) < 1e-10 * float(z["ynorm"])
+    assert rel_err(y, z["y"]) < 2e-7          # stored as float32
+    gs = torch.autograd.grad(y, [x] + list(sd.values()), dy)
+    assert abs(float(gs[0].norm()) - float(z["dxnorm"])) < 1e-10 * float(z["dxnorm"])
+    assert rel_err(gs[0], z["dx"]) < 2e-7
+    for k, g in zip(sd, gs[1:]):
+        gn = float(z["gnorm." + k])
+        assert abs(float(g.norm()) - gn) < 1e-10 * (1 + gn), k
+        samp = g.flatten()[::int(z["gstride." + k])][:4096]
+        assert float((samp - torch.as_tensor(z["gsamp." + k])).abs().max()) < 1e-10 * (1 + gn), k
 
 
 def test_concat_shape_contract():

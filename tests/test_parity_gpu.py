@@ -553,24 +553,24 @@ def test_graphed_train_step_matches_eager_and_keeps_dropout_random():
 
     for name, kind in (("avmnist_S", "avmnist"), ("mimic_H", "mimic")):
         batches = [to_dev(synthetic_batch(kind, 32, 10 + i)) for i in range(4)]
-        # ---- no dropout: graph == eager (3 warm-up steps on batch 0 inside the ctor are mirrored on the eager side)
+        # ---- no dropout: graph == eager.  The ctor's warm-up steps are undone (restore=True): replay 1 is training step 1.
         m, opt = build(name, 0.0, 1e-3)
         eager = []
-        for i in range(3 + 8):
-            bt = batches[0] if i < 3 else batches[(i - 3) % 4]
-            opt.zero_grad(); loss = m.training_step(bt); loss.backward(); opt.step()
+        for i in range(8):
+            opt.zero_grad(); loss = m.training_step(batches[i % 4]); loss.backward(); opt.step()
             eager.append(float(loss))
         m, opt = build(name, 0.0, 1e-3)
         step = GraphedTrainStep(m, opt, batches[0], warmup=3)
+        assert opt.step_count == 0
         graphed = [float(step(batches[i % 4])) for i in range(8)]
         step.close()
-        assert max(abs(a - b) for a, b in zip(eager[3:], graphed)) < 2e-3 * max(abs(v) for v in eager), (name, eager[3:], graphed)
+        assert max(abs(a - b) for a, b in zip(eager, graphed)) < 2e-3 * max(abs(v) for v in eager), (name, eager, graphed)
         # ---- dropout on, lr = 0: the weights never move, so the loss varies only through the masks
         m, opt = build(name, 0.3, 0.0)
         step = GraphedTrainStep(m, opt, batches[0], warmup=1)
         ls = [float(step(batches[0])) for _ in range(6)]
         assert len({round(v, 6) for v in ls}) >= 5, (name, ls)
-        assert int(step.epoch) == 1 + 6
+        assert int(step.epoch) == 6
         step.close()
         # ---- dropout on, training: learns
         m, opt = build(name, presets.get(name)["dropout"], 1e-2)
