@@ -77,10 +77,16 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH) or os.environ.get("M2B200_REBUILD"):
+    from . import build as _build
+    stale = False
+    if os.path.exists(LIB_PATH) and not os.environ.get("M2B200_SKIP_DIGEST"):
+        # an edited .cu / .cuh / header must never run against yesterday's binary: compare the source digest with the one
+        # the library was built from (build.py writes it next to the objects)
+        stamp = os.path.join(_build.OBJ, "digest.txt")
+        stale = not os.path.exists(stamp) or open(stamp).read() != _build._digest()
+    if not os.path.exists(LIB_PATH) or stale or os.environ.get("M2B200_REBUILD"):
         if not build_if_missing:
-            raise M2B200Error(f"{LIB_PATH} is missing (run `python -m m2_mixer_b200.build`)")
-        from . import build as _build
+            raise M2B200Error(f"{LIB_PATH} is missing or older than its sources (run `python -m m2_mixer_b200.build`)")
         _build.build(force=bool(os.environ.get("M2B200_REBUILD")))
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():

@@ -277,6 +277,8 @@ size_t m2b200_channel_mix_workspace_bytes(int M, int D, int C, int precision, in
     else if (path == kPathUnfusedBf16) b = up256(m * d * 2) + up256(m * c8 * 2);
   } else {
     if (path == kPathF32) b = 3 * up256(m * d * 4) + 3 * up256(m * c * 4);
+    else if (path == kPathFused && chain_generation() != 1 && chain_generation() != 3 && chain_fwd_ts_supported(D))
+      b = 2 * up256(m * d * 2);   // bf16 LN(u) and dY only: the weight-gradient kernel recomputes G / dH on chip
     else if (path == kPathFused) b = 2 * up256(m * d * 2) + 2 * up256(m * c8 * 2) + up256(m * d * 4);
     else b = 2 * up256(m * d * 2) + 2 * up256(m * c * 4) + 2 * up256(m * c8 * 2) + up256(m * d * 4);
   }
@@ -379,18 +381,20 @@ int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, c
   const size_t mc8 = static_cast<size_t>(M) * c8;
   __nv_bfloat16* xn_b = ws.take<__nv_bfloat16>(md);
   __nv_bfloat16* dy_b = ws.take<__nv_bfloat16>(md);
+  const bool gen2 = path == kPathFused && chain_generation() != 1 && chain_fwd_ts_supported(D);
+  if (gen2 && chain_generation() != 3) {
+    // generation 2: dgrad chain with the LayerNorm backward, dln_w / dln_b / db2 fused in (chain_ts.cu); no G / dH spill:
+    // the weight-gradient kernel recomputes them (wgrad_fused.cu), so the workspace is the two bf16 [M][D] operand copies
+    if (!ws.ok) return M2_ERR_WORKSPACE;
+    M2_TRY(chain_bwd_ts(u, ln_w, ln_b, w1b, b1, w2b, ldw2, dy, du, dln_w, dln_b, db2, xn_b, dy_b, nullptr, nullptr, c8, M, D,
+                        C, dropout_p, seed, s));
+    return wgrad_fused(xn_b, dy_b, w1b, w2b, ldw2, b1, dw1, db1, dw2, M, D, C, dropout_p, seed, s);
+  }
   __nv_bfloat16* g_b = ws.take<__nv_bfloat16>(mc8);
   __nv_bfloat16* dh_b = ws.take<__nv_bfloat16>(mc8);
   float* dxn = ws.take<float>(md);
-  const bool gen2 = path == kPathFused && chain_generation() != 1 && chain_fwd_ts_supported(D);
   if (gen2) {
-    // generation 2: dgrad chain with the LayerNorm backward, dln_w / dln_b / db2 fused in (chain_ts.cu)
     if (!ws.ok) return M2_ERR_WORKSPACE;
-    if (chain_generation() != 3) {   // no G / dH spill: the weight-gradient kernel recomputes them (wgrad_fused.cu)
-      M2_TRY(chain_bwd_ts(u, ln_w, ln_b, w1b, b1, w2b, ldw2, dy, du, dln_w, dln_b, db2, xn_b, dy_b, nullptr, nullptr, c8, M, D,
-                          C, dropout_p, seed, s));
-      return wgrad_fused(xn_b, dy_b, w1b, w2b, ldw2, b1, dw1, db1, dw2, M, D, C, dropout_p, seed, s);
-    }
     M2_TRY(chain_bwd_ts(u, ln_w, ln_b, w1b, b1, w2b, ldw2, dy, du, dln_w, dln_b, db2, xn_b, dy_b, g_b, dh_b, c8, M, D, C,
                         dropout_p, seed, s));
   } else if (path == kPathFused) {
