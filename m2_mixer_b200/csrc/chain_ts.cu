@@ -32,7 +32,7 @@ constexpr int kRows = 128;      // token rows per CTA (UMMA M)
 constexpr int kCc = 64;         // channels per chunk
 // forward: 96 + 128 kG threads (TMA warp, two MMA-issuing warps, kG epilogue groups of 4 warps), see chain_fwd_ts_kernel
 // backward: FOUR epilogue groups (16 warps, 4 per scheduler).  With two, the GELU' epilogue ran at 0.46 IPC per
-// scheduler - dependent FMA chains and MUFU latency, no pipe above 40 % (profiles/r01_ncu_chain_v9.md): latency bound,
+// scheduler - dependent FMA chains and MUFU latency, no pipe above 40 % (profiles/r01_ncu_final.md): latency bound,
 // so the cure is more warps in flight, each on a quarter (16 columns) of the chunk.
 constexpr int kGroupsB = 4;
 constexpr int kThreadsB = 96 + 128 * kGroupsB;
@@ -301,7 +301,7 @@ chain_fwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   // Roles by LOGICAL warp id (0 = TMA producer, 1 = GEMM2 issuer, 2.. = epilogue, -1 = GEMM1 issuer).  Physically the
   // epilogue warps come first and the single-thread roles LAST: the warp scheduler prefers the highest warp id on its
   // sub-partition, and a latency-critical issuer starved behind the busy epilogue warps when it was warp 1 (724-clk gaps
-  // between a commit and the next wait in the in-kernel timeline, profiles/r01_trace_dgrad.md).
+  // between a commit and the next wait in the in-kernel timeline, profiles/r01_trace_dgrad.log).
   //
   // TWO issuing warps: tcgen05.mma issue blocks at the execution rate (the queue holds only a few MMAs:
   // tools/umma_probe.cu, issue time == execution time) and every wait on an mbarrier costs the issuer ~200 clk even

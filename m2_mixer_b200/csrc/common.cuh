@@ -67,7 +67,7 @@ __device__ __forceinline__ float gelu_fast_grad(float x, float& dgelu) {
 }
 
 // ---- packed fp32x2 GELU used by every bf16-mode tensor-core epilogue.  The epilogues are CUDA-core ISSUE bound
-// (0.73 warp-instructions per hidden element in the weight-gradient kernel, profiles/r01_ncu_wgrad_v18.md), so the form
+// (0.73 warp-instructions per hidden element in the weight-gradient kernel, profiles/r01_ncu_final.md), so the form
 // is chosen for instruction count: tanh form with a CUBIC inner polynomial u = x (a + b x^2) fitted to the erf form
 // (max abs error 2.7e-4 on the value, 8.7e-4 on the derivative: below the bf16 rounding of the result for |G| > 0.1),
 // monotonic, so no clamping and no saturation fix-ups are needed (tanh.approx saturates to +-1):
@@ -331,7 +331,7 @@ __device__ __forceinline__ void mbar_wait3(uint64_t* bar_a, uint32_t parity_a, u
 // One lane of a CONVERGED warp (the lowest).  Roles that issue tcgen05.mma / TMA from a single thread walk their loop
 // with the whole warp and predicate only the issue on this: inside an `if (lane == 0)` region ptxas cannot prove
 // warp-uniformity and wraps every UTCHMMA in an elect / R2UR.BROADCAST / BRA.U.ANY serialisation loop (~250 clk per
-// MMA measured, profiles/r01_ncu_chain_v6.md), with it the operands stay in uniform registers.
+// MMA measured, profiles/r01_ncu_final.md), with it the operands stay in uniform registers.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));

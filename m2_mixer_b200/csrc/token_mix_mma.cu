@@ -25,6 +25,31 @@ namespace {
 
 constexpr int kWarps = 8;
 
+// WS warps share one sample (each owns DM / WS of its 16-column m-tiles).  One warp per sample (round 1) needs the whole
+// [N x D] tile plus every fragment in registers (128 / 255 registers: 16 / 8 warps per SM) and walks a ~6000-instruction
+// unrolled body per sample with 2 warps per scheduler: issue slots 35 % busy, stalls split between fixed-latency waits,
+// scoreboards and instruction fetch (profiles/r01_token_mix_bwd_hotspots_v38.txt).  The m-tiles of a sample are independent
+// once the LayerNorm row statistics are known, so WS warps split them and exchange the per-token partial sums through
+// shared memory (two named-barrier rounds forward, three backward): a quarter of the registers and of the unrolled body
+// per warp, four times the warps in flight.  The four warps of a sample sit on the four schedulers (wsub = warp % 4).
+__device__ __forceinline__ void group_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// Sum `v` (already reduced over the 8 lanes that share tq, i.e. replicated in them) over the WS warps of the sample.
+// buf: [WS][R][4] floats of this sample slot and exchange round; row = the value's index in [0, R).
+template <int WS, int R>
+__device__ __forceinline__ void xwarp_put(float* buf, int wsub, int row, int lane, float v) {
+  if (WS > 1 && lane < 4) buf[(wsub * R + row) * 4 + lane] = v;
+}
+template <int WS, int R>
+__device__ __forceinline__ float xwarp_get(const float* buf, int row, int tq, float own) {
+  if (WS == 1) return own;
+  float a = 0.f;
+#pragma unroll
+  for (int w = 0; w < WS; ++w) a += buf[(w * R + row) * 4 + tq];
+  return a;
+}
+
 __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -46,8 +71,8 @@ __device__ __forceinline__ float group_sum(float v) {
 }
 
 // D = 16 * DM, T <= TP (multiple of 16), N <= NP (8 or 16).
-template <int DM, int TP, int NP, bool kDrop>
-__global__ void __launch_bounds__(kWarps * 32)
+template <int DM, int TP, int NP, bool kDrop, int WS>
+__global__ void __launch_bounds__(kWarps * 32, WS == 4 ? 3 : 1)
 token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                          const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                          const float* __restrict__ b2, float* __restrict__ u, int B, int N, int T, const Drop dh,
@@ -56,8 +81,17 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
   constexpr int KN = NP / 8;      // 8-token groups (k halves of GEMM1 / n tiles of GEMM2)
   constexpr int NT1 = TP / 8;     // n tiles of GEMM1
   constexpr int KS2 = TP / 16;    // k steps of GEMM2
+  constexpr int DMW = DM / WS;    // m-tiles of this warp
+  constexpr int SPB = kWarps / WS;   // samples per CTA pass
+  constexpr int R = 2 * KN;       // token rows a lane quad position owns
+  static_assert(DM % WS == 0 && kWarps % WS == 0, "warps per sample");
+  __shared__ float sX[WS > 1 ? 2 * SPB * WS * R * 4 : 1];   // [round][slot][wsub][row][tq]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
+  const int slot = warp / WS, wsub = warp % WS;
+  const int mt0 = wsub * DMW;
+  float* xA = sX + (0 * SPB + slot) * (WS * R * 4);
+  float* xB = sX + (1 * SPB + slot) * (WS * R * 4);
 
   // ---- constant B fragments and biases (registers, loaded once per warp)
   uint32_t w1f[NT1][KN];          // B1[k = n][col = t] = W1[t][n]
@@ -102,12 +136,12 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
   const uint32_t dsh = (g & 1) * 16;
   const uint32_t lane_h = static_cast<uint32_t>(g >> 1) * kDropGolden + static_cast<uint32_t>(2 * tq) * kRowG;
   const uint32_t key_h = kDrop ? drop_key(dh) : 0u, key_o = kDrop ? drop_key(dout) : 0u;
-  for (int b = blockIdx.x * kWarps + warp; b < B; b += gridDim.x * kWarps) {
+  for (int b = blockIdx.x * SPB + slot; b < B; b += gridDim.x * SPB) {   // the WS warps of a slot walk the same samples
     const float* xb = x + static_cast<long long>(b) * N * D;
     const uint32_t hin_h = static_cast<uint32_t>(b) * static_cast<uint32_t>(T) * kRowG + lane_h + key_h;   // row b T + 2 tq
     const uint32_t hin_o = static_cast<uint32_t>(b) * static_cast<uint32_t>(N) * kRowG + lane_h + key_o;   // row b N + 2 tq
-    // raw tile: xr[mt][kh][nn] = x[n = 8 kh + 2 tq + nn][d = 16 mt + 2 g .. +1]
-    float2 xr[DM][KN][2];
+    // raw tile: xr[mt][kh][nn] = x[n = 8 kh + 2 tq + nn][d = 16 (mt0 + mt) + 2 g .. +1]
+    float2 xr[DMW][KN][2];
     float s[KN][2];
 #pragma unroll
     for (int kh = 0; kh < KN; ++kh)
@@ -116,30 +150,40 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
         const int n = 8 * kh + 2 * tq + nn;
         float acc = 0.f;
 #pragma unroll
-        for (int mt = 0; mt < DM; ++mt) {
-          xr[mt][kh][nn] = n < N ? *reinterpret_cast<const float2*>(xb + n * D + 16 * mt + 2 * g) : make_float2(0.f, 0.f);
+        for (int mt = 0; mt < DMW; ++mt) {
+          xr[mt][kh][nn] = n < N ? *reinterpret_cast<const float2*>(xb + n * D + 16 * (mt0 + mt) + 2 * g) : make_float2(0.f, 0.f);
           acc += xr[mt][kh][nn].x + xr[mt][kh][nn].y;
         }
-        s[kh][nn] = acc;
+        s[kh][nn] = group_sum(acc);
+        xwarp_put<WS, R>(xA, wsub, kh * 2 + nn, lane, s[kh][nn]);
       }
+    if (WS > 1) group_bar(1 + slot, 32 * WS);
     float mean[KN][2], rstd[KN][2];
 #pragma unroll
     for (int kh = 0; kh < KN; ++kh)
 #pragma unroll
       for (int nn = 0; nn < 2; ++nn) {
-        mean[kh][nn] = group_sum(s[kh][nn]) * inv_d;
+        mean[kh][nn] = xwarp_get<WS, R>(xA, kh * 2 + nn, tq, s[kh][nn]) * inv_d;
         float ss = 0.f;
 #pragma unroll
-        for (int mt = 0; mt < DM; ++mt) {
+        for (int mt = 0; mt < DMW; ++mt) {
           const float a = xr[mt][kh][nn].x - mean[kh][nn], c = xr[mt][kh][nn].y - mean[kh][nn];
           ss += a * a + c * c;
         }
-        rstd[kh][nn] = rsqrtf(group_sum(ss) * inv_d + kLnEps);
+        s[kh][nn] = group_sum(ss);
+        xwarp_put<WS, R>(xB, wsub, kh * 2 + nn, lane, s[kh][nn]);
       }
+    if (WS > 1) group_bar(1 + slot, 32 * WS);
+#pragma unroll
+    for (int kh = 0; kh < KN; ++kh)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn)
+        rstd[kh][nn] = rsqrtf(xwarp_get<WS, R>(xB, kh * 2 + nn, tq, s[kh][nn]) * inv_d + kLnEps);
 
 #pragma unroll
-    for (int mt = 0; mt < DM; ++mt) {
-      const int d_lo = 16 * mt + 2 * g;
+    for (int mt = 0; mt < DMW; ++mt) {
+      const int mtg = mt0 + mt;
+      const int d_lo = 16 * mtg + 2 * g;
       const float2 gm = *reinterpret_cast<const float2*>(ln_w + d_lo);
       const float2 bt = *reinterpret_cast<const float2*>(ln_b + d_lo);
       // A1: a0 = (row g = d_lo, k = 2tq..+1), a1 = (row g+8 = d_hi, same k), a2 / a3 = k + 8
@@ -168,7 +212,7 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
         float2 lo = gelu2(make_float2(c[j][0], c[j][1]), hs);
         float2 hi = gelu2(make_float2(c[j][2], c[j][3]), hs);
         if (kDrop) {   // hidden-site index (b T + t) D + d, t = 8 j + 2 tq: (d_lo, d_hi) is one hash pair
-          const uint32_t h0 = hin_h + static_cast<uint32_t>(8 * j) * kRowG + static_cast<uint32_t>(4 * mt) * kDropGolden;
+          const uint32_t h0 = hin_h + static_cast<uint32_t>(8 * j) * kRowG + static_cast<uint32_t>(4 * mtg) * kDropGolden;
           drop_zero2_hin(dh, lo.x, hi.x, h0, dsh);   // scale folded into the GELU (hs)
           drop_zero2_hin(dh, lo.y, hi.y, h0 + kRowG, dsh);
         }
@@ -194,7 +238,7 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
             float v_lo = o[jn][nn], v_hi = o[jn][2 + nn];
             const long long off = (static_cast<long long>(b) * N + n) * D + d_lo;
             if (kDrop)   // output-site index (b N + n) D + d, n = 8 jn + 2 tq + nn
-              drop_apply2_hin(dout, v_lo, v_hi, hin_o + static_cast<uint32_t>(8 * jn + nn) * kRowG + static_cast<uint32_t>(4 * mt) * kDropGolden, dsh);
+              drop_apply2_hin(dout, v_lo, v_hi, hin_o + static_cast<uint32_t>(8 * jn + nn) * kRowG + static_cast<uint32_t>(4 * mtg) * kDropGolden, dsh);
             *reinterpret_cast<float2*>(u + off) = make_float2(xr[mt][jn][nn].x + v_lo, xr[mt][jn][nn].y + v_hi);
           }
         }
@@ -204,9 +248,9 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Backward.  dx = du + LN'(dXn);  dln_w, dln_b, dw1, db1, dw2, db2 are accumulated (per-CTA shared-memory partials, then
-// one global atomic per element and CTA).  kW warps per CTA; sDxn is the lane-private spill of the dXn tile that the
-// LayerNorm backward needs after the per-row sums over the whole hidden axis are known.
-template <int DM, int TP, int NP, bool kDrop, int kW, int kMinB>
+// one global atomic per element and CTA).  kW warps per CTA, WS of them per sample; sDxn is the lane-private spill of the dXn
+// tile that the LayerNorm backward needs after the per-row sums over the whole hidden axis are known.
+template <int DM, int TP, int NP, bool kDrop, int kW, int kMinB, int WS>
 __global__ void __launch_bounds__(kW * 32, kMinB)
 token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__ x, const float* __restrict__ ln_w,
                          const float* __restrict__ ln_b, const float* __restrict__ w1, const float* __restrict__ b1,
@@ -217,15 +261,25 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
   constexpr int KN = NP / 8;      // 8-token groups
   constexpr int NT1 = TP / 8;     // 8-wide hidden-unit tiles
   constexpr int KS2 = TP / 16;    // 16-wide hidden-unit steps (k steps of the dXn GEMM, m tiles of the weight-gradient GEMMs)
-  constexpr int DQ = (DM + 3) / 4;
+  constexpr int DMW = DM / WS;    // m-tiles of this warp
+  constexpr int SPB = kW / WS;    // samples per CTA pass
+  constexpr int R = 2 * KN;       // token rows a lane quad position owns
+  constexpr int DQ = (DMW + 3) / 4;
+  static_assert(DM % WS == 0 && kW % WS == 0, "warps per sample");
   extern __shared__ float smem_f[];
   float* sAcc = smem_f;                               // [2][TP][NP] dw1^T / dw2^T partials, [TP] db1, [NP] db2, [2][D] dln_w / dln_b
-  float* sDxn = sAcc + 2 * TP * NP + TP + NP + 2 * D; // [kW][DM * KN * 4][32] lane-private
   constexpr int kAcc = 2 * TP * NP + TP + NP + 2 * D;
+  float* sDxn = sAcc + kAcc;                          // [kW][DMW * KN * 4][32] lane-private
+  float* sX = sDxn + kW * (DMW * KN * 4 * 32);        // [3 rounds][SPB][WS][2 R][4] cross-warp partial sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
+  const int slot = warp / WS, wsub = warp % WS;
+  const int mt0 = wsub * DMW;
+  float* xA = sX + (0 * SPB + slot) * (WS * 2 * R * 4);
+  float* xB = sX + (1 * SPB + slot) * (WS * 2 * R * 4);
+  float* xC = sX + (2 * SPB + slot) * (WS * 2 * R * 4);
   for (int i = threadIdx.x; i < kAcc; i += kW * 32) sAcc[i] = 0.f;
-  float* myDxn = sDxn + warp * (DM * KN * 4 * 32) + lane;
+  float* myDxn = sDxn + warp * (DMW * KN * 4 * 32) + lane;
 
   // ---- constant B fragments
   uint32_t w1f[NT1][KN];          // GEMM1  B[k = n][col = t]  = W1[t][n]
@@ -280,13 +334,13 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
   const uint32_t dsh = (g & 1) * 16;
   const uint32_t lane_h = static_cast<uint32_t>(g >> 1) * kDropGolden + static_cast<uint32_t>(2 * tq) * kRowG;
   const uint32_t key_h = kDrop ? drop_key(dh) : 0u, key_o = kDrop ? drop_key(dout) : 0u;
-  for (int b = blockIdx.x * kW + warp; b < B; b += gridDim.x * kW) {
+  for (int b = blockIdx.x * SPB + slot; b < B; b += gridDim.x * SPB) {   // the WS warps of a slot walk the same samples
     const long long sbase = static_cast<long long>(b) * N * D;
     const uint32_t hin_h = static_cast<uint32_t>(b) * static_cast<uint32_t>(T) * kRowG + lane_h + key_h;   // row b T + 2 tq
     const uint32_t hin_o = static_cast<uint32_t>(b) * static_cast<uint32_t>(N) * kRowG + lane_h + key_o;   // row b N + 2 tq
     const float* xb = x + sbase;
     const float* dub = du + sbase;
-    float2 xr[DM][KN][2];
+    float2 xr[DMW][KN][2];
     float mean[KN][2], rstd[KN][2];
 #pragma unroll
     for (int kh = 0; kh < KN; ++kh)
@@ -295,26 +349,42 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
         const int n = 8 * kh + 2 * tq + nn;
         float acc = 0.f;
 #pragma unroll
-        for (int mt = 0; mt < DM; ++mt) {
-          xr[mt][kh][nn] = n < N ? *reinterpret_cast<const float2*>(xb + n * D + 16 * mt + 2 * g) : make_float2(0.f, 0.f);
+        for (int mt = 0; mt < DMW; ++mt) {
+          xr[mt][kh][nn] = n < N ? *reinterpret_cast<const float2*>(xb + n * D + 16 * (mt0 + mt) + 2 * g) : make_float2(0.f, 0.f);
           acc += xr[mt][kh][nn].x + xr[mt][kh][nn].y;
         }
-        mean[kh][nn] = group_sum(acc) * inv_d;
+        mean[kh][nn] = group_sum(acc);
+        xwarp_put<WS, 2 * R>(xA, wsub, kh * 2 + nn, lane, mean[kh][nn]);
+      }
+    if (WS > 1) group_bar(1 + slot, 32 * WS);
+#pragma unroll
+    for (int kh = 0; kh < KN; ++kh)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        mean[kh][nn] = xwarp_get<WS, 2 * R>(xA, kh * 2 + nn, tq, mean[kh][nn]) * inv_d;
         float ss = 0.f;
 #pragma unroll
-        for (int mt = 0; mt < DM; ++mt) {
+        for (int mt = 0; mt < DMW; ++mt) {
           const float a = xr[mt][kh][nn].x - mean[kh][nn], c = xr[mt][kh][nn].y - mean[kh][nn];
           ss += a * a + c * c;
         }
-        rstd[kh][nn] = rsqrtf(group_sum(ss) * inv_d + kLnEps);
+        rstd[kh][nn] = group_sum(ss);
+        xwarp_put<WS, 2 * R>(xB, wsub, kh * 2 + nn, lane, rstd[kh][nn]);
       }
+    if (WS > 1) group_bar(1 + slot, 32 * WS);
+#pragma unroll
+    for (int kh = 0; kh < KN; ++kh)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn)
+        rstd[kh][nn] = rsqrtf(xwarp_get<WS, 2 * R>(xB, kh * 2 + nn, tq, rstd[kh][nn]) * inv_d + kLnEps);
     float s1[KN][2], s2[KN][2];   // per-token sums over d of gamma dXn and gamma dXn xhat
 #pragma unroll
     for (int kh = 0; kh < KN; ++kh) { s1[kh][0] = s1[kh][1] = s2[kh][0] = s2[kh][1] = 0.f; }
 
 #pragma unroll
-    for (int mt = 0; mt < DM; ++mt) {
-      const int d_lo = 16 * mt + 2 * g;
+    for (int mt = 0; mt < DMW; ++mt) {
+      const int mtg = mt0 + mt;
+      const int d_lo = 16 * mtg + 2 * g;
       const float2 gm = *reinterpret_cast<const float2*>(ln_w + d_lo);
       const float2 bt = *reinterpret_cast<const float2*>(ln_b + d_lo);
       uint32_t a1f[4] = {0u, 0u, 0u, 0u}, a3f[4] = {0u, 0u, 0u, 0u};
@@ -333,7 +403,7 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
         float2 u0 = v0 ? *reinterpret_cast<const float2*>(dub + n * D + d_lo) : make_float2(0.f, 0.f);
         float2 u1 = v1 ? *reinterpret_cast<const float2*>(dub + (n + 1) * D + d_lo) : make_float2(0.f, 0.f);
         if (kDrop) {   // gradient of the dropped branch output: rows b N + n, n = 8 kh + 2 tq (+ 1)
-          const uint32_t h0 = hin_o + static_cast<uint32_t>(8 * kh) * kRowG + static_cast<uint32_t>(4 * mt) * kDropGolden;
+          const uint32_t h0 = hin_o + static_cast<uint32_t>(8 * kh) * kRowG + static_cast<uint32_t>(4 * mtg) * kDropGolden;
           drop_apply2_hin(dout, u0.x, u0.y, h0, dsh);
           drop_apply2_hin(dout, u1.x, u1.y, h0 + kRowG, dsh);
         }
@@ -361,7 +431,7 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
         float2 h_lo = __fmul2_rn(make_float2(c3[j][0], c3[j][1]), dg_lo);
         float2 h_hi = __fmul2_rn(make_float2(c3[j][2], c3[j][3]), dg_hi);
         if (kDrop) {   // rows b T + t, t = 8 j + 2 tq (+ 1)
-          const uint32_t h0 = hin_h + static_cast<uint32_t>(8 * j) * kRowG + static_cast<uint32_t>(4 * mt) * kDropGolden;
+          const uint32_t h0 = hin_h + static_cast<uint32_t>(8 * j) * kRowG + static_cast<uint32_t>(4 * mtg) * kDropGolden;
           drop_zero2x2_hin(dh, g_lo.x, g_hi.x, h_lo.x, h_hi.x, h0, dsh);   // scale folded into gelu2_grad
           drop_zero2x2_hin(dh, g_lo.y, g_hi.y, h_lo.y, h_hi.y, h0 + kRowG, dsh);
         }
@@ -427,12 +497,22 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
     for (int kh = 0; kh < KN; ++kh)
 #pragma unroll
       for (int nn = 0; nn < 2; ++nn) {
-        s1[kh][nn] = group_sum(s1[kh][nn]) * inv_d;
-        s2[kh][nn] = group_sum(s2[kh][nn]) * inv_d;
+        s1[kh][nn] = group_sum(s1[kh][nn]);
+        s2[kh][nn] = group_sum(s2[kh][nn]);
+        xwarp_put<WS, 2 * R>(xC, wsub, kh * 2 + nn, lane, s1[kh][nn]);
+        xwarp_put<WS, 2 * R>(xC, wsub, R + kh * 2 + nn, lane, s2[kh][nn]);
+      }
+    if (WS > 1) group_bar(1 + slot, 32 * WS);
+#pragma unroll
+    for (int kh = 0; kh < KN; ++kh)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        s1[kh][nn] = xwarp_get<WS, 2 * R>(xC, kh * 2 + nn, tq, s1[kh][nn]) * inv_d;
+        s2[kh][nn] = xwarp_get<WS, 2 * R>(xC, R + kh * 2 + nn, tq, s2[kh][nn]) * inv_d;
       }
 #pragma unroll
-    for (int mt = 0; mt < DM; ++mt) {
-      const int d_lo = 16 * mt + 2 * g;
+    for (int mt = 0; mt < DMW; ++mt) {
+      const int d_lo = 16 * (mt0 + mt) + 2 * g;
       const float2 gm = *reinterpret_cast<const float2*>(ln_w + d_lo);
 #pragma unroll
       for (int kh = 0; kh < KN; ++kh)
@@ -481,9 +561,9 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
     if (g == 0) { atomicAdd(&sB2[8 * kh + 2 * tq], v0); atomicAdd(&sB2[8 * kh + 2 * tq + 1], v1); }
   }
 #pragma unroll
-  for (int mt = 0; mt < DM; ++mt)
+  for (int mt = 0; mt < DMW; ++mt)
     if ((mt & 3) == tq) {
-      const int d_lo = 16 * mt + 2 * g;
+      const int d_lo = 16 * (mt0 + mt) + 2 * g;
       atomicAdd(&sGam[d_lo], dgam[mt >> 2][0]); atomicAdd(&sGam[d_lo + 1], dgam[mt >> 2][1]);
       atomicAdd(&sBet[d_lo], dbet[mt >> 2][0]); atomicAdd(&sBet[d_lo + 1], dbet[mt >> 2][1]);
     }
@@ -500,14 +580,28 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
   for (int i = threadIdx.x; i < D; i += kW * 32) { atomicAdd(dln_w + i, sGam[i]); atomicAdd(dln_b + i, sBet[i]); }
 }
 
-template <int DM, int TP, int NP, int kW = 8, int kMinB = 1>
-int launch_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
+// Warps per sample: M2B200_TOKEN_WS = 1 | 2 | 4 overrides (A/B runs); default 4 for D >= 128, 2 for D = 64, else 1.
+inline int token_ws(int dm) {
+  static const int env = [] {
+    const char* e = getenv("M2B200_TOKEN_WS");
+    return e ? atoi(e) : 0;
+  }();
+  int ws = env > 0 ? env : (dm >= 8 ? 4 : (dm >= 4 ? 2 : 1));
+  while (ws > 1 && (dm % ws || ws > 4)) ws >>= 1;
+  return ws == 3 ? 2 : ws;
+}
+
+template <int DM, int TP, int NP, int WS, int kW = 8, int kMinB = 1>
+int launch_bwd_ws(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
                const float* w2, float* dx, float* dln_w, float* dln_b, float* dw1, float* db1, float* dw2, float* db2, int B,
                int N, int T, const Drop& dh, const Drop& dout, cudaStream_t s) {
-  constexpr int D = 16 * DM, KN = NP / 8;
-  constexpr size_t smem = (2 * TP * NP + TP + NP + 2 * D + static_cast<size_t>(kW) * DM * KN * 4 * 32) * sizeof(float);
-  int grid = ceil_div(B, kW);
-  if (grid > 148 * 2 * kMinB) grid = 148 * 2 * kMinB;   // persistent: the per-CTA gradient partials cost one atomic round per CTA
+  constexpr int D = 16 * DM, KN = NP / 8, DMW = DM / WS, SPB = kW / WS;
+  constexpr size_t smem = (2 * TP * NP + TP + NP + 2 * D + static_cast<size_t>(kW) * DMW * KN * 4 * 32 +
+                           3 * SPB * WS * 4 * KN * 4) * sizeof(float);
+  int grid = ceil_div(B, SPB);
+  // persistent: the per-CTA gradient partials cost one atomic round per CTA; as many CTAs as can be resident
+  const int per_sm = 2 * kMinB;
+  if (grid > 148 * per_sm) grid = 148 * per_sm;
   LaunchScope scope("token_mix_mma_bwd", s);
   auto launch = [&](auto kern) -> int {
     static bool configured = false;   // per instantiation of this generic lambda
@@ -519,25 +613,46 @@ int launch_bwd(const float* du, const float* x, const float* ln_w, const float* 
     return M2_OK;
   };
   int rc;
-  if (dh.thresh || dout.thresh) rc = launch(token_mix_mma_bwd_kernel<DM, TP, NP, true, kW, kMinB>);
-  else rc = launch(token_mix_mma_bwd_kernel<DM, TP, NP, false, kW, kMinB>);
+  if (dh.thresh || dout.thresh) rc = launch(token_mix_mma_bwd_kernel<DM, TP, NP, true, kW, kMinB, WS>);
+  else rc = launch(token_mix_mma_bwd_kernel<DM, TP, NP, false, kW, kMinB, WS>);
   if (rc) return rc;
   M2_LAUNCH_CHECK();
   return M2_OK;
 }
+template <int DM, int TP, int NP>
+int launch_bwd(const float* du, const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
+               const float* w2, float* dx, float* dln_w, float* dln_b, float* dw1, float* db1, float* dw2, float* db2, int B,
+               int N, int T, const Drop& dh, const Drop& dout, cudaStream_t s) {
+  const int ws = token_ws(DM);
+  if constexpr (DM % 4 == 0)
+    if (ws == 4) return launch_bwd_ws<DM, TP, NP, 4, 8, 2>(du, x, ln_w, ln_b, w1, b1, w2, dx, dln_w, dln_b, dw1, db1, dw2, db2, B, N, T, dh, dout, s);
+  if constexpr (DM % 2 == 0)
+    if (ws >= 2) return launch_bwd_ws<DM, TP, NP, 2>(du, x, ln_w, ln_b, w1, b1, w2, dx, dln_w, dln_b, dw1, db1, dw2, db2, B, N, T, dh, dout, s);
+  return launch_bwd_ws<DM, TP, NP, 1>(du, x, ln_w, ln_b, w1, b1, w2, dx, dln_w, dln_b, dw1, db1, dw2, db2, B, N, T, dh, dout, s);
+}
 
+template <int DM, int TP, int NP, int WS>
+int launch_fwd_ws(const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1, const float* w2,
+                  const float* b2, float* u, int B, int N, int T, const Drop& dh, const Drop& dout, cudaStream_t s) {
+  int grid = ceil_div(B, kWarps / WS);
+  if (grid > 148 * 8) grid = 148 * 8;
+  LaunchScope scope("token_mix_mma_fwd", s);
+  if (dh.thresh || dout.thresh)
+    token_mix_mma_fwd_kernel<DM, TP, NP, true, WS><<<grid, kWarps * 32, 0, s>>>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, T, dh, dout);
+  else
+    token_mix_mma_fwd_kernel<DM, TP, NP, false, WS><<<grid, kWarps * 32, 0, s>>>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, T, dh, dout);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
 template <int DM, int TP, int NP>
 int launch_fwd(const float* x, const float* ln_w, const float* ln_b, const float* w1, const float* b1, const float* w2,
                const float* b2, float* u, int B, int N, int T, const Drop& dh, const Drop& dout, cudaStream_t s) {
-  int grid = ceil_div(B, kWarps);
-  if (grid > 148 * 4) grid = 148 * 4;
-  LaunchScope scope("token_mix_mma_fwd", s);
-  if (dh.thresh || dout.thresh)
-    token_mix_mma_fwd_kernel<DM, TP, NP, true><<<grid, kWarps * 32, 0, s>>>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, T, dh, dout);
-  else
-    token_mix_mma_fwd_kernel<DM, TP, NP, false><<<grid, kWarps * 32, 0, s>>>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, T, dh, dout);
-  M2_LAUNCH_CHECK();
-  return M2_OK;
+  const int ws = token_ws(DM);
+  if constexpr (DM % 4 == 0)
+    if (ws == 4) return launch_fwd_ws<DM, TP, NP, 4>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, T, dh, dout, s);
+  if constexpr (DM % 2 == 0)
+    if (ws >= 2) return launch_fwd_ws<DM, TP, NP, 2>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, T, dh, dout, s);
+  return launch_fwd_ws<DM, TP, NP, 1>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, T, dh, dout, s);
 }
 
 }  // namespace

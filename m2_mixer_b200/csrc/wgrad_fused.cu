@@ -22,7 +22,7 @@
 namespace m2 {
 namespace {
 
-// A CTA owns 128 channels and walks 96-row tiles.  Why these numbers (measured, profiles/r01_chain_tuning.md):
+// A CTA owns 128 channels and walks 96-row tiles.  Why these numbers (measured, profiles/r01_chain_microbench_v25.log, profiles/r01_trace_wgrad_final.log):
 //  * every wake-up of the single MMA-issuing thread costs several hundred cycles (mbarrier waits, burst start-up), so the
 //    work per wake-up must be large: 128-channel GEMMs (N = 128, 64 clk per MMA instead of 48 for N = 64: the same
 //    wake-ups now feed twice the channels, and A is read from shared memory once per 128 instead of per 64 channels);
