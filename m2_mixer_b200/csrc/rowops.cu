@@ -108,6 +108,54 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   }
 }
 
+
+// float4 form (D % 4 == 0, 16-byte aligned rows, D <= 128 * kV): the row is read ONCE into registers (the scalar kernel
+// above walks it three times through L1) with 16-byte loads; one warp per row.
+template <bool kBf16Out, int kV>
+__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ b, void* __restrict__ out, int rows, int D,
+                                                         int N, long long out_bstride, float* __restrict__ mean_out,
+                                                         float* __restrict__ rstd_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float inv_d = 1.f / D;
+  for (int row = warp; row < rows; row += nwarps) {
+    const float* xr = x + static_cast<long long>(row) * D;
+    float4 v[kV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      v[i] = c < D ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i)
+      if ((lane + 32 * i) * 4 < D) {
+        const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
+        ss += a * a + bb * bb + cc * cc + dd * dd;
+      }
+    const float rstd = rsqrtf(warp_sum(ss) * inv_d + kLnEps);
+    const long long o = static_cast<long long>(row / N) * out_bstride + static_cast<long long>(row % N) * D;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < D) {
+        const float4 ww = *reinterpret_cast<const float4*>(w + c), bv = *reinterpret_cast<const float4*>(b + c);
+        const float4 r = make_float4((v[i].x - mean) * rstd * ww.x + bv.x, (v[i].y - mean) * rstd * ww.y + bv.y,
+                                     (v[i].z - mean) * rstd * ww.z + bv.z, (v[i].w - mean) * rstd * ww.w + bv.w);
+        if (kBf16Out)
+          *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + o + c) = make_uint2(pack_bf16(r.x, r.y), pack_bf16(r.z, r.w));
+        else
+          *reinterpret_cast<float4*>(static_cast<float*>(out) + o + c) = r;
+      }
+    }
+    if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ LayerNorm backward
 // dy = grad wrt LN output (row (b,n) at dy + b*dy_bstride + n*D), x = LN input.
 // dx[row] = (dres ? dres[row] : 0) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * w
@@ -175,6 +223,92 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   for (int i = 0; i < kMaxPer; ++i) {
     const int c = lane + 32 * i;
     if (c < D) { atomicAdd(&sdw[c], pdw[i]); atomicAdd(&sdb[c], pdb[i]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) { atomicAdd(&dw[c], sdw[c]); atomicAdd(&db[c], sdb[c]); }
+}
+
+
+// float4 form of the above (D % 4 == 0, 16-byte aligned rows, D <= 128 * kV).  The scalar kernel keeps a D = 768 row in
+// 24 + 24 scalar registers per lane plus 48 accumulators and issues 4-byte accesses: 160-236 registers, 8 warps per SM,
+// 6x off its HBM floor on the Scaled config (profiles/r01_large_configs.json).  Here: 16-byte accesses (a quarter of the
+// memory instructions), at most two CTAs' worth of registers, x and dy still read exactly once.
+template <int kV>
+__global__ void __launch_bounds__(256, kV <= 2 ? 4 : (kV <= 6 ? 2 : 1))
+ln_bwd_vec_kernel(const float* __restrict__ dy, long long dy_bstride, int N, const float* __restrict__ x,
+                  const float* __restrict__ w, const float* __restrict__ dres, float* __restrict__ dx,
+                  float* __restrict__ dw, float* __restrict__ db, int rows, int D) {
+  extern __shared__ float sm[];   // [2][D] per-CTA partial dw/db
+  float* sdw = sm;
+  float* sdb = sm + D;
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float inv_d = 1.f / D;
+  float4 pdw[kV], pdb[kV];
+#pragma unroll
+  for (int i = 0; i < kV; ++i) pdw[i] = pdb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto wld = [&](int i) {   // gamma stays in L1 (D <= 1024 floats): re-read instead of holding kV float4 registers per lane
+    const int c = (lane + 32 * i) * 4;
+    return c < D ? __ldg(reinterpret_cast<const float4*>(w + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  for (int row = warp; row < rows; row += nwarps) {
+    const float* xr = x + static_cast<long long>(row) * D;
+    const float* gr = dy + static_cast<long long>(row / N) * dy_bstride + static_cast<long long>(row % N) * D;
+    float4 xv[kV], gv[kV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      const bool ok = c < D;
+      xv[i] = ok ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gv[i] = ok ? *reinterpret_cast<const float4*>(gr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i)
+      if ((lane + 32 * i) * 4 < D) {
+        xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+        ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+      }
+    const float rstd = rsqrtf(warp_sum(ss) * inv_d + kLnEps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {   // xv <- xhat (pad lanes hold zeros: they add nothing)
+      xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;
+      const float4 wv = wld(i);
+      const float g0 = gv[i].x * wv.x, g1 = gv[i].y * wv.y, g2 = gv[i].z * wv.z, g3 = gv[i].w * wv.w;
+      sg += g0 + g1 + g2 + g3;
+      sgx += g0 * xv[i].x + g1 * xv[i].y + g2 * xv[i].z + g3 * xv[i].w;
+    }
+    sg = warp_sum(sg) * inv_d; sgx = warp_sum(sgx) * inv_d;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < D) {
+        const float4 wv = wld(i);
+        float4 v = make_float4(rstd * (gv[i].x * wv.x - sg - xv[i].x * sgx), rstd * (gv[i].y * wv.y - sg - xv[i].y * sgx),
+                               rstd * (gv[i].z * wv.z - sg - xv[i].z * sgx), rstd * (gv[i].w * wv.w - sg - xv[i].w * sgx));
+        if (dres) {
+          const float4 r = *reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * D + c);
+          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        *reinterpret_cast<float4*>(dx + static_cast<long long>(row) * D + c) = v;
+        pdw[i].x += gv[i].x * xv[i].x; pdw[i].y += gv[i].y * xv[i].y; pdw[i].z += gv[i].z * xv[i].z; pdw[i].w += gv[i].w * xv[i].w;
+        pdb[i].x += gv[i].x; pdb[i].y += gv[i].y; pdb[i].z += gv[i].z; pdb[i].w += gv[i].w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    if (c < D) {
+      atomicAdd(&sdw[c], pdw[i].x); atomicAdd(&sdw[c + 1], pdw[i].y); atomicAdd(&sdw[c + 2], pdw[i].z); atomicAdd(&sdw[c + 3], pdw[i].w);
+      atomicAdd(&sdb[c], pdb[i].x); atomicAdd(&sdb[c + 1], pdb[i].y); atomicAdd(&sdb[c + 2], pdb[i].z); atomicAdd(&sdb[c + 3], pdb[i].w);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) { atomicAdd(&dw[c], sdw[c]); atomicAdd(&db[c], sdb[c]); }
@@ -491,6 +625,20 @@ int ln_fwd(const float* x, const float* w, const float* b, void* out, int out_bf
   LaunchScope scope("ln_fwd", s);
   if (rows <= 0 || D <= 0 || N <= 0) return M2_ERR_ARG;
   const int grid = grid_for(static_cast<long long>(rows) * 32, 256);
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b) |
+                    reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (D % 4 == 0 && D <= 1024 && al && out_bstride % 4 == 0) {
+    const int kv = ceil_div(D, 128);
+#define M2_LNF(V_)                                                                                                       \
+  do {                                                                                                                   \
+    if (out_bf16) ln_fwd_vec_kernel<true, V_><<<grid, 256, 0, s>>>(x, w, b, out, rows, D, N, out_bstride, mean, rstd);     \
+    else ln_fwd_vec_kernel<false, V_><<<grid, 256, 0, s>>>(x, w, b, out, rows, D, N, out_bstride, mean, rstd);             \
+  } while (0)
+    if (kv <= 1) M2_LNF(1); else if (kv <= 2) M2_LNF(2); else if (kv <= 4) M2_LNF(4); else if (kv <= 6) M2_LNF(6); else M2_LNF(8);
+#undef M2_LNF
+    M2_LAUNCH_CHECK();
+    return M2_OK;
+  }
   if (out_bf16) ln_fwd_kernel<true><<<grid, 256, 0, s>>>(x, w, b, out, rows, D, N, out_bstride, mean, rstd);
   else ln_fwd_kernel<false><<<grid, 256, 0, s>>>(x, w, b, out, rows, D, N, out_bstride, mean, rstd);
   M2_LAUNCH_CHECK();
@@ -504,6 +652,16 @@ int ln_bwd(const float* dy, long long dy_bstride, int N, const float* x, const f
   int grid = grid_for(static_cast<long long>(rows) * 32, 256);
   if (grid > kNumSms * 8) grid = kNumSms * 8;   // 64 resident warps per SM: the kernel is load-latency bound
   const size_t sm = 2 * D * sizeof(float);
+  const bool al = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) |
+                    reinterpret_cast<uintptr_t>(dres) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  if (D % 4 == 0 && al && dy_bstride % 4 == 0) {
+    const int kv = ceil_div(D, 128);
+#define M2_LNBV(V_) ln_bwd_vec_kernel<V_><<<grid, 256, sm, s>>>(dy, dy_bstride, N, x, w, dres, dx, dw, db, rows, D)
+    if (kv <= 1) M2_LNBV(1); else if (kv <= 2) M2_LNBV(2); else if (kv <= 4) M2_LNBV(4); else if (kv <= 6) M2_LNBV(6); else M2_LNBV(8);
+#undef M2_LNBV
+    M2_LAUNCH_CHECK();
+    return M2_OK;
+  }
   const int per = ceil_div(D, 32);
 #define M2_LNB(P_) ln_bwd_kernel<P_><<<grid, 256, sm, s>>>(dy, dy_bstride, N, x, w, dres, dx, dw, db, rows, D)
   if (per <= 1) M2_LNB(1); else if (per <= 2) M2_LNB(2); else if (per <= 4) M2_LNB(4); else if (per <= 8) M2_LNB(8);
