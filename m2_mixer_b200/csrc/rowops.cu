@@ -423,6 +423,37 @@ __global__ void gelu_fwd_bwd_kernel(const float* __restrict__ h, const float* dg
   }
 }
 
+// Four consecutive columns per thread (cols, leading dimensions and the mask row stride multiples of 4, 16-byte aligned
+// bases): 16-byte loads, one mask hash per thread, 8- / 16-byte stores.  The scalar kernel above ran at a sixth of the HBM
+// rate on the Scaled config's [tokens x 3072] tensors (profiles/r01_large_configs.json).
+template <typename TO>
+__global__ void __launch_bounds__(256) gelu_fwd_bwd_vec4_kernel(const float* __restrict__ h, const float* dg, long long n4,
+                                                                int cols4, long long ld_in, TO* __restrict__ g_out, TO* dh_out,
+                                                                long long ld_out, const Drop drop, long long drop_ld) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = static_cast<int>(i - r * cols4) * 4;
+    const float4 x = *reinterpret_cast<const float4*>(h + r * ld_in + c);
+    const float4 dgv = *reinterpret_cast<const float4*>(dg + r * ld_in + c);
+    float4 g = make_float4(gelu_erf(x.x), gelu_erf(x.y), gelu_erf(x.z), gelu_erf(x.w));
+    float4 d = make_float4(dgv.x * gelu_erf_grad(x.x), dgv.y * gelu_erf_grad(x.y), dgv.z * gelu_erf_grad(x.z),
+                           dgv.w * gelu_erf_grad(x.w));
+    if (drop.thresh) {
+      const unsigned long long idx = static_cast<unsigned long long>(r) * drop_ld + c;
+      drop_apply4(drop, g, idx);
+      drop_apply4(drop, d, idx);
+    }
+    if (sizeof(TO) == 2) {
+      *reinterpret_cast<uint2*>(g_out + r * ld_out + c) = make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
+      *reinterpret_cast<uint2*>(dh_out + r * ld_out + c) = make_uint2(pack_bf16(d.x, d.y), pack_bf16(d.z, d.w));
+    } else {
+      *reinterpret_cast<float4*>(g_out + r * ld_out + c) = g;
+      *reinterpret_cast<float4*>(dh_out + r * ld_out + c) = d;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ patch gather
 // img [B][cin][H][W] -> cols [(b, gy, gx)][(ci, py, px)], row stride ld (pad columns zeroed).
 // Reference: Conv2d(cin, D, p, p) + 'b c h w -> b (h w) c', modules/mixer.py:143-146.
@@ -728,6 +759,18 @@ int gelu_fwd_bwd(const float* h, const float* dg, int rows, int cols, long long 
   LaunchScope scope("gelu_fwd_bwd", s);
   const long long n = static_cast<long long>(rows) * cols;
   if (n <= 0) return M2_ERR_ARG;
+  const bool al = ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dg) | reinterpret_cast<uintptr_t>(g_out) |
+                    reinterpret_cast<uintptr_t>(dh_out)) & 15) == 0;
+  if (al && cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && drop_ld % 4 == 0) {
+    if (out_bf16)
+      gelu_fwd_bwd_vec4_kernel<__nv_bfloat16><<<grid_for(n / 4, 256), 256, 0, s>>>(
+          h, dg, n / 4, cols / 4, ld_in, static_cast<__nv_bfloat16*>(g_out), static_cast<__nv_bfloat16*>(dh_out), ld_out, drop, drop_ld);
+    else
+      gelu_fwd_bwd_vec4_kernel<float><<<grid_for(n / 4, 256), 256, 0, s>>>(h, dg, n / 4, cols / 4, ld_in, static_cast<float*>(g_out),
+                                                                         static_cast<float*>(dh_out), ld_out, drop, drop_ld);
+    M2_LAUNCH_CHECK();
+    return M2_OK;
+  }
   if (out_bf16)
     gelu_fwd_bwd_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>(h, dg, n, cols, ld_in, static_cast<__nv_bfloat16*>(g_out),
                                                                        static_cast<__nv_bfloat16*>(dh_out), ld_out, drop, drop_ld);

@@ -418,4 +418,8 @@ def heads_loss(toks: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs: Seq
                head_weight: Sequence[float], loss_kind: int = 0, pos_weight: Optional[torch.Tensor] = None):
     """Returns (losses[4] = total, L_0, L_1, L_2; logits [3,B,K]; preds)."""
     n = len(toks)
+    # The heads kernels give one WARP a sample (mean-pool, Linear, loss in one pass): right for the shipped configs (4-49
+    # tokens of 32-128 floats).  With hundreds of wide tokens per sample and a small batch (the Scaled config: 392 x 768
+    # floats per sample, batch 64 = 64 warps on the whole GPU) the pooling is done first by the batch x dim parallel kernel.
+    toks = [mean_pool(t).unsqueeze(1) if (t.dim() == 3 and t.shape[1] * t.shape[2] >= 16384) else t for t in toks]
     return _HeadsLoss.apply(labels, pos_weight, tuple(float(h) for h in head_weight), loss_kind, n, *toks, *ws, *bs)

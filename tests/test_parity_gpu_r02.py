@@ -236,9 +236,12 @@ def test_fused_adam_state_dict_round_trip_and_frozen_parameters():
     cfg = dict(presets.get("avmnist_S"), dropout=0.0)
     bt = {k: v.cuda() for k, v in synthetic_batch("avmnist", 16, 3).items()}
 
-    def make():
+    def make_model():
         torch.manual_seed(0)
-        m = models.AVMnistMixerMultiLoss(cfg, {}).cuda().set_precision("fp32").train()
+        return models.AVMnistMixerMultiLoss(cfg, {}).cuda().set_precision("fp32").train()
+
+    def make():
+        m = make_model()
         return m, FusedAdam(m.parameters(), lr=1e-2, weight_decay=0.01)
 
     def run(m, opt, n):
@@ -260,7 +263,7 @@ def test_fused_adam_state_dict_round_trip_and_frozen_parameters():
     b = run(m3, o3, 3)
     assert max(abs(x - y) for x, y in zip(a[3:], b)) < 1e-6 * max(a), (a, b)
     # a torch.optim.Adam checkpoint loads too, and the resumed curves agree
-    m4, _ = make()
+    m4 = make_model()       # plain parameters: no FusedAdam has flattened them
     t4 = torch.optim.Adam(m4.parameters(), lr=1e-2, weight_decay=0.01)
     for _ in range(3):
         t4.zero_grad(); m4.training_step(bt).backward(); t4.step()
