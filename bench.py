@@ -42,6 +42,9 @@ def parse():
                          "(under the backward), 'split' is one allreduce between two graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-host-dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="dtype of the IMAGE tensors in the pinned host batches of the e2e leg (bf16 halves the host link "
+                         "bytes; the bf16 GEMM operand is the pixel rounded to bf16 either way, results are bit-identical)")
     ap.add_argument("--dropout", type=float, default=None, help="override the cfg's dropout (default: the reference cfg's value)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying one CUDA graph per step")
     return ap.parse_args()
@@ -364,7 +367,9 @@ def run_ours(args, cfg):
         from m2_mixer_b200.data import DevicePrefetcher
         as_dict = lambda b: b if isinstance(b, dict) else {str(i): v for i, v in enumerate(b)}   # noqa: E731  (MIMIC: tuples)
         from_dict = lambda d: d if isinstance(batches[0], dict) else tuple(d[str(i)] for i in range(len(d)))   # noqa: E731
-        host = [{k: v.cpu().pin_memory() for k, v in as_dict(b).items()} for b in batches[:2]]
+        from m2_mixer_b200.data import pin_host_batch
+        host = [pin_host_batch(as_dict(b), image_dtype=torch.bfloat16 if args.e2e_host_dtype == "bf16" else None)
+                for b in batches[:2]]
         sink = []
 
         def host_stream(n):
@@ -417,7 +422,11 @@ def run_ours(args, cfg):
         h2d = sum(v.numel() * v.element_size() for v in host[0].values())
         e2e = {"value": world * B * args.steps / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": ems / args.steps,
-               "note": "H2D of each step's batch from pinned memory (double-buffered on a copy stream) + D2H of each step's loss"}
+               "host_image_dtype": args.e2e_host_dtype,
+               "note": "H2D of each step's batch from pinned memory (double-buffered on a copy stream) + D2H of each step's loss; "
+                       "host image tensors are " + ("bf16 (the patch-embedding GEMM rounds pixels to bf16 anyway: same bits as "
+                       "fp32 host batches, half the link bytes; --e2e-host-dtype fp32 for the other form)"
+                       if args.e2e_host_dtype == "bf16" else "fp32")}
 
     # ---- per-kernel device time (CUDA events on the launching stream) for the roofline of the dominant kernel
     roof = None

@@ -128,16 +128,21 @@ int m2b200_linear_fwd(const float* x, const float* w, const void* w_bf16, int ld
 int m2b200_linear_bwd(float* dy, const float* x, const float* y, const float* w, const void* w_bf16, int ldwb, int act,
                       float* dx, float* dw, float* db, int M, int N, int K, int precision, float dropout_p, uint64_t seed,
                       void* workspace, size_t workspace_bytes, void* stream);
-/* Patch embedding as gather + GEMM (modules/mixer.py:143-146).  `cols` (m2b200_patch_embed_cols_bytes) receives the
- * gathered patch rows - bf16 [M][up8(K)] in BF16 mode, fp32 [M][K] in FP32 mode, M = B*(H/P)*(W/P), K = cin*P*P -
- * and is what the backward's weight-gradient GEMM reads (there is no input gradient).  w is [D][K] (Conv2d weight
- * [D][cin][P][P] viewed flat), y is [M][D] in 'b (h w) c' order.                                                    */
-size_t m2b200_patch_embed_cols_bytes(int B, int cin, int H, int W, int P, int precision);
-int m2b200_patch_embed_fwd(const float* img, const float* w, const void* w_bf16, int ldwb, const float* bias, void* cols,
-                           float* y, int B, int cin, int H, int W, int P, int D, int precision, void* stream);
-size_t m2b200_patch_embed_bwd_workspace_bytes(int M, int D, int precision);
-int m2b200_patch_embed_bwd(const float* dy, const void* cols, float* dw, float* db, int M, int D, int K, int precision,
-                           void* workspace, size_t workspace_bytes, void* stream);
+/* Patch embedding, Conv2d(cin, D, k = stride = P) + Rearrange('b c h w -> b (h w) c') (modules/mixer.py:143-146), as a
+ * GEMM over the patch rows: y [M][D] in 'b (h w) c' order, M = B*(H/P)*(W/P), K = cin*P*P, w [D][K] = the Conv2d weight
+ * [D][cin][P][P] viewed flat.  img is [B][cin][H][W], fp32 (img_bf16 = 0) or bf16 (img_bf16 = 1: BF16 mode only; the bf16
+ * GEMM operand is the pixel rounded to bf16 either way, so both give the same bits).  BF16 mode with P % 8 == 0 and a
+ * 16-byte aligned image: the tcgen05 GEMMs gather their image-side operand tile from the pixels themselves (no im2col
+ * buffer, workspace = the bf16 dY of the backward only).  Other shapes / FP32 mode: gather into the workspace + GEMM.
+ * The backward takes the IMAGE again (nothing else is kept from the forward; there is no input gradient), accumulates
+ * dw [D][K] and db [D] (db may be NULL).                                                                              */
+size_t m2b200_patch_embed_workspace_bytes(const void* img, int img_bf16, int B, int cin, int H, int W, int P, int D,
+                                          int precision, int backward);
+int m2b200_patch_embed_fwd(const void* img, int img_bf16, const float* w, const void* w_bf16, int ldwb, const float* bias,
+                           float* y, int B, int cin, int H, int W, int P, int D, int precision, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int m2b200_patch_embed_bwd(const float* dy, const void* img, int img_bf16, float* dw, float* db, int B, int cin, int H, int W,
+                           int P, int D, int precision, void* workspace, size_t workspace_bytes, void* stream);
 /* img [B][cin][H][W] -> cols [B*(H/P)*(W/P)][cin*P*P]  (row = patch in (h w) order, col = (c, py, px))              */
 int m2b200_patch_gather(const float* img, float* cols, int B, int cin, int H, int W, int P, void* stream);
 

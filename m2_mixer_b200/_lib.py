@@ -43,10 +43,9 @@ PROTOTYPES = {
     "m2b200_dropout_mask": (i32, [vp, i32, i32, i64, f32, u64, i32, vp]),
     "m2b200_set_dropout_epoch_ptr": (None, [vp]),
     "m2b200_dropout_epoch_advance": (i32, [vp, vp]),
-    "m2b200_patch_embed_cols_bytes": (sz, [i32] * 6),
-    "m2b200_patch_embed_fwd": (i32, [vp, vp, vp, i32, vp, vp, vp] + [i32] * 7 + [vp]),
-    "m2b200_patch_embed_bwd_workspace_bytes": (sz, [i32] * 3),
-    "m2b200_patch_embed_bwd": (i32, [vp, vp, vp, vp] + [i32] * 4 + [vp, sz, vp]),
+    "m2b200_patch_embed_workspace_bytes": (sz, [vp] + [i32] * 9),
+    "m2b200_patch_embed_fwd": (i32, [vp, i32, vp, vp, i32, vp, vp] + [i32] * 7 + [vp, sz, vp]),
+    "m2b200_patch_embed_bwd": (i32, [vp, vp, i32, vp, vp] + [i32] * 7 + [vp, sz, vp]),
     "m2b200_patch_gather": (i32, [vp, vp] + [i32] * 5 + [vp]),
     "m2b200_copy_tokens": (i32, [vp, i64, vp, i64, i32, i64, i32, vp]),
     "m2b200_add": (i32, [vp, vp, vp, i64, vp]),

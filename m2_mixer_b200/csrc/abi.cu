@@ -521,53 +521,76 @@ int m2b200_linear_bwd(float* dy, const float* x, const float* y, const float* w,
   return M2_OK;
 }
 
-// Patch embedding = gather (img -> one row per patch, bf16 in BF16 mode) + GEMM; the gathered rows are an explicit
-// output because the weight-gradient GEMM of the backward consumes them again (no dgrad: the image needs no gradient).
-size_t m2b200_patch_embed_cols_bytes(int B, int cin, int H, int W, int P, int precision) {
+// Patch embedding.  BF16 mode with P % 8 == 0: the GEMMs gather their image-side operand themselves (patch_gemm.cu), no
+// im2col buffer exists.  Otherwise (FP32 parity mode, odd patch sizes): gather into the workspace + GEMM, and the backward
+// gathers again - the image is the only thing the forward keeps for the backward (there is no input gradient).
+static bool patch_fused(const void* img, int img_bf16, int B, int cin, int H, int W, int P, int precision) {
+  return precision == M2B200_BF16 && patch_gemm_supported(img, img_bf16, B, cin, H, W, P);
+}
+size_t m2b200_patch_embed_workspace_bytes(const void* img, int img_bf16, int B, int cin, int H, int W, int P, int D,
+                                          int precision, int backward) {
   if (P <= 0 || H % P || W % P) return 0;
   const size_t rows = static_cast<size_t>(B) * (H / P) * (W / P), k = static_cast<size_t>(cin) * P * P;
-  return precision == M2B200_FP32 ? rows * k * 4 : rows * static_cast<size_t>(up8(static_cast<int>(k))) * 2;
+  const bool fused = patch_fused(img, img_bf16, B, cin, H, W, P, precision);
+  size_t n = 0;
+  if (!fused) n += up256(precision == M2B200_FP32 ? rows * k * 4 : rows * static_cast<size_t>(up8(static_cast<int>(k))) * 2);
+  if (backward && precision != M2B200_FP32) n += up256(rows * up8(D) * 2);   // bf16 dY
+  return n;
 }
 
-int m2b200_patch_embed_fwd(const float* img, const float* w, const void* w_bf16, int ldwb, const float* bias, void* cols,
-                           float* y, int B, int cin, int H, int W, int P, int D, int precision, void* stream) {
-  if (!img || !cols || !y || B <= 0 || cin <= 0 || P <= 0 || D <= 0 || H % P || W % P) return M2_ERR_ARG;
+int m2b200_patch_embed_fwd(const void* img, int img_bf16, const float* w, const void* w_bf16, int ldwb, const float* bias,
+                           float* y, int B, int cin, int H, int W, int P, int D, int precision, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (!img || !y || B <= 0 || cin <= 0 || P <= 0 || D <= 0 || H % P || W % P) return M2_ERR_ARG;
   cudaStream_t s = S(stream);
   const int M = B * (H / P) * (W / P), K = cin * P * P;
+  if (patch_fused(img, img_bf16, B, cin, H, W, P, precision)) {
+    if (!w_bf16 || ldwb % 8 || ldwb < K) return M2_ERR_ARG;
+    return patch_gemm_fwd(img, img_bf16, w_bf16, ldwb, bias, y, B, cin, H, W, P, D, s);
+  }
+  Carver ws(workspace, workspace_bytes);
   if (precision == M2B200_FP32) {
     if (!w) return M2_ERR_ARG;
-    M2_TRY(patch_gather(img, cols, 0, B, cin, H, W, P, K, s));
+    float* cols = ws.take<float>(static_cast<size_t>(M) * K);
+    if (!ws.ok) return M2_ERR_WORKSPACE;
+    M2_TRY(patch_gather(img, img_bf16, cols, 0, B, cin, H, W, P, K, s));
     GemmArgs g = gemm_args(cols, 0, K, w, 0, K, M, D, K, y, 0, D);
     g.bias = bias; g.bias_mode = bias ? 1 : 0;
     return gemm_f32_simt(g, s);
   }
   const int k8 = up8(K);
   if (!w_bf16 || ldwb % 8 || ldwb < K) return M2_ERR_ARG;
-  M2_TRY(patch_gather(img, cols, 1, B, cin, H, W, P, k8, s));
+  __nv_bfloat16* cols = ws.take<__nv_bfloat16>(static_cast<size_t>(M) * k8);
+  if (!ws.ok) return M2_ERR_WORKSPACE;
+  M2_TRY(patch_gather(img, img_bf16, cols, 1, B, cin, H, W, P, k8, s));
   GemmArgs g = gemm_args(cols, 0, k8, w_bf16, 0, ldwb, M, D, K, y, 0, D);
   g.bias = bias; g.bias_mode = bias ? 1 : 0;
   return gemm_bf16_umma(g, s);
 }
 
-size_t m2b200_patch_embed_bwd_workspace_bytes(int M, int D, int precision) {
-  return precision == M2B200_FP32 ? 0 : up256(static_cast<size_t>(M) * up8(D) * 2);
-}
-
-int m2b200_patch_embed_bwd(const float* dy, const void* cols, float* dw, float* db, int M, int D, int K, int precision,
-                           void* workspace, size_t workspace_bytes, void* stream) {
-  if (!dy || !cols || !dw || M <= 0 || D <= 0 || K <= 0) return M2_ERR_ARG;
+int m2b200_patch_embed_bwd(const float* dy, const void* img, int img_bf16, float* dw, float* db, int B, int cin, int H, int W,
+                           int P, int D, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dy || !img || !dw || B <= 0 || cin <= 0 || P <= 0 || D <= 0 || H % P || W % P) return M2_ERR_ARG;
   cudaStream_t s = S(stream);
+  const int M = B * (H / P) * (W / P), K = cin * P * P;
   if (db) M2_TRY(colsum_f32(dy, D, M, D, db, s));
+  Carver ws(workspace, workspace_bytes);
   if (precision == M2B200_FP32) {
+    float* cols = ws.take<float>(static_cast<size_t>(M) * K);
+    if (!ws.ok) return M2_ERR_WORKSPACE;
+    M2_TRY(patch_gather(img, img_bf16, cols, 0, B, cin, H, W, P, K, s));
     GemmArgs gw = gemm_args(dy, 1, D, cols, 1, K, D, K, M, dw, 0, K);     // dW[D][K] += dY^T cols
     gw.accumulate = 1;
     return gemm_f32_simt(gw, s);
   }
   const int k8 = up8(K), d8 = up8(D);
-  Carver ws(workspace, workspace_bytes);
+  const bool fused = patch_fused(img, img_bf16, B, cin, H, W, P, precision);
+  __nv_bfloat16* cols = fused ? nullptr : ws.take<__nv_bfloat16>(static_cast<size_t>(M) * k8);
   __nv_bfloat16* dyb = ws.take<__nv_bfloat16>(static_cast<size_t>(M) * d8);
   if (!ws.ok) return M2_ERR_WORKSPACE;
   M2_TRY(cast_pad_bf16(dy, D, dyb, d8, M, D, s));
+  if (fused) return patch_gemm_wgrad(img, img_bf16, dyb, d8, dw, B, cin, H, W, P, D, s);
+  M2_TRY(patch_gather(img, img_bf16, cols, 1, B, cin, H, W, P, k8, s));
   GemmArgs gw = gemm_args(dyb, 1, d8, cols, 1, k8, D, K, M, dw, 0, K);
   gw.splitk = wgrad_splitk(D, K, M);
   if (gw.splitk == 1) gw.accumulate = 1;
@@ -576,7 +599,7 @@ int m2b200_patch_embed_bwd(const float* dy, const void* cols, float* dw, float* 
 
 int m2b200_patch_gather(const float* img, float* cols, int B, int cin, int H, int W, int P, void* stream) {
   if (!img || !cols) return M2_ERR_ARG;
-  return patch_gather(img, cols, 0, B, cin, H, W, P, static_cast<long long>(cin) * P * P, S(stream));
+  return patch_gather(img, 0, cols, 0, B, cin, H, W, P, static_cast<long long>(cin) * P * P, S(stream));
 }
 
 int m2b200_dropout_mask(float* out, int rows, int cols, int64_t ld, float dropout_p, uint64_t seed, int site, void* stream) {

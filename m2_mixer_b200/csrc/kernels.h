@@ -76,7 +76,14 @@ int mask_scale(const float* src, long long lds, void* dst, int dst_bf16, long lo
                unsigned long long seed, int site, long long drop_ld, cudaStream_t s);
 // out[r][c] = 1/0 keep mask of (seed, site) at index r*ld + c  (test / debugging export of the kernels' mask function)
 int dropout_mask(float* out, int rows, int cols, long long ld, float drop_p, unsigned long long seed, int site, cudaStream_t s);
-int patch_gather(const float* img, void* cols, int out_bf16, int B, int cin, int H, int W, int P, long long ld, cudaStream_t s);
+int patch_gather(const void* img, int img_bf16, void* cols, int out_bf16, int B, int cin, int H, int W, int P, long long ld,
+                 cudaStream_t s);
+// patch embedding with the image-side operand gathered inside the GEMM (patch_gemm.cu): bf16 mode, P % 8 == 0
+bool patch_gemm_supported(const void* img, int img_bf16, int B, int cin, int H, int W, int P);
+int patch_gemm_fwd(const void* img, int img_bf16, const void* w_bf16, int ldwb, const float* bias, float* y, int B, int cin,
+                   int H, int W, int P, int D, cudaStream_t s);
+int patch_gemm_wgrad(const void* img, int img_bf16, const void* dy_b, int ldd, float* dw, int B, int cin, int H, int W, int P,
+                     int D, cudaStream_t s);
 int concat_copy(const float* src, long long src_bstride, float* dst, long long dst_bstride, int B, long long per_batch,
                 int accumulate, cudaStream_t s);
 int add_f32(const float* a, const float* b, float* o, long long n, cudaStream_t s);

@@ -457,48 +457,32 @@ __global__ void __launch_bounds__(256) gelu_fwd_bwd_vec4_kernel(const float* __r
 // ------------------------------------------------------------------------------------------ patch gather
 // img [B][cin][H][W] -> cols [(b, gy, gx)][(ci, py, px)], row stride ld (pad columns zeroed).
 // Reference: Conv2d(cin, D, p, p) + 'b c h w -> b (h w) c', modules/mixer.py:143-146.
-// 8 consecutive px per thread (needs P % 8 == 0, W % 4 == 0, 16-byte aligned image): two float4 loads, one 16 B store
-__global__ void patch_gather_bf16x8_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ cols, int B, int cin,
-                                           int H, int W, int P, long long ld) {
-  const int gh = H / P, gw = W / P;
-  const int K = cin * P * P, K8 = K / 8;
-  const long long total = static_cast<long long>(B) * gh * gw * (ld / 8);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = i / (ld / 8);
-    const int k8 = static_cast<int>(i - row * (ld / 8));
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (k8 < K8) {
-      const int k = k8 * 8;
-      const int px = k % P, py = (k / P) % P, ci = k / (P * P);
-      const int gx = static_cast<int>(row % gw), gy = static_cast<int>((row / gw) % gh);
-      const long long b = row / (static_cast<long long>(gw) * gh);
-      const float* p = img + ((b * cin + ci) * H + gy * P + py) * W + gx * P + px;
-      const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
-      o = make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
-    }
-    *reinterpret_cast<uint4*>(cols + row * ld + k8 * 8) = o;
-  }
-}
-
-template <typename TO>
-__global__ void patch_gather_kernel(const float* __restrict__ img, TO* __restrict__ cols, int B, int cin, int H, int W,
-                                    int P, long long ld) {
-  const int gh = H / P, gw = W / P;
-  const int K = cin * P * P;
-  const long long total = static_cast<long long>(B) * gh * gw * ld;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = i / ld;
-    const int k = static_cast<int>(i - row * ld);
-    float v = 0.f;
+// (patch sizes with P % 8 == 0 never come here in BF16 mode: patch_gemm.cu gathers inside the GEMM)
+// One block walks whole patch rows; the k -> pixel offset table of a patch is built once per block in shared memory, so
+// the per-element work is one table read, one load and one store (the first version spent ~300 instructions per element
+// on 64-bit index divisions: 38 us for the 3.3 M elements of the AV-MNIST image branch).
+template <typename TI, typename TO>
+__global__ void patch_gather_kernel(const TI* __restrict__ img, TO* __restrict__ cols, int rows, int cin, int H, int W,
+                                    int P, int ld) {
+  extern __shared__ int koff[];   // [ld], -1 = pad column
+  const int K = cin * P * P, gw = W / P, gh = H / P;
+  for (int k = threadIdx.x; k < ld; k += blockDim.x) {
+    int o = -1;
     if (k < K) {
       const int px = k % P, py = (k / P) % P, ci = k / (P * P);
-      const int gx = static_cast<int>(row % gw), gy = static_cast<int>((row / gw) % gh);
-      const long long b = row / (static_cast<long long>(gw) * gh);
-      v = img[((b * cin + ci) * H + gy * P + py) * W + gx * P + px];
+      o = (ci * H + py) * W + px;
     }
-    cols[i] = static_cast<TO>(v);
+    koff[k] = o;
+  }
+  __syncthreads();
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int gx = row % gw, gy = (row / gw) % gh, b = row / (gw * gh);
+    const TI* base = img + (static_cast<long long>(b) * cin * H + gy * P) * W + gx * P;
+    TO* dst = cols + static_cast<long long>(row) * ld;
+    for (int k = threadIdx.x; k < ld; k += blockDim.x) {
+      const int o = koff[k];
+      dst[k] = static_cast<TO>(o >= 0 ? static_cast<float>(base[o]) : 0.f);
+    }
   }
 }
 
@@ -781,15 +765,22 @@ int gelu_fwd_bwd(const float* h, const float* dg, int rows, int cols, long long 
   return M2_OK;
 }
 
-int patch_gather(const float* img, void* cols, int out_bf16, int B, int cin, int H, int W, int P, long long ld, cudaStream_t s) {
+int patch_gather(const void* img, int img_bf16, void* cols, int out_bf16, int B, int cin, int H, int W, int P, long long ld,
+                 cudaStream_t s) {
   LaunchScope scope("patch_gather", s);
-  if (B <= 0 || cin <= 0 || P <= 0 || H % P || W % P || ld < static_cast<long long>(cin) * P * P) return M2_ERR_ARG;
-  const long long total = static_cast<long long>(B) * (H / P) * (W / P) * ld;
-  if (out_bf16 && P % 8 == 0 && W % 4 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(cols) & 15) == 0)
-    patch_gather_bf16x8_kernel<<<grid_for(total / 8, 256), 256, 0, s>>>(img, static_cast<__nv_bfloat16*>(cols), B, cin, H, W, P, ld);
-  else if (out_bf16) patch_gather_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(img, static_cast<__nv_bfloat16*>(cols), B, cin, H, W, P, ld);
-  else patch_gather_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(img, static_cast<float*>(cols), B, cin, H, W, P, ld);
+  if (B <= 0 || cin <= 0 || P <= 0 || H % P || W % P || ld < static_cast<long long>(cin) * P * P || ld > 12000) return M2_ERR_ARG;
+  const long long rows_ll = static_cast<long long>(B) * (H / P) * (W / P);
+  if (rows_ll >= (1ll << 31)) return M2_ERR_ARG;
+  const int rows = static_cast<int>(rows_ll), ldi = static_cast<int>(ld);
+  const int threads = ld >= 1024 ? 256 : 128;
+  const int grid = rows < 148 * 16 ? rows : 148 * 16;
+  const size_t smem = ld * sizeof(int);
+  const float* f = static_cast<const float*>(img);
+  const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(img);
+  if (out_bf16 && img_bf16) patch_gather_kernel<<<grid, threads, smem, s>>>(h, static_cast<__nv_bfloat16*>(cols), rows, cin, H, W, P, ldi);
+  else if (out_bf16) patch_gather_kernel<<<grid, threads, smem, s>>>(f, static_cast<__nv_bfloat16*>(cols), rows, cin, H, W, P, ldi);
+  else if (img_bf16) patch_gather_kernel<<<grid, threads, smem, s>>>(h, static_cast<float*>(cols), rows, cin, H, W, P, ldi);
+  else patch_gather_kernel<<<grid, threads, smem, s>>>(f, static_cast<float*>(cols), rows, cin, H, W, P, ldi);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }

@@ -131,21 +131,22 @@ class _Linear(Function):
 
 
 class _PatchEmbed(Function):
-    """Conv2d(k = stride = patch) + 'b c h w -> b (h w) c' as gather + GEMM; the gathered (bf16) patch rows are
-    kept for the weight-gradient GEMM, there is no input gradient."""
+    """Conv2d(k = stride = patch) + 'b c h w -> b (h w) c' as one GEMM whose image-side operand is gathered from the pixels
+    inside the kernel; the backward's weight-gradient GEMM gathers from the same image again (nothing but the input batch
+    is kept), there is no input gradient."""
 
     @staticmethod
     def forward(ctx, img, w, bias, wb, patch, precision):
-        y, cols = _O.patch_embed_fwd(img, w, wb, bias, patch, precision)
-        ctx.save_for_backward(cols, w)
-        ctx.precision, ctx.has_bias, ctx.params = precision, bias is not None, (w, bias)
+        y = _O.patch_embed_fwd(img, w, wb, bias, patch, precision)
+        ctx.save_for_backward(img, w)
+        ctx.precision, ctx.patch, ctx.has_bias, ctx.params = precision, patch, bias is not None, (w, bias)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        cols, w = ctx.saved_tensors
+        img, w = ctx.saved_tensors
         direct = _direct(ctx.params) if ctx.has_bias else None
-        dw, db = _O.patch_embed_bwd(dy.contiguous(), cols, w, ctx.has_bias, ctx.precision, direct)
+        dw, db = _O.patch_embed_bwd(dy.contiguous(), img, w, ctx.patch, ctx.has_bias, ctx.precision, direct)
         if direct is not None:
             _notify(ctx.params)
             dw = db = None

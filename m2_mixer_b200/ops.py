@@ -244,40 +244,50 @@ _define("linear_fwd", "(Tensor x, Tensor w, Tensor? wb, Tensor? bias, int act, i
 _define("linear_bwd", "(Tensor dy, Tensor x, Tensor? y, Tensor w, Tensor? wb, int act, bool need_dx, int precision, "
         "float dropout_p=0.0, int seed=0, Tensor?[]? grads=None) -> "
         "(Tensor, Tensor, Tensor)", linear_bwd)
+def _img(img: torch.Tensor, precision: int) -> torch.Tensor:
+    """Pixels as the kernels take them: contiguous CUDA fp32, or bf16 in BF16 mode (what DevicePrefetcher stages when the
+    host batches are bf16 - the GEMM operand is the pixel rounded to bf16 either way)."""
+    if img.dtype == torch.bfloat16 and precision == BF16 and img.is_cuda:
+        return img if img.is_contiguous() else img.contiguous()
+    return _f32c(img, "img")
+
+
 def patch_embed_fwd(img, w, wb, bias, patch: int, precision: int):
-    img = _f32c(img, "img")
+    img = _img(img, precision)
     B, cin, H, W = img.shape
     if H % patch or W % patch:
         raise AssertionError("Image dimensions must be divisible by the patch size.")
     D = w.shape[0]
     n = (H // patch) * (W // patch)
-    nbytes = _L().m2b200_patch_embed_cols_bytes(B, cin, H, W, patch, precision)
-    cols = torch.empty(nbytes, dtype=torch.uint8, device=img.device)
+    is_bf16 = int(img.dtype == torch.bfloat16)
+    nbytes = _L().m2b200_patch_embed_workspace_bytes(img.data_ptr(), is_bf16, B, cin, H, W, patch, D, precision, 0)
+    ws, wsp = _ws(nbytes, img)
     y = torch.empty(B, n, D, dtype=torch.float32, device=img.device)
     w2d = _f32c(w, "w").reshape(D, -1)
-    check(_L().m2b200_patch_embed_fwd(img.data_ptr(), w2d.data_ptr(), _ptr(wb), 0 if wb is None else wb.shape[1],
-                                      None if bias is None else _f32c(bias, "bias").data_ptr(), cols.data_ptr(), y.data_ptr(),
-                                      B, cin, H, W, patch, D, precision, _stream()), "patch_embed_fwd")
-    return y, cols
+    check(_L().m2b200_patch_embed_fwd(img.data_ptr(), is_bf16, w2d.data_ptr(), _ptr(wb), 0 if wb is None else wb.shape[1],
+                                      None if bias is None else _f32c(bias, "bias").data_ptr(), y.data_ptr(),
+                                      B, cin, H, W, patch, D, precision, wsp, nbytes, _stream()), "patch_embed_fwd")
+    return y
 
 
-def patch_embed_bwd(dy, cols, w, has_bias: bool, precision: int, grads=None):
+def patch_embed_bwd(dy, img, w, patch: int, has_bias: bool, precision: int, grads=None):
     dy = _f32c(dy, "dy")
+    img = _img(img, precision)
+    B, cin, H, W = img.shape
     D = dy.shape[-1]
-    M = dy.numel() // D
-    K = w[0].numel()
+    is_bf16 = int(img.dtype == torch.bfloat16)
     dw = _grad_dst(grads, 0, w)
     db = _grad_dst(grads, 1, w.reshape(D, -1)[:, 0]) if has_bias else None
-    nbytes = _L().m2b200_patch_embed_bwd_workspace_bytes(M, D, precision)
+    nbytes = _L().m2b200_patch_embed_workspace_bytes(img.data_ptr(), is_bf16, B, cin, H, W, patch, D, precision, 1)
     ws, wsp = _ws(nbytes, dy)
-    check(_L().m2b200_patch_embed_bwd(dy.data_ptr(), cols.data_ptr(), dw.data_ptr(), _ptr(db), M, D, K, precision, wsp,
-                                      nbytes, _stream()), "patch_embed_bwd")
+    check(_L().m2b200_patch_embed_bwd(dy.data_ptr(), img.data_ptr(), is_bf16, dw.data_ptr(), _ptr(db), B, cin, H, W, patch, D,
+                                      precision, wsp, nbytes, _stream()), "patch_embed_bwd")
     return dw, (db if db is not None else torch.empty(0, dtype=torch.float32, device=dy.device))
 
 
-_define("patch_embed_fwd", "(Tensor img, Tensor w, Tensor? wb, Tensor? bias, int patch, int precision) -> (Tensor, Tensor)",
+_define("patch_embed_fwd", "(Tensor img, Tensor w, Tensor? wb, Tensor? bias, int patch, int precision) -> Tensor",
         patch_embed_fwd)
-_define("patch_embed_bwd", "(Tensor dy, Tensor cols, Tensor w, bool has_bias, int precision, Tensor?[]? grads=None) -> "
+_define("patch_embed_bwd", "(Tensor dy, Tensor img, Tensor w, int patch, bool has_bias, int precision, Tensor?[]? grads=None) -> "
         "(Tensor, Tensor)", patch_embed_bwd)
 _define("patch_gather", "(Tensor img, int patch) -> Tensor", patch_gather)
 

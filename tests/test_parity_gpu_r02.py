@@ -340,3 +340,33 @@ def test_nccl_world2_shard_gradients_equal_single_process_large_batch():
     r = _run_world2([])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DDP_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_bf16_host_images_give_the_same_bits_as_fp32_images():
+    """data.pin_host_batch(image_dtype=bf16) + DevicePrefetcher: the bf16-mode patch embedding (reference Conv2d,
+    modules/mixer.py:143-146) rounds every pixel to bf16 as its first operation, so a training step fed bf16 images must
+    reproduce the fp32-fed step bit for bit - logits, loss and the patch-embedding weight gradients (M2-Mixer-B: the audio
+    branch takes the gather-inside-the-GEMM kernels of patch_gemm.cu, the 28x28 image branch the gather + GEMM fallback)."""
+    from m2_mixer_b200 import models, presets
+    from m2_mixer_b200.data import DevicePrefetcher, pin_host_batch
+    from oracle.seeding import seeded_state_dict, synthetic_batch
+    cfg = dict(presets.get("avmnist_B"), dropout=0.0)
+    m = models.AVMnistMixerMultiLoss(cfg, {}).cuda().set_precision("bf16").train()
+    m.load_state_dict(seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 5))
+    batch = synthetic_batch("avmnist", 24, 5)
+    res = []
+    for dt in (None, torch.bfloat16):
+        host = pin_host_batch(batch, image_dtype=dt)
+        dev = next(iter(DevicePrefetcher([host], torch.device("cuda"))))
+        assert dev["audio"].dtype == (torch.float32 if dt is None else torch.bfloat16)
+        m.zero_grad()
+        out = m.shared_step(dev, mode="train")
+        out["loss"].backward()
+        torch.cuda.synchronize()
+        res.append((out["logits"].clone(), out["loss"].clone(),
+                    m.audio_mixer.to_patch_embedding[0].weight.grad.clone(), m.image_mixer.to_patch_embedding[0].weight.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    assert abs(float(res[0][1]) - float(res[1][1])) < 1e-6 * float(res[0][1])   # the loss mean is an atomic reduction
+    # the weight-gradient GEMMs reduce their row splits with fp32 atomics: equal up to summation order
+    assert rel_err(res[1][2], res[0][2]) < 1e-5 and rel_err(res[1][3], res[0][3]) < 1e-5
+

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 GROUPS = ["gemm_f32", "gemm_bf16_kk", "gemm_bf16_mn", "gemm_bf16_batch", "rowops", "token_mix", "chain_f32", "chain_fwd",
-          "chain_bwd", "chain_unfused", "linear", "heads", "adam"]
+          "chain_bwd", "chain_unfused", "linear", "heads", "adam", "patch_embed"]
 
 
 def rel(a, b):
@@ -206,6 +206,28 @@ def run_group(g):
                 ok &= report(f"heads kind{kind} dtok{i}", rel(dt[i], td[i].grad), 1e-5)
                 ok &= report(f"heads kind{kind} dw{i}", rel(dw[i], wd[i].grad), 1e-5)
                 ok &= report(f"heads kind{kind} db{i}", rel(db[i], bd[i].grad), 1e-5)
+    elif g == "patch_embed":
+        # (B, cin, H, W, P, D): fused gather-GEMM shapes (P % 8 == 0), ragged M / D / K tiles, and the fallback (P = 14, fp32)
+        for (B, cin, H, W, P, D) in [(64, 1, 112, 112, 56, 128), (37, 3, 32, 48, 16, 200), (5, 2, 16, 24, 8, 72),
+                                     (300, 1, 112, 112, 56, 128), (9, 1, 28, 28, 14, 128)]:
+            for prec, in_bf16 in ((BF16, False), (BF16, True), (FP32, False)):
+                img = rn(B, cin, H, W)
+                w, b = rn(D, cin, P, P) / (cin * P * P) ** 0.5, 0.1 * rn(D)
+                dy = rn(B, (H // P) * (W // P), D)
+                imgr = img.bfloat16().double() if prec == BF16 else img.double()
+                wr = (w.bfloat16().double() if prec == BF16 else w.double()).requires_grad_(True)
+                bd = b.double().requires_grad_(True)
+                ref = O.patch_embed(imgr, wr, bd)
+                ref.backward((dy.bfloat16() if prec == BF16 else dy).double())
+                wb = ops.cast_bf16(w.reshape(D, -1), (cin * P * P + 7) // 8 * 8) if prec == BF16 else None
+                x = img.bfloat16() if in_bf16 else img
+                y = ops.patch_embed_fwd(x, w, wb, b, P, prec)
+                dw, db = ops.patch_embed_bwd(dy, x, w, P, True, prec)
+                torch.cuda.synchronize()
+                tag = f"patch_embed B{B} c{cin} {H}x{W} P{P} D{D} p{prec} bf16in={int(in_bf16)}"
+                ok &= report(tag + " fwd", rel(y, ref), 1e-5)
+                ok &= report(tag + " dw", rel(dw, wr.grad), 2e-5)
+                ok &= report(tag + " db", rel(db, dy.double().sum((0, 1))), 2e-6)
     elif g == "adam":
         n = 100003
         p0, gr = rn(n), rn(n)
