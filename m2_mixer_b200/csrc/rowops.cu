@@ -475,13 +475,23 @@ __global__ void patch_gather_kernel(const TI* __restrict__ img, TO* __restrict__
     koff[k] = o;
   }
   __syncthreads();
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int gx = row % gw, gy = (row / gw) % gh, b = row / (gw * gh);
-    const TI* base = img + (static_cast<long long>(b) * cin * H + gy * P) * W + gx * P;
-    TO* dst = cols + static_cast<long long>(row) * ld;
+  // four patch rows per pass: their loads are independent, so four times the bytes are in flight per thread
+  for (int row0 = blockIdx.x * 4; row0 < rows; row0 += gridDim.x * 4) {
+    const TI* base[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = min(row0 + r, rows - 1);
+      const int gx = row % gw, gy = (row / gw) % gh, b = row / (gw * gh);
+      base[r] = img + (static_cast<long long>(b) * cin * H + gy * P) * W + gx * P;
+    }
     for (int k = threadIdx.x; k < ld; k += blockDim.x) {
       const int o = koff[k];
-      dst[k] = static_cast<TO>(o >= 0 ? static_cast<float>(base[o]) : 0.f);
+      float v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[r] = o >= 0 ? static_cast<float>(base[r][o]) : 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (row0 + r < rows) cols[static_cast<long long>(row0 + r) * ld + k] = static_cast<TO>(v[r]);
     }
   }
 }
@@ -773,7 +783,7 @@ int patch_gather(const void* img, int img_bf16, void* cols, int out_bf16, int B,
   if (rows_ll >= (1ll << 31)) return M2_ERR_ARG;
   const int rows = static_cast<int>(rows_ll), ldi = static_cast<int>(ld);
   const int threads = ld >= 1024 ? 256 : 128;
-  const int grid = rows < 148 * 16 ? rows : 148 * 16;
+  const int grid = (rows + 3) / 4 < 148 * 16 ? (rows + 3) / 4 : 148 * 16;
   const size_t smem = ld * sizeof(int);
   const float* f = static_cast<const float*>(img);
   const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(img);

@@ -9,6 +9,8 @@
 //   weight-gradient GEMMs (dW = dY^T . X, contraction over the token axis) and the transpose-free token-mixing
 //   GEMMs need, so no transposed copy is ever materialised ("operand layouts swapped").
 //   Ragged M/N/K edges rely on TMA out-of-bounds zero fill; stores are masked.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap.cuh"
@@ -34,6 +36,69 @@ struct GemmDev {
   int atomic;
   Drop drop; long long drop_ld;
 };
+
+// One accumulator row x 32 columns: bias / activation / dropout / residual, then the store the output mode asks for.
+__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&r)[32], int row, bool row_ok, int ncol0,
+                                               long long coff, const float* res, float rbias, bool lead) {
+  if (!row_ok || ncol0 >= p.N) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int col = ncol0 + j;
+    float x = __uint_as_float(r[j]);
+    if (col < p.N) {
+      if (lead) {
+        if (p.bias_mode == 1) x += p.bias[col];
+        x += rbias;
+      }
+      if (p.act == 1) x = gelu_erf(x);
+      else if (p.act == 2) x = fmaxf(x, 0.f);
+      if (p.drop.thresh) x = drop_apply(p.drop, x, static_cast<unsigned long long>(row) * p.drop_ld + col);
+      if (res) x += res[col];
+    }
+    v[j] = x;
+  }
+  const bool full_chunk = (ncol0 + 32 <= p.N);
+  if (p.c_bf16) {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + coff + ncol0;
+    if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 o = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
+                             pack_bf16(v[j + 6], v[j + 7]));
+        *reinterpret_cast<uint4*>(c + j) = o;
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (ncol0 + j < p.N) c[j] = __float2bfloat16(v[j]);
+    }
+  } else {
+    float* c = reinterpret_cast<float*>(p.C) + coff + ncol0;
+    if (p.splitk > 1 || p.atomic) {
+      if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)   // 128-bit reductions (red.global.add.v4.f32)
+          atomicAdd(reinterpret_cast<float4*>(c + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+      } else {
+        for (int j = 0; j < 32; ++j)
+          if (ncol0 + j < p.N) atomicAdd(c + j, v[j]);
+      }
+    } else if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (p.accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(c + j);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        *reinterpret_cast<float4*>(c + j) = o;
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (ncol0 + j < p.N) c[j] = p.accumulate ? c[j] + v[j] : v[j];
+    }
+  }
+}
 
 template <bool kAMn, bool kBMn>
 __global__ void __launch_bounds__(192, 2)
@@ -137,64 +202,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t r[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
       tmem_ld_wait();
-      if (!row_ok || n0 + c0 >= p.N) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = n0 + c0 + j;
-        float x = __uint_as_float(r[j]);
-        if (col < p.N) {
-          if (lead) {
-            if (p.bias_mode == 1) x += p.bias[col];
-            x += rbias;
-          }
-          if (p.act == 1) x = gelu_erf(x);
-          else if (p.act == 2) x = fmaxf(x, 0.f);
-          if (p.drop.thresh) x = drop_apply(p.drop, x, static_cast<unsigned long long>(row) * p.drop_ld + col);
-          if (res) x += res[col];
-        }
-        v[j] = x;
-      }
-      const bool full_chunk = (n0 + c0 + 32 <= p.N);
-      if (p.c_bf16) {
-        __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + coff + n0 + c0;
-        if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
-                                 pack_bf16(v[j + 6], v[j + 7]));
-            *reinterpret_cast<uint4*>(c + j) = o;
-          }
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.N) c[j] = __float2bfloat16(v[j]);
-        }
-      } else {
-        float* c = reinterpret_cast<float*>(p.C) + coff + n0 + c0;
-        if (p.splitk > 1 || p.atomic) {
-          if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)   // 128-bit reductions (red.global.add.v4.f32)
-              atomicAdd(reinterpret_cast<float4*>(c + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c0 + j < p.N) atomicAdd(c + j, v[j]);
-          }
-        } else if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(c + j);
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            *reinterpret_cast<float4*>(c + j) = o;
-          }
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.N) c[j] = p.accumulate ? c[j] + v[j] : v[j];
-        }
-      }
+      epilogue_chunk(p, r, row, row_ok, n0 + c0, coff, res, rbias, lead);
     }
   }
 
@@ -217,6 +225,183 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, dim3 
   return M2_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Generation 2: PERSISTENT CTAs, 128 x 256 x 64 tiles, two accumulator buffers in tensor memory.
+//
+// The kernel above is one tile per CTA: TMEM allocation, barrier set-up, the pipeline fill and the 64 KB epilogue of
+// every 128 x 128 tile are serial with its (often short: K = 768 is 12 k-steps) main loop, and a 128 x 128 x 64 step needs
+// 32 KB of operands for 256 clk of tensor work = 128 B/clk/SM out of L2, which is what bounds it (BASELINE configs 4 / 5 ran
+// at 16 % of the bf16 peak on it).  Here one CTA per SM walks tiles (m fastest: the CTAs of a wave share the B panel):
+//   warp 0     TMA producer: a 4-stage ring of (16 KB A + 32 KB B), filled across tile boundaries
+//   warp 1     MMA issuer:   4 x tcgen05.mma M128 N256 K16 per stage into accumulator buffer (tile & 1)
+//   warps 2-9  epilogue:     buffer (tile & 1) -> registers -> bias / GELU / dropout / residual -> global, while the
+//                            MMA warp fills the other buffer (acc_full / acc_empty barriers); two warps per TMEM lane
+//                            quadrant, 128 columns each
+// 48 KB of operands per 512 clk = 94 B/clk/SM.  Same operand layouts, batching, split-K and epilogue as generation 1.
+constexpr int kBN2 = 256;
+constexpr int kStages2 = 4;
+constexpr int kTileA2 = kBM * kBK * 2;                     // 16 KB
+constexpr int kTileB2 = kBN2 * kBK * 2;                    // 32 KB
+constexpr int kSmem2 = kStages2 * (kTileA2 + kTileB2) + 256 + 1024;
+constexpr int kThreads2 = 320;
+
+struct Sched2 { int tiles_m, tiles_n, total; };
+
+template <bool kAMn, bool kBMn>
+__global__ void __launch_bounds__(kThreads2, 1)
+umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p,
+                  const Sched2 sc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages2 * kTileA2;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages2 * (kTileA2 + kTileB2));
+  uint64_t* empty = full + kStages2;
+  uint64_t* acc_full = empty + kStages2;      // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k_tiles = ceil_div(p.K, kBK);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int per_z = sc.tiles_m * sc.tiles_n;
+
+  if (warp == 0) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < sc.total; tile += gridDim.x) {
+      const int z = tile / per_z, r = tile - z * per_z;
+      const int m0 = (r % sc.tiles_m) * kBM, n0 = (r / sc.tiles_m) * kBN2;
+      const int batch = z / p.splitk, split = z - batch * p.splitk;
+      const int kt_begin = split * p.k_tiles_per_split, kt_end = min(k_tiles, kt_begin + p.k_tiles_per_split);
+      const int a_row0 = batch * p.a_batch_rows, b_row0 = batch * p.b_batch_rows;
+      for (int kt = kt_begin; kt < kt_end; ++kt, ++it) {
+        const int s = it % kStages2;
+        mbar_wait(&empty[s], ((it / kStages2) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[s], kTileA2 + kTileB2);
+          const int k0 = kt * kBK;
+          uint8_t* a = sA + s * kTileA2;
+          uint8_t* b = sB + s * kTileB2;
+          if (!kAMn) {
+            tma_load_2d(a, &tmA, &full[s], k0, a_row0 + m0);
+          } else {
+            tma_load_2d(a, &tmA, &full[s], m0, a_row0 + k0);
+            tma_load_2d(a + kTileA2 / 2, &tmA, &full[s], m0 + 64, a_row0 + k0);
+          }
+          if (!kBMn) {
+            tma_load_2d(b, &tmB, &full[s], k0, b_row0 + n0);            // [256 n][64 k] in one box
+          } else {
+#pragma unroll
+            for (int pnl = 0; pnl < 4; ++pnl) tma_load_2d(b + pnl * (kTileB2 / 4), &tmB, &full[s], n0 + 64 * pnl, b_row0 + k0);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN2, kAMn ? 1 : 0, kBMn ? 1 : 0);
+    const uint64_t a_desc0 = kAMn ? umma_desc_sw128(smem_u32(sA), kTileA2 / 2, 1024) : umma_desc_sw128(smem_u32(sA), 16, 1024);
+    const uint64_t b_desc0 = kBMn ? umma_desc_sw128(smem_u32(sB), kTileB2 / 4, 1024) : umma_desc_sw128(smem_u32(sB), 16, 1024);
+    int it = 0, t = 0;
+    for (int tile = blockIdx.x; tile < sc.total; tile += gridDim.x, ++t) {
+      const int z = tile / per_z;
+      const int split = z % p.splitk;
+      const int kt_begin = split * p.k_tiles_per_split, kt_end = min(k_tiles, kt_begin + p.k_tiles_per_split);
+      const int buf = t & 1;
+      mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);     // the epilogue has drained this buffer (tile t - 2)
+      tc_fence_after();
+      const uint32_t acc = tmem_base + buf * kBN2;
+      for (int kt = kt_begin; kt < kt_end; ++kt, ++it) {
+        const int s = it % kStages2;
+        mbar_wait(&full[s], (it / kStages2) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = a_desc0 + static_cast<uint64_t>((s * kTileA2) >> 4);
+          const uint64_t bd = b_desc0 + static_cast<uint64_t>((s * kTileB2) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk)
+            umma_bf16(acc, ad + ((kk * (kAMn ? 2048 : 32)) >> 4), bd + ((kk * (kBMn ? 2048 : 32)) >> 4), idesc,
+                      (kt > kt_begin || kk > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;                       // TMEM lane quadrant of this warp
+    const int half = (warp - 2) >> 2;             // which 128 of the 256 accumulator columns
+    int t = 0;
+    for (int tile = blockIdx.x; tile < sc.total; tile += gridDim.x, ++t) {
+      const int z = tile / per_z, r = tile - z * per_z;
+      const int m0 = (r % sc.tiles_m) * kBM, n0 = (r / sc.tiles_m) * kBN2;
+      const int batch = z / p.splitk, split = z - batch * p.splitk;
+      const int buf = t & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool lead = (split == 0);
+      const float rbias = (p.bias_mode == 2 && row_ok && lead) ? p.bias[row] : 0.f;
+      const long long coff = static_cast<long long>(batch) * p.c_batch_stride + static_cast<long long>(row) * p.ldc;
+      const float* res = (p.residual && lead) ? p.residual + static_cast<long long>(batch) * p.r_batch_stride +
+                                                    static_cast<long long>(row) * p.ldr : nullptr;
+      mbar_wait(&acc_full[buf], (t >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+        uint32_t rg[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kBN2 + c0, rg);
+        tmem_ld_wait();
+        if (c0 + 32 == half * 128 + 128) {        // last piece in registers: hand the buffer back before the math
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        epilogue_chunk(p, rg, row, row_ok, n0 + c0, coff, res, rbias, lead);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <bool kAMn, bool kBMn>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, const Sched2& sc, cudaStream_t s) {
+  auto kern = umma_gemm2_kernel<kAMn, kBMn>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2) != cudaSuccess) return M2_ERR_LAUNCH;
+    configured = true;
+  }
+  LaunchScope scope(kAMn ? (kBMn ? "umma_gemm2_tn" : "umma_gemm2_tk") : (kBMn ? "umma_gemm2_kn" : "umma_gemm2_kk"), s);
+  const int grid = sc.total < 148 ? sc.total : 148;
+  kern<<<grid, kThreads2, kSmem2, s>>>(ta, tb, d, sc);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
+// M2B200_GEMM_GEN=1 keeps every GEMM on the one-tile-per-CTA kernel (A/B measurements)
+int gemm_generation() {
+  static const int gen = [] {
+    const char* e = getenv("M2B200_GEMM_GEN");
+    return e ? atoi(e) : 2;
+  }();
+  return gen;
+}
+
 }  // namespace
 
 int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
@@ -224,6 +409,9 @@ int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
   if (g.splitk < 1 || (g.splitk > 1 && (g.c_bf16 || g.act))) return M2_ERR_ARG;
   if (g.atomic_out && (g.c_bf16 || g.act || g.bias_mode || g.residual)) return M2_ERR_ARG;
   if (g.bias_mode && !g.bias) return M2_ERR_ARG;
+  // wide persistent tiles when the output is wide enough to fill them and there is more than a wave of work
+  const bool wide = gemm_generation() >= 2 && g.N > 128 &&
+                    static_cast<long long>(ceil_div(g.M, kBM)) * ceil_div(g.N, kBN2) * g.batch * g.splitk >= 64;
   CUtensorMap ta, tb;
   int rc;
   {
@@ -235,7 +423,7 @@ int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
   {
     const uint64_t ext = g.b_mn ? g.K : g.N, cols = g.b_mn ? g.N : g.K;
     const uint64_t rows = static_cast<uint64_t>(g.batch - 1) * g.b_batch_rows + ext;
-    rc = make_tmap_bf16(&tb, g.B, rows, cols, g.ldb, g.b_mn ? 64 : 128, 64);
+    rc = make_tmap_bf16(&tb, g.B, rows, cols, g.ldb, g.b_mn ? 64 : (wide ? 256 : 128), 64);
     if (rc) return rc;
   }
   GemmDev d;
@@ -251,6 +439,15 @@ int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
   d.accumulate = g.accumulate;
   d.atomic = (g.atomic_out && !g.c_bf16) ? 1 : 0;
   d.drop = make_drop(g.drop_p, g.drop_seed, g.drop_site); d.drop_ld = g.drop_ld;
+  if (wide) {
+    Sched2 sc;
+    sc.tiles_m = ceil_div(g.M, kBM); sc.tiles_n = ceil_div(g.N, kBN2);
+    const long long total = static_cast<long long>(sc.tiles_m) * sc.tiles_n * g.batch * d.splitk;
+    if (total >= (1ll << 31)) return M2_ERR_ARG;
+    sc.total = static_cast<int>(total);
+    if (g.a_mn) return g.b_mn ? launch2<true, true>(ta, tb, d, sc, s) : launch2<true, false>(ta, tb, d, sc, s);
+    return g.b_mn ? launch2<false, true>(ta, tb, d, sc, s) : launch2<false, false>(ta, tb, d, sc, s);
+  }
   dim3 grid(ceil_div(g.M, kBM), ceil_div(g.N, kBN), g.batch * d.splitk);
   if (grid.y > 65535 || grid.z > 65535) return M2_ERR_ARG;
   if (g.a_mn) return g.b_mn ? launch<true, true>(ta, tb, d, grid, s) : launch<true, false>(ta, tb, d, grid, s);

@@ -7,7 +7,7 @@ channel mixing) - no [tokens x channel_dim] hidden tensor is ever kept alive bet
 from __future__ import annotations
 
 import os
-from typing import List, Optional, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 from torch.autograd import Function
@@ -107,6 +107,30 @@ class _LayerNorm(Function):
         if direct is not None:
             _notify(ctx.params)
         return (dx, *_ret(direct, g))
+
+
+class _LayerNormConcat(Function):
+    """fused = cat([LN_i(x_i)], dim=1) with every LayerNorm writing (and its backward reading) its token slice of the fused
+    buffer in place: the closing LayerNorms of two encoders + ConcatFusion (modules/mixer.py:161, modules/fusion.py:117)."""
+
+    @staticmethod
+    def forward(ctx, n, *tensors):
+        xs, ws, bs = list(tensors[:n]), list(tensors[n:2 * n]), list(tensors[2 * n:3 * n])
+        ctx.save_for_backward(*xs, *ws)
+        ctx.n, ctx.params = n, tuple(ws) + tuple(bs)
+        return _O.layernorm_concat_fwd(xs, ws, bs)
+
+    @staticmethod
+    def backward(ctx, g):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        xs, ws = list(saved[:n]), list(saved[n:2 * n])
+        direct = _direct(ctx.params)
+        dxs, dws, dbs = _O.layernorm_concat_bwd(g.contiguous(), xs, ws, direct)
+        if direct is not None:
+            _notify(ctx.params)
+            dws, dbs = [None] * n, [None] * n
+        return (None, *dxs, *dws, *dbs)
 
 
 class _Linear(Function):
@@ -223,11 +247,13 @@ class _HeadsLoss(Function):
     """(losses[4], logits[3,B,K], preds) = heads+loss; only losses[0] (the weighted total) is differentiable."""
 
     @staticmethod
-    def forward(ctx, labels, pos_weight, head_weight, loss_kind, n, *tensors):
+    def forward(ctx, labels, pos_weight, head_weight, loss_kind, n, slices, *tensors):
         toks, ws, bs = list(tensors[:n]), list(tensors[n:2 * n]), list(tensors[2 * n:3 * n])
-        losses, logits, preds = _O.heads_loss_fwd(toks, ws, bs, labels, pos_weight, list(head_weight), loss_kind)
+        st = None if slices is None else [s for s, _ in slices]
+        ln = None if slices is None else [l for _, l in slices]
+        losses, logits, preds = _O.heads_loss_fwd(toks, ws, bs, labels, pos_weight, list(head_weight), loss_kind, st, ln)
         ctx.save_for_backward(labels, pos_weight, logits, *tensors)
-        ctx.head_weight, ctx.loss_kind, ctx.n = list(head_weight), loss_kind, n
+        ctx.head_weight, ctx.loss_kind, ctx.n, ctx.slices = list(head_weight), loss_kind, n, (st, ln)
         ctx.params = tuple(ws) + tuple(bs)
         ctx.mark_non_differentiable(logits, preds)
         ctx.tok_shapes = [t.shape for t in toks]
@@ -242,12 +268,13 @@ class _HeadsLoss(Function):
         # (passed as a device scalar: no host sync, CUDA-graph capturable)
         direct = _direct(ctx.params)
         dt, dw, db = _O.heads_loss_bwd(toks, ws, bs, labels, pos_weight, ctx.head_weight, ctx.loss_kind, logits, 1.0,
-                                       dlosses.contiguous(), direct)
-        dt = [g.reshape(s) for g, s in zip(dt, ctx.tok_shapes)]
+                                       dlosses.contiguous(), direct, ctx.slices[0], ctx.slices[1])
+        # heads that pool slices of ONE base tensor share its gradient: returned once (autograd sums the input slots)
+        dt = [g.reshape(s) if g.numel() else None for g, s in zip(dt, ctx.tok_shapes)]
         if direct is not None:
             _notify(ctx.params)
             dw, db = [None] * n, [None] * n
-        return (None, None, None, None, None, *dt, *dw, *db)
+        return (None, None, None, None, None, None, *dt, *dw, *db)
 
 
 # ---------------------------------------------------------------------------------------------------- public API
@@ -361,6 +388,11 @@ def channel_mix(u, ln_w, ln_b, w1, b1, w2, b2, precision, w1b=None, w2b=None, dr
     return _ChannelMix.apply(u, ln_w, ln_b, w1, b1, w2, b2, w1b, w2b, prec, p, seed)
 
 
+def layer_norm_concat(xs: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor]) -> torch.Tensor:
+    """cat([LayerNorm_i(xs[i])], dim=1) without the copy: each LayerNorm writes its token slice of the result."""
+    return _LayerNormConcat.apply(len(xs), *xs, *ws, *bs)
+
+
 def layer_norm(x, w, b) -> torch.Tensor:
     return _LayerNorm.apply(x, w, b)
 
@@ -416,11 +448,18 @@ def add(a, b) -> torch.Tensor:
 
 
 def heads_loss(toks: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], labels,
-               head_weight: Sequence[float], loss_kind: int = 0, pos_weight: Optional[torch.Tensor] = None):
-    """Returns (losses[4] = total, L_0, L_1, L_2; logits [3,B,K]; preds)."""
+               head_weight: Sequence[float], loss_kind: int = 0, pos_weight: Optional[torch.Tensor] = None,
+               slices: Optional[Sequence[Tuple[int, int]]] = None):
+    """Returns (losses[4] = total, L_0, L_1, L_2; logits [3,B,K]; preds).  ``slices[h] = (start, len)``: head h pools that
+    token range of toks[h] in place (per-modality heads on the fused-token buffer of ``layer_norm_concat``)."""
     n = len(toks)
+    if slices is not None and any(t.dim() == 3 and l * t.shape[2] >= 16384 for t, (_, l) in zip(toks, slices)):
+        toks = [t[:, s0:s0 + l] for t, (s0, l) in zip(toks, slices)]     # wide token sets: pooled by the batch-parallel kernel below
+        slices = None
     # The heads kernels give one WARP a sample (mean-pool, Linear, loss in one pass): right for the shipped configs (4-49
     # tokens of 32-128 floats).  With hundreds of wide tokens per sample and a small batch (the Scaled config: 392 x 768
     # floats per sample, batch 64 = 64 warps on the whole GPU) the pooling is done first by the batch x dim parallel kernel.
     toks = [mean_pool(t).unsqueeze(1) if (t.dim() == 3 and t.shape[1] * t.shape[2] >= 16384) else t for t in toks]
-    return _HeadsLoss.apply(labels, pos_weight, tuple(float(h) for h in head_weight), loss_kind, n, *toks, *ws, *bs)
+    if slices is not None:
+        slices = tuple((int(s0), int(l)) for s0, l in slices)
+    return _HeadsLoss.apply(labels, pos_weight, tuple(float(h) for h in head_weight), loss_kind, n, slices, *toks, *ws, *bs)

@@ -57,17 +57,16 @@ class AVMnistMixerMultiLoss(TrainTestModule):
             elif self.mute == 'audio':
                 audio = torch.zeros_like(audio)
 
-        image_tokens = self.image_mixer(image)
-        audio_tokens = self.audio_mixer(audio)
-        fused_tokens = self.fusion_mixer(self.fusion_function(image_tokens, audio_tokens))
+        toks, slices, _ = self._encode_and_fuse(self.image_mixer, image, self.audio_mixer, audio, self.fusion_function,
+                                                self.fusion_mixer)
 
         # three mean-pool + Linear heads, three cross entropies and their weighted sum: one kernel
         cf = self.classifier_fusion.classifer
         losses, logits, preds = F.heads_loss(
-            [image_tokens, audio_tokens, fused_tokens],
+            toks,
             [self.classifier_image.weight, self.classifier_audio.weight, cf.weight],
             [self.classifier_image.bias, self.classifier_audio.bias, cf.bias],
-            labels, self.head_weights(mode), loss_kind=0)
+            labels, self.head_weights(mode), loss_kind=0, slices=slices)
         return {'preds': preds[2], 'preds_image': preds[0], 'preds_audio': preds[1], 'labels': labels,
                 'loss': losses[0], 'loss_image': losses[1], 'loss_audio': losses[2], 'loss_fusion': losses[3],
                 'image_logits': logits[0], 'audio_logits': logits[1], 'logits': logits[2]}

@@ -50,6 +50,29 @@ class TrainTestModule(nn.Module):
         model.checkpoint_path = checkpoint_path
         return model
 
+    # --- two encoders -> ConcatFusion -> fusion mixer -> three heads ----------------------------------------------
+    def _encode_and_fuse(self, mixer_a, xa, mixer_b, xb, fusion_function, fusion_mixer):
+        """(tokens per head, token slices, fused tokens) of the reference's
+        ``fusion_mixer(fusion_function(mixer_a(xa), mixer_b(xb)))`` (models/avmnist.py:262-266, models/mmimdb.py:100-104).
+        When the fusion is ConcatFusion(dim=1) over two Mixer stacks of one width, the closing LayerNorms write straight
+        into the fused-token buffer (no concat copy, no split copies in the backward) and the per-modality heads pool their
+        slices of that buffer in place."""
+        from .. import functional as F
+        from ..modules.fusion import ConcatFusion
+        from ..modules.mixer import _Stack
+        if (isinstance(fusion_function, ConcatFusion) and fusion_function.dim == 1 and isinstance(mixer_a, _Stack)
+                and isinstance(mixer_b, _Stack)
+                and mixer_a.layer_norm.weight.shape == mixer_b.layer_norm.weight.shape):
+            fa, fb = mixer_a.forward_features(xa), mixer_b.forward_features(xb)
+            la, lb = mixer_a.layer_norm, mixer_b.layer_norm
+            cat = F.layer_norm_concat([fa, fb], [la.weight, lb.weight], [la.bias, lb.bias])
+            fused = fusion_mixer(cat)
+            na, nb = fa.shape[1], fb.shape[1]
+            return [cat, cat, fused], [(0, na), (na, nb), (0, fused.shape[1])], fused
+        ta, tb = mixer_a(xa), mixer_b(xb)
+        fused = fusion_mixer(fusion_function(ta, tb))
+        return [ta, tb, fused], None, fused
+
     def set_precision(self, p: str) -> "TrainTestModule":
         for m in self.modules():
             if hasattr(m, "precision") and m is not self:

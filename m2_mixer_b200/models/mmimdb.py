@@ -32,16 +32,15 @@ class MMIMDBMixerMultiLoss(TrainTestModule):
 
     def shared_step(self, batch, **kwargs):
         image, text, labels = batch['image'], batch['text'], batch['label']
-        image_tokens = self.image_mixer(image)
-        text_tokens = self.text_mixer(text)
-        fused = self.fusion_mixer(self.fusion_function(image_tokens, text_tokens))
+        toks, slices, _ = self._encode_and_fuse(self.image_mixer, image, self.text_mixer, text, self.fusion_function,
+                                                self.fusion_mixer)
         hw = (0.0, 0.0, 1.0) if (self.modalities_freezed and kwargs.get('mode') == 'train') else (1.0, 1.0, 1.0)
         cf = self.classifier_fusion.classifer
         losses, logits, preds = F.heads_loss(
-            [image_tokens, text_tokens, fused],
+            toks,
             [self.classifier_image.weight, self.classifier_text.weight, cf.weight],
             [self.classifier_image.bias, self.classifier_text.bias, cf.bias],
-            labels, hw, loss_kind=1, pos_weight=self.pos_weight)
+            labels, hw, loss_kind=1, pos_weight=self.pos_weight, slices=slices)
         return {'preds': preds[2], 'preds_image': preds[0], 'preds_text': preds[1], 'labels': labels, 'loss': losses[0],
                 'loss_image': losses[1], 'loss_text': losses[2], 'loss_fusion': losses[3], 'image_logits': logits[0],
                 'text_logits': logits[1], 'logits': logits[2]}

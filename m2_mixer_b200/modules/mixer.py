@@ -109,10 +109,16 @@ class _Stack(nn.Module):
         for _ in range(num_mixers):
             self.mixer_blocks.append(MixerBlock(hidden_dim, num_patch, token_dim, channel_dim, dropout=dropout))
 
-    def _run_stack(self, x):
+    def _run_blocks(self, x):
         for blk in self.mixer_blocks:
             x = blk(x)
-        return F.layer_norm(x, self.layer_norm.weight, self.layer_norm.bias)
+        return x
+
+    def _run_stack(self, x):
+        return F.layer_norm(self._run_blocks(x), self.layer_norm.weight, self.layer_norm.bias)
+
+    def forward(self, x):
+        return F.layer_norm(self.forward_features(x), self.layer_norm.weight, self.layer_norm.bias)
 
     @property
     def precision(self) -> str:
@@ -134,8 +140,10 @@ class FusionMixer(_Stack):
         self._build_stack(hidden_dim, self.num_patch, num_mixers, token_dim, channel_dim, dropout)
         self.layer_norm = nn.LayerNorm(hidden_dim)
 
-    def forward(self, x):
-        return self._run_stack(x)
+    def forward_features(self, x):
+        """The stack WITHOUT its closing LayerNorm (the task modules normalise two encoders straight into the fused-token
+        buffer with F.layer_norm_concat: zero-copy ConcatFusion)."""
+        return self._run_blocks(x)
 
 
 class MLPMixer(_Stack):
@@ -153,10 +161,10 @@ class MLPMixer(_Stack):
         self._build_stack(hidden_dim, self.num_patch, num_mixers, token_dim, channel_dim, dropout)
         self.layer_norm = nn.LayerNorm(hidden_dim)
 
-    def forward(self, x):
+    def forward_features(self, x):
         conv = self.to_patch_embedding[0]
         x = F.patch_embed(x, conv.weight, conv.bias, self.patch_size, self.precision)
-        return self._run_stack(x)
+        return self._run_blocks(x)
 
 
 class MLPMixerNoPatching(_Stack):
@@ -169,9 +177,9 @@ class MLPMixerNoPatching(_Stack):
         self._build_stack(hidden_dim, self.num_patch, num_mixers, token_dim, channel_dim, dropout)
         self.layer_norm = nn.LayerNorm(hidden_dim)
 
-    def forward(self, x):
+    def forward_features(self, x):
         x = F.linear(x, self.proj.weight, self.proj.bias, ACT_NONE, self.precision)
-        return self._run_stack(x)
+        return self._run_blocks(x)
 
 
 class PNLPMixer(_Stack):
@@ -186,6 +194,6 @@ class PNLPMixer(_Stack):
             self.mixer_blocks.append(MixerBlock(hidden_dim, max_seq_len, mlp_hidden_dim, mlp_hidden_dim, dropout=dropout))
         self.layer_norm = nn.LayerNorm(hidden_dim)
 
-    def forward(self, x):
+    def forward_features(self, x):
         x = F.linear(x, self.bottleneck.weight, self.bottleneck.bias, ACT_NONE, self.precision)
-        return self._run_stack(x)
+        return self._run_blocks(x)

@@ -189,7 +189,45 @@ def layernorm_bwd(dy, x, w, grads=None):
     return dx, dw, db
 
 
+def layernorm_concat_fwd(xs: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor]):
+    """fused[:, off_i : off_i + N_i, :] = LayerNorm_i(xs[i]): every encoder normalises straight into its slice of the
+    fused-token buffer (ConcatFusion(dim=1) of the closing LayerNorms without a copy, modules/fusion.py:117)."""
+    xs = [_f32c(x, "x") for x in xs]
+    B, D = xs[0].shape[0], xs[0].shape[-1]
+    if any(x.dim() != 3 or x.shape[0] != B or x.shape[2] != D for x in xs):
+        raise ValueError("layernorm_concat expects [B, N_i, D] token tensors with equal B and D")
+    ntot = sum(x.shape[1] for x in xs)
+    out = torch.empty(B, ntot, D, dtype=torch.float32, device=xs[0].device)
+    off = 0
+    for x, w, b in zip(xs, ws, bs):
+        check(_L().m2b200_layernorm_fwd(x.data_ptr(), _f32c(w, "w").data_ptr(), _f32c(b, "b").data_ptr(),
+                                        out.data_ptr() + off * D * 4, B, x.shape[1], D, ntot * D, _stream()), "layernorm_concat_fwd")
+        off += x.shape[1]
+    return out
+
+
+def layernorm_concat_bwd(g, xs: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], grads=None):
+    """Backward of layernorm_concat_fwd: every LayerNorm backward reads its slice of the fused-token gradient in place."""
+    g = _f32c(g, "g")
+    xs = [_f32c(x, "x") for x in xs]
+    B, ntot, D = g.shape
+    n = len(xs)
+    dxs, dws, dbs, off = [], [], [], 0
+    for i, (x, w) in enumerate(zip(xs, ws)):
+        dx = torch.empty_like(x)
+        dw, db = _grad_dst(grads, i, w), _grad_dst(grads, n + i, w)
+        check(_L().m2b200_layernorm_bwd(g.data_ptr() + off * D * 4, ntot * D, x.data_ptr(), _f32c(w, "w").data_ptr(), None,
+                                        dx.data_ptr(), dw.data_ptr(), db.data_ptr(), B, x.shape[1], D, _stream()),
+              "layernorm_concat_bwd")
+        off += x.shape[1]
+        dxs.append(dx); dws.append(dw); dbs.append(db)
+    return dxs, dws, dbs
+
+
 _define("layernorm_fwd", "(Tensor x, Tensor w, Tensor b) -> Tensor", layernorm_fwd)
+_define("layernorm_concat_fwd", "(Tensor[] xs, Tensor[] ws, Tensor[] bs) -> Tensor", layernorm_concat_fwd)
+_define("layernorm_concat_bwd", "(Tensor g, Tensor[] xs, Tensor[] ws, Tensor?[]? grads=None) -> (Tensor[], Tensor[], Tensor[])",
+        layernorm_concat_bwd)
 _define("layernorm_bwd", "(Tensor dy, Tensor x, Tensor w, Tensor?[]? grads=None) -> (Tensor, Tensor, Tensor)", layernorm_bwd)
 
 
@@ -410,9 +448,29 @@ _define("fuse2_max_bwd", "(Tensor a, Tensor b, Tensor g) -> (Tensor, Tensor)", f
 
 
 # ------------------------------------------------------------------------------------------------ heads + loss
-def _heads_args(toks, ws, bs, head_weight):
+def _tok_slices(toks, tok_start, tok_len):
+    """Per head (start, len) token range of its [B, N, D] base tensor (default: all of it)."""
+    if tok_start is None:
+        return [(0, t.shape[1]) for t in toks]
+    sl = [(int(s), int(l)) for s, l in zip(tok_start, tok_len)]
+    for t, (s0, l0) in zip(toks, sl):
+        if s0 < 0 or l0 <= 0 or s0 + l0 > t.shape[1]:
+            raise ValueError("token slice outside its base tensor")
+    return sl
+
+
+def _heads_args(toks, ws, bs, head_weight, slices=None):
     n = len(toks)
     arr_p = (C.c_void_p * 3)
+    if slices is not None:
+        tok = arr_p(*[t.data_ptr() + s0 * t.shape[2] * 4 for t, (s0, _) in zip(toks, slices)] + [None] * (3 - n))
+        w = arr_p(*[t.data_ptr() for t in ws] + [None] * (3 - n))
+        b = arr_p(*[t.data_ptr() for t in bs] + [None] * (3 - n))
+        bstride = (C.c_int64 * 3)(*[t.shape[1] * t.shape[2] for t in toks] + [0] * (3 - n))
+        ntok = (C.c_int * 3)(*[l0 for _, l0 in slices] + [0] * (3 - n))
+        dim = (C.c_int * 3)(*[t.shape[2] for t in toks] + [0] * (3 - n))
+        hw = (C.c_float * 3)(*list(head_weight) + [0.0] * (3 - n))
+        return tok, bstride, ntok, dim, w, b, hw
     tok = arr_p(*[t.data_ptr() for t in toks] + [None] * (3 - n))
     w = arr_p(*[t.data_ptr() for t in ws] + [None] * (3 - n))
     b = arr_p(*[t.data_ptr() for t in bs] + [None] * (3 - n))
@@ -429,8 +487,11 @@ def _as_tokens(t: torch.Tensor) -> torch.Tensor:
 
 
 def heads_loss_fwd(toks: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], labels,
-                   pos_weight, head_weight: Sequence[float], loss_kind: int):
+                   pos_weight, head_weight: Sequence[float], loss_kind: int, tok_start=None, tok_len=None):
+    """``tok_start`` / ``tok_len``: head h pools tokens [start, start + len) of toks[h] - the per-modality heads read their
+    slices of the fused-token buffer in place (the same tensor may be given for several heads)."""
     toks = [_as_tokens(t) for t in toks]
+    slices = _tok_slices(toks, tok_start, tok_len)
     ws = [_f32c(w, "w") for w in ws]
     bs = [_f32c(b, "b") for b in bs]
     n, B, K = len(toks), toks[0].shape[0], ws[0].shape[0]
@@ -442,7 +503,7 @@ def heads_loss_fwd(toks: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs:
     logits = torch.empty(3, B, K, dtype=torch.float32, device=dev)
     losses = torch.empty(4, dtype=torch.float32, device=dev)
     preds = torch.zeros((3, B) if loss_kind == 0 else (3, B, K), dtype=torch.int64, device=dev)
-    tok, bstride, ntok, dim, w, b, hw = _heads_args(toks, ws, bs, head_weight)
+    tok, bstride, ntok, dim, w, b, hw = _heads_args(toks, ws, bs, head_weight, slices)
     check(_L().m2b200_heads_loss_fwd(tok, bstride, ntok, dim, w, b, n, B, K, loss_kind, labels.data_ptr(),
                                      _ptr(pos_weight), hw, logits.data_ptr(), losses.data_ptr(), preds.data_ptr(),
                                      _stream()), "heads_loss_fwd")
@@ -450,19 +511,31 @@ def heads_loss_fwd(toks: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs:
 
 
 def heads_loss_bwd(toks, ws, bs, labels, pos_weight, head_weight, loss_kind: int, logits, grad_scale: float, grad_scale_dev=None,
-                   grads=None):
+                   grads=None, tok_start=None, tok_len=None):
+    """Returns (dtoks, dws, dbs); heads that share one base tensor (token slices) share ONE gradient tensor: it is returned
+    at the first head's position and the later positions hold an empty placeholder."""
     toks = [_as_tokens(t) for t in toks]
+    slices = _tok_slices(toks, tok_start, tok_len)
     ws = [_f32c(w, "w") for w in ws]
     bs = [_f32c(b, "b") for b in bs]
     n, B, K = len(toks), toks[0].shape[0], ws[0].shape[0]
     labels = labels.to(torch.int64).contiguous() if loss_kind == 0 else labels.to(torch.float32).contiguous()
-    dtoks = [torch.empty_like(t) for t in toks]
+    owner, dbase = {}, []
+    for i, t in enumerate(toks):                      # one gradient tensor per distinct base
+        key = (t.data_ptr(), tuple(t.shape))
+        if key not in owner:
+            covered = sum(l0 for u, (_, l0) in zip(toks, slices) if (u.data_ptr(), tuple(u.shape)) == key)
+            owner[key] = (torch.empty_like(t) if covered >= t.shape[1] else torch.zeros_like(t))
+            dbase.append(owner[key])
+        else:
+            dbase.append(None)
+    dfull = [owner[(t.data_ptr(), tuple(t.shape))] for t in toks]
     dws = [_grad_dst(grads, i, w) for i, w in enumerate(ws)]
     dbs = [_grad_dst(grads, n + i, b) for i, b in enumerate(bs)]
-    tok, bstride, ntok, dim, w, b, hw = _heads_args(toks, ws, bs, head_weight)
+    tok, bstride, ntok, dim, w, b, hw = _heads_args(toks, ws, bs, head_weight, slices)
     arr_p = (C.c_void_p * 3)
-    dtok = arr_p(*[t.data_ptr() for t in dtoks] + [None] * (3 - n))
-    dstride = (C.c_int64 * 3)(*[t.shape[1] * t.shape[2] for t in dtoks] + [0] * (3 - n))
+    dtok = arr_p(*[t.data_ptr() + s0 * t.shape[2] * 4 for t, (s0, _) in zip(dfull, slices)] + [None] * (3 - n))
+    dstride = (C.c_int64 * 3)(*[t.shape[1] * t.shape[2] for t in dfull] + [0] * (3 - n))
     acc = (C.c_int * 3)(0, 0, 0)
     dw = arr_p(*[t.data_ptr() for t in dws] + [None] * (3 - n))
     db = arr_p(*[t.data_ptr() for t in dbs] + [None] * (3 - n))
@@ -470,14 +543,15 @@ def heads_loss_bwd(toks, ws, bs, labels, pos_weight, head_weight, loss_kind: int
                                      _ptr(pos_weight), hw, _f32c(logits, "logits").data_ptr(), float(grad_scale),
                                      None if grad_scale_dev is None else _f32c(grad_scale_dev, "grad_scale_dev").data_ptr(), dtok,
                                      dstride, acc, dw, db, _stream()), "heads_loss_bwd")
+    dtoks = [d if d is not None else torch.empty(0, dtype=torch.float32, device=toks[0].device) for d in dbase]
     return dtoks, dws, dbs
 
 
 _define("heads_loss_fwd", "(Tensor[] toks, Tensor[] ws, Tensor[] bs, Tensor labels, Tensor? pos_weight, float[] head_weight, "
-        "int loss_kind) -> (Tensor, Tensor, Tensor)", heads_loss_fwd)
+        "int loss_kind, int[]? tok_start=None, int[]? tok_len=None) -> (Tensor, Tensor, Tensor)", heads_loss_fwd)
 _define("heads_loss_bwd", "(Tensor[] toks, Tensor[] ws, Tensor[] bs, Tensor labels, Tensor? pos_weight, float[] head_weight, "
-        "int loss_kind, Tensor logits, float grad_scale, Tensor? grad_scale_dev, Tensor?[]? grads=None) -> "
-        "(Tensor[], Tensor[], Tensor[])", heads_loss_bwd)
+        "int loss_kind, Tensor logits, float grad_scale, Tensor? grad_scale_dev, Tensor?[]? grads=None, int[]? tok_start=None, "
+        "int[]? tok_len=None) -> (Tensor[], Tensor[], Tensor[])", heads_loss_bwd)
 
 
 # ------------------------------------------------------------------------------------------------ optimiser / gemm

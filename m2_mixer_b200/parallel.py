@@ -54,6 +54,7 @@ class GradSync:
                 self.buckets.append([cur_start, cur_end, count])
                 cur_end, count = None, 0
         self._pending = [b[2] for b in self.buckets]
+        self._fired = [False] * len(params)          # a parameter counts ONCE per step (see _make_hook)
         self._launched = [False] * len(self.buckets)
         self._handles = []
         self.enabled = True       # False: the hooks do nothing (graph.GraphedTrainStep reduces the whole buffer between graphs)
@@ -72,8 +73,13 @@ class GradSync:
         b = self.bucket_of[i]
 
         def hook(_p):
-            if not self.enabled:
+            # Called through p._m2_ready by the kernels that accumulate straight into the flat buffer AND by autograd's
+            # post-accumulate hook: torch runs that hook even when the Function returned None for the parameter (measured
+            # on 2 x B200, tools/ddp_debug.py: every parameter reported twice and every bucket was reduced half way through
+            # its gradients).  The first report is the one that follows the producing kernels in stream order.
+            if not self.enabled or self._fired[i]:
                 return
+            self._fired[i] = True
             self._pending[b] -= 1
             if self._pending[b] == 0:
                 self._launch(b)
@@ -104,6 +110,7 @@ class GradSync:
         if self.cuda:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         self._pending = list(self._static_pending)
+        self._fired = [False] * len(self._fired)
         self._launched = [False] * len(self.buckets)
 
 

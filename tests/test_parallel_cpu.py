@@ -74,6 +74,21 @@ def _worker(rank, world, port, q):
     (params[2].sum() * (rank + 1)).backward()
     sync.finish()
     ok &= bool(torch.allclose(flat_g[offs[2]:offs[2] + 21], torch.full((21,), 3.0)))
+    # the CUDA kernels that accumulate straight into the flat buffer report a parameter through p._m2_ready, and torch
+    # ALSO runs the post-accumulate hook of that parameter (seen on 2 x B200): a parameter must count once per step, or
+    # its bucket is reduced before the later gradients of the bucket exist.  Here: parameter 3 (the last one of its bucket
+    # in backward order) reports twice before parameter 2's gradient has been produced.
+    flat_g.zero_()
+    b3 = sync.bucket_of[3]
+    assert sync.bucket_of[4] == b3 and sync.buckets[b3][2] == 2
+    params[4]._m2_ready(); params[4]._m2_ready()
+    ok &= not sync._launched[b3]
+    h = torch.tanh(xs @ params[0].t() + params[1].sum())
+    ((h @ params[2].t() + params[3]) ** 2).mean().backward()
+    ok &= all(v >= 0 for v in sync._pending)
+    sync.finish()
+    ok &= bool(torch.allclose(flat_g[offs[3]:offs[3] + 3] / world, ps[3].grad, atol=1e-6))
+    ok &= bool(torch.allclose(flat_g[offs[2]:offs[2] + 21].view(3, 7) / world, ps[2].grad, atol=1e-6))
     q.put((rank, ok))
     dist.destroy_process_group()
 

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 GROUPS = ["gemm_f32", "gemm_bf16_kk", "gemm_bf16_mn", "gemm_bf16_batch", "rowops", "token_mix", "chain_f32", "chain_fwd",
-          "chain_bwd", "chain_unfused", "linear", "heads", "adam", "patch_embed"]
+          "chain_bwd", "chain_unfused", "linear", "heads", "adam", "patch_embed", "gemm_bf16_wide"]
 
 
 def rel(a, b):
@@ -73,6 +73,23 @@ def run_group(g):
             for (M, N, K) in [(128, 128, 64), (128, 128, 256), (200, 136, 328)]:
                 ok &= report(f"umma a_mn={am} b_mn={bm} {M}x{N}x{K}", gemm_case(BF16, M, N, K, am, bm), 1e-5)
         ok &= report("umma wgrad-like TN 128x3072x16384 splitk=6", gemm_case(BF16, 128, 3072, 16384, 1, 1, splitk=6), 1e-5)
+    elif g == "gemm_bf16_wide":
+        # shapes that take the persistent 128 x 256 kernel (N > 128, >= 64 tiles): every operand layout, ragged M / N / K,
+        # epilogue variants, split-K, several tiles per CTA (double-buffered accumulators), batches
+        for (am, bm) in [(0, 0), (0, 1), (1, 0), (1, 1)]:
+            ok &= report(f"umma2 a_mn={am} b_mn={bm} 4100x648x328", gemm_case(BF16, 4100, 648, 328, am, bm), 1e-5)
+        ok &= report("umma2 KK 12544x3072x768 (13 tiles per CTA)", gemm_case(BF16, 12544, 3072, 768, 0, 0), 1e-5)
+        ok &= report("umma2 KK epilogue bias+gelu+res", gemm_case(BF16, 4100, 648, 328, 0, 0, bias_mode=1, act=1, use_res=True), 1e-5)
+        ok &= report("umma2 KK bf16 out row bias", gemm_case(BF16, 4100, 648, 328, 0, 0, bias_mode=2, out_bf16=True), 5e-3)
+        ok &= report("umma2 KK splitk=3", gemm_case(BF16, 4100, 648, 1000, 0, 0, splitk=3, bias_mode=1), 1e-5)
+        ok &= report("umma2 TN wgrad-like 768x3072x12544 splitk=2", gemm_case(BF16, 768, 3072, 12544, 1, 1, splitk=2), 1e-5)
+        Bt, T, N, D = 70, 384, 196, 768
+        W = rn(T, N).bfloat16()
+        X = rn(Bt * N, D).bfloat16()
+        bias = rn(T)
+        out = ops.gemm(BF16, W, False, X, True, T, D, N, batch=Bt, a_batch_rows=0, b_batch_rows=N, bias=bias, bias_mode=2)
+        ref = torch.einsum("tn,bnd->btd", W.double(), X.double().view(Bt, N, D)) + bias.double()[None, :, None]
+        ok &= report("umma2 batched shared-A MN-major-B (token mixing of the Scaled config)", rel(out, ref), 1e-5)
     elif g == "gemm_bf16_batch":
         # token-mix shaped: shared A [T,N] (K-major), per-sample B = Xn[b] [N, D] MN-major
         Bt, T, N, D = 5, 200, 72, 136
