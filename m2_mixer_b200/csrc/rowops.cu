@@ -412,7 +412,14 @@ __global__ void gelu_fwd_bwd_kernel(const float* __restrict__ h, const float* dg
     const long long r = i / cols;
     const int c = static_cast<int>(i - r * cols);
     const float x = h[r * ld_in + c];
-    float g = gelu_erf(x), d = dg[r * ld_in + c] * gelu_erf_grad(x);
+    float g, d;
+    if (sizeof(TO) == 2) {      // bf16 mode: the tanh form every bf16 kernel of the library differentiates (common.cuh)
+      float dgel;
+      g = gelu_fast_grad(x, dgel);
+      d = dg[r * ld_in + c] * dgel;
+    } else {                    // fp32 parity mode: exact erf GELU
+      g = gelu_erf(x); d = dg[r * ld_in + c] * gelu_erf_grad(x);
+    }
     if (drop.thresh) {
       const bool keep = drop_keep(drop, static_cast<unsigned long long>(r) * drop_ld + c);
       g = keep ? g * drop.scale : 0.f;
@@ -436,9 +443,17 @@ __global__ void __launch_bounds__(256) gelu_fwd_bwd_vec4_kernel(const float* __r
     const int c = static_cast<int>(i - r * cols4) * 4;
     const float4 x = *reinterpret_cast<const float4*>(h + r * ld_in + c);
     const float4 dgv = *reinterpret_cast<const float4*>(dg + r * ld_in + c);
-    float4 g = make_float4(gelu_erf(x.x), gelu_erf(x.y), gelu_erf(x.z), gelu_erf(x.w));
-    float4 d = make_float4(dgv.x * gelu_erf_grad(x.x), dgv.y * gelu_erf_grad(x.y), dgv.z * gelu_erf_grad(x.z),
-                           dgv.w * gelu_erf_grad(x.w));
+    float4 g, d;
+    if (sizeof(TO) == 2) {      // bf16 mode: packed tanh-form GELU and derivative (common.cuh gelu2_grad)
+      float2 d0, d1;
+      const float2 g0 = gelu2_grad(make_float2(x.x, x.y), d0), g1 = gelu2_grad(make_float2(x.z, x.w), d1);
+      g = make_float4(g0.x, g0.y, g1.x, g1.y);
+      d = make_float4(dgv.x * d0.x, dgv.y * d0.y, dgv.z * d1.x, dgv.w * d1.y);
+    } else {                    // fp32 parity mode: exact erf GELU
+      g = make_float4(gelu_erf(x.x), gelu_erf(x.y), gelu_erf(x.z), gelu_erf(x.w));
+      d = make_float4(dgv.x * gelu_erf_grad(x.x), dgv.y * gelu_erf_grad(x.y), dgv.z * gelu_erf_grad(x.z),
+                      dgv.w * gelu_erf_grad(x.w));
+    }
     if (drop.thresh) {
       const unsigned long long idx = static_cast<unsigned long long>(r) * drop_ld + c;
       drop_apply4(drop, g, idx);

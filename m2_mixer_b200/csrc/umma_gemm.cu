@@ -42,23 +42,53 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
                                                long long coff, const float* res, float rbias, bool lead) {
   if (!row_ok || ncol0 >= p.N) return;
   float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int col = ncol0 + j;
-    float x = __uint_as_float(r[j]);
-    if (col < p.N) {
-      if (lead) {
-        if (p.bias_mode == 1) x += p.bias[col];
-        x += rbias;
-      }
-      if (p.act == 1) x = gelu_erf(x);
-      else if (p.act == 2) x = fmaxf(x, 0.f);
-      if (p.drop.thresh) x = drop_apply(p.drop, x, static_cast<unsigned long long>(row) * p.drop_ld + col);
-      if (res) x += res[col];
-    }
-    v[j] = x;
-  }
   const bool full_chunk = (ncol0 + 32 <= p.N);
+  const bool vec_ok = full_chunk && (p.bias_mode != 1 || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
+                      (!res || (reinterpret_cast<uintptr_t>(res + ncol0) & 15) == 0) && (!p.drop.thresh || (p.drop_ld & 3) == 0);
+  if (vec_ok) {
+    // whole chunk in range: 16-byte bias / residual loads, packed GELU, one mask hash per four columns, no predicates.
+    // (The epilogue, not the tensor pipe, bounds the K = 768 GEMMs of the Scaled config: 64 KB of fp32 per 6 k clk of MMAs.)
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 x = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      if (lead) {
+        if (p.bias_mode == 1) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + j));
+          x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+        }
+        x.x += rbias; x.y += rbias; x.z += rbias; x.w += rbias;
+      }
+      if (p.act == 1) {
+        const float2 a = gelu2(make_float2(x.x, x.y)), b = gelu2(make_float2(x.z, x.w));
+        x = make_float4(a.x, a.y, b.x, b.y);
+      } else if (p.act == 2) {
+        x = make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
+      }
+      if (p.drop.thresh) drop_apply4(p.drop, x, static_cast<unsigned long long>(row) * p.drop_ld + ncol0 + j);
+      if (res) {
+        const float4 rv = *reinterpret_cast<const float4*>(res + ncol0 + j);
+        x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
+      }
+      v[j] = x.x; v[j + 1] = x.y; v[j + 2] = x.z; v[j + 3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = ncol0 + j;
+      float x = __uint_as_float(r[j]);
+      if (col < p.N) {
+        if (lead) {
+          if (p.bias_mode == 1) x += p.bias[col];
+          x += rbias;
+        }
+        if (p.act == 1) x = gelu_fast(x);
+        else if (p.act == 2) x = fmaxf(x, 0.f);
+        if (p.drop.thresh) x = drop_apply(p.drop, x, static_cast<unsigned long long>(row) * p.drop_ld + col);
+        if (res) x += res[col];
+      }
+      v[j] = x;
+    }
+  }
   if (p.c_bf16) {
     __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + coff + ncol0;
     if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
@@ -234,16 +264,17 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, dim3 
 // at 16 % of the bf16 peak on it).  Here one CTA per SM walks tiles (m fastest: the CTAs of a wave share the B panel):
 //   warp 0     TMA producer: a 4-stage ring of (16 KB A + 32 KB B), filled across tile boundaries
 //   warp 1     MMA issuer:   4 x tcgen05.mma M128 N256 K16 per stage into accumulator buffer (tile & 1)
-//   warps 2-9  epilogue:     buffer (tile & 1) -> registers -> bias / GELU / dropout / residual -> global, while the
-//                            MMA warp fills the other buffer (acc_full / acc_empty barriers); two warps per TMEM lane
-//                            quadrant, 128 columns each
+//   warps 2-17 epilogue:     buffer (tile & 1) -> registers -> bias / GELU / dropout / residual -> global, while the
+//                            MMA warp fills the other buffer (acc_full / acc_empty barriers); four warps per TMEM lane
+//                            quadrant, 64 columns each
 // 48 KB of operands per 512 clk = 94 B/clk/SM.  Same operand layouts, batching, split-K and epilogue as generation 1.
 constexpr int kBN2 = 256;
 constexpr int kStages2 = 4;
 constexpr int kTileA2 = kBM * kBK * 2;                     // 16 KB
 constexpr int kTileB2 = kBN2 * kBK * 2;                    // 32 KB
 constexpr int kSmem2 = kStages2 * (kTileA2 + kTileB2) + 256 + 1024;
-constexpr int kThreads2 = 320;
+constexpr int kEpiWarps2 = 16;               // four per TMEM lane quadrant, 64 accumulator columns each
+constexpr int kThreads2 = (2 + kEpiWarps2) * 32;
 
 struct Sched2 { int tiles_m, tiles_n, total; };
 
@@ -265,7 +296,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps2); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -342,7 +373,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     const int q = warp & 3;                       // TMEM lane quadrant of this warp
-    const int half = (warp - 2) >> 2;             // which 128 of the 256 accumulator columns
+    const int part = (warp - 2) >> 2;             // which 64 of the 256 accumulator columns
     int t = 0;
     for (int tile = blockIdx.x; tile < sc.total; tile += gridDim.x, ++t) {
       const int z = tile / per_z, r = tile - z * per_z;
@@ -359,11 +390,11 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&acc_full[buf], (t >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+      for (int c0 = part * 64; c0 < part * 64 + 64; c0 += 32) {
         uint32_t rg[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kBN2 + c0, rg);
         tmem_ld_wait();
-        if (c0 + 32 == half * 128 + 128) {        // last piece in registers: hand the buffer back before the math
+        if (c0 + 32 == part * 64 + 64) {          // last piece in registers: hand the buffer back before the math
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
