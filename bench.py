@@ -264,6 +264,12 @@ def run_ours(args, cfg):
     saved_fd = os.dup(1)
     os.dup2(2, 1)
     try:
+        # The captured allreduces run UNDER the backward kernels, which are one persistent CTA per SM with all of its shared
+        # memory and tensor memory: an NCCL kernel that spreads over many SMs delays them by more than the collective takes.
+        # Eight CTAs move the 33 MB of gradients well inside the backward's time (measured on 2 x B200:
+        # profiles/r02_bench_n2_nccl_ctas.md); an explicit NCCL_MAX_CTAS in the environment wins.
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            os.environ.setdefault("NCCL_MAX_CTAS", "8")
         rank, local, world = parallel.init_from_env()
         if world > 1 and torch.cuda.is_available():
             t = torch.zeros(1, device=torch.device("cuda", local))

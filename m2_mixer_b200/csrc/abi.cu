@@ -114,7 +114,7 @@ bool token_mix_gemm_path(int precision, int N, int D, int T) {
 }
 
 struct TokWs {
-  __nv_bfloat16 *xn_b, *w1b, *w2b, *g_b, *du_b, *dh_b;
+  __nv_bfloat16 *xn_b, *w1b, *w2b, *g_b, *du_b, *dh_b, *h_b, *dg_b;
   float *f1, *f2, *dxn;
 };
 size_t token_mix_gemm_ws(int B, int N, int D, int T, bool backward, TokWs* out, void* base, size_t bytes, bool* ok) {
@@ -125,13 +125,14 @@ size_t token_mix_gemm_ws(int B, int N, int D, int T, bool backward, TokWs* out, 
   w.w1b = ws.take<__nv_bfloat16>(static_cast<size_t>(T) * up8(N));
   w.w2b = ws.take<__nv_bfloat16>(static_cast<size_t>(N) * up8(T));
   w.g_b = ws.take<__nv_bfloat16>(bt);
-  w.f1 = ws.take<float>(bt);          // fwd: GELU output before the mask (dropout only) | bwd: H pre-activation
   if (backward) {
-    w.f2 = ws.take<float>(bt);        // dG
+    w.h_b = ws.take<__nv_bfloat16>(bt);     // H pre-activation and dG: bf16 (rounded to bf16 as G / dH right after anyway)
+    w.dg_b = ws.take<__nv_bfloat16>(bt);
     w.du_b = ws.take<__nv_bfloat16>(bn);
     w.dh_b = ws.take<__nv_bfloat16>(bt);
     w.dxn = ws.take<float>(bn);
   } else {
+    w.f1 = ws.take<float>(bt);        // GELU output before the mask (dropout only)
     w.f2 = ws.take<float>(bn);        // branch output before the mask (dropout only)
   }
   if (out) *out = w;
@@ -143,9 +144,9 @@ size_t token_mix_gemm_ws_bytes(int B, int N, int D, int T, bool backward) {
   Carver ws(reinterpret_cast<void*>(256), ~size_t(0) >> 1);
   const size_t bn = static_cast<size_t>(B) * N * D, bt = static_cast<size_t>(B) * T * D;
   ws.take<__nv_bfloat16>(bn); ws.take<__nv_bfloat16>(static_cast<size_t>(T) * up8(N)); ws.take<__nv_bfloat16>(static_cast<size_t>(N) * up8(T));
-  ws.take<__nv_bfloat16>(bt); ws.take<float>(bt);
-  if (backward) { ws.take<float>(bt); ws.take<__nv_bfloat16>(bn); ws.take<__nv_bfloat16>(bt); ws.take<float>(bn); }
-  else ws.take<float>(bn);
+  ws.take<__nv_bfloat16>(bt);
+  if (backward) { ws.take<__nv_bfloat16>(bt); ws.take<__nv_bfloat16>(bt); ws.take<__nv_bfloat16>(bn); ws.take<__nv_bfloat16>(bt); ws.take<float>(bn); }
+  else { ws.take<float>(bt); ws.take<float>(bn); }
   return ws.off;
 }
 
@@ -194,16 +195,16 @@ int token_mix_gemm_bwd(const float* du, const float* x, const float* ln_w, const
   // gradient of the dropped branch output (mask + scale), as the bf16 GEMM operand
   if (p > 0.f) M2_TRY(mask_scale(du, D, w.du_b, 1, D, B * N, D, p, seed, kSiteTokenOut, D, s));
   else M2_TRY(cast_pad_bf16(du, D, w.du_b, D, B * N, D, s));
-  // recompute H_b = W1 . Xn_b + b1 (pre-activation, fp32)
-  GemmArgs gh = gemm_args(w.w1b, 0, n8, w.xn_b, 1, D, T, D, N, w.f1, 0, D);
+  // recompute H_b = W1 . Xn_b + b1 (pre-activation, bf16)
+  GemmArgs gh = gemm_args(w.w1b, 0, n8, w.xn_b, 1, D, T, D, N, w.h_b, 1, D);
   gh.batch = B; gh.b_batch_rows = N; gh.c_batch_stride = td; gh.bias = b1; gh.bias_mode = 2;
   M2_TRY(gemm_bf16_umma(gh, s));
   // dG_b [T x D] = W2^T [T x N] . dU_b [N x D]      (A = W2 [N][T] consumed MN-major)
-  GemmArgs gg = gemm_args(w.w2b, 1, t8, w.du_b, 1, D, T, D, N, w.f2, 0, D);
+  GemmArgs gg = gemm_args(w.w2b, 1, t8, w.du_b, 1, D, T, D, N, w.dg_b, 1, D);
   gg.batch = B; gg.b_batch_rows = N; gg.c_batch_stride = td;
   M2_TRY(gemm_bf16_umma(gg, s));
   // G = Drop(GELU(H)), dH = dG * Drop'(.) * GELU'(H)
-  M2_TRY(gelu_fwd_bwd(w.f1, w.f2, B * T, D, D, w.g_b, w.dh_b, D, 1, p, seed, kSiteTokenHidden, D, s));
+  M2_TRY(gelu_fwd_bwd(w.h_b, w.dg_b, 1, B * T, D, D, w.g_b, w.dh_b, D, 1, p, seed, kSiteTokenHidden, D, s));
   // dW2 [N x T] += sum_b dU_b [N x D] . G_b^T [D x T] ;  dW1 [T x N] += sum_b dH_b [T x D] . Xn_b^T [D x N]
   GemmArgs gw2 = gemm_args(w.du_b, 0, D, w.g_b, 0, D, N, T, D, dw2, 0, T);
   gw2.batch = B; gw2.a_batch_rows = N; gw2.b_batch_rows = T; gw2.c_batch_stride = 0; gw2.atomic_out = 1;
@@ -280,7 +281,7 @@ size_t m2b200_channel_mix_workspace_bytes(int M, int D, int C, int precision, in
     else if (path == kPathFused && chain_generation() != 1 && chain_generation() != 3 && chain_fwd_ts_supported(D))
       b = 2 * up256(m * d * 2);   // bf16 LN(u) and dY only: the weight-gradient kernel recomputes G / dH on chip
     else if (path == kPathFused) b = 2 * up256(m * d * 2) + 2 * up256(m * c8 * 2) + up256(m * d * 4);
-    else b = 2 * up256(m * d * 2) + 2 * up256(m * c * 4) + 2 * up256(m * c8 * 2) + up256(m * d * 4);
+    else b = 2 * up256(m * d * 2) + 4 * up256(m * c8 * 2) + up256(m * d * 4);   // bf16 LN(u), dY; bf16 G, dH, H, dG; fp32 dXn
   }
   return b;
 }
@@ -364,7 +365,7 @@ int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, c
     M2_TRY(gemm_f32_simt(gh, s));
     GemmArgs gg = gemm_args(dyb, 0, D, w2, 1, C, M, C, D, dh, 0, C);         // dG = dY W2   (W2 [D][C] as [K][N])
     M2_TRY(gemm_f32_simt(gg, s));
-    M2_TRY(gelu_fwd_bwd(h, dh, M, C, C, gbuf, dh, C, 0, dropout_p, seed, kSiteChannelHidden, c8, s));   // G, dH in place
+    M2_TRY(gelu_fwd_bwd(h, dh, 0, M, C, C, gbuf, dh, C, 0, dropout_p, seed, kSiteChannelHidden, c8, s));   // G, dH in place
     GemmArgs gw2 = gemm_args(dyb, 1, D, gbuf, 1, C, D, C, M, dw2, 0, C);     // dW2 += dY^T G
     gw2.accumulate = 1;
     M2_TRY(gemm_f32_simt(gw2, s));
@@ -401,21 +402,24 @@ int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, c
     if (!ws.ok) return M2_ERR_WORKSPACE;
     M2_TRY(chain_bwd(u, ln_w, ln_b, w1b, b1, w2b, ldw2, dy, xn_b, dy_b, g_b, dh_b, c8, dxn, M, D, C, 0, dropout_p, seed, s));
   } else {
-    float* h = ws.take<float>(mc);
-    float* dg = ws.take<float>(mc);
+    // the [M x C] intermediates H and dG stay bf16 (they are rounded to bf16 as G / dH right after anyway): half the bytes
+    // of the fp32 round trip, which is what bounds the K = D GEMMs that write them
+    __nv_bfloat16* h = ws.take<__nv_bfloat16>(mc8);
+    __nv_bfloat16* dg = ws.take<__nv_bfloat16>(mc8);
     if (!ws.ok) return M2_ERR_WORKSPACE;
     M2_TRY(ln_fwd(u, ln_w, ln_b, xn_b, 1, M, D, M, 0, nullptr, nullptr, s));
-    M2_TRY(mask_scale(dy, D, dy_b, 1, D, M, D, dropout_p, seed, kSiteChannelOut, D, s));
-    GemmArgs gh = gemm_args(xn_b, 0, D, w1b, 0, D, M, C, D, h, 0, C);
+    if (drop) M2_TRY(mask_scale(dy, D, dy_b, 1, D, M, D, dropout_p, seed, kSiteChannelOut, D, s));
+    else M2_TRY(cast_pad_bf16(dy, D, dy_b, D, M, D, s));
+    GemmArgs gh = gemm_args(xn_b, 0, D, w1b, 0, D, M, C, D, h, 1, c8);
     gh.bias = b1; gh.bias_mode = 1;
     M2_TRY(gemm_bf16_umma(gh, s));
-    GemmArgs gg = gemm_args(dy_b, 0, D, w2b, 1, ldw2, M, C, D, dg, 0, C);
+    GemmArgs gg = gemm_args(dy_b, 0, D, w2b, 1, ldw2, M, C, D, dg, 1, c8);
     M2_TRY(gemm_bf16_umma(gg, s));
     if (c8 != C) {   // pad columns of the bf16 G / dH buffers must be finite (they are never contracted over)
       if (cudaMemsetAsync(g_b, 0, mc8 * 2, s) != cudaSuccess || cudaMemsetAsync(dh_b, 0, mc8 * 2, s) != cudaSuccess)
         return M2_ERR_LAUNCH;
     }
-    M2_TRY(gelu_fwd_bwd(h, dg, M, C, C, g_b, dh_b, c8, 1, dropout_p, seed, kSiteChannelHidden, c8, s));
+    M2_TRY(gelu_fwd_bwd(h, dg, 1, M, C, c8, g_b, dh_b, c8, 1, dropout_p, seed, kSiteChannelHidden, c8, s));
     GemmArgs gx = gemm_args(dh_b, 0, c8, w1b, 1, D, M, D, C, dxn, 0, D);
     M2_TRY(gemm_bf16_umma(gx, s));
   }

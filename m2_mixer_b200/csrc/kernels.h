@@ -68,7 +68,8 @@ int colsum_f32(const float* src, long long ld, int rows, int cols, float* out, c
 int colsum_bf16(const void* src, long long ld, int rows, int cols, float* out, cudaStream_t s);
 // out[r % period] += sum_c src[r][c]   (bf16 rows; bias gradients of the GEMM-composed token mixing)
 int rowsum_mod_bf16(const void* src, long long ld, int rows, int cols, int period, float* out, cudaStream_t s);
-int gelu_fwd_bwd(const float* h, const float* dg, int rows, int cols, long long ld_in, void* g_out, void* dh_out,
+// h / dg: fp32, or bf16 (in_bf16 = 1, bf16 outputs only) with leading dimension ld_in
+int gelu_fwd_bwd(const void* h, const void* dg, int in_bf16, int rows, int cols, long long ld_in, void* g_out, void* dh_out,
                  long long ld_out, int out_bf16, float drop_p, unsigned long long seed, int site, long long drop_ld,
                  cudaStream_t s);
 // dst = src * mask * scale (dst fp32 or bf16; dst may alias src when fp32); index = r * drop_ld + c

@@ -403,22 +403,23 @@ __global__ void __launch_bounds__(256) rowsum_mod_bf16_kernel(const __nv_bfloat1
 }
 
 // h = pre-activation (bias already added). g_out = gelu(h) ; dh = dg * gelu'(h)  (dh may alias dg)
-template <typename TO>
-__global__ void gelu_fwd_bwd_kernel(const float* __restrict__ h, const float* dg, long long n, int cols,
+template <typename TO, typename TI = float>
+__global__ void gelu_fwd_bwd_kernel(const TI* __restrict__ h, const TI* dg, long long n, int cols,
                                     long long ld_in, TO* __restrict__ g_out, TO* dh_out, long long ld_out, const Drop drop,
                                     long long drop_ld) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / cols;
     const int c = static_cast<int>(i - r * cols);
-    const float x = h[r * ld_in + c];
+    const float x = static_cast<float>(h[r * ld_in + c]);
+    const float dgv = static_cast<float>(dg[r * ld_in + c]);
     float g, d;
     if (sizeof(TO) == 2) {      // bf16 mode: the tanh form every bf16 kernel of the library differentiates (common.cuh)
       float dgel;
       g = gelu_fast_grad(x, dgel);
-      d = dg[r * ld_in + c] * dgel;
+      d = dgv * dgel;
     } else {                    // fp32 parity mode: exact erf GELU
-      g = gelu_erf(x); d = dg[r * ld_in + c] * gelu_erf_grad(x);
+      g = gelu_erf(x); d = dgv * gelu_erf_grad(x);
     }
     if (drop.thresh) {
       const bool keep = drop_keep(drop, static_cast<unsigned long long>(r) * drop_ld + c);
@@ -696,6 +697,10 @@ int ln_bwd(const float* dy, long long dy_bstride, int N, const float* x, const f
                     reinterpret_cast<uintptr_t>(dres) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
   if (D % 4 == 0 && al && dy_bstride % 4 == 0) {
     const int kv = ceil_div(D, 128);
+    // exactly the CTAs that are resident (launch bounds of ln_bwd_vec_kernel): every CTA ends with 2 D global atomics on the
+    // same 2 D addresses, four waves of CTAs only multiplied those
+    const int resident = kNumSms * (kv <= 2 ? 4 : (kv <= 6 ? 2 : 1));
+    if (grid > resident) grid = resident;
 #define M2_LNBV(V_) ln_bwd_vec_kernel<V_><<<grid, 256, sm, s>>>(dy, dy_bstride, N, x, w, dres, dx, dw, db, rows, D)
     if (kv <= 1) M2_LNBV(1); else if (kv <= 2) M2_LNBV(2); else if (kv <= 4) M2_LNBV(4); else if (kv <= 6) M2_LNBV(6); else M2_LNBV(8);
 #undef M2_LNBV
@@ -740,6 +745,47 @@ int colsum_bf16(const void* src, long long ld, int rows, int cols, float* out, c
   return M2_OK;
 }
 
+// bf16 in, bf16 out, EIGHT consecutive columns per thread (16-byte accesses): the unfused bf16 backward keeps its
+// [rows x hidden] intermediates H and dG in bf16 (half the bytes of the fp32 round trip of round 1).
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__global__ void __launch_bounds__(256) gelu_fwd_bwd_bf16x8_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* dg,
+                                                                  long long n8, int cols8, long long ld_in,
+                                                                  __nv_bfloat16* __restrict__ g_out, __nv_bfloat16* dh_out,
+                                                                  long long ld_out, const Drop drop, long long drop_ld) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols8;
+    const int c = static_cast<int>(i - r * cols8) * 8;
+    const uint4 hv = *reinterpret_cast<const uint4*>(h + r * ld_in + c);
+    const uint4 dv = *reinterpret_cast<const uint4*>(dg + r * ld_in + c);
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+    float g[8], d[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 dgel;
+      const float2 gg = gelu2_grad(bf16x2_to_f2(hw[e]), dgel);
+      const float2 dd = bf16x2_to_f2(dw[e]);
+      g[2 * e] = gg.x; g[2 * e + 1] = gg.y;
+      d[2 * e] = dd.x * dgel.x; d[2 * e + 1] = dd.y * dgel.y;
+    }
+    if (drop.thresh) {
+      const unsigned long long idx = static_cast<unsigned long long>(r) * drop_ld + c;
+      float4 g0 = make_float4(g[0], g[1], g[2], g[3]), g1 = make_float4(g[4], g[5], g[6], g[7]);
+      float4 d0 = make_float4(d[0], d[1], d[2], d[3]), d1 = make_float4(d[4], d[5], d[6], d[7]);
+      drop_apply4(drop, g0, idx); drop_apply4(drop, g1, idx + 4);
+      drop_apply4(drop, d0, idx); drop_apply4(drop, d1, idx + 4);
+      g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+      d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
+    }
+    *reinterpret_cast<uint4*>(g_out + r * ld_out + c) =
+        make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
+    *reinterpret_cast<uint4*>(dh_out + r * ld_out + c) =
+        make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+  }
+}
+
 int mask_scale(const float* src, long long lds, void* dst, int dst_bf16, long long ldd, int rows, int cols, float drop_p,
                unsigned long long seed, int site, long long drop_ld, cudaStream_t s) {
   LaunchScope scope("mask_scale", s);
@@ -761,13 +807,29 @@ int dropout_mask(float* out, int rows, int cols, long long ld, float drop_p, uns
   return M2_OK;
 }
 
-int gelu_fwd_bwd(const float* h, const float* dg, int rows, int cols, long long ld_in, void* g_out, void* dh_out,
+int gelu_fwd_bwd(const void* h_, const void* dg_, int in_bf16, int rows, int cols, long long ld_in, void* g_out, void* dh_out,
                  long long ld_out, int out_bf16, float drop_p, unsigned long long seed, int site, long long drop_ld,
                  cudaStream_t s) {
   const Drop drop = make_drop(drop_p, seed, site);
   LaunchScope scope("gelu_fwd_bwd", s);
   const long long n = static_cast<long long>(rows) * cols;
-  if (n <= 0) return M2_ERR_ARG;
+  if (n <= 0 || (in_bf16 && !out_bf16)) return M2_ERR_ARG;
+  if (in_bf16) {
+    const __nv_bfloat16* hb = static_cast<const __nv_bfloat16*>(h_);
+    const __nv_bfloat16* dgb = static_cast<const __nv_bfloat16*>(dg_);
+    const bool al8 = ((reinterpret_cast<uintptr_t>(h_) | reinterpret_cast<uintptr_t>(dg_) | reinterpret_cast<uintptr_t>(g_out) |
+                       reinterpret_cast<uintptr_t>(dh_out)) & 15) == 0;
+    if (al8 && cols % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && drop_ld % 4 == 0)
+      gelu_fwd_bwd_bf16x8_kernel<<<grid_for(n / 8, 256), 256, 0, s>>>(hb, dgb, n / 8, cols / 8, ld_in, static_cast<__nv_bfloat16*>(g_out),
+                                                                     static_cast<__nv_bfloat16*>(dh_out), ld_out, drop, drop_ld);
+    else
+      gelu_fwd_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>(
+          hb, dgb, n, cols, ld_in, static_cast<__nv_bfloat16*>(g_out), static_cast<__nv_bfloat16*>(dh_out), ld_out, drop, drop_ld);
+    M2_LAUNCH_CHECK();
+    return M2_OK;
+  }
+  const float* h = static_cast<const float*>(h_);
+  const float* dg = static_cast<const float*>(dg_);
   const bool al = ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dg) | reinterpret_cast<uintptr_t>(g_out) |
                     reinterpret_cast<uintptr_t>(dh_out)) & 15) == 0;
   if (al && cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && drop_ld % 4 == 0) {
