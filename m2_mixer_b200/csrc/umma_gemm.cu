@@ -37,17 +37,14 @@ struct GemmDev {
   Drop drop; long long drop_ld;
 };
 
-// One accumulator row x 32 columns: bias / activation / dropout / residual, then the store the output mode asks for.
-__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&r)[32], int row, bool row_ok, int ncol0,
-                                               long long coff, const float* res, float rbias, bool lead) {
-  if (!row_ok || ncol0 >= p.N) return;
-  float v[32];
+// One accumulator row x 32 columns: bias / activation / dropout / residual -> v[32] (columns past N hold garbage).
+__device__ __forceinline__ void epilogue_math(const GemmDev& p, const uint32_t (&r)[32], float (&v)[32], int row, int ncol0,
+                                              const float* res, float rbias, bool lead) {
   const bool full_chunk = (ncol0 + 32 <= p.N);
   const bool vec_ok = full_chunk && (p.bias_mode != 1 || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
                       (!res || (reinterpret_cast<uintptr_t>(res + ncol0) & 15) == 0) && (!p.drop.thresh || (p.drop_ld & 3) == 0);
   if (vec_ok) {
-    // whole chunk in range: 16-byte bias / residual loads, packed GELU, one mask hash per four columns, no predicates.
-    // (The epilogue, not the tensor pipe, bounds the K = 768 GEMMs of the Scaled config: 64 KB of fp32 per 6 k clk of MMAs.)
+    // whole chunk in range: 16-byte bias / residual loads, packed GELU, one mask hash per four columns, no predicates
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       float4 x = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
@@ -89,6 +86,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
       v[j] = x;
     }
   }
+}
+
+// v[32] -> global, one row per thread (16-byte stores; reductions for split-K / shared outputs)
+__device__ __forceinline__ void epilogue_store(const GemmDev& p, const float (&v)[32], int ncol0, long long coff) {
+  const bool full_chunk = (ncol0 + 32 <= p.N);
   if (p.c_bf16) {
     __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + coff + ncol0;
     if (full_chunk && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
@@ -128,6 +130,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
         if (ncol0 + j < p.N) c[j] = p.accumulate ? c[j] + v[j] : v[j];
     }
   }
+}
+
+__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&r)[32], int row, bool row_ok, int ncol0,
+                                               long long coff, const float* res, float rbias, bool lead) {
+  if (!row_ok || ncol0 >= p.N) return;
+  float v[32];
+  epilogue_math(p, r, v, row, ncol0, res, rbias, lead);
+  epilogue_store(p, v, ncol0, coff);
 }
 
 template <bool kAMn, bool kBMn>
@@ -269,24 +279,36 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, dim3 
 //                            quadrant, 64 columns each
 // 48 KB of operands per 512 clk = 94 B/clk/SM.  Same operand layouts, batching, split-K and epilogue as generation 1.
 constexpr int kBN2 = 256;
-constexpr int kStages2 = 4;
+// four ring stages, or three + 64 KB of per-warp output staging for the TMA-store variant (short K: the epilogue bounds it)
 constexpr int kTileA2 = kBM * kBK * 2;                     // 16 KB
 constexpr int kTileB2 = kBN2 * kBK * 2;                    // 32 KB
-constexpr int kSmem2 = kStages2 * (kTileA2 + kTileB2) + 256 + 1024;
+constexpr int kStageOut2 = 4096;                           // one [32 rows][128 B] swizzled box per epilogue warp
+constexpr int smem2_bytes(bool tma_store) { return (tma_store ? 3 : 4) * (kTileA2 + kTileB2) + (tma_store ? 16 * kStageOut2 : 0) + 256 + 1024; }
 constexpr int kEpiWarps2 = 16;               // four per TMEM lane quadrant, 64 accumulator columns each
 constexpr int kThreads2 = (2 + kEpiWarps2) * 32;
 
 struct Sched2 { int tiles_m, tiles_n, total; };
 
-template <bool kAMn, bool kBMn>
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// kTmaStore: the output tile leaves through shared memory and cp.async.bulk.tensor stores (plain overwrite outputs only).
+// One row per thread is what TMEM hands out, and 16-byte global stores from it scatter over 32 rows per instruction: 8 k L2
+// sector writes per fp32 tile, more than the 6 k clk of MMAs a K = 768 tile has (the "no epilogue work" GEMM ran at 53 % of
+// the rate of the 8192^3 one).  Each epilogue warp stages its [32 rows x 128 B] piece in the 128-byte swizzle and one lane
+// stores the box; ragged edges are clipped by the tensor map.
+template <bool kAMn, bool kBMn, bool kTmaStore>
 __global__ void __launch_bounds__(kThreads2, 1)
-umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p,
-                  const Sched2 sc) {
+umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const GemmDev p, const Sched2 sc) {
+  constexpr int kStages2 = kTmaStore ? 3 : 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages2 * kTileA2;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages2 * (kTileA2 + kTileB2));
+  uint8_t* sOut = smem + kStages2 * (kTileA2 + kTileB2);      // [16 warps][4 KB], 1024-byte aligned (TMA-store variant only)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + (kTmaStore ? 16 * kStageOut2 : 0));
   uint64_t* empty = full + kStages2;
   uint64_t* acc_full = empty + kStages2;      // [2]
   uint64_t* acc_empty = acc_full + 2;         // [2]
@@ -300,6 +322,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (kTmaStore) tma_prefetch_desc(&tmC);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -389,6 +412,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                                     static_cast<long long>(row) * p.ldr : nullptr;
       mbar_wait(&acc_full[buf], (t >> 1) & 1);
       tc_fence_after();
+      const uint32_t stage = smem_u32(sOut + (warp - 2) * kStageOut2);
 #pragma unroll 1
       for (int c0 = part * 64; c0 < part * 64 + 64; c0 += 32) {
         uint32_t rg[32];
@@ -399,8 +423,57 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        epilogue_chunk(p, rg, row, row_ok, n0 + c0, coff, res, rbias, lead);
+        if (!kTmaStore) {
+          epilogue_chunk(p, rg, row, row_ok, n0 + c0, coff, res, rbias, lead);
+        } else {
+          const bool live = n0 + c0 < p.N;        // warp-uniform
+          float v[32];
+          if (live && row_ok) epilogue_math(p, rg, v, row, n0 + c0, res, rbias, lead);
+          if (p.c_bf16) {
+            // the warp's two 32-column pieces are the halves of ONE [32 x 64] bf16 box
+            const int hpc = (c0 - part * 64) >> 5;
+            if (hpc == 0) {                       // the previous tile's store must have read the staging buffer
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+            }
+            if (live && row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 o = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
+                                           pack_bf16(v[j + 6], v[j + 7]));
+                st_shared_v4(stage + sw128_offset(lane, hpc * 4 + (j >> 3)), o);
+              }
+            }
+            if (hpc == 1) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0 && n0 + part * 64 < p.N) {
+                tma_store_3d(&tmC, sOut + (warp - 2) * kStageOut2, n0 + part * 64, m0 + q * 32, batch);
+                tma_store_commit();
+              }
+            }
+          } else {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+            if (live && row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                st_shared_v4(stage + sw128_offset(lane, j >> 2),
+                             make_uint4(__float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3])));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && live) {
+              tma_store_3d(&tmC, sOut + (warp - 2) * kStageOut2, n0 + c0, m0 + q * 32, batch);
+              tma_store_commit();
+            }
+          }
+        }
       }
+    }
+    if (kTmaStore) {                              // the bulk stores must have left shared memory before the CTA exits
+      if (lane == 0) tma_store_wait_all();
+      __syncwarp();
     }
   }
 
@@ -409,19 +482,25 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <bool kAMn, bool kBMn>
-int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& d, const Sched2& sc, cudaStream_t s) {
-  auto kern = umma_gemm2_kernel<kAMn, kBMn>;
+template <bool kAMn, bool kBMn, bool kTmaStore>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmDev& d, const Sched2& sc, cudaStream_t s) {
+  auto kern = umma_gemm2_kernel<kAMn, kBMn, kTmaStore>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2) != cudaSuccess) return M2_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes(kTmaStore)) != cudaSuccess) return M2_ERR_LAUNCH;
     configured = true;
   }
   LaunchScope scope(kAMn ? (kBMn ? "umma_gemm2_tn" : "umma_gemm2_tk") : (kBMn ? "umma_gemm2_kn" : "umma_gemm2_kk"), s);
   const int grid = sc.total < 148 ? sc.total : 148;
-  kern<<<grid, kThreads2, kSmem2, s>>>(ta, tb, d, sc);
+  kern<<<grid, kThreads2, smem2_bytes(kTmaStore), s>>>(ta, tb, tc, d, sc);
   M2_LAUNCH_CHECK();
   return M2_OK;
+}
+template <bool kTmaStore>
+int launch2_layout(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmDev& d,
+                   const Sched2& sc, cudaStream_t s) {
+  if (a_mn) return b_mn ? launch2<true, true, kTmaStore>(ta, tb, tc, d, sc, s) : launch2<true, false, kTmaStore>(ta, tb, tc, d, sc, s);
+  return b_mn ? launch2<false, true, kTmaStore>(ta, tb, tc, d, sc, s) : launch2<false, false, kTmaStore>(ta, tb, tc, d, sc, s);
 }
 
 // M2B200_GEMM_GEN=1 keeps every GEMM on the one-tile-per-CTA kernel (A/B measurements)
@@ -476,8 +555,17 @@ int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
     const long long total = static_cast<long long>(sc.tiles_m) * sc.tiles_n * g.batch * d.splitk;
     if (total >= (1ll << 31)) return M2_ERR_ARG;
     sc.total = static_cast<int>(total);
-    if (g.a_mn) return g.b_mn ? launch2<true, true>(ta, tb, d, sc, s) : launch2<true, false>(ta, tb, d, sc, s);
-    return g.b_mn ? launch2<false, true>(ta, tb, d, sc, s) : launch2<false, false>(ta, tb, d, sc, s);
+    // plain overwrite outputs leave through TMA stores (M2B200_GEMM_TMA_STORE=0: per-thread stores, A/B measurements)
+    static const bool tma_env = [] { const char* e = getenv("M2B200_GEMM_TMA_STORE"); return !e || atoi(e) != 0; }();
+    CUtensorMap tc = ta;
+    // short K: the tile's epilogue, not its main loop, is what the SM waits for - worth a ring stage (measured: tools/bench_gemm.py)
+    bool tma_store = tma_env && d.splitk == 1 && !d.atomic && !d.accumulate && k_tiles <= 24;
+    if (tma_store) {
+      const int eb = g.c_bf16 ? 2 : 4;
+      if (make_tmap_store3d(&tc, g.C, eb, g.batch, g.M, g.N, g.ldc, g.c_batch_stride, 32, g.c_bf16 ? 64 : 32) != M2_OK)
+        tma_store = false;   // unaligned output: per-thread stores
+    }
+    return tma_store ? launch2_layout<true>(g.a_mn, g.b_mn, ta, tb, tc, d, sc, s) : launch2_layout<false>(g.a_mn, g.b_mn, ta, tb, tc, d, sc, s);
   }
   dim3 grid(ceil_div(g.M, kBM), ceil_div(g.N, kBN), g.batch * d.splitk);
   if (grid.y > 65535 || grid.z > 65535) return M2_ERR_ARG;
