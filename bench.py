@@ -41,6 +41,7 @@ def parse():
                     help="N > 1, graphed step: 'overlap' captures the bucketed NCCL allreduces on the communication stream "
                          "(under the backward), 'split' is one allreduce between two graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bucket-mb", type=float, default=2.0, help="N > 1: size of the gradient allreduce buckets (MiB)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-host-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="dtype of the IMAGE tensors in the pinned host batches of the e2e leg (bf16 halves the host link "
@@ -266,10 +267,10 @@ def run_ours(args, cfg):
     try:
         # The captured allreduces run UNDER the backward kernels, which are one persistent CTA per SM with all of its shared
         # memory and tensor memory: an NCCL kernel that spreads over many SMs delays them by more than the collective takes.
-        # Eight CTAs move the 33 MB of gradients well inside the backward's time (measured on 2 x B200:
-        # profiles/r02_bench_n2_nccl_ctas.md); an explicit NCCL_MAX_CTAS in the environment wins.
-        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-            os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        # Sixteen CTAs and 2 MiB buckets move the 33 MB of gradients well inside the backward's time (measured on 2 and
+        # 8 x B200: profiles/r02_multi_gpu.md); an explicit NCCL_MAX_CTAS in the environment wins.
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "--graph-comm split" not in " ".join(sys.argv) and "--no-graph" not in sys.argv:
+            os.environ.setdefault("NCCL_MAX_CTAS", "16")
         rank, local, world = parallel.init_from_env()
         if world > 1 and torch.cuda.is_available():
             t = torch.zeros(1, device=torch.device("cuda", local))
@@ -292,7 +293,7 @@ def run_ours(args, cfg):
     use_graph = not args.no_graph                    # N > 1: the bucketed NCCL allreduces are captured inside the graph (graph.py)
     lr = 1e-2 if args.config.startswith("avmnist") else (1e-4 if args.config == "scaled_C5" else 1e-3)   # cfg values; C5: tests
     opt = FusedAdam(model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, capturable=use_graph)
-    sync = parallel.attach(opt) if world > 1 else None
+    sync = parallel.attach(opt, bucket_bytes=int(args.bucket_mb * (1 << 20))) if world > 1 else None
 
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     NB = 4   # rotate distinct batches: M2-Mixer-B's is 218 MB of fp32 input, larger than the 126 MB L2

@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(kThreads) heads_bwd_reg_kernel(const HeadsDev 
   extern __shared__ float red[];   // [kWarps][K * dim + K]
   __shared__ float s_dl[kWarps][kKr];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int h = 0; h < a.nheads; ++h) {
+  {
+    const int h = blockIdx.y;   // one head per CTA row: the heads are independent, three times the CTAs in flight
     const int dim = a.dim[h];
     const int slot = a.K * dim + a.K;
     float dwacc[kKr][kMaxPer];
@@ -390,7 +391,7 @@ int heads_loss_bwd(const HeadsArgs& a, const float* logits, float grad_scale, co
     int rgrid = ceil_div(a.B, kWarps * 4);   // >= 4 samples per warp: the per-head flush is amortised
     if (rgrid > 148 * 2) rgrid = 148 * 2;
     if (rgrid < 1) rgrid = 1;
-    kern<<<rgrid, kThreads, rsm, s>>>(d, g, logits);
+    kern<<<dim3(rgrid, a.nheads), kThreads, rsm, s>>>(d, g, logits);
     M2_LAUNCH_CHECK();
     return M2_OK;
   }

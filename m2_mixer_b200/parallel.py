@@ -35,7 +35,7 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
 
 class GradSync:
     def __init__(self, params: Sequence[torch.nn.Parameter], offsets: Sequence[int], flat_grad: torch.Tensor,
-                 bucket_bytes: int = 8 << 20, group=None):
+                 bucket_bytes: int = 2 << 20, group=None):
         self.flat_grad, self.group = flat_grad, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.cuda = flat_grad.is_cuda
@@ -121,7 +121,7 @@ class GradSync:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
 
 
-def attach(optimizer, bucket_bytes: int = 8 << 20, group=None) -> GradSync:
+def attach(optimizer, bucket_bytes: int = 2 << 20, group=None) -> GradSync:
     """Wire a FusedAdam to data-parallel gradient averaging: sum-allreduce buckets + 1/world folded into Adam."""
     sync = GradSync(optimizer._params, optimizer._offsets, optimizer.flat_grad, bucket_bytes, group)
     optimizer.grad_scale = 1.0 / sync.world
