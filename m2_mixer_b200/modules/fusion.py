@@ -14,7 +14,9 @@ class ConcatFusion:
 
     def __call__(self, *args):
         if self.dim != 1 or any(a.dim() != 3 for a in args):
-            raise NotImplementedError("m2b200 ConcatFusion concatenates [B, N_i, D] token tensors along dim=1")
+            # any other rank / dim (the reference accepts them, modules/fusion.py:117): torch.cat on the device tensors -
+            # plumbing outside the hot path, which is token concatenation (and zero-copy inside the task modules)
+            return torch.cat(args, dim=self.dim)
         return F.concat_tokens(*args)
 
     def get_output_shape(self, *args, dim=None):

@@ -593,3 +593,64 @@ def set_dropout_epoch(t: Optional[torch.Tensor]) -> None:
 
 def dropout_epoch_advance(t: torch.Tensor) -> None:
     check(_L().m2b200_dropout_epoch_advance(t.data_ptr(), _stream()), "dropout_epoch_advance")
+
+
+# ------------------------------------------------------------------------------------------------ fake (meta) kernels
+# Shape / dtype propagation for FakeTensor and meta tracing (torch.compile, torch.export, make_fx): the ops stay opaque
+# CUDA kernels, but a tracer can see what they return without launching them.  (register_fake.)
+def _f32_like(t, shape=None):
+    return torch.empty(t.shape if shape is None else shape, dtype=torch.float32, device=t.device)
+
+
+def _register_fakes() -> None:
+    fake = torch.library.register_fake
+    ns = "m2b200::"
+
+    fake(ns + "token_mix_fwd")(lambda x, *a, **k: _f32_like(x))
+    fake(ns + "token_mix_bwd")(lambda du, x, ln_w, ln_b, w1, b1, w2, *a, **k: (
+        _f32_like(x), _f32_like(ln_w), _f32_like(ln_b), _f32_like(w1), _f32_like(b1), _f32_like(w2), _f32_like(w2, (w2.shape[0],))))
+    fake(ns + "channel_mix_fwd")(lambda u, *a, **k: _f32_like(u))
+    fake(ns + "channel_mix_bwd")(lambda dy, u, ln_w, ln_b, w1, b1, w2, *a, **k: (
+        _f32_like(u), _f32_like(ln_w), _f32_like(ln_b), _f32_like(w1), _f32_like(b1), _f32_like(w2), _f32_like(ln_w)))
+    fake(ns + "layernorm_fwd")(lambda x, w, b: _f32_like(x))
+    fake(ns + "layernorm_bwd")(lambda dy, x, w, grads=None: (_f32_like(x), _f32_like(w), _f32_like(w)))
+    fake(ns + "layernorm_concat_fwd")(lambda xs, ws, bs: _f32_like(xs[0], (xs[0].shape[0], sum(x.shape[1] for x in xs), xs[0].shape[2])))
+    fake(ns + "layernorm_concat_bwd")(lambda g, xs, ws, grads=None: (
+        [_f32_like(x) for x in xs], [_f32_like(w) for w in ws], [_f32_like(w) for w in ws]))
+    fake(ns + "linear_fwd")(lambda x, w, wb, bias, act, precision, dropout_p=0.0, seed=0: _f32_like(x, (*x.shape[:-1], w.shape[0])))
+    fake(ns + "linear_bwd")(lambda dy, x, y, w, wb, act, need_dx, precision, dropout_p=0.0, seed=0, grads=None: (
+        _f32_like(x) if need_dx else _f32_like(x, (0,)), _f32_like(w), _f32_like(w, (w.shape[0],))))
+
+    def _patch_fwd(img, w, wb, bias, patch, precision):
+        B, _, H, W = img.shape
+        return _f32_like(img, (B, (H // patch) * (W // patch), w.shape[0]))
+
+    fake(ns + "patch_embed_fwd")(_patch_fwd)
+    fake(ns + "patch_embed_bwd")(lambda dy, img, w, patch, has_bias, precision, grads=None: (
+        _f32_like(w), _f32_like(w, (w.shape[0] if has_bias else 0,))))
+    fake(ns + "patch_gather")(lambda img, patch: _f32_like(img, (img.shape[0], (img.shape[2] // patch) * (img.shape[3] // patch),
+                                                                   img.shape[1] * patch * patch)))
+    fake(ns + "mean_pool_fwd")(lambda x: _f32_like(x, (x.shape[0], x.shape[-1])))
+    fake(ns + "mean_pool_bwd")(lambda dp, n: _f32_like(dp, (dp.shape[0], n, dp.shape[-1])))
+    fake(ns + "concat_tokens")(lambda xs: _f32_like(xs[0], (xs[0].shape[0], sum(x.shape[1] for x in xs), xs[0].shape[2])))
+    fake(ns + "split_tokens")(lambda g, sizes: [_f32_like(g, (g.shape[0], n, g.shape[2])) for n in sizes])
+    fake(ns + "add")(lambda a, b: _f32_like(a))
+    fake(ns + "gate_fwd")(lambda h1, h2, zh: _f32_like(h1))
+    fake(ns + "gate_bwd")(lambda h1, h2, zh, g: (_f32_like(h1), _f32_like(h1), _f32_like(h1)))
+    fake(ns + "fuse2_fwd")(lambda a, b, mode: _f32_like(a))
+    fake(ns + "fuse2_max_bwd")(lambda a, b, g: (_f32_like(a), _f32_like(a)))
+    fake(ns + "cast_bf16")(lambda w, ld: torch.empty((w.shape[0], ld), dtype=torch.bfloat16, device=w.device))
+
+    def _heads_fwd(toks, ws, bs, labels, pos_weight, head_weight, loss_kind, tok_start=None, tok_len=None):
+        B, K = toks[0].shape[0], ws[0].shape[0]
+        dev = toks[0].device
+        return (torch.empty(4, dtype=torch.float32, device=dev), torch.empty(3, B, K, dtype=torch.float32, device=dev),
+                torch.empty((3, B) if loss_kind == 0 else (3, B, K), dtype=torch.int64, device=dev))
+
+    fake(ns + "heads_loss_fwd")(_heads_fwd)
+    fake(ns + "heads_loss_bwd")(lambda toks, ws, bs, *a, **k: ([_f32_like(t) for t in toks], [_f32_like(w) for w in ws],
+                                                               [_f32_like(b) for b in bs]))
+    fake(ns + "adam_step")(lambda *a, **k: None)
+
+
+_register_fakes()

@@ -220,3 +220,27 @@ def test_reference_yaml_files_build_the_drop_in_models(rel):
     assert ours == theirs
     ref.load_state_dict(m.state_dict(), strict=True)          # and the tensors move across in both directions
     m.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_ops_have_fake_kernels_for_meta_tracing():
+    """SURVEY 8(b): every m2b200:: op carries a fake (meta) kernel, so FakeTensor / torch.compile tracing sees shapes and
+    dtypes without launching anything (runs without a GPU: fake CUDA tensors)."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from m2_mixer_b200 import ops  # noqa: F401  registers the ops
+    o = torch.ops.m2b200
+    with FakeTensorMode():
+        f = lambda *s: torch.empty(*s, device="cuda")
+        x, ln = f(8, 4, 128), f(128)
+        w1, b1, w2, b2 = f(32, 4), f(32), f(4, 32), f(4)
+        assert o.token_mix_fwd(x, ln, ln, w1, b1, w2, b2, 1).shape == (8, 4, 128)
+        g = o.token_mix_bwd(x, x, ln, ln, w1, b1, w2, 1)
+        assert [tuple(t.shape) for t in g] == [(8, 4, 128), (128,), (128,), (32, 4), (32,), (4, 32), (4,)]
+        cw1, cb1, cw2 = f(3072, 128), f(3072), f(128, 3072)
+        assert o.channel_mix_fwd(x, ln, ln, cw1, cb1, cw2, ln, None, None, 1).shape == (8, 4, 128)
+        assert o.channel_mix_bwd(x, x, ln, ln, cw1, cb1, cw2, None, None, 1)[3].shape == (3072, 128)
+        assert o.patch_embed_fwd(f(8, 1, 112, 112), f(128, 1, 56, 56), None, None, 56, 1).shape == (8, 4, 128)
+        assert o.layernorm_concat_fwd([x, x], [ln, ln], [ln, ln]).shape == (8, 8, 128)
+        losses, logits, preds = o.heads_loss_fwd([x, x, x], [f(10, 128)] * 3, [f(10)] * 3, torch.empty(8, dtype=torch.int64, device="cuda"),
+                                                 None, [1.0, 1.0, 1.0], 0)
+        assert losses.shape == (4,) and logits.shape == (3, 8, 10) and preds.dtype == torch.int64
