@@ -362,6 +362,24 @@ def refresh_bf16_weights() -> None:
         _WCACHE._refresh(dev)
 
 
+def ensure_bf16_weights_fresh() -> None:
+    """Refresh the bf16 weight copies on the CURRENT stream if any is stale.  Called before the forward forks onto a second
+    stream (models/base.py): a lazy refresh issued by whichever branch looks a weight up first would race with the other."""
+    stale = set()
+    for e in _WCACHE.entries.values():
+        p = e[0]()
+        if p is not None and (e[5] != p.data_ptr() or e[6] != p._version or e[7] != _WCACHE.epoch):
+            stale.add(p.device)
+    for dev in stale:
+        _WCACHE._refresh(dev)
+
+
+# The streams the current step's forward / backward run on when the two encoders are forked (models/base.py: the caller's
+# stream and the second encoder's).  The data-parallel bucket allreduces wait for all of them (parallel.GradSync._launch):
+# a bucket may hold gradients produced on either, whichever stream the last "gradient ready" report came from.
+COMPUTE_STREAMS: List["torch.cuda.Stream"] = []
+
+
 def bf16_weight(param: torch.Tensor, rows: Optional[int] = None, cols: Optional[int] = None) -> torch.Tensor:
     """bf16 [rows][up8(cols)] operand copy of a weight parameter viewed as [rows][cols] (default: its first axis x the rest)."""
     rows = param.shape[0] if rows is None else rows

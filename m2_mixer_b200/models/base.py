@@ -63,15 +63,44 @@ class TrainTestModule(nn.Module):
         if (isinstance(fusion_function, ConcatFusion) and fusion_function.dim == 1 and isinstance(mixer_a, _Stack)
                 and isinstance(mixer_b, _Stack)
                 and mixer_a.layer_norm.weight.shape == mixer_b.layer_norm.weight.shape):
-            fa, fb = mixer_a.forward_features(xa), mixer_b.forward_features(xb)
+            fa, fb = self._two_branches(lambda: mixer_a.forward_features(xa), lambda: mixer_b.forward_features(xb))
             la, lb = mixer_a.layer_norm, mixer_b.layer_norm
             cat = F.layer_norm_concat([fa, fb], [la.weight, lb.weight], [la.bias, lb.bias])
             fused = fusion_mixer(cat)
             na, nb = fa.shape[1], fb.shape[1]
             return [cat, cat, fused], [(0, na), (na, nb), (0, fused.shape[1])], fused
-        ta, tb = mixer_a(xa), mixer_b(xb)
+        ta, tb = self._two_branches(lambda: mixer_a(xa), lambda: mixer_b(xb))
         fused = fusion_mixer(fusion_function(ta, tb))
         return [ta, tb, fused], None, fused
+
+    def _two_branches(self, fn_a, fn_b):
+        """Run the two encoders on two streams (autograd then runs their backwards on the same two streams).  Every kernel of
+        an M2-Mixer-B encoder block is ONE persistent CTA per SM on 128 (channel mixing) or 144 (weight gradients) of the 148
+        SMs: alone, each leaves 3-14 % of the GPU idle for its whole duration, and the next kernel of the same branch cannot
+        start before its last CTA retires.  The two branches are independent until the fusion, so the block scheduler fills
+        one's idle SMs and tails with the other's CTAs - also inside a captured graph (fork / join become graph edges).
+        M2B200_BRANCH_STREAMS=0 keeps one stream (A/B measurements)."""
+        import os
+        from .. import functional as F
+        if not torch.cuda.is_available() or os.environ.get("M2B200_BRANCH_STREAMS", "1") == "0":
+            return fn_a(), fn_b()
+        cur = torch.cuda.current_stream()
+        side = getattr(self, "_side_stream", None)
+        if side is None or side.device != cur.device:
+            side = torch.cuda.Stream(device=cur.device)
+            object.__setattr__(self, "_side_stream", side)
+        F.COMPUTE_STREAMS[:] = [cur, side]
+        F.ensure_bf16_weights_fresh()              # on the caller's stream, before the fork (see functional.py)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            b = fn_b()
+        a = fn_a()
+        cur.wait_stream(side)
+        if not torch.cuda.is_current_stream_capturing():
+            for t in (b if isinstance(b, (tuple, list)) else (b,)):
+                if torch.is_tensor(t):
+                    t.record_stream(cur)           # allocated on the side stream, consumed on the caller's
+        return a, b
 
     def set_precision(self, p: str) -> "TrainTestModule":
         for m in self.modules():

@@ -91,6 +91,10 @@ class GradSync:
         self._launched[b] = True
         if self.cuda:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
+            from .functional import COMPUTE_STREAMS   # forked encoders: this bucket may hold gradients of both streams
+            for st in COMPUTE_STREAMS:
+                if st.device == self.flat_grad.device:
+                    self.comm_stream.wait_stream(st)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
         else:
