@@ -37,11 +37,12 @@ def parse():
                     help="per-GPU batch (weak scaling); default per config: avmnist_* 4096, mimic_H 4096, mmimdb_C4 256, scaled_C5 64")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=None, help="bounded sample for the CPU legs (default per config)")
-    ap.add_argument("--graph-comm", default=None, choices=["overlap", "split"],
-                    help="N > 1, graphed step: 'overlap' captures the bucketed NCCL allreduces on the communication stream "
-                         "(under the backward), 'split' is one allreduce between two graphs")
+    ap.add_argument("--graph-comm", default="split", choices=["overlap", "split"],
+                    help="N > 1, graphed step: 'split' (default: the faster one since both encoders keep every SM busy, "
+                         "profiles/r02_multi_gpu.md) is one allreduce between two graphs, 'overlap' captures the bucketed NCCL "
+                         "allreduces on the communication stream under the backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--bucket-mb", type=float, default=2.0, help="N > 1: size of the gradient allreduce buckets (MiB)")
+    ap.add_argument("--bucket-mb", type=float, default=16.0, help="N > 1: size of the gradient allreduce buckets (MiB)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-host-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="dtype of the IMAGE tensors in the pinned host batches of the e2e leg (bf16 halves the host link "
@@ -265,12 +266,12 @@ def run_ours(args, cfg):
     saved_fd = os.dup(1)
     os.dup2(2, 1)
     try:
-        # The captured allreduces run UNDER the backward kernels, which are one persistent CTA per SM with all of its shared
-        # memory and tensor memory: an NCCL kernel that spreads over many SMs delays them by more than the collective takes.
-        # Sixteen CTAs and 2 MiB buckets move the 33 MB of gradients well inside the backward's time (measured on 2 and
-        # 8 x B200: profiles/r02_multi_gpu.md); an explicit NCCL_MAX_CTAS in the environment wins.
-        if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "--graph-comm split" not in " ".join(sys.argv) and "--no-graph" not in sys.argv:
-            os.environ.setdefault("NCCL_MAX_CTAS", "16")
+        # Captured allreduces (--graph-comm overlap) run UNDER the backward kernels, which are one persistent CTA per SM with
+        # all of its shared memory and tensor memory: an NCCL kernel that spreads over many SMs delays them by more than the
+        # collective takes, so its CTAs are capped (measured on 2 and 8 x B200: profiles/r02_multi_gpu.md); an explicit
+        # NCCL_MAX_CTAS in the environment wins.  The split form (default) keeps NCCL's own choice.
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.graph_comm == "overlap" and not args.no_graph:
+            os.environ.setdefault("NCCL_MAX_CTAS", "32")
         rank, local, world = parallel.init_from_env()
         if world > 1 and torch.cuda.is_available():
             t = torch.zeros(1, device=torch.device("cuda", local))

@@ -7,13 +7,15 @@ and replays it with one ``cudaGraphLaunch`` per step:
 
 * inputs are copied into static tensors (the graph's kernels hold raw pointers),
 * the optimizer must be ``FusedAdam(..., capturable=True)`` (lr and the step counter live in device memory),
-* data parallel (``grad_sync=parallel.attach(opt)``), ``comm="overlap"`` (default): ONE graph per static batch; the
-  bucketed NCCL sum-allreduces of ``parallel.GradSync`` are captured on its communication stream, forked from the
-  compute stream as soon as the last gradient of a bucket has been produced and joined before the optimizer step, so the
-  collectives run under the remaining backward kernels (the north_star's "bucketed and overlapped with backward").
+* data parallel (``grad_sync=parallel.attach(opt)``), ``comm="overlap"`` (or ``M2B200_GRAPH_COMM=overlap``): ONE graph per
+  static batch; the bucketed NCCL sum-allreduces of ``parallel.GradSync`` are captured on its communication stream, forked
+  from the compute streams as soon as the last gradient of a bucket has been produced and joined before the optimizer step,
+  so the collectives run under the remaining backward kernels (the north_star's "bucketed and overlapped with backward").
   Call ``close()`` before ``destroy_process_group``: graphs that hold NCCL kernel nodes must die before the communicator.
-  ``comm="split"`` (or ``M2B200_GRAPH_COMM=split``) is round 1's form: TWO graphs - (zero_grad, forward, backward) and
-  (optimizer step) - around one eager, un-overlapped allreduce of the whole flat gradient buffer,
+  ``comm="split"`` (default) is TWO graphs - (zero_grad, forward, backward) and (optimizer step) - around one eager allreduce
+  of the whole flat gradient buffer.  Measured on 2 and 8 x B200 (profiles/r02_multi_gpu.md): since the two encoders run
+  on two streams every SM is busy during the backward, and a collective underneath displaces more compute than it hides
+  (8 x B200: 2.98 ms overlapped with 16 MiB buckets vs 2.95 ms split; 2 x B200: 2.98 vs 2.87 ms),
 * dropout stays random: (p, seed) are launch parameters and would be frozen by the capture, so a device-resident epoch
   counter is registered with the library (``ops.set_dropout_epoch``); every kernel folds it into its mask key at run time
   and the captured step ends by advancing it.
@@ -96,7 +98,7 @@ class GraphedTrainStep:
         _EPOCH_OWNER = self
         optimizer.sync_lr_to_device()
         dp = self.sync is not None and getattr(self.sync, "world", 1) > 1
-        comm = comm or os.environ.get("M2B200_GRAPH_COMM", "overlap")
+        comm = comm or os.environ.get("M2B200_GRAPH_COMM", "split")
         if comm not in ("overlap", "split"):
             raise ValueError("comm must be 'overlap' or 'split'")
         self.split = dp and comm == "split"

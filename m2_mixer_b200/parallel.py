@@ -39,7 +39,10 @@ class GradSync:
         self.flat_grad, self.group = flat_grad, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.cuda = flat_grad.is_cuda
-        self.comm_stream = torch.cuda.Stream(device=flat_grad.device) if self.cuda else None
+        # high priority: a collective's CTAs should take the next SMs that free up - a half-scheduled NCCL kernel spins on its
+        # peers while it holds SMs the persistent one-CTA-per-SM compute kernels are waiting for
+        prio = int(os.environ.get("M2B200_COMM_PRIORITY", "-1"))
+        self.comm_stream = torch.cuda.Stream(device=flat_grad.device, priority=prio) if self.cuda else None
         # buckets over contiguous flat ranges, last parameters first
         ends = [o + (p.numel() + 3) // 4 * 4 for p, o in zip(params, offsets)]
         self.buckets: List[list] = []      # [start, end, n_params]
