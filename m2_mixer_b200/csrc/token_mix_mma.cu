@@ -187,7 +187,7 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
       const float2 gm = *reinterpret_cast<const float2*>(ln_w + d_lo);
       const float2 bt = *reinterpret_cast<const float2*>(ln_b + d_lo);
       // A1: a0 = (row g = d_lo, k = 2tq..+1), a1 = (row g+8 = d_hi, same k), a2 / a3 = k + 8
-      uint32_t a1f[4] = {0u, 0u, 0u, 0u};
+      uint32_t a1f[KN > 2 ? 2 * KN : 4] = {};   // KN = 1: the upper k half stays zero
 #pragma unroll
       for (int kh = 0; kh < KN; ++kh) {
         const float x00 = (xr[mt][kh][0].x - mean[kh][0]) * rstd[kh][0] * gm.x + bt.x;
@@ -203,7 +203,9 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
       for (int j = 0; j < NT1; ++j) {
         c[j][0] = c[j][2] = b1f[j][0];
         c[j][1] = c[j][3] = b1f[j][1];
-        mma_bf16(c[j], a1f[0], a1f[1], a1f[2], a1f[3], w1f[j][0], KN > 1 ? w1f[j][KN - 1] : 0u);
+        mma_bf16(c[j], a1f[0], a1f[1], a1f[2], a1f[3], w1f[j][0], KN > 1 ? w1f[j][1] : 0u);
+        if constexpr (KN > 2)      // N up to 32 tokens: a second k-step (MIMIC-H's 24 time steps / 25 fused tokens)
+          mma_bf16(c[j], a1f[4], a1f[5], a1f[6], a1f[7], w1f[j][2], w1f[j][3]);
       }
       // GELU (+ dropout) -> A2 fragments; C tile j: c0 = (d_lo, t), c1 = (d_lo, t+1), c2 = (d_hi, t), c3 = (d_hi, t+1)
       uint32_t a2f[KS2][4];
@@ -387,7 +389,7 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
       const int d_lo = 16 * mtg + 2 * g;
       const float2 gm = *reinterpret_cast<const float2*>(ln_w + d_lo);
       const float2 bt = *reinterpret_cast<const float2*>(ln_b + d_lo);
-      uint32_t a1f[4] = {0u, 0u, 0u, 0u}, a3f[4] = {0u, 0u, 0u, 0u};
+      uint32_t a1f[KN > 2 ? 2 * KN : 4] = {}, a3f[KN > 2 ? 2 * KN : 4] = {};
       float2 xh[KN][2];            // xhat of this tile
 #pragma unroll
       for (int kh = 0; kh < KN; ++kh) {
@@ -418,8 +420,12 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
         c1[j][0] = c1[j][2] = b1f[j][0];
         c1[j][1] = c1[j][3] = b1f[j][1];
         c3[j][0] = c3[j][1] = c3[j][2] = c3[j][3] = 0.f;
-        mma_bf16(c1[j], a1f[0], a1f[1], a1f[2], a1f[3], w1f[j][0], KN > 1 ? w1f[j][KN - 1] : 0u);
-        mma_bf16(c3[j], a3f[0], a3f[1], a3f[2], a3f[3], w2g[j][0], KN > 1 ? w2g[j][KN - 1] : 0u);
+        mma_bf16(c1[j], a1f[0], a1f[1], a1f[2], a1f[3], w1f[j][0], KN > 1 ? w1f[j][1] : 0u);
+        mma_bf16(c3[j], a3f[0], a3f[1], a3f[2], a3f[3], w2g[j][0], KN > 1 ? w2g[j][1] : 0u);
+        if constexpr (KN > 2) {
+          mma_bf16(c1[j], a1f[4], a1f[5], a1f[6], a1f[7], w1f[j][2], w1f[j][3]);
+          mma_bf16(c3[j], a3f[4], a3f[5], a3f[6], a3f[7], w2g[j][2], w2g[j][3]);
+        }
       }
       // G = Drop(GELU(H)), dH = dG * Drop'(.) * GELU'(H); packs: lo = (rows 0-7 = d_lo set), hi = (rows 8-15 = d_hi set)
       uint32_t pG[NT1][2], pH[NT1][2];
@@ -658,10 +664,11 @@ int launch_fwd(const float* x, const float* ln_w, const float* ln_b, const float
 }  // namespace
 
 // Shapes the warp-level tensor-core path covers (bf16 mode only): the register tile is DM * (N / 8) * 4 floats per lane.
+// N <= 32 (two k-steps in GEMM1 / the dG GEMM) for D <= 64: MIMIC-H's 24 time steps and 25 fused tokens.
 bool token_mix_mma_supported(int N, int D, int T) {
   if (!(D == 32 || D == 64 || D == 128 || D == 256)) return false;
-  if (N < 1 || N > 16 || T < 1 || T > 32) return false;
-  const int kn = N <= 8 ? 1 : 2;
+  if (N < 1 || N > 32 || T < 1 || T > 32) return false;
+  const int kn = N <= 8 ? 1 : (N <= 16 ? 2 : 4);
   return (D / 16) * kn <= 16;
 }
 
@@ -670,11 +677,12 @@ int token_mix_mma_fwd(const float* x, const float* ln_w, const float* ln_b, cons
                       cudaStream_t s) {
   if (!token_mix_mma_supported(N, D, T)) return M2_ERR_ARG;
   const Drop dh = make_drop(drop_p, seed, kSiteTokenHidden), dout = make_drop(drop_p, seed, kSiteTokenOut);
-  const int dm = D / 16, tp = T <= 16 ? 16 : 32, np = N <= 8 ? 8 : 16;
+  const int dm = D / 16, tp = T <= 16 ? 16 : 32, np = N <= 8 ? 8 : (N <= 16 ? 16 : 32);
 #define M2_TMF(DM_, TP_, NP_) \
   if (dm == DM_ && tp == TP_ && np == NP_) return launch_fwd<DM_, TP_, NP_>(x, ln_w, ln_b, w1, b1, w2, b2, u, B, N, T, dh, dout, s);
   M2_TMF(2, 16, 8) M2_TMF(2, 32, 8) M2_TMF(4, 16, 8) M2_TMF(4, 32, 8) M2_TMF(8, 16, 8) M2_TMF(8, 32, 8) M2_TMF(16, 16, 8) M2_TMF(16, 32, 8)
   M2_TMF(2, 16, 16) M2_TMF(2, 32, 16) M2_TMF(4, 16, 16) M2_TMF(4, 32, 16) M2_TMF(8, 16, 16) M2_TMF(8, 32, 16)
+  M2_TMF(2, 16, 32) M2_TMF(2, 32, 32) M2_TMF(4, 16, 32) M2_TMF(4, 32, 32)
 #undef M2_TMF
   return M2_ERR_ARG;
 }
@@ -685,12 +693,13 @@ int token_mix_mma_bwd(const float* du, const float* x, const float* ln_w, const 
                       int B, int N, int D, int T, float drop_p, unsigned long long seed, cudaStream_t s) {
   if (!token_mix_mma_supported(N, D, T)) return M2_ERR_ARG;
   const Drop dh = make_drop(drop_p, seed, kSiteTokenHidden), dout = make_drop(drop_p, seed, kSiteTokenOut);
-  const int dm = D / 16, tp = T <= 16 ? 16 : 32, np = N <= 8 ? 8 : 16;
+  const int dm = D / 16, tp = T <= 16 ? 16 : 32, np = N <= 8 ? 8 : (N <= 16 ? 16 : 32);
 #define M2_TMB(DM_, TP_, NP_)              \
   if (dm == DM_ && tp == TP_ && np == NP_) \
     return launch_bwd<DM_, TP_, NP_>(du, x, ln_w, ln_b, w1, b1, w2, dx, dln_w, dln_b, dw1, db1, dw2, db2, B, N, T, dh, dout, s);
   M2_TMB(2, 16, 8) M2_TMB(2, 32, 8) M2_TMB(4, 16, 8) M2_TMB(4, 32, 8) M2_TMB(8, 16, 8) M2_TMB(8, 32, 8) M2_TMB(16, 16, 8) M2_TMB(16, 32, 8)
   M2_TMB(2, 16, 16) M2_TMB(2, 32, 16) M2_TMB(4, 16, 16) M2_TMB(4, 32, 16) M2_TMB(8, 16, 16) M2_TMB(8, 32, 16)
+  M2_TMB(2, 16, 32) M2_TMB(2, 32, 32) M2_TMB(4, 16, 32) M2_TMB(4, 32, 32)
 #undef M2_TMB
   return M2_ERR_ARG;
 }

@@ -12,6 +12,9 @@ from ..config import Cfg, wrap
 from ..optim import FusedAdam
 
 
+_SIDE_STREAMS: Dict[Any, "torch.cuda.Stream"] = {}
+
+
 class TrainTestModule(nn.Module):
     def __init__(self, optimizer_cfg=None, **kwargs):
         super().__init__()
@@ -85,10 +88,9 @@ class TrainTestModule(nn.Module):
         if not torch.cuda.is_available() or os.environ.get("M2B200_BRANCH_STREAMS", "1") == "0":
             return fn_a(), fn_b()
         cur = torch.cuda.current_stream()
-        side = getattr(self, "_side_stream", None)
-        if side is None or side.device != cur.device:
-            side = torch.cuda.Stream(device=cur.device)
-            object.__setattr__(self, "_side_stream", side)
+        side = _SIDE_STREAMS.get(cur.device)      # one per device, shared by every model (not module state: deepcopy / pickle)
+        if side is None:
+            side = _SIDE_STREAMS[cur.device] = torch.cuda.Stream(device=cur.device)
         F.COMPUTE_STREAMS[:] = [cur, side]
         F.ensure_bf16_weights_fresh()              # on the caller's stream, before the fork (see functional.py)
         side.wait_stream(cur)

@@ -34,8 +34,9 @@ class MimicMixerMultiLoss(TrainTestModule):
 
     def shared_step(self, batch, mode='train', **kwargs):
         static, time, labels = batch
-        static_feat = self.static_extractor(static)                 # [B, 64]
-        time_tokens = self.time_mixer(time)                         # [B, 24, 64]
+        # the two modality encoders are independent: two streams (models/base.py _two_branches), the short MLP beside the mixer
+        time_tokens, static_feat = self._two_branches(lambda: self.time_mixer(time),            # [B, 24, 64]
+                                                      lambda: self.static_extractor(static))    # [B, 64]
         fused = self.fusion_mixer(self.fusion_function(static_feat.unsqueeze(1), time_tokens))
         cf = self.classifier_fusion.classifer
         losses, logits, _ = F.heads_loss(

@@ -129,7 +129,8 @@ def run_group(g):
         for (B, N, D, T, prec, tol) in [(9, 4, 128, 32, FP32, 2e-6), (9, 4, 128, 32, BF16, 1e-2), (5, 25, 64, 8, FP32, 2e-6),
                                         (3, 40, 48, 16, FP32, 2e-6), (2, 196, 96, 64, FP32, 2e-6), (70, 8, 128, 32, BF16, 1e-2),
                                         (5, 4, 32, 8, BF16, 1e-2), (11, 8, 64, 16, BF16, 1e-2), (3, 12, 64, 32, BF16, 1e-2),
-                                        (6, 4, 256, 32, BF16, 1e-2), (4, 25, 64, 8, BF16, 1e-2), (2100, 4, 128, 32, BF16, 1e-2)]:
+                                        (6, 4, 256, 32, BF16, 1e-2), (4, 25, 64, 8, BF16, 1e-2), (2100, 4, 128, 32, BF16, 1e-2),
+                                        (7, 24, 64, 16, BF16, 1e-2), (130, 32, 32, 32, BF16, 1e-2), (5, 17, 64, 20, BF16, 1e-2)]:
             x = rn(B, N, D)
             p = dict(ln_w=1 + 0.1 * rn(D), ln_b=0.1 * rn(D), w1=rn(T, N) / N ** 0.5, b1=0.1 * rn(T), w2=rn(N, T) / T ** 0.5, b2=0.1 * rn(N))
             pd = {k: v.double().requires_grad_(True) for k, v in p.items()}
