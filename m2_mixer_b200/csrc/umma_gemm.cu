@@ -503,11 +503,276 @@ int launch2_layout(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap&
   return b_mn ? launch2<false, true, kTmaStore>(ta, tb, tc, d, sc, s) : launch2<false, false, kTmaStore>(ta, tb, tc, d, sc, s);
 }
 
-// M2B200_GEMM_GEN=1 keeps every GEMM on the one-tile-per-CTA kernel (A/B measurements)
+
+// ---------------------------------------------------------------------------------------------------------------
+// Generation 3: the same persistent kernel on CTA PAIRS (thread-block cluster of 2 = the two SMs of a TPC,
+// tcgen05.mma.cta_group::2).  A pair owns a 256 x 256 tile: CTA r loads ITS 128 rows of A and ITS 128 columns of B per
+// k-step (32 KB instead of the 48 KB a single CTA needs for 128 x 256: 64 instead of 94 B/clk/SM out of L2), the leader's
+// one MMA thread issues M256 N256 K16 instructions that read both CTAs' shared memory and write both CTAs' tensor memory
+// (each CTA keeps the accumulator rows of its own A half: 128 lanes x 256 columns, two buffers), and each CTA runs the
+// epilogue of its half.  Barriers: the leader's `full` counts the bytes of BOTH CTAs' TMA loads (cp.async.bulk.tensor
+// .cta_group::2 with the barrier address of the even CTA), `empty` / `acc_full` are signalled in both CTAs by multicast
+// commits, the peer's epilogue warps arrive on the leader's `acc_empty` through the cluster address of its barrier.
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared-window address: the even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {   // one warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// box -> THIS CTA's shared memory, bytes counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+
+constexpr int kTileBh = kTileB2 / 2;                       // this CTA's 128 columns of B: 16 KB
+constexpr int smem2c_bytes(bool tma_store) {
+  return (tma_store ? 5 : 6) * (kTileA2 + kTileBh) + (tma_store ? 16 * kStageOut2 : 0) + 256 + 1024;
+}
+
+template <bool kAMn, bool kBMn, bool kTmaStore>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+umma_gemm2c_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmC, const GemmDev p, const Sched2 sc) {
+  constexpr int kStagesC = kTmaStore ? 5 : 6;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStagesC * kTileA2;
+  uint8_t* sOut = smem + kStagesC * (kTileA2 + kTileBh);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOut + (kTmaStore ? 16 * kStageOut2 : 0));
+  uint64_t* empty = full + kStagesC;
+  uint64_t* acc_full = empty + kStagesC;      // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2]  (the leader's are the live ones)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int k_tiles = ceil_div(p.K, kBK);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStagesC; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * kEpiWarps2); }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (kTmaStore) tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();           // both CTAs' barriers exist before any remote arrive / remote transaction count
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int per_z = sc.tiles_m * sc.tiles_n;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    int it = 0;
+    for (int tile = pair; tile < sc.total; tile += npairs) {
+      const int z = tile / per_z, r = tile - z * per_z;
+      const int m0 = (r % sc.tiles_m) * 256 + rank * 128, n0 = (r / sc.tiles_m) * 256 + rank * 128;
+      const int batch = z / p.splitk, split = z - batch * p.splitk;
+      const int kt_begin = split * p.k_tiles_per_split, kt_end = min(k_tiles, kt_begin + p.k_tiles_per_split);
+      const int a_row0 = batch * p.a_batch_rows, b_row0 = batch * p.b_batch_rows;
+      for (int kt = kt_begin; kt < kt_end; ++kt, ++it) {
+        const int s = it % kStagesC;
+        mbar_wait(&empty[s], ((it / kStagesC) & 1) ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * (kTileA2 + kTileBh));   // both CTAs' boxes land on this barrier
+          const int k0 = kt * kBK;
+          uint8_t* a = sA + s * kTileA2;
+          uint8_t* b = sB + s * kTileBh;
+          if (!kAMn) {
+            tma_load_2d_pair(a, &tmA, &full[s], k0, a_row0 + m0);
+          } else {
+            tma_load_2d_pair(a, &tmA, &full[s], m0, a_row0 + k0);
+            tma_load_2d_pair(a + kTileA2 / 2, &tmA, &full[s], m0 + 64, a_row0 + k0);
+          }
+          if (!kBMn) {
+            tma_load_2d_pair(b, &tmB, &full[s], k0, b_row0 + n0);              // [128 n][64 k]
+          } else {
+            tma_load_2d_pair(b, &tmB, &full[s], n0, b_row0 + k0);
+            tma_load_2d_pair(b + kTileBh / 2, &tmB, &full[s], n0 + 64, b_row0 + k0);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, kBN2, kAMn ? 1 : 0, kBMn ? 1 : 0);
+      const uint64_t a_desc0 = kAMn ? umma_desc_sw128(smem_u32(sA), kTileA2 / 2, 1024) : umma_desc_sw128(smem_u32(sA), 16, 1024);
+      const uint64_t b_desc0 = kBMn ? umma_desc_sw128(smem_u32(sB), kTileBh / 2, 1024) : umma_desc_sw128(smem_u32(sB), 16, 1024);
+      int it = 0, t = 0;
+      for (int tile = pair; tile < sc.total; tile += npairs, ++t) {
+        const int z = tile / per_z;
+        const int split = z % p.splitk;
+        const int kt_begin = split * p.k_tiles_per_split, kt_end = min(k_tiles, kt_begin + p.k_tiles_per_split);
+        const int buf = t & 1;
+        mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);     // both CTAs' epilogues have drained this buffer
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * kBN2;
+        for (int kt = kt_begin; kt < kt_end; ++kt, ++it) {
+          const int s = it % kStagesC;
+          mbar_wait(&full[s], (it / kStagesC) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = a_desc0 + static_cast<uint64_t>((s * kTileA2) >> 4);
+            const uint64_t bd = b_desc0 + static_cast<uint64_t>((s * kTileBh) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < kBK / 16; ++kk)
+              umma_bf16_pair(acc, ad + ((kk * (kAMn ? 2048 : 32)) >> 4), bd + ((kk * (kBMn ? 2048 : 32)) >> 4), idesc,
+                             (kt > kt_begin || kk > 0) ? 1u : 0u);
+            umma_commit_pair(&empty[s]);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit_pair(&acc_full[buf]);
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;
+    int t = 0;
+    for (int tile = pair; tile < sc.total; tile += npairs, ++t) {
+      const int z = tile / per_z, r = tile - z * per_z;
+      const int m0 = (r % sc.tiles_m) * 256 + rank * 128, n0 = (r / sc.tiles_m) * 256;
+      const int batch = z / p.splitk, split = z - batch * p.splitk;
+      const int buf = t & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool lead = (split == 0);
+      const float rbias = (p.bias_mode == 2 && row_ok && lead) ? p.bias[row] : 0.f;
+      const long long coff = static_cast<long long>(batch) * p.c_batch_stride + static_cast<long long>(row) * p.ldc;
+      const float* res = (p.residual && lead) ? p.residual + static_cast<long long>(batch) * p.r_batch_stride +
+                                                    static_cast<long long>(row) * p.ldr : nullptr;
+      mbar_wait(&acc_full[buf], (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t stage = smem_u32(sOut + (warp - 2) * kStageOut2);
+#pragma unroll 1
+      for (int c0 = part * 64; c0 < part * 64 + 64; c0 += 32) {
+        uint32_t rg[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kBN2 + c0, rg);
+        tmem_ld_wait();
+        if (c0 + 32 == part * 64 + 64) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);
+        }
+        if (!kTmaStore) {
+          epilogue_chunk(p, rg, row, row_ok, n0 + c0, coff, res, rbias, lead);
+        } else {
+          const bool live = n0 + c0 < p.N;
+          float v[32];
+          if (live && row_ok) epilogue_math(p, rg, v, row, n0 + c0, res, rbias, lead);
+          if (p.c_bf16) {
+            const int hpc = (c0 - part * 64) >> 5;
+            if (hpc == 0) {
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+            }
+            if (live && row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 o = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
+                                           pack_bf16(v[j + 6], v[j + 7]));
+                st_shared_v4(stage + sw128_offset(lane, hpc * 4 + (j >> 3)), o);
+              }
+            }
+            if (hpc == 1) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0 && n0 + part * 64 < p.N) {
+                tma_store_3d(&tmC, sOut + (warp - 2) * kStageOut2, n0 + part * 64, m0 + q * 32, batch);
+                tma_store_commit();
+              }
+            }
+          } else {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+            if (live && row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                st_shared_v4(stage + sw128_offset(lane, j >> 2),
+                             make_uint4(__float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3])));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && live) {
+              tma_store_3d(&tmC, sOut + (warp - 2) * kStageOut2, n0 + c0, m0 + q * 32, batch);
+              tma_store_commit();
+            }
+          }
+        }
+      }
+    }
+    if (kTmaStore) {
+      if (lane == 0) tma_store_wait_all();
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();           // the peer's shared memory and barriers stay alive until both CTAs are done
+  if (warp == 1) tmem_dealloc2(tmem_base, 512);
+}
+
+template <bool kAMn, bool kBMn, bool kTmaStore>
+int launch2c(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmDev& d, const Sched2& sc, cudaStream_t s) {
+  auto kern = umma_gemm2c_kernel<kAMn, kBMn, kTmaStore>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2c_bytes(kTmaStore)) != cudaSuccess) return M2_ERR_LAUNCH;
+    configured = true;
+  }
+  LaunchScope scope(kAMn ? (kBMn ? "umma_gemm2c_tn" : "umma_gemm2c_tk") : (kBMn ? "umma_gemm2c_kn" : "umma_gemm2c_kk"), s);
+  int grid = 2 * sc.total < 148 ? 2 * sc.total : 148;
+  kern<<<grid, kThreads2, smem2c_bytes(kTmaStore), s>>>(ta, tb, tc, d, sc);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+template <bool kTmaStore>
+int launch2c_layout(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmDev& d,
+                    const Sched2& sc, cudaStream_t s) {
+  if (a_mn) return b_mn ? launch2c<true, true, kTmaStore>(ta, tb, tc, d, sc, s) : launch2c<true, false, kTmaStore>(ta, tb, tc, d, sc, s);
+  return b_mn ? launch2c<false, true, kTmaStore>(ta, tb, tc, d, sc, s) : launch2c<false, false, kTmaStore>(ta, tb, tc, d, sc, s);
+}
+
+// M2B200_GEMM_GEN=1 keeps every GEMM on the one-tile-per-CTA kernel, 2 on single-CTA persistent tiles (A/B measurements)
 int gemm_generation() {
   static const int gen = [] {
     const char* e = getenv("M2B200_GEMM_GEN");
-    return e ? atoi(e) : 2;
+    return e ? atoi(e) : 3;
   }();
   return gen;
 }
@@ -522,6 +787,9 @@ int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
   // wide persistent tiles when the output is wide enough to fill them and there is more than a wave of work
   const bool wide = gemm_generation() >= 2 && g.N > 128 &&
                     static_cast<long long>(ceil_div(g.M, kBM)) * ceil_div(g.N, kBN2) * g.batch * g.splitk >= 64;
+  // CTA pairs (256 x 256 tiles) when at least one wave of pairs exists
+  const bool pairs = wide && gemm_generation() >= 3 && g.M > 128 &&
+                     static_cast<long long>(ceil_div(g.M, 256)) * ceil_div(g.N, kBN2) * g.batch * g.splitk >= 74;
   CUtensorMap ta, tb;
   int rc;
   {
@@ -533,7 +801,7 @@ int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
   {
     const uint64_t ext = g.b_mn ? g.K : g.N, cols = g.b_mn ? g.N : g.K;
     const uint64_t rows = static_cast<uint64_t>(g.batch - 1) * g.b_batch_rows + ext;
-    rc = make_tmap_bf16(&tb, g.B, rows, cols, g.ldb, g.b_mn ? 64 : (wide ? 256 : 128), 64);
+    rc = make_tmap_bf16(&tb, g.B, rows, cols, g.ldb, g.b_mn ? 64 : ((wide && !pairs) ? 256 : 128), 64);
     if (rc) return rc;
   }
   GemmDev d;
@@ -551,7 +819,7 @@ int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
   d.drop = make_drop(g.drop_p, g.drop_seed, g.drop_site); d.drop_ld = g.drop_ld;
   if (wide) {
     Sched2 sc;
-    sc.tiles_m = ceil_div(g.M, kBM); sc.tiles_n = ceil_div(g.N, kBN2);
+    sc.tiles_m = ceil_div(g.M, pairs ? 256 : kBM); sc.tiles_n = ceil_div(g.N, kBN2);
     const long long total = static_cast<long long>(sc.tiles_m) * sc.tiles_n * g.batch * d.splitk;
     if (total >= (1ll << 31)) return M2_ERR_ARG;
     sc.total = static_cast<int>(total);
@@ -565,6 +833,8 @@ int gemm_bf16_umma(const GemmArgs& g, cudaStream_t s) {
       if (make_tmap_store3d(&tc, g.C, eb, g.batch, g.M, g.N, g.ldc, g.c_batch_stride, 32, g.c_bf16 ? 64 : 32) != M2_OK)
         tma_store = false;   // unaligned output: per-thread stores
     }
+    if (pairs)
+      return tma_store ? launch2c_layout<true>(g.a_mn, g.b_mn, ta, tb, tc, d, sc, s) : launch2c_layout<false>(g.a_mn, g.b_mn, ta, tb, tc, d, sc, s);
     return tma_store ? launch2_layout<true>(g.a_mn, g.b_mn, ta, tb, tc, d, sc, s) : launch2_layout<false>(g.a_mn, g.b_mn, ta, tb, tc, d, sc, s);
   }
   dim3 grid(ceil_div(g.M, kBM), ceil_div(g.N, kBN), g.batch * d.splitk);

@@ -79,6 +79,12 @@ def run_group(g):
         for (am, bm) in [(0, 0), (0, 1), (1, 0), (1, 1)]:
             ok &= report(f"umma2 a_mn={am} b_mn={bm} 4104x648x328", gemm_case(BF16, 4104, 648, 328, am, bm), 1e-5)
         ok &= report("umma2 KK 12544x3072x768 (13 tiles per CTA)", gemm_case(BF16, 12544, 3072, 768, 0, 0), 1e-5)
+        # CTA pairs (cta_group::2, >= 74 tiles of 256 x 256): every layout, a last pair tile whose second CTA is all out of range
+        for (am, bm) in [(0, 0), (0, 1), (1, 0), (1, 1)]:
+            ok &= report(f"umma2c a_mn={am} b_mn={bm} 9576x648x328", gemm_case(BF16, 9576, 648, 328, am, bm), 1e-5)
+        ok &= report("umma2c KK epilogue bias+gelu+res fp32 out", gemm_case(BF16, 9576, 648, 328, 0, 0, bias_mode=1, act=1, use_res=True), 1e-3)
+        ok &= report("umma2c KK bf16 out row bias, long K (per-thread stores)", gemm_case(BF16, 9576, 648, 2000, 0, 0, bias_mode=2, out_bf16=True), 5e-3)
+        ok &= report("umma2c KK splitk=2", gemm_case(BF16, 9576, 648, 1000, 0, 0, splitk=2, bias_mode=1), 1e-5)
         ok &= report("umma2 KK epilogue bias+gelu+res", gemm_case(BF16, 4104, 648, 328, 0, 0, bias_mode=1, act=1, use_res=True), 1e-3)
         ok &= report("umma2 KK bf16 out row bias", gemm_case(BF16, 4104, 648, 328, 0, 0, bias_mode=2, out_bf16=True), 5e-3)
         ok &= report("umma2 KK splitk=3", gemm_case(BF16, 4104, 648, 1000, 0, 0, splitk=3, bias_mode=1), 1e-5)
