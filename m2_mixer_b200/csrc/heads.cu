@@ -74,18 +74,33 @@ __global__ void __launch_bounds__(kThreads) heads_fwd_kernel(const HeadsDev a, f
     for (int h = 0; h < a.nheads; ++h) {
       float pooled[kMaxPer];
       pool_tokens<kMaxPer>(a.tok[h] + b * a.tok_bstride[h], a.ntok[h], a.dim[h], lane, pooled);
-      for (int k = 0; k < a.K; ++k) {
-        const float* wr = a.w[h] + static_cast<long long>(k) * a.dim[h];
-        float acc = 0.f;
+      // eight classes at a time: their dot products are independent, so the eight warp reductions run interleaved
+      // (one class after the other was a chain of K x 5 dependent shuffles per head and sample: the kernel was latency bound)
+      for (int k0 = 0; k0 < a.K; k0 += 8) {
+        float acc[8];
 #pragma unroll
-        for (int i = 0; i < kMaxPer; ++i) {
-          const int d = lane + 32 * i;
-          if (d < a.dim[h]) acc = fmaf(wr[d], pooled[i], acc);
+        for (int kk = 0; kk < 8; ++kk) {
+          acc[kk] = 0.f;
+          if (k0 + kk < a.K) {
+            const float* wr = a.w[h] + static_cast<long long>(k0 + kk) * a.dim[h];
+#pragma unroll
+            for (int i = 0; i < kMaxPer; ++i) {
+              const int d = lane + 32 * i;
+              if (d < a.dim[h]) acc[kk] = fmaf(__ldg(wr + d), pooled[i], acc[kk]);
+            }
+          }
         }
-        acc = warp_sum(acc) + a.b[h][k];
-        if (lane == 0) {
-          s_logit[warp][k] = acc;
-          logits[(static_cast<long long>(h) * a.B + b) * a.K + k] = acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) acc[kk] += __shfl_xor_sync(0xffffffffu, acc[kk], o);
+        if (lane < 8 && k0 + lane < a.K) {
+          float v = acc[0];
+#pragma unroll
+          for (int kk = 1; kk < 8; ++kk) v = lane == kk ? acc[kk] : v;
+          v += a.b[h][k0 + lane];
+          s_logit[warp][k0 + lane] = v;
+          logits[(static_cast<long long>(h) * a.B + b) * a.K + k0 + lane] = v;
         }
       }
       __syncwarp();
