@@ -278,6 +278,8 @@ size_t m2b200_channel_mix_workspace_bytes(int M, int D, int C, int precision, in
     else if (path == kPathUnfusedBf16) b = up256(m * d * 2) + up256(m * c8 * 2);
   } else {
     if (path == kPathF32) b = 3 * up256(m * d * 4) + 3 * up256(m * c * 4);
+    else if (path == kPathFused && chain_generation() == 4 && chain_fwd_ts_supported(D))
+      b = 2 * up256(m * d * 2) + up256(m * ((c + 63) / 64 * 64) * 2);   // bf16 LN(u), dY and the spilled dH (chunk-major)
     else if (path == kPathFused && chain_generation() != 1 && chain_generation() != 3 && chain_fwd_ts_supported(D))
       b = 2 * up256(m * d * 2);   // bf16 LN(u) and dY only: the weight-gradient kernel recomputes G / dH on chip
     else if (path == kPathFused) b = 2 * up256(m * d * 2) + 2 * up256(m * c8 * 2) + up256(m * d * 4);
@@ -383,6 +385,15 @@ int m2b200_channel_mix_bwd(const float* dy, const float* u, const float* ln_w, c
   __nv_bfloat16* xn_b = ws.take<__nv_bfloat16>(md);
   __nv_bfloat16* dy_b = ws.take<__nv_bfloat16>(md);
   const bool gen2 = path == kPathFused && chain_generation() != 1 && chain_fwd_ts_supported(D);
+  if (gen2 && chain_generation() == 4) {
+    // generation 4: the dgrad chain also spills dH (bf16, TMA stores); the weight-gradient kernel reads it back with TMA and
+    // recomputes only G (wgrad_dh): half the epilogue work of generation 2 for 2 M C bytes written and read once
+    __nv_bfloat16* dh_sp = ws.take<__nv_bfloat16>(static_cast<size_t>(M) * ((C + 63) / 64 * 64));
+    if (!ws.ok) return M2_ERR_WORKSPACE;
+    M2_TRY(chain_bwd_ts(u, ln_w, ln_b, w1b, b1, w2b, ldw2, dy, du, dln_w, dln_b, db2, xn_b, dy_b, nullptr, dh_sp, c8, M, D, C,
+                        dropout_p, seed, s));
+    return wgrad_dh(xn_b, dy_b, dh_sp, c8, w1b, b1, dw1, db1, dw2, M, D, C, dropout_p, seed, s);
+  }
   if (gen2 && chain_generation() != 3) {
     // generation 2: dgrad chain with the LayerNorm backward, dln_w / dln_b / db2 fused in (chain_ts.cu); no G / dH spill:
     // the weight-gradient kernel recomputes them (wgrad_fused.cu), so the workspace is the two bf16 [M][D] operand copies

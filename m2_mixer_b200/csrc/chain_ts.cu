@@ -88,6 +88,7 @@ struct TsParams {
   __nv_bfloat16* dh_b;   // optional out: dH bf16 [M][ldh]
   int M, D, C, ldh;
   int bias_smem;
+  int dbg;               // timing experiments only (M2B200_DBG), 0 in production
   Drop dh, dout;
 };
 
@@ -598,7 +599,13 @@ struct CfgB {
   static constexpr int kOPitch = DP * 4 + 16;
   static_assert(kRows * kOPitch <= kRingBytes, "output staging must fit in the weight ring");
   static constexpr int kStatBytes = 2 * kRows * 4 + 3 * DP * 4;   // mean, rstd, column partials [3][DP]
-  static constexpr int kSmem = kRingBytes + 2 * kXStage + kStatBytes + kBarBytes + 1024;
+  // dH spill (kStore == 2): once the prologue has copied LN(u) / dY to tensor memory the two row staging tiles are dead;
+  // the same region then holds kDhSlots [128 rows][64 c] bf16 tiles (128-byte swizzle) that leave through TMA stores.
+  static constexpr int kDhSlot = kRows * 128;
+  static constexpr int kDhSlots = 4;
+  static constexpr int kStageRegion = 2 * kXStage > kDhSlots * kDhSlot ? 2 * kXStage : kDhSlots * kDhSlot;
+  static_assert(kRingBytes % 1024 == 0, "the dH slots must be 1024-byte aligned");
+  static constexpr int kSmem = kRingBytes + kStageRegion + kStatBytes + kBarBytes + 1024;
   static constexpr int kMaxBias = 16 * 1024;
   static constexpr int kTmemCols = 512;
   static constexpr int kColDX = 0;
@@ -630,9 +637,14 @@ __device__ __forceinline__ void dy_rows_to_stage(const TsParams& p, int m0, uint
   }
 }
 
-template <int DP, bool kDrop, bool kStoreGH>
+// kStore: 0 = nothing but du / LN(u) / dY leaves the kernel (wgrad_fused recomputes G and dH), 1 = G and dH with per-thread
+// 16-byte stores (M2B200_CHAIN_GEN=3, the A/B reference), 2 = dH only, staged in shared memory in the 128-byte swizzle and
+// written by TMA stores, chunk-major [C / 64][M][64] (wgrad_dh consumes it with TMA loads and recomputes only G).
+template <int DP, bool kDrop, int kStore>
 __global__ void __launch_bounds__(kThreadsB, 1)
-chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TsParams p) {
+chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                    const __grid_constant__ CUtensorMap tmDH, const TsParams p) {
+  constexpr bool kStoreGH = kStore == 1;
   using C = CfgB<DP>;
   constexpr int S1 = C::S1, S2 = C::S2;
   extern __shared__ uint8_t smem_raw[];
@@ -642,7 +654,8 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
   uint8_t* sStageX = sW2 + S2 * C::kW2Bytes;
   uint8_t* sStageDY = sStageX + C::kXStage;
   uint8_t* sOut = smem;                              // fp32 dXn staging (aliases the ring once every MMA is done)
-  float* sMean = reinterpret_cast<float*>(sStageDY + C::kXStage);
+  uint8_t* sDH = sStageX;                            // kStore == 2: dH store slots (alias the row staging after the prologue)
+  float* sMean = reinterpret_cast<float*>(sStageX + C::kStageRegion);
   float* sRstd = sMean + kRows;
   float* sCol = sRstd + kRows;                       // [3][DP]: dln_w, dln_b, db2 partial column sums
   uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 3 * DP);
@@ -674,6 +687,7 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     fence_mbar_init();
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
+    if (kStore == 2) tma_prefetch_desc(&tmDH);
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
   for (int i = threadIdx.x; i < 3 * DP; i += blockDim.x) sCol[i] = 0.f;
@@ -791,7 +805,12 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
       else mbar_wait(&dhfull[b], (j >> 1) & 1);
       M2_TR(4 * j + 1, 2, j);
       tc_fence_after();
-      if (elect_one()) {
+      if (elect_one()) {   // elect.sync names the same leader every time: the bulk groups below belong to ONE thread
+        // kStore == 2: the dG GEMM issued below lets the epilogue of chunk j + 2 overwrite the store slot of chunk j - 2: that
+        // store (two chunk periods old) must have finished READING shared memory.  No extra barrier carries the dH stores:
+        // the slot of chunk j is complete because its writers arrived on dhfull after writing it, and hfull(j + 2) cannot
+        // complete before this thread has passed the wait.
+        if (kStore == 2) tma_store_wait_read_n<1>();
         const uint64_t bd = w1m_desc0 + static_cast<uint64_t>((s1 * C::kW1Bytes) >> 4);
         const uint32_t tG = tmem_base + C::kColG + b * kCc;
 #pragma unroll
@@ -799,11 +818,21 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
           umma_bf16_ts(tDX, tG + kk * 16, bd + ((kk * 2048) >> 4), idescX, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&w1empty[s1]);
         if (jn < nch) issue_dg(jn);
+        if (kStore == 2) {
+          // ONE generic -> async proxy fence, by the thread that has acquired the writers' stores through dhfull (a fence in
+          // each of the 512 writers cost 4-5 us per launch, profiles/r02_dh_spill.md)
+          fence_proxy_async();
+          if (!(p.dbg & 1)) tma_store_3d(&tmDH, sDH + (j % C::kDhSlots) * C::kDhSlot, 0, m0, j);   // one contiguous 16 KB piece
+          tma_store_commit();
+        }
         M2_TR(4 * j + 2, 10, j);
       }
       __syncwarp();
     }
-    if (elect_one()) umma_commit(yfull);
+    if (elect_one()) {
+      umma_commit(yfull);
+      if (kStore == 2) tma_store_wait_all();
+    }
     __syncwarp();
   } else {
     const int q = pwarp & 3;
@@ -871,6 +900,13 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                 make_uint4(dhp[ch * 4], dhp[ch * 4 + 1], dhp[ch * 4 + 2], dhp[ch * 4 + 3]);
           }
         }
+      }
+      if (kStore == 2 && !(p.dbg & 2)) {
+        // the same 16 dH values -> this row's 128-byte line of the chunk's store slot (16-byte chunks 2 grp, 2 grp + 1), BEFORE
+        // the arrival on dhfull: the dXn / dG issuer that dhfull wakes also issues the slot's TMA store
+        uint8_t* dst = sDH + (j % C::kDhSlots) * C::kDhSlot;
+        *reinterpret_cast<uint4*>(dst + sw128_offset(r, 2 * grp)) = make_uint4(dhp[0], dhp[1], dhp[2], dhp[3]);
+        *reinterpret_cast<uint4*>(dst + sw128_offset(r, 2 * grp + 1)) = make_uint4(dhp[4], dhp[5], dhp[6], dhp[7]);
       }
       // dH (bf16, 8 columns) over the first half of the dG columns this thread has just read: the groups never touch
       // each other's columns, the tensor pipe reads them (dXn GEMM) before chunk j + 2 overwrites the buffer.
@@ -991,31 +1027,35 @@ int launch_fwd(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p, 
   return fwd_groups() == 2 ? launch_fwd_g<DP, kDrop, 2>(t1, t2, p, s) : launch_fwd_g<DP, kDrop, 4>(t1, t2, p, s);
 }
 
-template <int DP, bool kDrop, bool kStoreGH>
-int launch_bwd(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p, cudaStream_t s) {
+template <int DP, bool kDrop, int kStore>
+int launch_bwd(const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& tdh, const TsParams& p, cudaStream_t s) {
   const int bias_bytes = ceil_div(p.C, kCc) * kCc * 4;
   TsParams pp = p;
   pp.bias_smem = (bias_bytes <= CfgB<DP>::kMaxBias && bias_bytes / 4 <= 16 * kThreadsB) ? 1 : 0;   // one bias_load round
   const int smem = CfgB<DP>::kSmem + (pp.bias_smem ? bias_bytes : 0);
   static int configured = 0;
   if (smem > configured) {
-    if (cudaFuncSetAttribute(chain_bwd_ts_kernel<DP, kDrop, kStoreGH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+    if (cudaFuncSetAttribute(chain_bwd_ts_kernel<DP, kDrop, kStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
         cudaSuccess)
       return M2_ERR_LAUNCH;
     configured = smem;
   }
   LaunchScope scope("chain_bwd", s);
-  chain_bwd_ts_kernel<DP, kDrop, kStoreGH><<<ceil_div(p.M, kRows), kThreadsB, smem, s>>>(t1, t2, pp);
+  chain_bwd_ts_kernel<DP, kDrop, kStore><<<ceil_div(p.M, kRows), kThreadsB, smem, s>>>(t1, t2, tdh, pp);
   M2_LAUNCH_CHECK();
   return M2_OK;
 }
 
 template <int DP>
-int launch_bwd_d(const CUtensorMap& t1, const CUtensorMap& t2, const TsParams& p, cudaStream_t s) {
+int launch_bwd_d(const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& tdh, const TsParams& p, cudaStream_t s) {
   const bool drop = p.dh.thresh || p.dout.thresh;
-  const bool store = p.g_b != nullptr;
-  if (drop) return store ? launch_bwd<DP, true, true>(t1, t2, p, s) : launch_bwd<DP, true, false>(t1, t2, p, s);
-  return store ? launch_bwd<DP, false, true>(t1, t2, p, s) : launch_bwd<DP, false, false>(t1, t2, p, s);
+  const int store = p.g_b != nullptr ? 1 : (p.dh_b != nullptr ? 2 : 0);
+  if (drop) {
+    if (store == 2) return launch_bwd<DP, true, 2>(t1, t2, tdh, p, s);
+    return store ? launch_bwd<DP, true, 1>(t1, t2, tdh, p, s) : launch_bwd<DP, true, 0>(t1, t2, tdh, p, s);
+  }
+  if (store == 2) return launch_bwd<DP, false, 2>(t1, t2, tdh, p, s);
+  return store ? launch_bwd<DP, false, 1>(t1, t2, tdh, p, s) : launch_bwd<DP, false, 0>(t1, t2, tdh, p, s);
 }
 
 }  // namespace
@@ -1049,27 +1089,35 @@ int chain_fwd_ts(const float* u, const float* ln_w, const float* ln_b, const voi
 }
 
 // Backward dgrad chain + fused LayerNorm backward.  du = dy + LN'(dXn); dln_w, dln_b, db2 accumulate (atomics).
-// xn_b / dy_b (bf16 [M][D]) are always written; g_b / dh_b (bf16 [M][ldh]) only when non-null.
+// xn_b / dy_b (bf16 [M][D]) are always written; g_b / dh_b (bf16 [M][ldh]) only when non-null: both = per-thread stores
+// (generation 3), dh_b alone = the dH spill through TMA stores (generation 4, consumed by wgrad_dh): CHUNK-MAJOR
+// [ceil(C / 64)][M][64] (every store is one contiguous 16 KB piece); ldh then only is the row stride of the dropout mask.
 int chain_bwd_ts(const float* u, const float* ln_w, const float* ln_b, const void* w1b, const float* b1, const void* w2b,
                  int ldw2, const float* dy, float* du, float* dln_w, float* dln_b, float* db2, void* xn_b, void* dy_b,
                  void* g_b, void* dh_b, int ldh, int M, int D, int C, float drop_p, unsigned long long seed, cudaStream_t s) {
   if (!chain_fwd_ts_supported(D) || ldw2 % 8 || ldw2 < C || ldh % 8 || ldh < C) return M2_ERR_ARG;
-  if ((g_b == nullptr) != (dh_b == nullptr)) return M2_ERR_ARG;
+  if (g_b != nullptr && dh_b == nullptr) return M2_ERR_ARG;
   const int DP = D <= 64 ? 64 : 128;
-  CUtensorMap t1, t2;
+  CUtensorMap t1, t2, tdh;
   int rc = make_tmap_bf16(&t1, w1b, C, D, D, kCc, 64);
   if (rc) return rc;
   rc = make_tmap_bf16(&t2, w2b, D, ldw2, ldw2, DP, kCc);
   if (rc) return rc;
+  tdh = t1;   // unused unless dH leaves through TMA stores: chunk-major bf16 [C / 64][M][64], box = one chunk of the row tile
+  if (dh_b != nullptr && g_b == nullptr) {
+    rc = make_tmap_store3d(&tdh, dh_b, 2, ceil_div(C, kCc), M, kCc, kCc, static_cast<uint64_t>(M) * kCc, kRows, kCc);
+    if (rc) return rc;
+  }
   TsParams p = {};
   p.u = u; p.ln_w = ln_w; p.ln_b = ln_b; p.b1 = b1; p.dy = dy; p.du = du;
   p.dln_w = dln_w; p.dln_b = dln_b; p.db2 = db2;
   p.xn_b = static_cast<__nv_bfloat16*>(xn_b); p.dy_b = static_cast<__nv_bfloat16*>(dy_b);
   p.g_b = static_cast<__nv_bfloat16*>(g_b); p.dh_b = static_cast<__nv_bfloat16*>(dh_b);
   p.M = M; p.D = D; p.C = C; p.ldh = ldh;
+  p.dbg = dbg_flags();
   p.dh = make_drop(drop_p, seed, kSiteChannelHidden); p.dout = make_drop(drop_p, seed, kSiteChannelOut);
-  if (DP == 64) return launch_bwd_d<64>(t1, t2, p, s);
-  return launch_bwd_d<128>(t1, t2, p, s);
+  if (DP == 64) return launch_bwd_d<64>(t1, t2, tdh, p, s);
+  return launch_bwd_d<128>(t1, t2, tdh, p, s);
 }
 
 }  // namespace m2

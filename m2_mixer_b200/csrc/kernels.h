@@ -52,6 +52,9 @@ int chain_bwd_ts(const float* u, const float* ln_w, const float* ln_b, const voi
 // fused recompute weight gradients (wgrad_fused.cu): dw1 / db1 / dw2 accumulate; xn_b / dy_b from chain_bwd_ts
 int wgrad_fused(const void* xn_b, const void* dy_b, const void* w1b, const void* w2b, int ldw2, const float* b1, float* dw1,
                 float* db1, float* dw2, int M, int D, int C, float drop_p, unsigned long long seed, cudaStream_t s);
+// generation 4 (dH spilled by chain_bwd_ts through TMA stores, only G recomputed): dw1 / db1 / dw2 accumulate
+int wgrad_dh(const void* xn_b, const void* dy_b, const void* dh_b, int ldh, const void* w1b, const float* b1, float* dw1,
+             float* db1, float* dw2, int M, int D, int C, float drop_p, unsigned long long seed, cudaStream_t s);
 // env M2B200_CHAIN_GEN: 1 = generation-1 kernels, 3 = generation-2 dgrad + G/dH spill + GEMM weight gradients,
 // default 2 = generation-2 dgrad + fused recompute weight gradients.  A/B measurements only.
 int chain_generation();

@@ -77,6 +77,7 @@ struct WgParams {
   float* db1;   // [C]
   int M, D, C, ldh;
   int ntiles, R;
+  int dbg;      // timing experiments only (M2B200_DBG), 0 in production
   Drop dh;
 };
 
@@ -397,6 +398,339 @@ int launch_wg(const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& t
   return M2_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Generation 4: the dgrad chain spills dH (bf16, chunk-major [C / 64][M][64], TMA stores, chain_ts.cu kStore == 2) and this
+// kernel only recomputes G.  Per 96-row tile:
+//     H = Xn_i . W1c^T                                   one recompute GEMM instead of two
+//     epilogue: G = Drop(GELU(H + b1)) -> bf16 -> shared memory   (forward GELU only: no GELU', no dG, no dH, no db1 partials:
+//                                                                  about half the instructions of wgrad_fused's epilogue)
+//     dH_i arrives by TMA straight in the MN-major B operand layout (from HBM / L2, requested two tiles ahead)
+//     dW2c += dY_i^T . G_i      dW1c^T += Xn_i^T . dH_i      dB += 1 . dH_i
+// db1 = colsum(dH) is a third gradient GEMM whose A operand is a constant tile of ones (2 KB: the two 64-row halves of the
+// M = 128 operand and all six 16-row k-steps alias it), so every accumulator row of dB holds db1; lane 0 is read at the end.
+// With the epilogue halved the kernel would be paced by load -> gradient GEMMs -> load on a single gradient-side row tile
+// (3040 clk per tile measured in that form), so the gradient GEMMs' LN(u) tiles sit in a 2-slot ring that is loaded a tile
+// ahead; dY has one buffer, released by the dW2 GEMM that is issued first.
+// Algorithmic HBM bytes: the dH tensor once (2 M C bytes).
+constexpr int kNSH = 2;         // dH ring slots
+constexpr int kNSX = 3;         // LN(u) ring slots (a tile is fetched once and read by the recompute AND the dW1 GEMM)
+
+template <int DP>
+struct CfgD {
+  static constexpr int kPanel = kRows * 128;            // [96 rows][64 d or c] SW128 panel
+  static constexpr int kTile = (DP / 64) * kPanel;      // LN(u) or dY row tile
+  static constexpr int kW1Panel = kCc * 128;            // [128 c][64 d]
+  static constexpr int kW1Bytes = (DP / 64) * kW1Panel;
+  static constexpr int kGPanel = kMmaM * 128;           // [128 rows][64 c] (epilogue-written G)
+  static constexpr int kGBytes = 2 * kGPanel;
+  static constexpr int kDhBytes = 2 * kPanel;           // [96 rows][128 c] as two 64-channel panels
+  static constexpr int kOnesBytes = 2048;               // [16 k-rows][64 m] of bf16 1.0
+  static constexpr int kSmem = (1 + kNSX) * kTile + kW1Bytes + kGBytes + kNSH * kDhBytes + kOnesBytes + 1280 + 1024;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kColW1 = 0, kColW2 = 128, kColH = 256, kColDB = 384;
+};
+
+template <int DP, bool kDrop>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmDH, const WgParams p) {
+  using C = CfgD<DP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sXg = smem;                                 // [kNSX] LN(u) tiles: K-major A of the recompute GEMM, MN-major A of dW1
+  uint8_t* sDY = sXg + kNSX * C::kTile;                // dY tile of the dW2 GEMM
+  uint8_t* sW1 = sDY + C::kTile;
+  uint8_t* sG = sW1 + C::kW1Bytes;
+  uint8_t* sDH = sG + C::kGBytes;                      // [kNSH] dH tiles (TMA)
+  uint8_t* sOnes = sDH + kNSH * C::kDhBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::kOnesBytes);
+  uint64_t* wfull = bars;             // [1]   W1c landed
+  uint64_t* xgfull = wfull + 1;       // [kNSX]
+  uint64_t* xgempty = xgfull + kNSX;  // [kNSX] recompute GEMM AND dW1 GEMM done with the tile (two arrivals)
+  uint64_t* dyfull = xgempty + kNSX;  // [1]
+  uint64_t* dyempty = dyfull + 1;     // [1]   dW2 GEMM done with the dY tile
+  uint64_t* hfull = dyempty + 1;      // [1]   H accumulator ready -> epilogue
+  uint64_t* hempty = hfull + 1;       // [1]   epilogue has it in registers -> MMA
+  uint64_t* gfull = hempty + 1;       // [1]   epilogue wrote sG -> MMA
+  uint64_t* gempty = gfull + 1;       // [1]   dW2 GEMM done with sG -> epilogue
+  uint64_t* dhfull = gempty + 1;      // [kNSH] dH tile landed
+  uint64_t* dhempty = dhfull + kNSH;  // [kNSH] gradient GEMMs done with the dH tile -> TMA
+  uint64_t* accfull = dhempty + kNSH; // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+  float* sB1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [128] b1 of the chunk
+
+  const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = pwarp & 3;             // TMEM lane quadrant (= scheduler)
+  const int grp = pwarp >> 2;          // column group
+  const bool is_tma = pwarp == 3, is_mma_hg = pwarp == 7, is_mma_wg = pwarp == 11, is_tma_b = pwarp == 15;
+  const int c0 = blockIdx.x * kCc;
+  const int t_lo = static_cast<int>(static_cast<long long>(p.ntiles) * blockIdx.y / p.R);
+  const int t_hi = static_cast<int>(static_cast<long long>(p.ntiles) * (blockIdx.y + 1) / p.R);
+  const int nt = t_hi - t_lo;
+  if (nt <= 0) return;   // uniform for the CTA
+
+  if (threadIdx.x == 0) {
+    mbar_init(wfull, 1);
+    for (int i = 0; i < kNSX; ++i) { mbar_init(&xgfull[i], 1); mbar_init(&xgempty[i], 2); }
+    mbar_init(dyfull, 1); mbar_init(dyempty, 1);
+    mbar_init(hfull, 1);
+    mbar_init(hempty, kLiveThreads);
+    mbar_init(gfull, kLiveThreads);
+    mbar_init(gempty, 1);
+    for (int i = 0; i < kNSH; ++i) { mbar_init(&dhfull[i], 1); mbar_init(&dhempty[i], 1); }
+    mbar_init(accfull, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDY); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmDH);
+  }
+  if (pwarp == 0) tmem_alloc(tmem_slot, C::kTmemCols);
+  if (threadIdx.x < kCc) sB1[threadIdx.x] = (c0 + threadIdx.x < p.C) ? p.b1[c0 + threadIdx.x] : 0.f;
+  reinterpret_cast<uint32_t*>(sOnes)[threadIdx.x] = 0x3F803F80u;   // 512 threads x 4 B = the 2 KB tile of bf16 ones
+  fence_proxy_async();                                             // read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (is_tma) {
+    // ---- producer A: W1c once; per tile the dY tile (one buffer, freed by the dW2 GEMM of tile i - 1, which is issued first)
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull, C::kW1Bytes);
+#pragma unroll
+      for (int pnl = 0; pnl < DP / 64; ++pnl)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)   // [64 c][64 d] boxes: d panel pnl, channel half h
+          tma_load_2d(sW1 + pnl * C::kW1Panel + h * (64 * 128), &tmW1, wfull, pnl * 64, c0 + h * 64);
+    }
+    __syncwarp();
+    for (int i = 0; i < nt; ++i) {
+      mbar_wait(dyempty, (i & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(dyfull, C::kTile);
+#pragma unroll
+        for (int pnl = 0; pnl < DP / 64; ++pnl) tma_load_2d(sDY + pnl * C::kPanel, &tmDY, dyfull, pnl * 64, (t_lo + i) * kRows);
+      }
+      __syncwarp();
+    }
+  } else if (is_tma_b) {
+    // ---- producer B: the two rings.  LN(u) tile i is fetched ONCE (3 slots) and read twice: K-major by the recompute GEMM
+    // of tile i (which runs under the epilogue of tile i - 1) and MN-major by the dW1 GEMM (after the epilogue of tile i);
+    // its slot is free when both GEMMs of tile i - 3 are done.  dH tile i (2 slots, from HBM / L2) is released by the
+    // gradient GEMMs of tile i - 2.  In time the releases alternate as wg(i - 2), wg(i - 1), ...: LN(u) runs two tiles ahead
+    // of dH so that neither wait delays the other.
+    const int zc = c0 / 64;
+    auto load_xg = [&](int i) {
+      const int sx = i % kNSX;
+      mbar_wait(&xgempty[sx], ((i / kNSX) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&xgfull[sx], C::kTile);
+#pragma unroll
+        for (int pnl = 0; pnl < DP / 64; ++pnl)
+          tma_load_2d(sXg + sx * C::kTile + pnl * C::kPanel, &tmX, &xgfull[sx], pnl * 64, (t_lo + i) * kRows);
+      }
+      __syncwarp();
+    };
+    load_xg(0);
+    if (nt > 1) load_xg(1);
+    for (int i = 0; i < nt; ++i) {
+      const int sh = i % kNSH;
+      mbar_wait(&dhempty[sh], ((i / kNSH) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&dhfull[sh], C::kDhBytes);
+        const int rr = (p.dbg & 4) ? 0 : (t_lo + i) * kRows;
+        tma_load_3d(sDH + sh * C::kDhBytes, &tmDH, &dhfull[sh], 0, rr, zc);
+        tma_load_3d(sDH + sh * C::kDhBytes + C::kPanel, &tmDH, &dhfull[sh], 0, rr, zc + 1);
+      }
+      __syncwarp();
+      if (i + 2 < nt) load_xg(i + 2);
+    }
+  } else if (is_mma_hg) {
+    // ---- recompute issuer: H = Xn_i . W1c^T (N = 128) as soon as the epilogue has tile i - 1's accumulator in registers
+    constexpr uint32_t idescH = umma_idesc_bf16(kMmaM, kCc, 0, 0);   // A row tile K-major,  B = W1c K-major (N = 128 rows)
+    const uint64_t xk0 = umma_desc_sw128(smem_u32(sXg), 16, 1024);
+    const uint64_t w1d = umma_desc_sw128(smem_u32(sW1), 16, 1024);
+    mbar_wait(wfull, 0);
+    for (int i = 0; i < nt; ++i) {
+      const int sx = i % kNSX;
+      mbar_wait2(&xgfull[sx], (i / kNSX) & 1, hempty, (i & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t xa = xk0 + static_cast<uint64_t>((sx * C::kTile) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < DP / 16; ++kk)
+          umma_bf16(tmem_base + C::kColH, xa + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4),
+                    w1d + (((kk >> 2) * C::kW1Panel + (kk & 3) * 32) >> 4), idescH, kk > 0 ? 1u : 0u);
+        umma_commit(&xgempty[sx]);
+        umma_commit(hfull);
+      }
+      __syncwarp();
+    }
+  } else if (is_mma_wg) {
+    // ---- gradient issuer (contraction over the 96 rows): dW2c += dY_i^T . G_i ; dW1c^T += Xn_i^T . dH_i ; dB += 1 . dH_i
+    constexpr uint32_t idescW = umma_idesc_bf16(kMmaM, kCc, 1, 1);   // A row tile MN-major (M = d), B = sDH / sG MN-major
+    constexpr uint32_t kLboA = DP == 128 ? C::kPanel : 0;            // DP = 64: M rows 64..127 alias the only panel
+    const uint64_t xg0 = umma_desc_sw128(smem_u32(sXg), kLboA, 1024);
+    const uint64_t ya = umma_desc_sw128(smem_u32(sDY), kLboA, 1024);
+    const uint64_t gd = umma_desc_sw128(smem_u32(sG), C::kGPanel, 1024);
+    const uint64_t dh0 = umma_desc_sw128(smem_u32(sDH), C::kPanel, 1024);
+    const uint64_t ones = umma_desc_sw128(smem_u32(sOnes), 0, 1024);   // both M halves alias the one panel
+    for (int i = 0; i < nt; ++i) {
+      const int sh = i % kNSH, sx = i % kNSX;
+      const uint32_t acc = i > 0 ? 1u : 0u;
+      mbar_wait2(gfull, i & 1, dyfull, i & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kRows / 16; ++kk)   // 16 rows per step = 2048 B in both operands
+          umma_bf16(tmem_base + C::kColW2, ya + ((kk * 2048) >> 4), gd + ((kk * 2048) >> 4), idescW, (kk > 0) ? 1u : acc);
+        umma_commit(gempty);
+        umma_commit(dyempty);
+      }
+      __syncwarp();
+      mbar_wait2(&xgfull[sx], (i / kNSX) & 1, &dhfull[sh], (i / kNSH) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t xa = xg0 + static_cast<uint64_t>((sx * C::kTile) >> 4);
+        const uint64_t dhd = dh0 + static_cast<uint64_t>((sh * C::kDhBytes) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < kRows / 16; ++kk)
+          umma_bf16(tmem_base + C::kColW1, xa + ((kk * 2048) >> 4), dhd + ((kk * 2048) >> 4), idescW, (kk > 0) ? 1u : acc);
+        umma_commit(&xgempty[sx]);
+        if (!(p.dbg & 8)) {
+#pragma unroll
+          for (int kk = 0; kk < kRows / 16; ++kk)
+            umma_bf16(tmem_base + C::kColDB, ones, dhd + ((kk * 2048) >> 4), idescW, (kk > 0) ? 1u : acc);
+        }
+        umma_commit(&dhempty[sh]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(accfull);
+    __syncwarp();
+  } else if (q < 3) {
+    // ---- epilogue: thread = row of the tile (TMEM lane), group g = columns [32 g, 32 g + 32) in two 16-column pieces
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int cg = c0 + grp * 32;
+    const uint32_t bias_addr = smem_u32(sB1 + grp * 32);
+    const float hs = kDrop ? 0.5f * p.dh.scale : 0.5f;          // dropout scale folded into the GELU
+    uint8_t* gdst = sG + (grp >> 1) * C::kGPanel;               // [128 rows][64 c] SW128 panel; this group: 16-byte chunks
+    const int chunk0 = (grp & 1) * 4;                           //   4 (grp & 1) .. 4 (grp & 1) + 3 of the row
+    const uint32_t dkey = drop_key(p.dh);
+    bool ready = false;                              // hfull of the tile already observed by an early probe
+    for (int i = 0; i < nt; ++i) {
+      if (!ready) mbar_wait(hfull, i & 1);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t hin = ((static_cast<uint32_t>((t_lo + i) * kRows + r) * static_cast<uint32_t>(p.ldh) + static_cast<uint32_t>(cg)) >> 2) * kDropGolden + dkey;
+      uint32_t hA[16], hB[16];
+      tmem_ld16(tmem_base + C::kColH + lane_addr + grp * 32, hA);
+      tmem_ld16(tmem_base + C::kColH + lane_addr + grp * 32 + 16, hB);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(hempty);                           // the recompute GEMM of tile i + 1 runs under this tile's math
+#pragma unroll
+      for (int pc = 0; pc < 2; ++pc) {
+        uint32_t (&h)[16] = pc ? hB : hA;
+        float bias[16];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+              : "=f"(bias[4 * e]), "=f"(bias[4 * e + 1]), "=f"(bias[4 * e + 2]), "=f"(bias[4 * e + 3])
+              : "r"(bias_addr + (pc * 16 + 4 * e) * 4));
+        uint32_t gp[8];
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {   // quads of channels: one mask hash each
+          uint32_t flags = 0;
+          if (kDrop) flags = drop_flags_from_hash_input(p.dh, hin + static_cast<uint32_t>(pc * 4 + qd) * kDropGolden);
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int e = qd * 2 + e2;
+            const float2 gv = gelu2(__fadd2_rn(make_float2(__uint_as_float(h[2 * e]), __uint_as_float(h[2 * e + 1])),
+                                               make_float2(bias[2 * e], bias[2 * e + 1])), hs);
+            gp[e] = pack_bf16(gv.x, gv.y);
+            if (kDrop) gp[e] &= e2 ? drop_mask_bf16x2<1>(flags) : drop_mask_bf16x2<0>(flags);
+          }
+        }
+        // (keeping all 32 values in registers and storing them after the gempty wait at the END of the tile measured
+        // slower, 60.2 vs 56.4 us per launch: the kernel is bound by shared-memory bandwidth, not by this wait)
+        if (pc == 0) mbar_wait(gempty, (i & 1) ^ 1);   // the dW2 GEMM of tile i - 1 has consumed sG
+        else ready = (i + 1 < nt) && mbar_probe(hfull, (i + 1) & 1);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          *reinterpret_cast<uint4*>(gdst + sw128_offset(r, chunk0 + pc * 2 + k)) = make_uint4(gp[4 * k], gp[4 * k + 1], gp[4 * k + 2], gp[4 * k + 3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(gfull);
+    }
+  }
+  // ---- all 16 warps: accumulators -> global.  TMEM lane = d.  groups 0 / 1: dW1^T columns [0,64) / [64,128) -> dw1[c][d]
+  // (lanes contiguous in d: coalesced reductions); groups 2 / 3: dW2 columns likewise -> dw2[d][c]; quadrant-0 warps: db1
+  __syncwarp();
+  mbar_wait(accfull, 0);
+  tc_fence_after();
+  {
+    const int d = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const bool first = grp < 2;
+    const int cbase = (grp & 1) * 64;
+#pragma unroll 1
+    for (int cb = cbase; cb < cbase + 64; cb += 32) {
+      uint32_t a[32];
+      tmem_ld32(tmem_base + (first ? C::kColW1 : C::kColW2) + lane_addr + cb, a);
+      tmem_ld_wait();
+      if (d < p.D) {
+        if (first) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (c0 + cb + k < p.C) atomicAdd(p.dw1 + static_cast<long long>(c0 + cb + k) * p.D + d, __uint_as_float(a[k]));
+        } else {
+          float* dst = p.dw2 + static_cast<long long>(d) * p.C + c0 + cb;
+          if ((p.C & 3) == 0 && c0 + cb + 32 <= p.C) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+              atomicAdd(reinterpret_cast<float4*>(dst + k), make_float4(__uint_as_float(a[k]), __uint_as_float(a[k + 1]),
+                                                                        __uint_as_float(a[k + 2]), __uint_as_float(a[k + 3])));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (c0 + cb + k < p.C) atomicAdd(dst + k, __uint_as_float(a[k]));
+          }
+        }
+      }
+    }
+    if (q == 0) {   // every row of dB holds db1: lane 0 of quadrant 0, this group's 32 channels
+      uint32_t a[32];
+      tmem_ld32(tmem_base + C::kColDB + grp * 32, a);
+      tmem_ld_wait();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (c0 + grp * 32 + k < p.C) atomicAdd(p.db1 + c0 + grp * 32 + k, __uint_as_float(a[k]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (pwarp == 0) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+template <int DP, bool kDrop>
+int launch_wd(const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& t1, const CUtensorMap& tdh, const WgParams& p,
+              cudaStream_t s) {
+  auto kern = wgrad_dh_kernel<DP, kDrop>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgD<DP>::kSmem) != cudaSuccess) return M2_ERR_LAUNCH;
+    configured = true;
+  }
+  LaunchScope scope("wgrad_dh", s);
+  dim3 grid(ceil_div(p.C, kCc), p.R);
+  kern<<<grid, kThreads, CfgD<DP>::kSmem, s>>>(tx, ty, t1, tdh, p);
+  M2_LAUNCH_CHECK();
+  return M2_OK;
+}
+
 }  // namespace
 
 #ifdef M2_TRACE
@@ -432,6 +766,37 @@ int wgrad_fused(const void* xn_b, const void* dy_b, const void* w1b, const void*
   const bool drop = p.dh.thresh != 0;
   if (DP == 64) return drop ? launch_wg<64, true>(tx, ty, t1, t2, p, s) : launch_wg<64, false>(tx, ty, t1, t2, p, s);
   return drop ? launch_wg<128, true>(tx, ty, t1, t2, p, s) : launch_wg<128, false>(tx, ty, t1, t2, p, s);
+}
+
+// Generation 4: dH (bf16, chunk-major [ceil(C / 64)][M][64], written by chain_bwd_ts through TMA stores) is an input; only G is
+// recomputed.  ldh is the row stride of the dropout mask (up8(C)), not of the dH buffer.
+int wgrad_dh(const void* xn_b, const void* dy_b, const void* dh_b, int ldh, const void* w1b, const float* b1, float* dw1,
+             float* db1, float* dw2, int M, int D, int C, float drop_p, unsigned long long seed, cudaStream_t s) {
+  if (!chain_fwd_ts_supported(D) || ldh % 8 || ldh < C) return M2_ERR_ARG;
+  const int DP = D <= 64 ? 64 : 128;
+  CUtensorMap tx, ty, t1, tdh;
+  int rc = make_tmap_bf16(&tx, xn_b, M, D, D, kRows, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&ty, dy_b, M, D, D, kRows, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&t1, w1b, C, D, D, 64, 64);
+  if (rc) return rc;
+  rc = make_tmap_store3d(&tdh, dh_b, 2, ceil_div(C, 64), M, 64, 64, static_cast<uint64_t>(M) * 64, kRows, 64);   // chunk-major
+  if (rc) return rc;
+  WgParams p = {};
+  p.b1 = b1; p.dw1 = dw1; p.dw2 = dw2; p.db1 = db1;
+  p.M = M; p.D = D; p.C = C; p.ldh = ldh;
+  p.ntiles = ceil_div(M, kRows);
+  const int nch = ceil_div(C, kCc);
+  int R = 148 / nch;
+  if (R < 1) R = 1;
+  if (R > p.ntiles) R = p.ntiles;
+  p.R = R;
+  p.dbg = dbg_flags();
+  p.dh = make_drop(drop_p, seed, kSiteChannelHidden);
+  const bool drop = p.dh.thresh != 0;
+  if (DP == 64) return drop ? launch_wd<64, true>(tx, ty, t1, tdh, p, s) : launch_wd<64, false>(tx, ty, t1, tdh, p, s);
+  return drop ? launch_wd<128, true>(tx, ty, t1, tdh, p, s) : launch_wd<128, false>(tx, ty, t1, tdh, p, s);
 }
 
 }  // namespace m2
