@@ -467,8 +467,9 @@ def run_ours(args, cfg):
         # the three tcgen05 kernels of a channel-mixing block; each carries 4*M*D*C ALGORITHMIC FLOPs per launch:
         #   chain_fwd   : the two forward GEMMs
         #   chain_bwd   : dG = dY W2 and dXn = dH W1            (its recomputed H GEMM is not counted)
-        #   wgrad_fused : dW1 = dH^T LN(u) and dW2 = dY^T G      (its recomputed H and dG GEMMs are not counted)
-        cands = {k: v for k, v in table.items() if k in ("chain_fwd", "chain_bwd", "wgrad_fused")}
+        #   wgrad_dh    : dW1 = dH^T LN(u) and dW2 = dY^T G      (its recomputed H GEMM and the ones-GEMM of db1 are not counted;
+        #                 wgrad_fused with M2B200_CHAIN_GEN=2: recomputes H and dG)
+        cands = {k: v for k, v in table.items() if k in ("chain_fwd", "chain_bwd", "wgrad_fused", "wgrad_dh")}
         share = {k: round(v[1] / 3, 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])}
         if cands:
             name = max(cands, key=lambda k: cands[k][1])

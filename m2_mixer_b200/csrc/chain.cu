@@ -641,7 +641,7 @@ int make_weight_maps(CUtensorMap* t1, CUtensorMap* t2, const void* w1b, const vo
 int chain_generation() {
   static const int gen = []() {
     const char* e = getenv("M2B200_CHAIN_GEN");
-    return e ? atoi(e) : 2;
+    return e ? atoi(e) : 4;
   }();
   return gen;
 }

@@ -88,7 +88,6 @@ struct TsParams {
   __nv_bfloat16* dh_b;   // optional out: dH bf16 [M][ldh]
   int M, D, C, ldh;
   int bias_smem;
-  int dbg;               // timing experiments only (M2B200_DBG), 0 in production
   Drop dh, dout;
 };
 
@@ -822,7 +821,7 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
           // ONE generic -> async proxy fence, by the thread that has acquired the writers' stores through dhfull (a fence in
           // each of the 512 writers cost 4-5 us per launch, profiles/r02_dh_spill.md)
           fence_proxy_async();
-          if (!(p.dbg & 1)) tma_store_3d(&tmDH, sDH + (j % C::kDhSlots) * C::kDhSlot, 0, m0, j);   // one contiguous 16 KB piece
+          tma_store_3d(&tmDH, sDH + (j % C::kDhSlots) * C::kDhSlot, 0, m0, j);   // one contiguous 16 KB piece
           tma_store_commit();
         }
         M2_TR(4 * j + 2, 10, j);
@@ -901,7 +900,7 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
           }
         }
       }
-      if (kStore == 2 && !(p.dbg & 2)) {
+      if (kStore == 2) {
         // the same 16 dH values -> this row's 128-byte line of the chunk's store slot (16-byte chunks 2 grp, 2 grp + 1), BEFORE
         // the arrival on dhfull: the dXn / dG issuer that dhfull wakes also issues the slot's TMA store
         uint8_t* dst = sDH + (j % C::kDhSlots) * C::kDhSlot;
@@ -1114,7 +1113,6 @@ int chain_bwd_ts(const float* u, const float* ln_w, const float* ln_b, const voi
   p.xn_b = static_cast<__nv_bfloat16*>(xn_b); p.dy_b = static_cast<__nv_bfloat16*>(dy_b);
   p.g_b = static_cast<__nv_bfloat16*>(g_b); p.dh_b = static_cast<__nv_bfloat16*>(dh_b);
   p.M = M; p.D = D; p.C = C; p.ldh = ldh;
-  p.dbg = dbg_flags();
   p.dh = make_drop(drop_p, seed, kSiteChannelHidden); p.dout = make_drop(drop_p, seed, kSiteChannelOut);
   if (DP == 64) return launch_bwd_d<64>(t1, t2, tdh, p, s);
   return launch_bwd_d<128>(t1, t2, tdh, p, s);

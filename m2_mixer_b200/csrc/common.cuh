@@ -126,7 +126,6 @@ struct Drop {
 // has registered a device-resident epoch counter (m2b200_set_dropout_epoch_ptr; the graphed training step advances it once
 // per replay) every kernel folds it into its key: same kernels, same parameters, fresh masks per replay.
 extern const uint32_t* g_drop_epoch_ptr;   // profile.cu
-int dbg_flags();                           // profile.cu: M2B200_DBG (timing experiments), 0 by default
 __device__ __forceinline__ uint32_t drop_key(const Drop& d) {
   return d.epoch ? d.key + __ldg(d.epoch) * 0x85EBCA6BU : d.key;
 }

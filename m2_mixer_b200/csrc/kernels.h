@@ -55,8 +55,9 @@ int wgrad_fused(const void* xn_b, const void* dy_b, const void* w1b, const void*
 // generation 4 (dH spilled by chain_bwd_ts through TMA stores, only G recomputed): dw1 / db1 / dw2 accumulate
 int wgrad_dh(const void* xn_b, const void* dy_b, const void* dh_b, int ldh, const void* w1b, const float* b1, float* dw1,
              float* db1, float* dw2, int M, int D, int C, float drop_p, unsigned long long seed, cudaStream_t s);
-// env M2B200_CHAIN_GEN: 1 = generation-1 kernels, 3 = generation-2 dgrad + G/dH spill + GEMM weight gradients,
-// default 2 = generation-2 dgrad + fused recompute weight gradients.  A/B measurements only.
+// env M2B200_CHAIN_GEN (A/B measurements): 1 = generation-1 kernels, 2 = generation-2 dgrad + weight gradients that recompute
+// G and dH (wgrad_fused), 3 = generation-2 dgrad + G/dH spill with per-thread stores + GEMM weight gradients,
+// default 4 = generation-2 dgrad + dH spill through TMA stores + weight gradients that recompute only G (wgrad_dh).
 int chain_generation();
 
 // ---- row kernels (rowops.cu)

@@ -17,10 +17,6 @@
 
 namespace m2 {
 const uint32_t* g_drop_epoch_ptr = nullptr;   // device counter folded into every dropout key (common.cuh drop_key)
-int dbg_flags() {
-  static const int f = [] { const char* e = getenv("M2B200_DBG"); return e ? atoi(e) : 0; }();
-  return f;
-}
 namespace {
 __global__ void epoch_advance_kernel(uint32_t* e) { *e += 1u; }
 std::atomic<unsigned long long> g_launches{0};

@@ -77,7 +77,6 @@ struct WgParams {
   float* db1;   // [C]
   int M, D, C, ldh;
   int ntiles, R;
-  int dbg;      // timing experiments only (M2B200_DBG), 0 in production
   Drop dh;
 };
 
@@ -537,7 +536,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_wait(&dhempty[sh], ((i / kNSH) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&dhfull[sh], C::kDhBytes);
-        const int rr = (p.dbg & 4) ? 0 : (t_lo + i) * kRows;
+        const int rr = (t_lo + i) * kRows;
         tma_load_3d(sDH + sh * C::kDhBytes, &tmDH, &dhfull[sh], 0, rr, zc);
         tma_load_3d(sDH + sh * C::kDhBytes + C::kPanel, &tmDH, &dhfull[sh], 0, rr, zc + 1);
       }
@@ -552,7 +551,9 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_wait(wfull, 0);
     for (int i = 0; i < nt; ++i) {
       const int sx = i % kNSX;
+      M2_WTR(4 * i + 0, 1, i);
       mbar_wait2(&xgfull[sx], (i / kNSX) & 1, hempty, (i & 1) ^ 1);
+      M2_WTR(4 * i + 1, 2, i);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t xa = xk0 + static_cast<uint64_t>((sx * C::kTile) >> 4);
@@ -562,6 +563,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     w1d + (((kk >> 2) * C::kW1Panel + (kk & 3) * 32) >> 4), idescH, kk > 0 ? 1u : 0u);
         umma_commit(&xgempty[sx]);
         umma_commit(hfull);
+        M2_WTR(4 * i + 2, 3, i);
       }
       __syncwarp();
     }
@@ -577,7 +579,9 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     for (int i = 0; i < nt; ++i) {
       const int sh = i % kNSH, sx = i % kNSX;
       const uint32_t acc = i > 0 ? 1u : 0u;
+      M2_WTR(200 + 4 * i + 0, 4, i);
       mbar_wait2(gfull, i & 1, dyfull, i & 1);
+      M2_WTR(200 + 4 * i + 1, 5, i);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -588,6 +592,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       __syncwarp();
       mbar_wait2(&xgfull[sx], (i / kNSX) & 1, &dhfull[sh], (i / kNSH) & 1);
+      M2_WTR(200 + 4 * i + 2, 11, i);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t xa = xg0 + static_cast<uint64_t>((sx * C::kTile) >> 4);
@@ -596,12 +601,11 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int kk = 0; kk < kRows / 16; ++kk)
           umma_bf16(tmem_base + C::kColW1, xa + ((kk * 2048) >> 4), dhd + ((kk * 2048) >> 4), idescW, (kk > 0) ? 1u : acc);
         umma_commit(&xgempty[sx]);
-        if (!(p.dbg & 8)) {
 #pragma unroll
-          for (int kk = 0; kk < kRows / 16; ++kk)
-            umma_bf16(tmem_base + C::kColDB, ones, dhd + ((kk * 2048) >> 4), idescW, (kk > 0) ? 1u : acc);
-        }
+        for (int kk = 0; kk < kRows / 16; ++kk)
+          umma_bf16(tmem_base + C::kColDB, ones, dhd + ((kk * 2048) >> 4), idescW, (kk > 0) ? 1u : acc);
         umma_commit(&dhempty[sh]);
+        M2_WTR(200 + 4 * i + 3, 6, i);
       }
       __syncwarp();
     }
@@ -619,8 +623,10 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t dkey = drop_key(p.dh);
     bool ready = false;                              // hfull of the tile already observed by an early probe
     for (int i = 0; i < nt; ++i) {
+      if (pwarp == 0) M2_WTR(400 + 4 * i + 0, 7, i);
       if (!ready) mbar_wait(hfull, i & 1);
       __syncwarp();
+      if (pwarp == 0) M2_WTR(400 + 4 * i + 1, 8, i);
       tc_fence_after();
       const uint32_t hin = ((static_cast<uint32_t>((t_lo + i) * kRows + r) * static_cast<uint32_t>(p.ldh) + static_cast<uint32_t>(cg)) >> 2) * kDropGolden + dkey;
       uint32_t hA[16], hB[16];
@@ -629,6 +635,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(hempty);                           // the recompute GEMM of tile i + 1 runs under this tile's math
+      if (pwarp == 0) M2_WTR(600 + 2 * i + 1, 9, i);
 #pragma unroll
       for (int pc = 0; pc < 2; ++pc) {
         uint32_t (&h)[16] = pc ? hB : hA;
@@ -654,7 +661,9 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
         // (keeping all 32 values in registers and storing them after the gempty wait at the END of the tile measured
         // slower, 60.2 vs 56.4 us per launch: the kernel is bound by shared-memory bandwidth, not by this wait)
+        if (pc == 0 && pwarp == 0) M2_WTR(600 + 2 * i, 13, i);
         if (pc == 0) mbar_wait(gempty, (i & 1) ^ 1);   // the dW2 GEMM of tile i - 1 has consumed sG
+        if (pc == 0 && pwarp == 0) M2_WTR(400 + 4 * i + 2, 12, i);
         else ready = (i + 1 < nt) && mbar_probe(hfull, (i + 1) & 1);
 #pragma unroll
         for (int k = 0; k < 2; ++k)
@@ -662,6 +671,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       fence_proxy_async();
       mbar_arrive(gfull);
+      if (pwarp == 0) M2_WTR(400 + 4 * i + 3, 10, i);
     }
   }
   // ---- all 16 warps: accumulators -> global.  TMEM lane = d.  groups 0 / 1: dW1^T columns [0,64) / [64,128) -> dw1[c][d]
@@ -792,7 +802,6 @@ int wgrad_dh(const void* xn_b, const void* dy_b, const void* dh_b, int ldh, cons
   if (R < 1) R = 1;
   if (R > p.ntiles) R = p.ntiles;
   p.R = R;
-  p.dbg = dbg_flags();
   p.dh = make_drop(drop_p, seed, kSiteChannelHidden);
   const bool drop = p.dh.thresh != 0;
   if (DP == 64) return drop ? launch_wd<64, true>(tx, ty, t1, tdh, p, s) : launch_wd<64, false>(tx, ty, t1, tdh, p, s);

@@ -30,8 +30,9 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.m2b200_status_string(0) == b"ok"
     # workspace queries are pure host arithmetic
     assert lib.m2b200_channel_mix_workspace_bytes(16384, 128, 3072, 1, 0) == 0          # fused forward: nothing
-    # fused backward: the two bf16 [M][D] operand copies only (the weight-gradient kernel recomputes G / dH on chip)
-    assert lib.m2b200_channel_mix_workspace_bytes(16384, 128, 3072, 1, 1) == 2 * 16384 * 128 * 2
+    # fused backward (generation 4): bf16 LN(u) and dY operand copies + the spilled dH, chunk-major [ceil(C / 64)][M][64]
+    assert lib.m2b200_channel_mix_workspace_bytes(16384, 128, 3072, 1, 1) == 2 * 16384 * 128 * 2 + 16384 * 3072 * 2
+    assert lib.m2b200_channel_mix_workspace_bytes(256, 128, 3078, 1, 1) == 2 * 256 * 128 * 2 + 256 * 49 * 64 * 2
     assert lib.m2b200_channel_mix_workspace_bytes(12544, 768, 3072, 1, 1) > 2 * 12544 * 3072 * 2   # unfused D > 128: G / dH spill
     assert lib.m2b200_channel_mix_workspace_bytes(100, 128, 64, 0, 0) >= 100 * (128 + 64) * 4
 

@@ -1,5 +1,5 @@
 """One launch of every hot kernel at the M2-Mixer-B encoder shapes (and one wide GEMM at the Scaled config's shape), twice:
-the command ncu captures (`-k regex:"patch_embed|token_mix_mma|chain_.*_ts|wgrad_fused|umma_gemm2" -s 8 -c 8`)."""
+the command ncu captures (`-k regex:"patch_embed|token_mix_mma|chain_.*_ts|wgrad_dh|wgrad_fused|umma_gemm2" -s 8 -c 8`)."""
 import os
 import sys
 

@@ -3,7 +3,7 @@
     compute-sanitizer --tool racecheck python tools/sanitize_chain.py
     compute-sanitizer --tool memcheck  python tools/sanitize_chain.py
 
-One channel-mixing forward, dgrad chain and weight-gradient launch (chain_fwd_ts, chain_bwd_ts, wgrad_fused) plus one
+One channel-mixing forward, dgrad chain and weight-gradient launch (chain_fwd_ts, chain_bwd_ts, wgrad_dh; wgrad_fused with M2B200_CHAIN_GEN=2) plus one
 token-mixing forward/backward at a shape small enough for the sanitizer's serialised execution.
 """
 import os
