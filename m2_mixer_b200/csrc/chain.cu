@@ -646,6 +646,14 @@ int chain_generation() {
   return gen;
 }
 
+int dh_l2_hint() {
+  static const int on = []() {
+    const char* e = getenv("M2B200_DH_L2HINT");
+    return e ? atoi(e) : 1;
+  }();
+  return on;
+}
+
 // Which hidden sizes the fused chains cover (others take the unfused GEMM path in abi.cu).
 bool chain_fwd_supported(int D) { return D >= 16 && D <= 256 && D % 8 == 0; }
 bool chain_bwd_supported(int D) { return D >= 16 && D <= 128 && D % 8 == 0; }

@@ -88,6 +88,7 @@ struct TsParams {
   __nv_bfloat16* dh_b;   // optional out: dH bf16 [M][ldh]
   int M, D, C, ldh;
   int bias_smem;
+  int l2_hint;           // dH stores carry an L2 evict_first policy (M2B200_DH_L2HINT, default on)
   Drop dh, dout;
 };
 
@@ -780,6 +781,7 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     constexpr uint32_t idescG = umma_idesc_bf16(kRows, kCc, 0, 1);    // B (W2 tile)  MN-major
     const uint64_t w1m_desc0 = umma_desc_sw128(smem_u32(sW1), kCc * 128, 1024);   // W1 chunk as MN-major B (dXn GEMM)
     const uint64_t w2m_desc0 = umma_desc_sw128(smem_u32(sW2), 8192, 1024);        // W2 tile as MN-major B (dG GEMM)
+    const uint64_t dh_policy = l2_policy_evict_first();
     auto issue_dg = [&](int jn) {   // elected lane only
       const int s2 = jn % S2, b = jn & 1;
       const uint64_t bd2 = w2m_desc0 + static_cast<uint64_t>((s2 * C::kW2Bytes) >> 4);
@@ -821,7 +823,8 @@ chain_bwd_ts_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
           // ONE generic -> async proxy fence, by the thread that has acquired the writers' stores through dhfull (a fence in
           // each of the 512 writers cost 4-5 us per launch, profiles/r02_dh_spill.md)
           fence_proxy_async();
-          tma_store_3d(&tmDH, sDH + (j % C::kDhSlots) * C::kDhSlot, 0, m0, j);   // one contiguous 16 KB piece
+          if (p.l2_hint) tma_store_3d_hint(&tmDH, sDH + (j % C::kDhSlots) * C::kDhSlot, 0, m0, j, dh_policy);
+          else tma_store_3d(&tmDH, sDH + (j % C::kDhSlots) * C::kDhSlot, 0, m0, j);   // one contiguous 16 KB piece
           tma_store_commit();
         }
         M2_TR(4 * j + 2, 10, j);
@@ -1113,6 +1116,7 @@ int chain_bwd_ts(const float* u, const float* ln_w, const float* ln_b, const voi
   p.xn_b = static_cast<__nv_bfloat16*>(xn_b); p.dy_b = static_cast<__nv_bfloat16*>(dy_b);
   p.g_b = static_cast<__nv_bfloat16*>(g_b); p.dh_b = static_cast<__nv_bfloat16*>(dh_b);
   p.M = M; p.D = D; p.C = C; p.ldh = ldh;
+  p.l2_hint = dh_l2_hint();
   p.dh = make_drop(drop_p, seed, kSiteChannelHidden); p.dout = make_drop(drop_p, seed, kSiteChannelOut);
   if (DP == 64) return launch_bwd_d<64>(t1, t2, tdh, p, s);
   return launch_bwd_d<128>(t1, t2, tdh, p, s);

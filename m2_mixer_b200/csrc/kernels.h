@@ -59,6 +59,8 @@ int wgrad_dh(const void* xn_b, const void* dy_b, const void* dh_b, int ldh, cons
 // G and dH (wgrad_fused), 3 = generation-2 dgrad + G/dH spill with per-thread stores + GEMM weight gradients,
 // default 4 = generation-2 dgrad + dH spill through TMA stores + weight gradients that recompute only G (wgrad_dh).
 int chain_generation();
+// env M2B200_DH_L2HINT (A/B): 0 = the spilled dH moves without an L2 eviction policy; default 1 = evict_first
+int dh_l2_hint();
 
 // ---- row kernels (rowops.cu)
 int cast_pad_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols, cudaStream_t s);

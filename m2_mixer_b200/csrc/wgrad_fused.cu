@@ -77,6 +77,7 @@ struct WgParams {
   float* db1;   // [C]
   int M, D, C, ldh;
   int ntiles, R;
+  int l2_hint;  // dH loads carry an L2 evict_first policy (M2B200_DH_L2HINT, default on)
   Drop dh;
 };
 
@@ -518,6 +519,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // gradient GEMMs of tile i - 2.  In time the releases alternate as wg(i - 2), wg(i - 1), ...: LN(u) runs two tiles ahead
     // of dH so that neither wait delays the other.
     const int zc = c0 / 64;
+    const uint64_t dh_policy = l2_policy_evict_first();
     auto load_xg = [&](int i) {
       const int sx = i % kNSX;
       mbar_wait(&xgempty[sx], ((i / kNSX) & 1) ^ 1);
@@ -537,8 +539,13 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (elect_one()) {
         mbar_arrive_expect_tx(&dhfull[sh], C::kDhBytes);
         const int rr = (t_lo + i) * kRows;
-        tma_load_3d(sDH + sh * C::kDhBytes, &tmDH, &dhfull[sh], 0, rr, zc);
-        tma_load_3d(sDH + sh * C::kDhBytes + C::kPanel, &tmDH, &dhfull[sh], 0, rr, zc + 1);
+        if (p.l2_hint) {
+          tma_load_3d_hint(sDH + sh * C::kDhBytes, &tmDH, &dhfull[sh], 0, rr, zc, dh_policy);
+          tma_load_3d_hint(sDH + sh * C::kDhBytes + C::kPanel, &tmDH, &dhfull[sh], 0, rr, zc + 1, dh_policy);
+        } else {
+          tma_load_3d(sDH + sh * C::kDhBytes, &tmDH, &dhfull[sh], 0, rr, zc);
+          tma_load_3d(sDH + sh * C::kDhBytes + C::kPanel, &tmDH, &dhfull[sh], 0, rr, zc + 1);
+        }
       }
       __syncwarp();
       if (i + 2 < nt) load_xg(i + 2);
@@ -802,6 +809,7 @@ int wgrad_dh(const void* xn_b, const void* dy_b, const void* dh_b, int ldh, cons
   if (R < 1) R = 1;
   if (R > p.ntiles) R = p.ntiles;
   p.R = R;
+  p.l2_hint = dh_l2_hint();
   p.dh = make_drop(drop_p, seed, kSiteChannelHidden);
   const bool drop = p.dh.thresh != 0;
   if (DP == 64) return drop ? launch_wd<64, true>(tx, ty, t1, tdh, p, s) : launch_wd<64, false>(tx, ty, t1, tdh, p, s);
