@@ -422,11 +422,13 @@ struct CfgD {
   static constexpr int kTile = (DP / 64) * kPanel;      // LN(u) or dY row tile
   static constexpr int kW1Panel = kCc * 128;            // [128 c][64 d]
   static constexpr int kW1Bytes = (DP / 64) * kW1Panel;
-  static constexpr int kGPanel = kMmaM * 128;           // [128 rows][64 c] (epilogue-written G)
+  static constexpr int kGPanel = kPanel;                // [96 rows][64 c] (epilogue-written G)
   static constexpr int kGBytes = 2 * kGPanel;
   static constexpr int kDhBytes = 2 * kPanel;           // [96 rows][128 c] as two 64-channel panels
-  static constexpr int kOnesBytes = 2048;               // [16 k-rows][64 m] of bf16 1.0
-  static constexpr int kSmem = (1 + kNSX) * kTile + kW1Bytes + kGBytes + kNSH * kDhBytes + kOnesBytes + 1280 + 1024;
+  static constexpr int kOnesBytes = 1024;               // [8 k-rows][64 m] of bf16 1.0 (LBO = SBO = 0: every 8 x 64 atom aliases it)
+  static constexpr int kAux = 768;                      // barriers (< 256 B) + b1 of the chunk (512 B)
+  static constexpr int kSmem = (1 + kNSX) * kTile + kW1Bytes + 2 * kGBytes + kNSH * kDhBytes + kOnesBytes + kAux + 1024;
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
   static constexpr int kTmemCols = 512;
   static constexpr int kColW1 = 0, kColW2 = 128, kColH = 256, kColDB = 384;
 };
@@ -442,7 +444,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint8_t* sDY = sXg + kNSX * C::kTile;                // dY tile of the dW2 GEMM
   uint8_t* sW1 = sDY + C::kTile;
   uint8_t* sG = sW1 + C::kW1Bytes;
-  uint8_t* sDH = sG + C::kGBytes;                      // [kNSH] dH tiles (TMA)
+  uint8_t* sDH = sG + 2 * C::kGBytes;                  // [kNSH] dH tiles (TMA); sG: [2] G tiles
   uint8_t* sOnes = sDH + kNSH * C::kDhBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::kOnesBytes);
   uint64_t* wfull = bars;             // [1]   W1c landed
@@ -452,13 +454,13 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint64_t* dyempty = dyfull + 1;     // [1]   dW2 GEMM done with the dY tile
   uint64_t* hfull = dyempty + 1;      // [1]   H accumulator ready -> epilogue
   uint64_t* hempty = hfull + 1;       // [1]   epilogue has it in registers -> MMA
-  uint64_t* gfull = hempty + 1;       // [1]   epilogue wrote sG -> MMA
-  uint64_t* gempty = gfull + 1;       // [1]   dW2 GEMM done with sG -> epilogue
-  uint64_t* dhfull = gempty + 1;      // [kNSH] dH tile landed
+  uint64_t* gfull = hempty + 1;       // [2]   epilogue wrote sG[i & 1] -> MMA
+  uint64_t* gempty = gfull + 2;       // [2]   dW2 GEMM done with sG[i & 1] -> epilogue
+  uint64_t* dhfull = gempty + 2;      // [kNSH] dH tile landed
   uint64_t* dhempty = dhfull + kNSH;  // [kNSH] gradient GEMMs done with the dH tile -> TMA
   uint64_t* accfull = dhempty + kNSH; // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
-  float* sB1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [128] b1 of the chunk
+  float* sB1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [128] b1 of the chunk (kAux = 256 + 512)
 
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = pwarp & 3;             // TMEM lane quadrant (= scheduler)
@@ -476,8 +478,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_init(dyfull, 1); mbar_init(dyempty, 1);
     mbar_init(hfull, 1);
     mbar_init(hempty, kLiveThreads);
-    mbar_init(gfull, kLiveThreads);
-    mbar_init(gempty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&gfull[i], kLiveThreads); mbar_init(&gempty[i], 1); }
     for (int i = 0; i < kNSH; ++i) { mbar_init(&dhfull[i], 1); mbar_init(&dhempty[i], 1); }
     mbar_init(accfull, 1);
     fence_mbar_init();
@@ -485,7 +486,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
   if (pwarp == 0) tmem_alloc(tmem_slot, C::kTmemCols);
   if (threadIdx.x < kCc) sB1[threadIdx.x] = (c0 + threadIdx.x < p.C) ? p.b1[c0 + threadIdx.x] : 0.f;
-  reinterpret_cast<uint32_t*>(sOnes)[threadIdx.x] = 0x3F803F80u;   // 512 threads x 4 B = the 2 KB tile of bf16 ones
+  if (threadIdx.x < 256) reinterpret_cast<uint32_t*>(sOnes)[threadIdx.x] = 0x3F803F80u;   // the 1 KB atom of bf16 ones
   fence_proxy_async();                                             // read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
@@ -582,19 +583,20 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint64_t ya = umma_desc_sw128(smem_u32(sDY), kLboA, 1024);
     const uint64_t gd = umma_desc_sw128(smem_u32(sG), C::kGPanel, 1024);
     const uint64_t dh0 = umma_desc_sw128(smem_u32(sDH), C::kPanel, 1024);
-    const uint64_t ones = umma_desc_sw128(smem_u32(sOnes), 0, 1024);   // both M halves alias the one panel
+    const uint64_t ones = umma_desc_sw128(smem_u32(sOnes), 0, 0);      // both M halves and both 8-row k groups alias one atom
     for (int i = 0; i < nt; ++i) {
       const int sh = i % kNSH, sx = i % kNSX;
       const uint32_t acc = i > 0 ? 1u : 0u;
       M2_WTR(200 + 4 * i + 0, 4, i);
-      mbar_wait2(gfull, i & 1, dyfull, i & 1);
+      mbar_wait2(&gfull[i & 1], (i >> 1) & 1, dyfull, i & 1);
       M2_WTR(200 + 4 * i + 1, 5, i);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < kRows / 16; ++kk)   // 16 rows per step = 2048 B in both operands
-          umma_bf16(tmem_base + C::kColW2, ya + ((kk * 2048) >> 4), gd + ((kk * 2048) >> 4), idescW, (kk > 0) ? 1u : acc);
-        umma_commit(gempty);
+          umma_bf16(tmem_base + C::kColW2, ya + ((kk * 2048) >> 4), gd + (((i & 1) * C::kGBytes + kk * 2048) >> 4), idescW,
+                    (kk > 0) ? 1u : acc);
+        umma_commit(&gempty[i & 1]);
         umma_commit(dyempty);
       }
       __syncwarp();
@@ -625,12 +627,16 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int cg = c0 + grp * 32;
     const uint32_t bias_addr = smem_u32(sB1 + grp * 32);
     const float hs = kDrop ? 0.5f * p.dh.scale : 0.5f;          // dropout scale folded into the GELU
-    uint8_t* gdst = sG + (grp >> 1) * C::kGPanel;               // [128 rows][64 c] SW128 panel; this group: 16-byte chunks
+    uint8_t* gdst0 = sG + (grp >> 1) * C::kGPanel;              // [96 rows][64 c] SW128 panel; this group: 16-byte chunks
     const int chunk0 = (grp & 1) * 4;                           //   4 (grp & 1) .. 4 (grp & 1) + 3 of the row
     const uint32_t dkey = drop_key(p.dh);
     bool ready = false;                              // hfull of the tile already observed by an early probe
     for (int i = 0; i < nt; ++i) {
       if (pwarp == 0) M2_WTR(400 + 4 * i + 0, 7, i);
+      uint8_t* gdst = gdst0 + (i & 1) * C::kGBytes;
+      // two G buffers: the dW2 GEMM of tile i - 2 released this one long ago (with ONE buffer the loop gfull -> issuer wakes ->
+      // dW2 -> commit -> second half of the next epilogue -> gfull set the pace: 2100 clk per tile, profiles/r02_trace_wgrad_dh.log)
+      const bool gfree = mbar_probe(&gempty[i & 1], ((i >> 1) & 1) ^ 1);
       if (!ready) mbar_wait(hfull, i & 1);
       __syncwarp();
       if (pwarp == 0) M2_WTR(400 + 4 * i + 1, 8, i);
@@ -669,15 +675,15 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         // (keeping all 32 values in registers and storing them after the gempty wait at the END of the tile measured
         // slower, 60.2 vs 56.4 us per launch: the kernel is bound by shared-memory bandwidth, not by this wait)
         if (pc == 0 && pwarp == 0) M2_WTR(600 + 2 * i, 13, i);
-        if (pc == 0) mbar_wait(gempty, (i & 1) ^ 1);   // the dW2 GEMM of tile i - 1 has consumed sG
+        if (pc == 0 && !gfree) mbar_wait(&gempty[i & 1], ((i >> 1) & 1) ^ 1);   // the dW2 GEMM of tile i - 2 has consumed the buffer
         if (pc == 0 && pwarp == 0) M2_WTR(400 + 4 * i + 2, 12, i);
-        else ready = (i + 1 < nt) && mbar_probe(hfull, (i + 1) & 1);
+        if (pc == 1) ready = (i + 1 < nt) && mbar_probe(hfull, (i + 1) & 1);
 #pragma unroll
         for (int k = 0; k < 2; ++k)
           *reinterpret_cast<uint4*>(gdst + sw128_offset(r, chunk0 + pc * 2 + k)) = make_uint4(gp[4 * k], gp[4 * k + 1], gp[4 * k + 2], gp[4 * k + 3]);
       }
       fence_proxy_async();
-      mbar_arrive(gfull);
+      mbar_arrive(&gfull[i & 1]);
       if (pwarp == 0) M2_WTR(400 + 4 * i + 3, 10, i);
     }
   }
