@@ -425,12 +425,11 @@ struct CfgD {
   static constexpr int kGPanel = kPanel;                // [96 rows][64 c] (epilogue-written G)
   static constexpr int kGBytes = 2 * kGPanel;
   static constexpr int kDhBytes = 2 * kPanel;           // [96 rows][128 c] as two 64-channel panels
-  static constexpr int kOnesBytes = 1024;               // [8 k-rows][64 m] of bf16 1.0 (LBO = SBO = 0: every 8 x 64 atom aliases it)
   static constexpr int kAux = 768;                      // barriers (< 256 B) + b1 of the chunk (512 B)
-  static constexpr int kSmem = (1 + kNSX) * kTile + kW1Bytes + 2 * kGBytes + kNSH * kDhBytes + kOnesBytes + kAux + 1024;
+  static constexpr int kSmem = (1 + kNSX) * kTile + kW1Bytes + 2 * kGBytes + kNSH * kDhBytes + kAux + 1024;
   static_assert(kSmem <= 227 * 1024, "shared memory budget");
   static constexpr int kTmemCols = 512;
-  static constexpr int kColW1 = 0, kColW2 = 128, kColH = 256, kColDB = 384;
+  static constexpr int kColW1 = 0, kColW2 = 128, kColH = 256;   // H: two buffers of 128 columns
 };
 
 template <int DP, bool kDrop>
@@ -445,19 +444,18 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint8_t* sW1 = sDY + C::kTile;
   uint8_t* sG = sW1 + C::kW1Bytes;
   uint8_t* sDH = sG + 2 * C::kGBytes;                  // [kNSH] dH tiles (TMA); sG: [2] G tiles
-  uint8_t* sOnes = sDH + kNSH * C::kDhBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::kOnesBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDH + kNSH * C::kDhBytes);
   uint64_t* wfull = bars;             // [1]   W1c landed
   uint64_t* xgfull = wfull + 1;       // [kNSX]
   uint64_t* xgempty = xgfull + kNSX;  // [kNSX] recompute GEMM AND dW1 GEMM done with the tile (two arrivals)
   uint64_t* dyfull = xgempty + kNSX;  // [1]
   uint64_t* dyempty = dyfull + 1;     // [1]   dW2 GEMM done with the dY tile
-  uint64_t* hfull = dyempty + 1;      // [1]   H accumulator ready -> epilogue
-  uint64_t* hempty = hfull + 1;       // [1]   epilogue has it in registers -> MMA
-  uint64_t* gfull = hempty + 1;       // [2]   epilogue wrote sG[i & 1] -> MMA
+  uint64_t* hfull = dyempty + 1;      // [2]   H accumulator i & 1 ready -> epilogue
+  uint64_t* hempty = hfull + 2;       // [2]   epilogue has it in registers -> MMA
+  uint64_t* gfull = hempty + 2;       // [2]   epilogue wrote sG[i & 1] -> MMA
   uint64_t* gempty = gfull + 2;       // [2]   dW2 GEMM done with sG[i & 1] -> epilogue
   uint64_t* dhfull = gempty + 2;      // [kNSH] dH tile landed
-  uint64_t* dhempty = dhfull + kNSH;  // [kNSH] gradient GEMMs done with the dH tile -> TMA
+  uint64_t* dhempty = dhfull + kNSH;  // [kNSH] dW1 GEMM AND the db1 warp done with the dH tile (two arrivals) -> TMA
   uint64_t* accfull = dhempty + kNSH; // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
   float* sB1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [128] b1 of the chunk (kAux = 256 + 512)
@@ -465,7 +463,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = pwarp & 3;             // TMEM lane quadrant (= scheduler)
   const int grp = pwarp >> 2;          // column group
-  const bool is_tma = pwarp == 3, is_mma_hg = pwarp == 7, is_mma_wg = pwarp == 11, is_tma_b = pwarp == 15;
+  const bool is_tma = pwarp == 3, is_mma_hg = pwarp == 7, is_mma_wg = pwarp == 11, is_db = pwarp == 15;
   const int c0 = blockIdx.x * kCc;
   const int t_lo = static_cast<int>(static_cast<long long>(p.ntiles) * blockIdx.y / p.R);
   const int t_hi = static_cast<int>(static_cast<long long>(p.ntiles) * (blockIdx.y + 1) / p.R);
@@ -476,49 +474,26 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_init(wfull, 1);
     for (int i = 0; i < kNSX; ++i) { mbar_init(&xgfull[i], 1); mbar_init(&xgempty[i], 2); }
     mbar_init(dyfull, 1); mbar_init(dyempty, 1);
-    mbar_init(hfull, 1);
-    mbar_init(hempty, kLiveThreads);
+    for (int i = 0; i < 2; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], kLiveThreads); }
     for (int i = 0; i < 2; ++i) { mbar_init(&gfull[i], kLiveThreads); mbar_init(&gempty[i], 1); }
-    for (int i = 0; i < kNSH; ++i) { mbar_init(&dhfull[i], 1); mbar_init(&dhempty[i], 1); }
+    for (int i = 0; i < kNSH; ++i) { mbar_init(&dhfull[i], 1); mbar_init(&dhempty[i], 2); }
     mbar_init(accfull, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDY); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmDH);
   }
   if (pwarp == 0) tmem_alloc(tmem_slot, C::kTmemCols);
   if (threadIdx.x < kCc) sB1[threadIdx.x] = (c0 + threadIdx.x < p.C) ? p.b1[c0 + threadIdx.x] : 0.f;
-  if (threadIdx.x < 256) reinterpret_cast<uint32_t*>(sOnes)[threadIdx.x] = 0x3F803F80u;   // the 1 KB atom of bf16 ones
-  fence_proxy_async();                                             // read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (is_tma) {
-    // ---- producer A: W1c once; per tile the dY tile (one buffer, freed by the dW2 GEMM of tile i - 1, which is issued first)
-    if (elect_one()) {
-      mbar_arrive_expect_tx(wfull, C::kW1Bytes);
-#pragma unroll
-      for (int pnl = 0; pnl < DP / 64; ++pnl)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)   // [64 c][64 d] boxes: d panel pnl, channel half h
-          tma_load_2d(sW1 + pnl * C::kW1Panel + h * (64 * 128), &tmW1, wfull, pnl * 64, c0 + h * 64);
-    }
-    __syncwarp();
-    for (int i = 0; i < nt; ++i) {
-      mbar_wait(dyempty, (i & 1) ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(dyfull, C::kTile);
-#pragma unroll
-        for (int pnl = 0; pnl < DP / 64; ++pnl) tma_load_2d(sDY + pnl * C::kPanel, &tmDY, dyfull, pnl * 64, (t_lo + i) * kRows);
-      }
-      __syncwarp();
-    }
-  } else if (is_tma_b) {
-    // ---- producer B: the two rings.  LN(u) tile i is fetched ONCE (3 slots) and read twice: K-major by the recompute GEMM
-    // of tile i (which runs under the epilogue of tile i - 1) and MN-major by the dW1 GEMM (after the epilogue of tile i);
-    // its slot is free when both GEMMs of tile i - 3 are done.  dH tile i (2 slots, from HBM / L2) is released by the
-    // gradient GEMMs of tile i - 2.  In time the releases alternate as wg(i - 2), wg(i - 1), ...: LN(u) runs two tiles ahead
-    // of dH so that neither wait delays the other.
+    // ---- the producer: W1c once, then per tile three loads, issued in the order in which their buffers are released:
+    //   dY(i)      one buffer, freed by the dW2 GEMM of tile i - 1 (issued first, right after that tile's epilogue)
+    //   LN(u)(i+2) fetched ONCE into a 3-slot ring and read twice - K-major by the recompute GEMM of its tile (which runs a tile
+    //              ahead, under the previous epilogue) and MN-major by the dW1 GEMM; free when both GEMMs of tile i - 1 are done
+    //   dH(i+1)    2-slot ring from HBM / L2 (evict_first), free when the dW1 GEMM and the db1 warp are done with tile i - 1
     const int zc = c0 / 64;
     const uint64_t dh_policy = l2_policy_evict_first();
     auto load_xg = [&](int i) {
@@ -532,9 +507,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       __syncwarp();
     };
-    load_xg(0);
-    if (nt > 1) load_xg(1);
-    for (int i = 0; i < nt; ++i) {
+    auto load_dh = [&](int i) {
       const int sh = i % kNSH;
       mbar_wait(&dhempty[sh], ((i / kNSH) & 1) ^ 1);
       if (elect_one()) {
@@ -549,8 +522,60 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
       }
       __syncwarp();
-      if (i + 2 < nt) load_xg(i + 2);
+    };
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull, C::kW1Bytes);
+#pragma unroll
+      for (int pnl = 0; pnl < DP / 64; ++pnl)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)   // [64 c][64 d] boxes: d panel pnl, channel half h
+          tma_load_2d(sW1 + pnl * C::kW1Panel + h * (64 * 128), &tmW1, wfull, pnl * 64, c0 + h * 64);
     }
+    __syncwarp();
+    load_xg(0);
+    if (nt > 1) load_xg(1);
+    load_dh(0);
+    for (int i = 0; i < nt; ++i) {
+      mbar_wait(dyempty, (i & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(dyfull, C::kTile);
+#pragma unroll
+        for (int pnl = 0; pnl < DP / 64; ++pnl) tma_load_2d(sDY + pnl * C::kPanel, &tmDY, dyfull, pnl * 64, (t_lo + i) * kRows);
+      }
+      __syncwarp();
+      if (i + 2 < nt) load_xg(i + 2);
+      if (i + 1 < nt) load_dh(i + 1);
+    }
+  } else if (is_db) {
+    // ---- db1 = colsum(dH) on the CUDA cores of the scheduler that has no epilogue warp (quadrant 3): lane l owns channels
+    // 4 l .. 4 l + 3 of the chunk and walks the 96 rows of every dH tile in shared memory (8-byte reads; the tile is in the
+    // 128-byte swizzle: 16-byte chunk j of row r sits at j ^ (r & 7)).  It replaced a third gradient GEMM against a tile of
+    // ones, which cost 6 of the 26 MMAs per tile and the 128 tensor-memory columns the second H accumulator now uses.
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int jch = (lane & 15) >> 1;
+    uint32_t off[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) off[k] = static_cast<uint32_t>(k * 128 + ((jch ^ k) << 4));
+    const uint32_t lane_base = smem_u32(sDH) + static_cast<uint32_t>((lane >> 4) * C::kPanel + (lane & 1) * 8);
+    for (int i = 0; i < nt; ++i) {
+      const int sh = i % kNSH;
+      mbar_wait(&dhfull[sh], (i / kNSH) & 1);
+      const uint32_t base = lane_base + static_cast<uint32_t>(sh * C::kDhBytes);
+#pragma unroll
+      for (int r8 = 0; r8 < kRows / 8; ++r8)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          uint32_t v0, v1;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(base + r8 * 1024 + off[k]));
+          acc[0] += __uint_as_float(v0 << 16); acc[1] += __uint_as_float(v0 & 0xffff0000u);
+          acc[2] += __uint_as_float(v1 << 16); acc[3] += __uint_as_float(v1 & 0xffff0000u);
+        }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dhempty[sh]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c0 + 4 * lane + k < p.C) atomicAdd(p.db1 + c0 + 4 * lane + k, acc[k]);
   } else if (is_mma_hg) {
     // ---- recompute issuer: H = Xn_i . W1c^T (N = 128) as soon as the epilogue has tile i - 1's accumulator in registers
     constexpr uint32_t idescH = umma_idesc_bf16(kMmaM, kCc, 0, 0);   // A row tile K-major,  B = W1c K-major (N = 128 rows)
@@ -560,30 +585,29 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     for (int i = 0; i < nt; ++i) {
       const int sx = i % kNSX;
       M2_WTR(4 * i + 0, 1, i);
-      mbar_wait2(&xgfull[sx], (i / kNSX) & 1, hempty, (i & 1) ^ 1);
+      mbar_wait2(&xgfull[sx], (i / kNSX) & 1, &hempty[i & 1], ((i >> 1) & 1) ^ 1);
       M2_WTR(4 * i + 1, 2, i);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t xa = xk0 + static_cast<uint64_t>((sx * C::kTile) >> 4);
 #pragma unroll
         for (int kk = 0; kk < DP / 16; ++kk)
-          umma_bf16(tmem_base + C::kColH, xa + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4),
+          umma_bf16(tmem_base + C::kColH + (i & 1) * kCc, xa + (((kk >> 2) * C::kPanel + (kk & 3) * 32) >> 4),
                     w1d + (((kk >> 2) * C::kW1Panel + (kk & 3) * 32) >> 4), idescH, kk > 0 ? 1u : 0u);
         umma_commit(&xgempty[sx]);
-        umma_commit(hfull);
+        umma_commit(&hfull[i & 1]);
         M2_WTR(4 * i + 2, 3, i);
       }
       __syncwarp();
     }
   } else if (is_mma_wg) {
-    // ---- gradient issuer (contraction over the 96 rows): dW2c += dY_i^T . G_i ; dW1c^T += Xn_i^T . dH_i ; dB += 1 . dH_i
+    // ---- gradient issuer (contraction over the 96 rows): dW2c += dY_i^T . G_i ; dW1c^T += Xn_i^T . dH_i
     constexpr uint32_t idescW = umma_idesc_bf16(kMmaM, kCc, 1, 1);   // A row tile MN-major (M = d), B = sDH / sG MN-major
     constexpr uint32_t kLboA = DP == 128 ? C::kPanel : 0;            // DP = 64: M rows 64..127 alias the only panel
     const uint64_t xg0 = umma_desc_sw128(smem_u32(sXg), kLboA, 1024);
     const uint64_t ya = umma_desc_sw128(smem_u32(sDY), kLboA, 1024);
     const uint64_t gd = umma_desc_sw128(smem_u32(sG), C::kGPanel, 1024);
     const uint64_t dh0 = umma_desc_sw128(smem_u32(sDH), C::kPanel, 1024);
-    const uint64_t ones = umma_desc_sw128(smem_u32(sOnes), 0, 0);      // both M halves and both 8-row k groups alias one atom
     for (int i = 0; i < nt; ++i) {
       const int sh = i % kNSH, sx = i % kNSX;
       const uint32_t acc = i > 0 ? 1u : 0u;
@@ -610,9 +634,6 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int kk = 0; kk < kRows / 16; ++kk)
           umma_bf16(tmem_base + C::kColW1, xa + ((kk * 2048) >> 4), dhd + ((kk * 2048) >> 4), idescW, (kk > 0) ? 1u : acc);
         umma_commit(&xgempty[sx]);
-#pragma unroll
-        for (int kk = 0; kk < kRows / 16; ++kk)
-          umma_bf16(tmem_base + C::kColDB, ones, dhd + ((kk * 2048) >> 4), idescW, (kk > 0) ? 1u : acc);
         umma_commit(&dhempty[sh]);
         M2_WTR(200 + 4 * i + 3, 6, i);
       }
@@ -637,17 +658,17 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // two G buffers: the dW2 GEMM of tile i - 2 released this one long ago (with ONE buffer the loop gfull -> issuer wakes ->
       // dW2 -> commit -> second half of the next epilogue -> gfull set the pace: 2100 clk per tile, profiles/r02_trace_wgrad_dh.log)
       const bool gfree = mbar_probe(&gempty[i & 1], ((i >> 1) & 1) ^ 1);
-      if (!ready) mbar_wait(hfull, i & 1);
+      if (!ready) mbar_wait(&hfull[i & 1], (i >> 1) & 1);
       __syncwarp();
       if (pwarp == 0) M2_WTR(400 + 4 * i + 1, 8, i);
       tc_fence_after();
       const uint32_t hin = ((static_cast<uint32_t>((t_lo + i) * kRows + r) * static_cast<uint32_t>(p.ldh) + static_cast<uint32_t>(cg)) >> 2) * kDropGolden + dkey;
       uint32_t hA[16], hB[16];
-      tmem_ld16(tmem_base + C::kColH + lane_addr + grp * 32, hA);
-      tmem_ld16(tmem_base + C::kColH + lane_addr + grp * 32 + 16, hB);
+      tmem_ld16(tmem_base + C::kColH + (i & 1) * kCc + lane_addr + grp * 32, hA);
+      tmem_ld16(tmem_base + C::kColH + (i & 1) * kCc + lane_addr + grp * 32 + 16, hB);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(hempty);                           // the recompute GEMM of tile i + 1 runs under this tile's math
+      mbar_arrive(&hempty[i & 1]);                   // two H accumulators: the recompute GEMM runs a whole tile ahead
       if (pwarp == 0) M2_WTR(600 + 2 * i + 1, 9, i);
 #pragma unroll
       for (int pc = 0; pc < 2; ++pc) {
@@ -677,7 +698,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (pc == 0 && pwarp == 0) M2_WTR(600 + 2 * i, 13, i);
         if (pc == 0 && !gfree) mbar_wait(&gempty[i & 1], ((i >> 1) & 1) ^ 1);   // the dW2 GEMM of tile i - 2 has consumed the buffer
         if (pc == 0 && pwarp == 0) M2_WTR(400 + 4 * i + 2, 12, i);
-        if (pc == 1) ready = (i + 1 < nt) && mbar_probe(hfull, (i + 1) & 1);
+        if (pc == 1) ready = (i + 1 < nt) && mbar_probe(&hfull[(i + 1) & 1], ((i + 1) >> 1) & 1);
 #pragma unroll
         for (int k = 0; k < 2; ++k)
           *reinterpret_cast<uint4*>(gdst + sw128_offset(r, chunk0 + pc * 2 + k)) = make_uint4(gp[4 * k], gp[4 * k + 1], gp[4 * k + 2], gp[4 * k + 3]);
@@ -688,7 +709,7 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   }
   // ---- all 16 warps: accumulators -> global.  TMEM lane = d.  groups 0 / 1: dW1^T columns [0,64) / [64,128) -> dw1[c][d]
-  // (lanes contiguous in d: coalesced reductions); groups 2 / 3: dW2 columns likewise -> dw2[d][c]; quadrant-0 warps: db1
+  // (lanes contiguous in d: coalesced reductions); groups 2 / 3: dW2 columns likewise -> dw2[d][c]
   __syncwarp();
   mbar_wait(accfull, 0);
   tc_fence_after();
@@ -720,16 +741,6 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               if (c0 + cb + k < p.C) atomicAdd(dst + k, __uint_as_float(a[k]));
           }
         }
-      }
-    }
-    if (q == 0) {   // every row of dB holds db1: lane 0 of quadrant 0, this group's 32 channels
-      uint32_t a[32];
-      tmem_ld32(tmem_base + C::kColDB + grp * 32, a);
-      tmem_ld_wait();
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k)
-          if (c0 + grp * 32 + k < p.C) atomicAdd(p.db1 + c0 + grp * 32 + k, __uint_as_float(a[k]));
       }
     }
   }
