@@ -657,7 +657,6 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       uint8_t* gdst = gdst0 + (i & 1) * C::kGBytes;
       // two G buffers: the dW2 GEMM of tile i - 2 released this one long ago (with ONE buffer the loop gfull -> issuer wakes ->
       // dW2 -> commit -> second half of the next epilogue -> gfull set the pace: 2100 clk per tile, profiles/r02_trace_wgrad_dh.log)
-      const bool gfree = mbar_probe(&gempty[i & 1], ((i >> 1) & 1) ^ 1);
       if (!ready) mbar_wait(&hfull[i & 1], (i >> 1) & 1);
       __syncwarp();
       if (pwarp == 0) M2_WTR(400 + 4 * i + 1, 8, i);
@@ -666,6 +665,9 @@ wgrad_dh_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       uint32_t hA[16], hB[16];
       tmem_ld16(tmem_base + C::kColH + (i & 1) * kCc + lane_addr + grp * 32, hA);
       tmem_ld16(tmem_base + C::kColH + (i & 1) * kCc + lane_addr + grp * 32 + 16, hB);
+      // probed while the accumulator loads are in flight: an mbarrier probe has a ~200-clk round trip even when the phase
+      // completed long ago, and the twelve epilogue warps run in lockstep (nothing else would hide it)
+      const bool gfree = mbar_probe(&gempty[i & 1], ((i >> 1) & 1) ^ 1);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&hempty[i & 1]);                   // two H accumulators: the recompute GEMM runs a whole tile ahead

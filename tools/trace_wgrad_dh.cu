@@ -1,6 +1,6 @@
 // Debug tool: in-kernel timeline of the generation-4 weight-gradient kernel (wgrad_dh).  Build:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -DM2_TRACE -Im2_mixer_b200/csrc
-//        tools/trace_wgrad_dh.cu m2_mixer_b200/csrc/wgrad_fused.cu m2_mixer_b200/csrc/chain_ts.cu m2_mixer_b200/csrc/profile.cu -o tools/trace_wgrad_dh.bin
+//        tools/trace_wgrad_dh.cu m2_mixer_b200/csrc/wgrad_fused.cu m2_mixer_b200/csrc/chain_ts.cu m2_mixer_b200/csrc/chain.cu m2_mixer_b200/csrc/profile.cu -o tools/trace_wgrad_dh.bin
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
