@@ -342,6 +342,250 @@ __global__ void __launch_bounds__(kThreads) heads_bwd_reg_kernel(const HeadsDev 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Vectorised forms for the shipped head shapes (hidden dims that are multiples of 4 and <= 128 kV, K <= 16 classes, weights of
+// all heads <= 64 KB).  The kernels above spent 2760 / 970 warp instructions per sample (and head) on 4-byte token loads and on
+// re-reading the K weight rows from L1 / L2 for every sample (ncu: long-scoreboard stalls on those loads, 11 M warp
+// instructions per launch, 30 / 56 us at batch 4096 for 34 / 84 MB of traffic).  Here: the weight rows are staged in shared
+// memory once per CTA, a lane owns 4 kV adjacent columns (one 16-byte load per token row), every token row of a sample is
+// requested before the first is added, the K dot products are xor-reduced together so that every lane holds every logit
+// (the softmax / argmax then needs no further shuffle), and the backward broadcasts the K logit gradients with shuffles.
+template <int kV>
+__device__ __forceinline__ void pool_tokens_vec(const float* t, int ntok, int dim4, int lane, float4 (&pooled)[kV]) {
+#pragma unroll
+  for (int i = 0; i < kV; ++i) pooled[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* t4 = reinterpret_cast<const float4*>(t);
+  for (int n0 = 0; n0 < ntok; n0 += 8) {
+    float4 v[8][kV];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int i = 0; i < kV; ++i) {
+        const int c = lane + 32 * i;
+        v[k][i] = (n0 + k < ntok && c < dim4) ? t4[static_cast<long long>(n0 + k) * dim4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int i = 0; i < kV; ++i) {
+        pooled[i].x += v[k][i].x; pooled[i].y += v[k][i].y; pooled[i].z += v[k][i].z; pooled[i].w += v[k][i].w;
+      }
+  }
+  const float inv = 1.f / ntok;
+#pragma unroll
+  for (int i = 0; i < kV; ++i) { pooled[i].x *= inv; pooled[i].y *= inv; pooled[i].z *= inv; pooled[i].w *= inv; }
+}
+
+constexpr int kKv = 16;   // classes the vectorised kernels hold in registers
+
+// 4 CTAs per SM (<= 64 registers): at batch 4096 the 512 CTAs (one sample per warp) must all be resident - with 80 registers
+// 444 were, and the 68 left over ran as a second wave (53 us instead of 41 us for the launch).
+template <int kV>
+__global__ void __launch_bounds__(kThreads, 4) heads_fwd_vec_kernel(const HeadsDev a, float* __restrict__ logits,
+                                                                 float* __restrict__ losses, long long* __restrict__ preds) {
+  extern __shared__ float4 sW4[];   // per head [K][dim / 4]
+  __shared__ float s_loss[kWarps][3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int off[4];
+  off[0] = 0;
+  for (int h = 0; h < a.nheads; ++h) off[h + 1] = off[h] + a.K * (a.dim[h] >> 2);
+  // the weight rows are staged asynchronously (cp.async) while the first sample's token rows are on their way
+  for (int h = 0; h < a.nheads; ++h)
+    for (int i = threadIdx.x; i < a.K * (a.dim[h] >> 2); i += kThreads)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sW4 + off[h] + i)),
+                   "l"(reinterpret_cast<const float4*>(a.w[h]) + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  float lsum[3] = {0.f, 0.f, 0.f};
+  // the token rows of ALL heads are requested before the first dot product: one HBM round trip per sample instead of one
+  // per head (a warp's sample is a single dependency chain, and at one sample per warp the chain is the kernel)
+  float4 pooled_all[3][kV];
+  auto pool_all = [&](int b) {
+#pragma unroll
+    for (int h = 0; h < 3; ++h)
+      if (h < a.nheads) pool_tokens_vec<kV>(a.tok[h] + b * a.tok_bstride[h], a.ntok[h], a.dim[h] >> 2, lane, pooled_all[h]);
+  };
+  int b = blockIdx.x * kWarps + warp;
+  if (b < a.B) pool_all(b);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  for (; b < a.B;) {
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+      if (h >= a.nheads) break;
+      const int dim4 = a.dim[h] >> 2;
+      float4 (&pooled)[kV] = pooled_all[h];
+      float acc[kKv];
+#pragma unroll
+      for (int k = 0; k < kKv; ++k) {
+        acc[k] = 0.f;
+        if (k < a.K) {
+#pragma unroll
+          for (int i = 0; i < kV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < dim4) {
+              const float4 w = sW4[off[h] + k * dim4 + c];
+              acc[k] += w.x * pooled[i].x + w.y * pooled[i].y + w.z * pooled[i].z + w.w * pooled[i].w;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < kKv; ++k)
+          if (k < a.K) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      // every lane now holds every logit (minus the bias)
+      float mine = 0.f;
+#pragma unroll
+      for (int k = 0; k < kKv; ++k) {
+        if (k < a.K) acc[k] += __ldg(a.b[h] + k);
+        mine = lane == k ? acc[k] : mine;
+      }
+      if (lane < a.K) logits[(static_cast<long long>(h) * a.B + b) * a.K + lane] = mine;
+      if (a.loss_kind == 0) {
+        float mx = acc[0];
+        int arg = 0;
+#pragma unroll
+        for (int k = 1; k < kKv; ++k)
+          if (k < a.K && acc[k] > mx) { mx = acc[k]; arg = k; }   // first maximal index, as torch.argmax
+        float se = 0.f;
+#pragma unroll
+        for (int k = 0; k < kKv; ++k)
+          if (k < a.K) se += __expf(acc[k] - mx);
+        if (lane == 0) {
+          const int y = static_cast<int>(static_cast<const long long*>(a.labels)[b]);
+          float ly = acc[0];
+#pragma unroll
+          for (int k = 1; k < kKv; ++k) ly = y == k ? acc[k] : ly;
+          lsum[h] += (mx + logf(se)) - ly;
+          preds[static_cast<long long>(h) * a.B + b] = arg;
+        }
+      } else {
+        float l = 0.f;
+        if (lane < a.K) {
+          const float y = static_cast<const float*>(a.labels)[static_cast<long long>(b) * a.K + lane];
+          const float pw = a.pos_weight ? a.pos_weight[lane] : 1.f;
+          l = pw * y * softplus(-mine) + (1.f - y) * softplus(mine);
+          preds[(static_cast<long long>(h) * a.B + b) * a.K + lane] = mine > 0.f ? 1 : 0;
+        }
+        l = warp_sum(l);
+        if (lane == 0) lsum[h] += l;
+      }
+    }
+    b += gridDim.x * kWarps;
+    if (b < a.B) pool_all(b);
+  }
+  if (lane == 0) { s_loss[warp][0] = lsum[0]; s_loss[warp][1] = lsum[1]; s_loss[warp][2] = lsum[2]; }
+  __syncthreads();
+  if (threadIdx.x < a.nheads) {
+    const int h = threadIdx.x;
+    float t = 0.f;
+    for (int w = 0; w < kWarps; ++w) t += s_loss[w][h];
+    t *= (a.loss_kind == 0) ? 1.f / a.B : 1.f / (static_cast<float>(a.B) * a.K);
+    atomicAdd(&losses[1 + h], t);
+    atomicAdd(&losses[0], a.head_weight[h] * t);
+  }
+}
+
+// Backward, one head per CTA row (blockIdx.y), dim <= 128: a lane owns 4 adjacent columns; the weight-gradient outer products
+// of a warp's samples are summed in registers and leave the warp once (as heads_bwd_reg_kernel).
+__global__ void __launch_bounds__(kThreads, 2) heads_bwd_vec_kernel(const HeadsDev a, const HeadsBwdDev g,
+                                                                 const float* __restrict__ logits) {
+  extern __shared__ float4 sm4[];   // [K][dim / 4] weights of the head, then [kWarps][K * dim + K] reduction slots
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y;
+  const int dim = a.dim[h], dim4 = dim >> 2;
+  const int nred = a.K * dim + a.K;
+  const int slot = (nred + 3) & ~3;   // 16-byte aligned per-warp slots (float4 stores below)
+  float* red = reinterpret_cast<float*>(sm4 + a.K * dim4);
+  for (int i = threadIdx.x; i < a.K * dim4; i += kThreads) sm4[i] = reinterpret_cast<const float4*>(a.w[h])[i];
+  __syncthreads();
+  const bool live = lane < dim4;
+  float4 dwacc[kKv];
+#pragma unroll
+  for (int k = 0; k < kKv; ++k) dwacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float dbacc = 0.f;
+  const float hw = a.head_weight[h] * g.grad_scale * (g.grad_scale_dev ? g.grad_scale_dev[0] : 1.f);
+  for (int b = blockIdx.x * kWarps + warp; b < a.B; b += gridDim.x * kWarps) {
+    float4 pooled[1];
+    pool_tokens_vec<1>(a.tok[h] + b * a.tok_bstride[h], a.ntok[h], dim4, lane, pooled);
+    const float* lg = logits + (static_cast<long long>(h) * a.B + b) * a.K;
+    float dl_mine = 0.f;
+    if (a.loss_kind == 0) {
+      const float v = lane < a.K ? lg[lane] : -INFINITY;
+      const float mx = warp_max(v);
+      const float e = lane < a.K ? __expf(v - mx) : 0.f;
+      const float se = warp_sum(e);
+      const long long y = static_cast<const long long*>(a.labels)[b];
+      if (lane < a.K) dl_mine = (e / se - (lane == y ? 1.f : 0.f)) * hw / a.B;
+    } else if (lane < a.K) {
+      const float x = lg[lane];
+      const float y = static_cast<const float*>(a.labels)[static_cast<long long>(b) * a.K + lane];
+      const float pw = a.pos_weight ? a.pos_weight[lane] : 1.f;
+      const float sg = 1.f / (1.f + __expf(-x));
+      dl_mine = (-pw * y * (1.f - sg) + (1.f - y) * sg) * hw / (static_cast<float>(a.B) * a.K);
+    }
+    dbacc += dl_mine;
+    float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < kKv; ++k) {
+      if (k < a.K) {
+        const float dl = __shfl_sync(0xffffffffu, dl_mine, k);
+        if (live) {
+          const float4 w = sm4[k * dim4 + lane];
+          dwacc[k].x = fmaf(dl, pooled[0].x, dwacc[k].x); dwacc[k].y = fmaf(dl, pooled[0].y, dwacc[k].y);
+          dwacc[k].z = fmaf(dl, pooled[0].z, dwacc[k].z); dwacc[k].w = fmaf(dl, pooled[0].w, dwacc[k].w);
+          dp.x = fmaf(w.x, dl, dp.x); dp.y = fmaf(w.y, dl, dp.y); dp.z = fmaf(w.z, dl, dp.z); dp.w = fmaf(w.w, dl, dp.w);
+        }
+      }
+    }
+    if (g.dtok[h] && live) {
+      const float inv = 1.f / a.ntok[h];
+      dp.x *= inv; dp.y *= inv; dp.z *= inv; dp.w *= inv;
+      float4* dt = reinterpret_cast<float4*>(g.dtok[h] + b * g.dtok_bstride[h]) + lane;
+      if (g.accumulate[h]) {
+        for (int n0 = 0; n0 < a.ntok[h]; n0 += 4) {   // four rows requested before the first add
+          float4 o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (n0 + k < a.ntok[h]) o[k] = dt[static_cast<long long>(n0 + k) * dim4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (n0 + k < a.ntok[h])
+              dt[static_cast<long long>(n0 + k) * dim4] = make_float4(o[k].x + dp.x, o[k].y + dp.y, o[k].z + dp.z, o[k].w + dp.w);
+        }
+      } else {
+        for (int n = 0; n < a.ntok[h]; ++n) dt[static_cast<long long>(n) * dim4] = dp;
+      }
+    }
+  }
+  // ---- leave the warp once
+  float* mine = red + warp * slot;
+#pragma unroll
+  for (int k = 0; k < kKv; ++k)
+    if (k < a.K && live) *reinterpret_cast<float4*>(mine + k * dim + 4 * lane) = dwacc[k];
+  if (lane < a.K) mine[a.K * dim + lane] = dbacc;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nred; i += kThreads) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += red[w * slot + i];
+    if (i < a.K * dim) atomicAdd(&g.dw[h][i], t);
+    else atomicAdd(&g.db[h][i - a.K * dim], t);
+  }
+}
+
+// shapes the vectorised kernels cover: every head's dim a multiple of 4 (16-byte token rows), K <= 16
+bool heads_vec_ok(const HeadsArgs& a, int max_dim, const float* const* dtok, const long long* dtok_bstride) {
+  if (a.K > kKv) return false;
+  for (int h = 0; h < a.nheads; ++h) {
+    if (a.dim[h] % 4 || a.dim[h] > max_dim || a.tok_bstride[h] % 4) return false;
+    if ((reinterpret_cast<uintptr_t>(a.tok[h]) | reinterpret_cast<uintptr_t>(a.w[h])) & 15) return false;
+    if (dtok && dtok[h] && ((reinterpret_cast<uintptr_t>(dtok[h]) & 15) || dtok_bstride[h] % 4)) return false;
+  }
+  return true;
+}
+
 int fill_dev(const HeadsArgs& a, HeadsDev* d) {
   if (a.nheads < 1 || a.nheads > 3 || a.B <= 0 || a.K <= 0 || a.K > kMaxK || !a.labels) return M2_ERR_ARG;
   for (int h = 0; h < a.nheads; ++h) {
@@ -367,6 +611,20 @@ int heads_loss_fwd(const HeadsArgs& a, float* logits, float* losses, long long* 
   if (grid > 148 * 4) grid = 148 * 4;
   int per = 1;
   for (int h = 0; h < a.nheads; ++h) per = per > ceil_div(a.dim[h], 32) ? per : ceil_div(a.dim[h], 32);
+  if (heads_vec_ok(a, 256, nullptr, nullptr)) {
+    size_t wsm = 0;
+    for (int h = 0; h < a.nheads; ++h) wsm += static_cast<size_t>(a.K) * a.dim[h] * sizeof(float);
+    if (wsm <= 64 * 1024) {
+      auto kern = per <= 4 ? heads_fwd_vec_kernel<1> : heads_fwd_vec_kernel<2>;
+      if (wsm > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wsm)) != cudaSuccess)
+        return M2_ERR_LAUNCH;
+      int vgrid = ceil_div(a.B, kWarps);      // one sample per warp while the CTAs are co-resident: the per-sample chain is the
+      if (vgrid > 148 * 4) vgrid = 148 * 4;   // kernel's critical path (296 CTAs with two samples per warp measured 59 vs 41 us)
+      kern<<<vgrid, kThreads, wsm, s>>>(d, logits, losses, preds);
+      M2_LAUNCH_CHECK();
+      return M2_OK;
+    }
+  }
   if (per <= 2) heads_fwd_kernel<2><<<grid, kThreads, 0, s>>>(d, logits, losses, preds);
   else if (per <= 4) heads_fwd_kernel<4><<<grid, kThreads, 0, s>>>(d, logits, losses, preds);
   else if (per <= 8) heads_fwd_kernel<8><<<grid, kThreads, 0, s>>>(d, logits, losses, preds);
@@ -396,6 +654,19 @@ int heads_loss_bwd(const HeadsArgs& a, const float* logits, float grad_scale, co
   int grid = ceil_div(a.B, kWarps);
   if (grid > 148) grid = 148;
   LaunchScope scope("heads_loss_bwd", s);
+  if (heads_vec_ok(a, 128, dtok, dtok_bstride)) {   // vectorised register-accumulating variant
+    int maxdim = 0;
+    for (int h = 0; h < a.nheads; ++h) maxdim = maxdim > a.dim[h] ? maxdim : a.dim[h];
+    const size_t vsm = (static_cast<size_t>(a.K) * maxdim + static_cast<size_t>(kWarps) * ((static_cast<size_t>(a.K) * maxdim + a.K + 3) & ~size_t(3))) * sizeof(float);
+    if (vsm > 48 * 1024 && cudaFuncSetAttribute(heads_bwd_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(vsm)) != cudaSuccess)
+      return M2_ERR_LAUNCH;
+    int rgrid = ceil_div(a.B, kWarps * 4);   // >= 4 samples per warp: the per-head flush is amortised
+    if (rgrid > 148 * 2) rgrid = 148 * 2;
+    if (rgrid < 1) rgrid = 1;
+    heads_bwd_vec_kernel<<<dim3(rgrid, a.nheads), kThreads, vsm, s>>>(d, g, logits);
+    M2_LAUNCH_CHECK();
+    return M2_OK;
+  }
   if (a.K <= 16 && per <= 4) {   // register-accumulating variant
     int maxdim = 0;
     for (int h = 0; h < a.nheads; ++h) maxdim = maxdim > a.dim[h] ? maxdim : a.dim[h];

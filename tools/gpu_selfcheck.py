@@ -207,8 +207,7 @@ def run_group(g):
                     ok &= report(f"linear bwd dw act{act} p{prec}", rel(dw, wd.grad), tol * 3)
                     ok &= report(f"linear bwd db act{act} p{prec}", rel(db, bd.grad), tol * 3)
     elif g == "heads":
-        for kind in (0, 1):
-            B, K = 37, 10 if kind == 0 else 23
+        for kind, B, K in ((0, 37, 10), (1, 37, 23), (0, 1000, 10), (1, 300, 12)):   # K <= 16: vectorised kernels; 23: generic
             toks = [rn(B, 4, 128), rn(B, 1, 64), rn(B, 8, 128)]
             ws = [rn(K, 128) / 11, rn(K, 64) / 8, rn(K, 128) / 11]
             bs = [0.1 * rn(K) for _ in range(3)]
@@ -222,16 +221,16 @@ def run_group(g):
             Ls = [O.cross_entropy(l, labels) if kind == 0 else O.bce_pos_weight(l, labels.double(), pw.double()) for l in lg]
             tot = sum(h * L for h, L in zip(hw, Ls))
             losses, logits, preds = ops.heads_loss_fwd(toks, ws, bs, labels, pw, hw, kind)
-            ok &= report(f"heads kind{kind} logits", rel(logits, torch.stack(lg)), 1e-5)
-            ok &= report(f"heads kind{kind} losses", rel(losses, torch.stack([tot] + Ls)), 1e-5)
+            ok &= report(f"heads kind{kind} B{B} K{K} logits", rel(logits, torch.stack(lg)), 1e-5)
+            ok &= report(f"heads kind{kind} B{B} K{K} losses", rel(losses, torch.stack([tot] + Ls)), 1e-5)
             pr = torch.stack([l.argmax(1) for l in lg]) if kind == 0 else torch.stack([(l > 0).long() for l in lg])
-            ok &= report(f"heads kind{kind} preds", float((preds != pr).sum()), 0.5)
+            ok &= report(f"heads kind{kind} B{B} K{K} preds", float((preds != pr).sum()), 0.5)
             tot.backward()
             dt, dw, db = ops.heads_loss_bwd(toks, ws, bs, labels, pw, hw, kind, logits, 1.0, None)
             for i in range(3):
-                ok &= report(f"heads kind{kind} dtok{i}", rel(dt[i], td[i].grad), 1e-5)
-                ok &= report(f"heads kind{kind} dw{i}", rel(dw[i], wd[i].grad), 1e-5)
-                ok &= report(f"heads kind{kind} db{i}", rel(db[i], bd[i].grad), 1e-5)
+                ok &= report(f"heads kind{kind} B{B} K{K} dtok{i}", rel(dt[i], td[i].grad), 1e-5)
+                ok &= report(f"heads kind{kind} B{B} K{K} dw{i}", rel(dw[i], wd[i].grad), 1e-5)
+                ok &= report(f"heads kind{kind} B{B} K{K} db{i}", rel(db[i], bd[i].grad), 1e-5)
     elif g == "patch_embed":
         # (B, cin, H, W, P, D): fused gather-GEMM shapes (P % 8 == 0), ragged M / D / K tiles, and the fallback (P = 14, fp32)
         for (B, cin, H, W, P, D) in [(64, 1, 112, 112, 56, 128), (37, 3, 32, 48, 16, 200), (5, 2, 16, 24, 8, 72),
