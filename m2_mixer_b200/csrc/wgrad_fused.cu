@@ -1,20 +1,22 @@
-// Channel-mixing weight gradients with the hidden activation RECOMPUTED on chip (no G / dH round trip through HBM).
+// Channel-mixing weight gradients.  Two kernels:
+//   wgrad_dh_kernel     (default, M2B200_CHAIN_GEN=4): dH comes back from the dgrad chain's spill by TMA, only G is recomputed
+//   wgrad_fused_kernel  (M2B200_CHAIN_GEN=2, the A/B form): G AND dH recomputed on chip, nothing spilled
 //
 // Reference arithmetic (autograd of MixerBlock.channel_mix, modules/mixer.py:37-40):
 //     H = LN(u) W1^T + b1 ;  G = Drop(GELU(H)) ;  dG = dY W2 ;  dH = dG * Drop'(.) * GELU'(H)
 //     dW1 += dH^T LN(u)      dW2 += dY^T G      db1 += colsum(dH)
 //
 // The dgrad chain (chain_ts.cu) walks token-row tiles and needs every channel of a row; the weight gradients need
-// every ROW of a channel.  Instead of spilling G and dH ([M x C] bf16 each, 200 MB per block at B = 4096) this kernel
-// is tiled the other way round: a CTA owns one 64-channel chunk (its W1 / W2 slices stay resident in shared memory,
-// its dW1^T / dW2 slices accumulate in TMEM for the whole kernel) and streams the bf16 LN(u) / dY row tiles (8 MB per
-// block, L2 resident) through a TMA ring:
-//     per 128-row tile i:   H  = Xn_i . W1c^T        dG = dY_i . W2c                      (recompute, 2 x 8 MMA N=64)
-//                           epilogue: G, dH -> bf16 -> shared memory (MN-major B operands), db1 partials in registers
+// every ROW of a channel.  Both kernels here are tiled the other way round: a CTA owns one 128-channel slice (its W1 / W2
+// slices stay resident in shared memory, its dW1^T / dW2 slices accumulate in TMEM for the whole kernel) and streams the bf16
+// LN(u) / dY row tiles (8 MB per block, L2 resident) through TMA:
+//     per 96-row tile i:    H  = Xn_i . W1c^T      ( dG = dY_i . W2c  in wgrad_fused only )          recompute GEMMs, N = 128
+//                           epilogue: G ( and dH ) -> bf16 -> shared memory (MN-major B operands)
 //                           dW1c^T += Xn_i^T . dH    dW2c += dY_i^T . G                   (A = the SAME row tiles,
 //                                                                                          consumed MN-major)
-// grid = (C / 64 chunks) x R row splits, R chosen so that one wave fills the 148 SMs; the R partial sums of a chunk
-// are combined with fp32 reductions into the running gradients.
+// grid = (C / 128 slices) x R row splits, R chosen so that one wave fills the 148 SMs; the R partial sums of a slice
+// are combined with fp32 reductions into the running gradients.  wgrad_fused_kernel is described first (round 1), the
+// generation-4 kernel and what its measurements changed follow below.
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap.cuh"
