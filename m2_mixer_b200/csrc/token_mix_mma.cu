@@ -70,6 +70,33 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
+// Which hidden column an MMA row stands for.  The contractions run over tokens (k), so ANY row <-> column labelling works as
+// long as loads, stores, the LayerNorm affine and the dropout indices use the same one.
+//   pair form (warps with an ODD number of m-tiles): row g / g + 8 of m-tile mt = columns 16 mt + 2 g, + 1: a lane owns PAIRS
+//     of adjacent columns, and each dropout hash (one per quad of adjacent elements) serves one pair: half of it is unused;
+//   quad form (even number of m-tiles per warp, the shipped D = 128 shapes): the two m-tiles 2 p, 2 p + 1 of a pair cover 32
+//     columns and row g / g + 8 of tile 2 p + e = columns 32 p + 4 g + 2 e, + 1: a lane's four rows of the tile pair are ONE
+//     aligned quad, so both tiles ask for the same hash (the compiler computes it once): the mask arithmetic, ~a third of
+//     the forward's instructions (profiles/r02_token_mix_sass.md), halves.
+// bytes of (a | b << 32) selected by the nibbles of `sel`; a nibble with bit 3 set replicates the byte's sign bit
+__device__ __forceinline__ uint32_t prmt_rr(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+template <bool kQuad>
+__device__ __forceinline__ int tm_col(int mtg, int g) {
+  return kQuad ? 32 * (mtg >> 1) + 4 * g + 2 * (mtg & 1) : 16 * mtg + 2 * g;
+}
+template <bool kQuad>   // hash-input offset of the tile's quad within a row (the lane's part is tm_lane_quad)
+__device__ __forceinline__ uint32_t tm_tile_quad(int mtg) {
+  return static_cast<uint32_t>(kQuad ? 8 * (mtg >> 1) : 4 * mtg) * kDropGolden;
+}
+template <bool kQuad>
+__device__ __forceinline__ uint32_t tm_lane_quad(int g) { return static_cast<uint32_t>(kQuad ? g : (g >> 1)) * kDropGolden; }
+template <bool kQuad>   // which 16-bit half of the quad's flags belongs to this lane's pair of the tile
+__device__ __forceinline__ uint32_t tm_shift(int mtg, int g) { return static_cast<uint32_t>(kQuad ? (mtg & 1) : (g & 1)) * 16u; }
+
 // D = 16 * DM, T <= TP (multiple of 16), N <= NP (8 or 16).
 template <int DM, int TP, int NP, bool kDrop, int WS>
 __global__ void __launch_bounds__(kWarps * 32, WS == 4 ? 3 : 1)
@@ -133,8 +160,8 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
   //   ((row * D + 16 mt + 2 g) >> 2) * golden + key  =  base(row) + 4 mt * golden,   pair select shift = 16 (g & 1);
   // rows are (b T + t) for the hidden site and (b N + n) for the output site, t / n = 2 tq + compile-time offsets.
   constexpr uint32_t kRowG = static_cast<uint32_t>(D / 4) * kDropGolden;       // one row further
-  const uint32_t dsh = (g & 1) * 16;
-  const uint32_t lane_h = static_cast<uint32_t>(g >> 1) * kDropGolden + static_cast<uint32_t>(2 * tq) * kRowG;
+  constexpr bool kQuad = DMW % 2 == 0;
+  const uint32_t lane_h = tm_lane_quad<kQuad>(g) + static_cast<uint32_t>(2 * tq) * kRowG;
   const uint32_t key_h = kDrop ? drop_key(dh) : 0u, key_o = kDrop ? drop_key(dout) : 0u;
   for (int b = blockIdx.x * SPB + slot; b < B; b += gridDim.x * SPB) {   // the WS warps of a slot walk the same samples
     const float* xb = x + static_cast<long long>(b) * N * D;
@@ -151,7 +178,7 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
         float acc = 0.f;
 #pragma unroll
         for (int mt = 0; mt < DMW; ++mt) {
-          xr[mt][kh][nn] = n < N ? *reinterpret_cast<const float2*>(xb + n * D + 16 * (mt0 + mt) + 2 * g) : make_float2(0.f, 0.f);
+          xr[mt][kh][nn] = n < N ? *reinterpret_cast<const float2*>(xb + n * D + tm_col<kQuad>(mt0 + mt, g)) : make_float2(0.f, 0.f);
           acc += xr[mt][kh][nn].x + xr[mt][kh][nn].y;
         }
         s[kh][nn] = group_sum(acc);
@@ -183,7 +210,9 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
     for (int mt = 0; mt < DMW; ++mt) {
       const int mtg = mt0 + mt;
-      const int d_lo = 16 * mtg + 2 * g;
+      const int d_lo = tm_col<kQuad>(mtg, g);
+      const uint32_t dsh = tm_shift<kQuad>(mtg, g);
+      const uint32_t sel_lo = 0xCC88u + 0x1111u * (dsh >> 3);   // d_lo is byte dsh / 8 of the quad's flags, d_hi the next one
       const float2 gm = *reinterpret_cast<const float2*>(ln_w + d_lo);
       const float2 bt = *reinterpret_cast<const float2*>(ln_b + d_lo);
       // A1: a0 = (row g = d_lo, k = 2tq..+1), a1 = (row g+8 = d_hi, same k), a2 / a3 = k + 8
@@ -211,15 +240,19 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
       uint32_t a2f[KS2][4];
 #pragma unroll
       for (int j = 0; j < NT1; ++j) {
-        float2 lo = gelu2(make_float2(c[j][0], c[j][1]), hs);
-        float2 hi = gelu2(make_float2(c[j][2], c[j][3]), hs);
-        if (kDrop) {   // hidden-site index (b T + t) D + d, t = 8 j + 2 tq: (d_lo, d_hi) is one hash pair
-          const uint32_t h0 = hin_h + static_cast<uint32_t>(8 * j) * kRowG + static_cast<uint32_t>(4 * mtg) * kDropGolden;
-          drop_zero2_hin(dh, lo.x, hi.x, h0, dsh);   // scale folded into the GELU (hs)
-          drop_zero2_hin(dh, lo.y, hi.y, h0 + kRowG, dsh);
+        const float2 lo = gelu2(make_float2(c[j][0], c[j][1]), hs);   // scale folded into the GELU (hs)
+        const float2 hi = gelu2(make_float2(c[j][2], c[j][3]), hs);
+        uint32_t plo = pack_bf16(lo.x, lo.y), phi = pack_bf16(hi.x, hi.y);
+        if (kDrop) {   // hidden-site index (b T + t) D + d, t = 8 j + 2 tq (+ 1): the packed halves are two ROWS of one column
+          const uint32_t h0 = hin_h + static_cast<uint32_t>(8 * j) * kRowG + tm_tile_quad<kQuad>(mtg);
+          const uint32_t f0 = drop_flags_from_hash_input(dh, h0), f1 = drop_flags_from_hash_input(dh, h0 + kRowG);
+          // AND masks straight on the packed pairs: one sign-replicating PRMT over the two rows' flag words per pair (byte k of
+          // f0 -> low half, byte k of f1 -> high half) instead of a test, a compare and a select per element
+          plo &= prmt_rr(f0, f1, sel_lo);
+          phi &= prmt_rr(f0, f1, sel_lo + 0x1111u);
         }
-        a2f[j >> 1][(j & 1) * 2] = pack_bf16(lo.x, lo.y);
-        a2f[j >> 1][(j & 1) * 2 + 1] = pack_bf16(hi.x, hi.y);
+        a2f[j >> 1][(j & 1) * 2] = plo;
+        a2f[j >> 1][(j & 1) * 2 + 1] = phi;
       }
       float o[KN][4];
 #pragma unroll
@@ -240,7 +273,7 @@ token_mix_mma_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
             float v_lo = o[jn][nn], v_hi = o[jn][2 + nn];
             const long long off = (static_cast<long long>(b) * N + n) * D + d_lo;
             if (kDrop)   // output-site index (b N + n) D + d, n = 8 jn + 2 tq + nn
-              drop_apply2_hin(dout, v_lo, v_hi, hin_o + static_cast<uint32_t>(8 * jn + nn) * kRowG + static_cast<uint32_t>(4 * mtg) * kDropGolden, dsh);
+              drop_apply2_hin(dout, v_lo, v_hi, hin_o + static_cast<uint32_t>(8 * jn + nn) * kRowG + tm_tile_quad<kQuad>(mtg), dsh);
             *reinterpret_cast<float2*>(u + off) = make_float2(xr[mt][jn][nn].x + v_lo, xr[mt][jn][nn].y + v_hi);
           }
         }
@@ -333,8 +366,8 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
 
   // dropout index arithmetic in 32 bits, incrementally (see the forward kernel)
   constexpr uint32_t kRowG = static_cast<uint32_t>(D / 4) * kDropGolden;
-  const uint32_t dsh = (g & 1) * 16;
-  const uint32_t lane_h = static_cast<uint32_t>(g >> 1) * kDropGolden + static_cast<uint32_t>(2 * tq) * kRowG;
+  constexpr bool kQuad = DMW % 2 == 0;
+  const uint32_t lane_h = tm_lane_quad<kQuad>(g) + static_cast<uint32_t>(2 * tq) * kRowG;
   const uint32_t key_h = kDrop ? drop_key(dh) : 0u, key_o = kDrop ? drop_key(dout) : 0u;
   for (int b = blockIdx.x * SPB + slot; b < B; b += gridDim.x * SPB) {   // the WS warps of a slot walk the same samples
     const long long sbase = static_cast<long long>(b) * N * D;
@@ -352,7 +385,7 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
         float acc = 0.f;
 #pragma unroll
         for (int mt = 0; mt < DMW; ++mt) {
-          xr[mt][kh][nn] = n < N ? *reinterpret_cast<const float2*>(xb + n * D + 16 * (mt0 + mt) + 2 * g) : make_float2(0.f, 0.f);
+          xr[mt][kh][nn] = n < N ? *reinterpret_cast<const float2*>(xb + n * D + tm_col<kQuad>(mt0 + mt, g)) : make_float2(0.f, 0.f);
           acc += xr[mt][kh][nn].x + xr[mt][kh][nn].y;
         }
         mean[kh][nn] = group_sum(acc);
@@ -386,7 +419,8 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
 #pragma unroll
     for (int mt = 0; mt < DMW; ++mt) {
       const int mtg = mt0 + mt;
-      const int d_lo = 16 * mtg + 2 * g;
+      const int d_lo = tm_col<kQuad>(mtg, g);
+      const uint32_t dsh = tm_shift<kQuad>(mtg, g);
       const float2 gm = *reinterpret_cast<const float2*>(ln_w + d_lo);
       const float2 bt = *reinterpret_cast<const float2*>(ln_b + d_lo);
       uint32_t a1f[KN > 2 ? 2 * KN : 4] = {}, a3f[KN > 2 ? 2 * KN : 4] = {};
@@ -405,7 +439,7 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
         float2 u0 = v0 ? *reinterpret_cast<const float2*>(dub + n * D + d_lo) : make_float2(0.f, 0.f);
         float2 u1 = v1 ? *reinterpret_cast<const float2*>(dub + (n + 1) * D + d_lo) : make_float2(0.f, 0.f);
         if (kDrop) {   // gradient of the dropped branch output: rows b N + n, n = 8 kh + 2 tq (+ 1)
-          const uint32_t h0 = hin_o + static_cast<uint32_t>(8 * kh) * kRowG + static_cast<uint32_t>(4 * mtg) * kDropGolden;
+          const uint32_t h0 = hin_o + static_cast<uint32_t>(8 * kh) * kRowG + tm_tile_quad<kQuad>(mtg);
           drop_apply2_hin(dout, u0.x, u0.y, h0, dsh);
           drop_apply2_hin(dout, u1.x, u1.y, h0 + kRowG, dsh);
         }
@@ -437,7 +471,7 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
         float2 h_lo = __fmul2_rn(make_float2(c3[j][0], c3[j][1]), dg_lo);
         float2 h_hi = __fmul2_rn(make_float2(c3[j][2], c3[j][3]), dg_hi);
         if (kDrop) {   // rows b T + t, t = 8 j + 2 tq (+ 1)
-          const uint32_t h0 = hin_h + static_cast<uint32_t>(8 * j) * kRowG + static_cast<uint32_t>(4 * mtg) * kDropGolden;
+          const uint32_t h0 = hin_h + static_cast<uint32_t>(8 * j) * kRowG + tm_tile_quad<kQuad>(mtg);
           drop_zero2x2_hin(dh, g_lo.x, g_hi.x, h_lo.x, h_hi.x, h0, dsh);   // scale folded into gelu2_grad
           drop_zero2x2_hin(dh, g_lo.y, g_hi.y, h_lo.y, h_hi.y, h0 + kRowG, dsh);
         }
@@ -518,7 +552,7 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
       }
 #pragma unroll
     for (int mt = 0; mt < DMW; ++mt) {
-      const int d_lo = 16 * (mt0 + mt) + 2 * g;
+      const int d_lo = tm_col<kQuad>(mt0 + mt, g);
       const float2 gm = *reinterpret_cast<const float2*>(ln_w + d_lo);
 #pragma unroll
       for (int kh = 0; kh < KN; ++kh)
@@ -569,7 +603,7 @@ token_mix_mma_bwd_kernel(const float* __restrict__ du, const float* __restrict__
 #pragma unroll
   for (int mt = 0; mt < DMW; ++mt)
     if ((mt & 3) == tq) {
-      const int d_lo = 16 * (mt0 + mt) + 2 * g;
+      const int d_lo = tm_col<kQuad>(mt0 + mt, g);
       atomicAdd(&sGam[d_lo], dgam[mt >> 2][0]); atomicAdd(&sGam[d_lo + 1], dgam[mt >> 2][1]);
       atomicAdd(&sBet[d_lo], dbet[mt >> 2][0]); atomicAdd(&sBet[d_lo + 1], dbet[mt >> 2][1]);
     }
