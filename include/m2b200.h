@@ -97,7 +97,10 @@ int m2b200_token_mix_bwd(const float* du, const float* x, const float* ln_w, con
 
 /* ---- MixerBlock.channel_mix + residual: modules/mixer.py:37-40,45
  *   y = u + W2 . GELU(W1 . LN(u) + b1) + b2,   u,y [M][D] (M = B*N token rows), w1 [C][D], w2 [D][C]
- * BF16 mode reads the bf16 caches w1_bf16 [C][D] and w2_bf16 [D][ldw2] (ldw2 = C rounded up to 8, pad zero).   */
+ * BF16 mode reads the bf16 caches w1_bf16 [C][D] and w2_bf16 [D][ldw2] (ldw2 = C rounded up to 8, pad zero).
+ * Workspace: the fused forward (D <= 256) needs none; the fused backward (D <= 128) needs the bf16 copies of LN(u) and dY
+ * (2 M D bf16) plus the bf16 dH that the dgrad chain spills for the weight-gradient kernel (M * ceil(C / 64) * 64 bf16,
+ * written and read once); other shapes / FP32 mode materialise the [M][C] intermediates.  Always ask the query.   */
 size_t m2b200_channel_mix_workspace_bytes(int M, int D, int C, int precision, int backward);
 int m2b200_channel_mix_fwd(const float* u, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
                            const float* w2, const float* b2, const void* w1_bf16, const void* w2_bf16, int ldw2, float* y,

@@ -245,3 +245,23 @@ def test_ops_have_fake_kernels_for_meta_tracing():
         losses, logits, preds = o.heads_loss_fwd([x, x, x], [f(10, 128)] * 3, [f(10)] * 3, torch.empty(8, dtype=torch.int64, device="cuda"),
                                                  None, [1.0, 1.0, 1.0], 0)
         assert losses.shape == (4,) and logits.shape == (3, 8, 10) and preds.dtype == torch.int64
+
+
+def test_channel_mix_workspace_query_follows_the_backward_generation():
+    """The workspace query is the contract between the torch shim and the C ABI: with the default backward (dH spilled through
+    TMA stores) it includes the chunk-major dH buffer, with M2B200_CHAIN_GEN=2 (weight gradients recompute G and dH on chip)
+    only the two bf16 operand copies.  The generation is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("from m2_mixer_b200 import _lib; lib = _lib.load(); "
+            "print(lib.m2b200_channel_mix_workspace_bytes(16384, 128, 3072, 1, 1))")
+    out = {}
+    for gen in ("2", "4"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root,
+                           env=dict(os.environ, M2B200_CHAIN_GEN=gen), timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[gen] = int(r.stdout.strip().splitlines()[-1])
+    assert out["2"] == 2 * 16384 * 128 * 2
+    assert out["4"] == out["2"] + 16384 * 3072 * 2
